@@ -1,0 +1,208 @@
+/*
+ * mp2v_recon.h -- C ABI of the B200 MPEG-2 reconstruction back end (libmp2v_b200.so).
+ *
+ * This is the batched replacement of the reference decoder's per-block / per-macroblock
+ * reconstruction seam (fxslava/tiny_mp2v_dec):
+ *
+ *   reference call site (synchronous, on a CPU worker thread)           replaced by
+ *   ------------------------------------------------------------------  --------------------------------
+ *   parse_block<>: dequant + saturate + mismatch  mb_decoder.cpp:74-155   mp2v_coef_t stream  -> kernel
+ *   inverse_dct_template<add>(plane,F,stride)     idct_sse2.hpp:96-120    fused in the same kernel
+ *   mc_pred_16xh/8xh[4], mc_bidir_16xh/8xh[16]    mc.h:6-12, mc.cpp:4-25  mp2v_mb_info_t      -> kernel
+ *   base_motion_compensation<>                    mb_decoder.cpp:291-339  (per-MB flags + vectors)
+ *   mp2v_picture_c::init() quantiser_matrices     decoder.cpp:154-192     mp2v_pic_params_t.W
+ *   frame_c planes / strides / pool               decoder.cpp:44-105      device frame pool (frame ids)
+ *   picture dependencies + display hand-off       threads.cpp, decoder.cpp:346-379   submit order + map_frame
+ *
+ * The host slice parser (VLC, DC prediction, motion-vector prediction, skipped-macroblock
+ * resolution) fills one mp2v_picture_t per coded picture in pinned memory; mp2v_recon_submit()
+ * copies it to the device and reconstructs the whole picture (batched with any other submitted
+ * pictures that do not depend on each other) with hand-written sm_100a kernels.  There is no CPU
+ * fallback: every entry point fails with MP2V_ERR_CUDA when no device / kernel image is usable.
+ *
+ * Plain C: pointers and sizes only, no C++ or torch types.  Thread-safety: one context may be used
+ * from several threads for acquire / fill (disjoint pictures); submit, map and sync are serialised
+ * internally.
+ */
+#ifndef MP2V_RECON_H
+#define MP2V_RECON_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#if defined(__GNUC__)
+#define MP2V_API __attribute__((visibility("default")))
+#else
+#define MP2V_API
+#endif
+
+/* ---- status codes --------------------------------------------------------------------------- */
+enum {
+    MP2V_OK = 0,
+    MP2V_ERR_ARG = -1,      /* bad argument / geometry / id                                    */
+    MP2V_ERR_CUDA = -2,     /* CUDA runtime or launch failure (no device, no sm_100a image...)  */
+    MP2V_ERR_NOMEM = -3,
+    MP2V_ERR_STATE = -4,    /* call order violated (e.g. reference frame never written)          */
+    MP2V_ERR_RANGE = -5     /* picture data fails validation (motion vector outside the frame,
+                               coefficient index past the arena, ...)                           */
+};
+
+/* ---- per-macroblock record (16 bytes) --------------------------------------------------------
+ * One per macroblock in raster order (skipped macroblocks included, resolved by the host to a
+ * prediction-only record, mb_decoder.cpp:541-550).
+ *   coef_off : index of this macroblock's first mp2v_coef_t in the picture's coefficient arena
+ *   bits     : [ 9: 0] n_coef   number of coefficient records (<= 12*64)
+ *              [16:10] qscale   quantiser_scale 1..112 after q_scale_type mapping
+ *                               (decoder.cpp:140-145, mb_decoder.cpp:555-563)
+ *              [28:17] cbp      bit i = block i coded; block order Y0 Y1 Y2 Y3 Cb Cr, then
+ *                               Cb' Cr' (4:2:2 lower halves), then 4:4:4 right halves
+ *                               (mb_decoder.cpp:177-195)
+ *              [29]    intra    blocks overwrite (add=false); no prediction
+ *              [30]    fwd      prediction from L0 with mv[0]
+ *              [31]    bwd      prediction from L1 with mv[1]; fwd|bwd = rounding average
+ *              non-intra with neither fwd nor bwd is not emitted: the host resolves P "no-MC"
+ *              and P-skipped macroblocks to fwd with a zero vector (mb_decoder.cpp:329-338).
+ *   mv[s][t] : luma half-pel units, s = 0 forward / 1 backward, t = 0 x / 1 y
+ */
+typedef struct mp2v_mb_info {
+    uint32_t coef_off;
+    uint32_t bits;
+    int16_t  mv[2][2];
+} mp2v_mb_info_t;
+
+#define MP2V_MB_NCOEF(b)   ((b) & 0x3ffu)
+#define MP2V_MB_QSCALE(b)  (((b) >> 10) & 0x7fu)
+#define MP2V_MB_CBP(b)     (((b) >> 17) & 0xfffu)
+#define MP2V_MB_INTRA      (1u << 29)
+#define MP2V_MB_FWD        (1u << 30)
+#define MP2V_MB_BWD        (1u << 31)
+#define MP2V_MB_BITS(ncoef, qscale, cbp, flags) \
+    (((uint32_t)(ncoef) & 0x3ffu) | (((uint32_t)(qscale) & 0x7fu) << 10) | (((uint32_t)(cbp) & 0xfffu) << 17) | (flags))
+
+/* ---- coefficient record (4 bytes) ------------------------------------------------------------
+ * Run/level-decoded, NOT dequantised ("ship levels, not products").  Records of one macroblock are
+ * contiguous, block by block in coding order, each block's records in scan order.
+ *   [15: 0] level   signed; for MP2V_COEF_RAW the final intra DC value
+ *                   wrap16(dc_pred << (3 - intra_dc_precision)) (mb_decoder.cpp:46-72)
+ *   [21:16] pos     scan position i (index into W[set][], mb_decoder.cpp:140-143)
+ *   [25:22] blk     block index 0..11 inside the macroblock
+ *   [26]    RAW     intra DC: stored as is, excluded from the mismatch sum (mb_decoder.cpp:160)
+ *   [27]    FIRST   non-intra first coefficient coded "1s" (mb_decoder.cpp:79-88):
+ *                   val = (3*W[0]*qscale)>>5 with sign, NOT clamped, included in the mismatch sum
+ */
+typedef uint32_t mp2v_coef_t;
+#define MP2V_COEF_RAW    (1u << 26)
+#define MP2V_COEF_FIRST  (1u << 27)
+#define MP2V_COEF(level, pos, blk, flags) \
+    (((uint32_t)(uint16_t)(int16_t)(level)) | ((uint32_t)(pos) << 16) | ((uint32_t)(blk) << 22) | (flags))
+#define MP2V_COEF_LEVEL(c) ((int)(int16_t)((c) & 0xffffu))
+#define MP2V_COEF_POS(c)   (((c) >> 16) & 63u)
+#define MP2V_COEF_BLK(c)   (((c) >> 22) & 15u)
+
+/* ---- per-picture parameters ------------------------------------------------------------------ */
+typedef struct mp2v_pic_params {
+    uint8_t  W[4][64];             /* quantiser matrices indexed by SCAN POSITION, exactly the
+                                      reference's quantiser_matrices (decoder.cpp:185-191):
+                                      0 intra, 1 non-intra, 2 chroma intra, 3 chroma non-intra.
+                                      Blocks 0..5 use 0/1, blocks 6..11 use 2/3 (reference quirk,
+                                      mb_decoder.cpp:177-195).                                   */
+    int32_t  picture_coding_type;  /* 1 I, 2 P, 3 B                                              */
+    int32_t  alternate_scan;       /* selects g_scan_trans[alt] (scan_c.cpp:4-21)                 */
+    int32_t  dst_frame;            /* frame id written by this picture                           */
+    int32_t  l0_frame;             /* forward reference frame id, -1 if none                     */
+    int32_t  l1_frame;             /* backward reference frame id, -1 if none                    */
+    uint32_t n_coef;               /* coefficient records used (arena high-water mark)           */
+    uint32_t reserved[2];
+} mp2v_pic_params_t;
+
+/* ---- a picture's pinned SoA buffers (owned by the context) ------------------------------------ */
+typedef struct mp2v_picture {
+    mp2v_pic_params_t* params;     /* one                                                        */
+    mp2v_mb_info_t*    mb;         /* mb_count records, raster order                             */
+    mp2v_coef_t*       coef;       /* coef_capacity records                                      */
+    uint32_t           mb_count;
+    uint32_t           coef_capacity;
+    int32_t            slot;       /* context-internal                                           */
+    int32_t            reserved;
+} mp2v_picture_t;
+
+typedef struct mp2v_recon_config {
+    int32_t device;                /* CUDA device ordinal                                        */
+    int32_t width;                 /* coded luma width, multiple of 16 (decoder_config_t.width)   */
+    int32_t height;                /* coded luma height, multiple of 16                          */
+    int32_t chroma_format;         /* 1 = 4:2:0, 2 = 4:2:2, 3 = 4:4:4 (mp2v_hdr.h:56-58)          */
+    int32_t n_frames;              /* device frame pool size (>= 3)                              */
+    int32_t n_pictures;            /* picture slots in flight (pinned + device arenas)           */
+    int32_t max_batch;             /* max pictures fused into one launch (0 = default)           */
+    int32_t flags;                 /* MP2V_RECON_* below                                         */
+} mp2v_recon_config_t;
+
+#define MP2V_RECON_VALIDATE   1    /* check vectors / offsets on the host before launch          */
+
+typedef struct mp2v_recon mp2v_recon_t;
+
+/* frame geometry: the reference's frame_c rule (decoder.cpp:44-66) */
+typedef struct mp2v_frame_layout {
+    int32_t width[3], height[3], stride[3];
+    size_t  plane_offset[3];
+    size_t  bytes;                 /* one frame, all planes, 256-byte aligned planes             */
+} mp2v_frame_layout_t;
+
+MP2V_API int  mp2v_frame_layout(int width, int height, int chroma_format, mp2v_frame_layout_t* out);
+
+MP2V_API int  mp2v_recon_create(const mp2v_recon_config_t* cfg, mp2v_recon_t** out);
+MP2V_API void mp2v_recon_destroy(mp2v_recon_t* ctx);
+MP2V_API const char* mp2v_recon_last_error(mp2v_recon_t* ctx);   /* ctx may be NULL: creation errors */
+
+/* Blocks until a picture slot is free; the returned buffers stay valid until the picture's
+ * reconstruction has been issued (submit) or it is given back with release_picture. */
+MP2V_API int  mp2v_recon_acquire_picture(mp2v_recon_t* ctx, mp2v_picture_t** out);
+MP2V_API int  mp2v_recon_release_picture(mp2v_recon_t* ctx, mp2v_picture_t* pic);
+
+/* Queue one filled picture: H2D of its records + reconstruction.  Pictures must be submitted in
+ * coded order (references before the pictures that use them).  Asynchronous; consecutive
+ * submissions that do not depend on one another are fused into one launch. */
+MP2V_API int  mp2v_recon_submit(mp2v_recon_t* ctx, mp2v_picture_t* pic);
+MP2V_API int  mp2v_recon_flush(mp2v_recon_t* ctx);               /* launch whatever is queued       */
+MP2V_API int  mp2v_recon_sync(mp2v_recon_t* ctx);                /* flush + wait for the device     */
+
+/* Device-resident mode (benchmarks, re-decode): copy a filled picture to its device arena once,
+ * keep the slot, then reconstruct any list of resident pictures without host traffic.
+ * levels[] (optional) gives each picture's dependency level: pictures of equal level are fused into
+ * one launch, levels run in increasing order. */
+MP2V_API int  mp2v_recon_upload(mp2v_recon_t* ctx, mp2v_picture_t* pic);
+MP2V_API int  mp2v_recon_run_resident(mp2v_recon_t* ctx, mp2v_picture_t* const* pics, const int32_t* levels, int n);
+
+/* Copy a reconstructed frame to host memory (waits for the pictures that write it).
+ * dst[p] / dst_stride[p]: caller buffers (pinned or pageable); rows are width[p] bytes. */
+MP2V_API int  mp2v_recon_download_frame(mp2v_recon_t* ctx, int frame_id, uint8_t* const dst[3], const int32_t dst_stride[3]);
+/* Same, into the context's own pinned mirror of that frame; planes[] valid until the next map of
+ * the same frame id. */
+MP2V_API int  mp2v_recon_map_frame(mp2v_recon_t* ctx, int frame_id, uint8_t* planes[3], int32_t strides[3]);
+/* Test hook: fill a device frame from host planes (used to seed references in kernel unit tests). */
+MP2V_API int  mp2v_recon_upload_frame(mp2v_recon_t* ctx, int frame_id, const uint8_t* const src[3], const int32_t src_stride[3]);
+
+/* Device pointers of a frame's planes (zero-copy consumers, e.g. a CUDA renderer). */
+MP2V_API int  mp2v_recon_frame_device_ptrs(mp2v_recon_t* ctx, int frame_id, void* planes[3], int32_t strides[3]);
+
+/* Statistics of the context since creation / last reset. */
+typedef struct mp2v_recon_stats {
+    uint64_t pictures;             /* pictures reconstructed                                      */
+    uint64_t launches;             /* kernel launches issued                                      */
+    uint64_t h2d_bytes;
+    uint64_t d2h_bytes;
+    uint64_t algorithmic_bytes;    /* OUT + REF + COEF(128 B/coded block) + META   */
+    double   kernel_ms;            /* CUDA-event time of the reconstruction launches (when
+                                      timing is enabled)                                          */
+} mp2v_recon_stats_t;
+MP2V_API int  mp2v_recon_set_timing(mp2v_recon_t* ctx, int enable);
+MP2V_API int  mp2v_recon_get_stats(mp2v_recon_t* ctx, mp2v_recon_stats_t* out, int reset);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* MP2V_RECON_H */

@@ -1,0 +1,57 @@
+"""ctypes / numpy mirrors of include/mp2v_recon.h (one definition for every Python binding)."""
+import ctypes as C
+
+import numpy as np
+
+
+class MbInfo(C.Structure):
+    _fields_ = [("coef_off", C.c_uint32), ("bits", C.c_uint32), ("mv", (C.c_int16 * 2) * 2)]
+
+
+mb_dtype = np.dtype([("coef_off", "<u4"), ("bits", "<u4"), ("mv", "<i2", (2, 2))])
+assert mb_dtype.itemsize == 16 and C.sizeof(MbInfo) == 16
+
+MB_INTRA, MB_FWD, MB_BWD = 1 << 29, 1 << 30, 1 << 31
+COEF_RAW, COEF_FIRST = 1 << 26, 1 << 27
+
+
+def mb_ncoef(bits):
+    return bits & 0x3ff
+
+
+def mb_qscale(bits):
+    return (bits >> 10) & 0x7f
+
+
+def mb_cbp(bits):
+    return (bits >> 17) & 0xfff
+
+
+class PicParams(C.Structure):
+    _fields_ = [("W", (C.c_uint8 * 64) * 4), ("picture_coding_type", C.c_int32), ("alternate_scan", C.c_int32),
+                ("dst_frame", C.c_int32), ("l0_frame", C.c_int32), ("l1_frame", C.c_int32), ("n_coef", C.c_uint32),
+                ("reserved", C.c_uint32 * 2)]
+
+
+class Picture(C.Structure):
+    _fields_ = [("params", C.POINTER(PicParams)), ("mb", C.POINTER(MbInfo)), ("coef", C.POINTER(C.c_uint32)),
+                ("mb_count", C.c_uint32), ("coef_capacity", C.c_uint32), ("slot", C.c_int32), ("reserved", C.c_int32)]
+
+
+class ReconConfig(C.Structure):
+    _fields_ = [("device", C.c_int32), ("width", C.c_int32), ("height", C.c_int32), ("chroma_format", C.c_int32),
+                ("n_frames", C.c_int32), ("n_pictures", C.c_int32), ("max_batch", C.c_int32), ("flags", C.c_int32)]
+
+
+class FrameLayout(C.Structure):
+    _fields_ = [("width", C.c_int32 * 3), ("height", C.c_int32 * 3), ("stride", C.c_int32 * 3),
+                ("plane_offset", C.c_size_t * 3), ("bytes", C.c_size_t)]
+
+
+class ReconStats(C.Structure):
+    _fields_ = [("pictures", C.c_uint64), ("launches", C.c_uint64), ("h2d_bytes", C.c_uint64), ("d2h_bytes", C.c_uint64),
+                ("algorithmic_bytes", C.c_uint64), ("kernel_ms", C.c_double)]
+
+
+RECON_VALIDATE = 1
+OK, ERR_ARG, ERR_CUDA, ERR_NOMEM, ERR_STATE, ERR_RANGE = 0, -1, -2, -3, -4, -5
