@@ -40,7 +40,8 @@ class Picture(C.Structure):
 
 class ReconConfig(C.Structure):
     _fields_ = [("device", C.c_int32), ("width", C.c_int32), ("height", C.c_int32), ("chroma_format", C.c_int32),
-                ("n_frames", C.c_int32), ("n_pictures", C.c_int32), ("max_batch", C.c_int32), ("flags", C.c_int32)]
+                ("n_frames", C.c_int32), ("n_pictures", C.c_int32), ("max_batch", C.c_int32), ("flags", C.c_int32),
+                ("coef_capacity", C.c_uint32), ("reserved", C.c_uint32)]
 
 
 class FrameLayout(C.Structure):

@@ -1,0 +1,43 @@
+// MSB-first bit reader over a padded byte buffer (64-bit window, branch-light refill).
+//
+// Contract inherited from the reference's decode API: the caller pads the stream with
+// >= 64 readable bytes; like the reference's 32-bit word reader (bitstream.h:28-34) this reader may
+// touch a few bytes past the last syntax element but never more than 8 past the position it consumed.
+#pragma once
+#include <cstdint>
+#include <cstring>
+
+namespace mp2v {
+
+class bitreader_t {
+public:
+    bitreader_t() = default;
+    explicit bitreader_t(const uint8_t* p) { reset(p); }
+    void reset(const uint8_t* p) { ptr_ = p; buf_ = 0; cnt_ = 0; refill(); }
+
+    // make at least 56 bits available
+    inline void refill() {
+        uint64_t w;
+        memcpy(&w, ptr_, 8);
+        w = __builtin_bswap64(w);
+        buf_ |= w >> cnt_;
+        const int adv = (63 - cnt_) >> 3;
+        ptr_ += adv;
+        cnt_ += adv << 3;
+    }
+    // n in 1..32; valid after refill() as long as no more than 56 bits were consumed since
+    inline uint32_t peek(int n) const { return (uint32_t)(buf_ >> (64 - n)); }
+    inline uint32_t peek32() const { return (uint32_t)(buf_ >> 32); }
+    inline void skip(int n) { buf_ <<= n; cnt_ -= n; }
+    inline uint32_t get(int n) { refill(); const uint32_t v = peek(n); skip(n); return v; }
+    inline uint32_t get1() { refill(); const uint32_t v = (uint32_t)(buf_ >> 63); skip(1); return v; }
+    // position of the next unread bit, in bytes from `base` (rounded down)
+    inline const uint8_t* byte_pos() const { return ptr_ - ((cnt_ + 7) >> 3); }
+
+private:
+    const uint8_t* ptr_ = nullptr;
+    uint64_t buf_ = 0;   // unread bits, left aligned
+    int cnt_ = 0;        // number of valid bits in buf_
+};
+
+}  // namespace mp2v

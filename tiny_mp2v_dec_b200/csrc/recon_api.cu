@@ -1,0 +1,535 @@
+// C ABI of the reconstruction back end (include/mp2v_recon.h): device frame pool, pinned + device
+// picture arenas, launch batching and stream / event scheduling.  Replaces the roles of the
+// reference's frame_c pool (decoder.cpp:44-105) and task_queue_c dependency tracking
+// (threads.cpp) with CUDA streams and events.  No CPU reconstruction path exists in this library.
+#include <cuda_runtime.h>
+
+#include <algorithm>
+#include <condition_variable>
+#include <cstdio>
+#include <cstring>
+#include <mutex>
+#include <string>
+#include <vector>
+
+#include "mp2v_recon.h"
+#include "recon_kernels.cuh"
+
+using namespace mp2v;
+
+namespace {
+
+thread_local std::string g_create_error;
+
+enum slot_state_t { SLOT_FREE = 0, SLOT_FILLING, SLOT_QUEUED, SLOT_INFLIGHT, SLOT_RESIDENT };
+
+struct slot_t {
+    mp2v_picture_t pub{};
+    uint8_t* h_arena = nullptr;
+    uint8_t* d_arena = nullptr;
+    slot_state_t state = SLOT_FREE;
+    cudaEvent_t done = nullptr;        // recorded on the compute stream after the launch that consumed the slot
+    uint64_t alg_bytes = 0;
+    uint64_t seq = 0;                  // submission order, to recycle the oldest in-flight slot first
+};
+
+constexpr size_t kParamsBytes = 512;   // sizeof(mp2v_pic_params_t) rounded up; mb records follow
+
+}  // namespace
+
+struct mp2v_recon {
+    mp2v_recon_config_t cfg{};
+    mp2v_frame_layout_t lay{};
+    int nblk = 0, mbw = 0, mbh = 0, mb_count = 0, max_batch = 0;
+    size_t frame_alloc = 0, arena_bytes = 0, coef_off = 0;
+    uint8_t* d_frames = nullptr;
+    std::vector<uint8_t*> h_frames;            // pinned mirrors, allocated on first map
+    std::vector<cudaEvent_t> frame_ev;         // last writer of each frame
+    std::vector<uint8_t> frame_written;
+    cudaStream_t s_copy = nullptr, s_compute = nullptr, s_d2h = nullptr;
+    cudaEvent_t ev_h2d = nullptr;
+    std::vector<slot_t> slots;
+    std::vector<int> pending;                  // queued slots, submit order
+    std::mutex mu;
+    std::string err;
+    uint64_t seq = 0;
+    // statistics
+    mp2v_recon_stats_t stats{};
+    bool timing = false;
+    std::vector<std::pair<cudaEvent_t, cudaEvent_t>> timed;   // (start, stop) of launches not yet summed
+    std::vector<cudaEvent_t> ev_pool;
+
+    int fail(int code, const std::string& what) { err = what; return code; }
+    int cuda_fail(cudaError_t e, const char* what) {
+        err = std::string(what) + ": " + cudaGetErrorString(e);
+        return MP2V_ERR_CUDA;
+    }
+    uint8_t* frame_ptr(int id, int plane) const { return d_frames + (size_t)id * frame_alloc + lay.plane_offset[plane]; }
+    cudaEvent_t get_event() {
+        if (!ev_pool.empty()) { cudaEvent_t e = ev_pool.back(); ev_pool.pop_back(); return e; }
+        cudaEvent_t e = nullptr;
+        cudaEventCreate(&e);
+        return e;
+    }
+};
+
+extern "C" MP2V_API int mp2v_frame_layout(int width, int height, int chroma_format, mp2v_frame_layout_t* out) {
+    // frame_c::frame_c (decoder.cpp:44-66): 64-byte aligned strides, chroma per format
+    if (!out || width <= 0 || height <= 0 || (width & 15) || (height & 15) || chroma_format < 1 || chroma_format > 3) return MP2V_ERR_ARG;
+    out->width[0] = width; out->height[0] = height;
+    out->stride[0] = (width + 63) & ~63;
+    const bool full = chroma_format == 3;
+    out->width[1] = full ? width : width >> 1;
+    out->height[1] = chroma_format == 1 ? height >> 1 : height;
+    out->stride[1] = full ? out->stride[0] : ((out->stride[0] >> 1) + 63) & ~63;
+    out->width[2] = out->width[1]; out->height[2] = out->height[1]; out->stride[2] = out->stride[1];
+    size_t off = 0;
+    for (int p = 0; p < 3; p++) {
+        out->plane_offset[p] = off;
+        off += ((size_t)out->stride[p] * out->height[p] + 255) & ~(size_t)255;
+    }
+    out->bytes = off;
+    return MP2V_OK;
+}
+
+#define CK(call, what) do { cudaError_t e_ = (call); if (e_ != cudaSuccess) return ctx->cuda_fail(e_, what); } while (0)
+
+static void destroy_ctx(mp2v_recon* ctx) {
+    if (!ctx) return;
+    cudaSetDevice(ctx->cfg.device);
+    if (ctx->s_compute) cudaStreamSynchronize(ctx->s_compute);
+    if (ctx->s_copy) cudaStreamSynchronize(ctx->s_copy);
+    if (ctx->s_d2h) cudaStreamSynchronize(ctx->s_d2h);
+    for (auto& s : ctx->slots) {
+        if (s.h_arena) cudaFreeHost(s.h_arena);
+        if (s.d_arena) cudaFree(s.d_arena);
+        if (s.done) cudaEventDestroy(s.done);
+    }
+    for (auto* h : ctx->h_frames) if (h) cudaFreeHost(h);
+    for (auto e : ctx->frame_ev) if (e) cudaEventDestroy(e);
+    for (auto e : ctx->ev_pool) cudaEventDestroy(e);
+    for (auto& pr : ctx->timed) { cudaEventDestroy(pr.first); cudaEventDestroy(pr.second); }
+    if (ctx->ev_h2d) cudaEventDestroy(ctx->ev_h2d);
+    if (ctx->d_frames) cudaFree(ctx->d_frames);
+    if (ctx->s_copy) cudaStreamDestroy(ctx->s_copy);
+    if (ctx->s_compute) cudaStreamDestroy(ctx->s_compute);
+    if (ctx->s_d2h) cudaStreamDestroy(ctx->s_d2h);
+    delete ctx;
+}
+
+static int create_impl(mp2v_recon* ctx) {
+    const mp2v_recon_config_t& c = ctx->cfg;
+    if (mp2v_frame_layout(c.width, c.height, c.chroma_format, &ctx->lay) != MP2V_OK) return ctx->fail(MP2V_ERR_ARG, "bad geometry");
+    if (c.n_frames < 1 || c.n_pictures < 1 || c.max_batch < 0 || c.max_batch > kMaxBatch) return ctx->fail(MP2V_ERR_ARG, "bad pool sizes");
+    ctx->nblk = c.chroma_format == 1 ? 6 : c.chroma_format == 2 ? 8 : 12;
+    ctx->mbw = c.width / 16; ctx->mbh = c.height / 16; ctx->mb_count = ctx->mbw * ctx->mbh;
+    ctx->max_batch = c.max_batch ? c.max_batch : 8;
+    int ndev = 0;
+    cudaError_t e = cudaGetDeviceCount(&ndev);
+    if (e != cudaSuccess || ndev == 0) return ctx->fail(MP2V_ERR_CUDA, std::string("no CUDA device: ") + cudaGetErrorString(e));
+    if (c.device < 0 || c.device >= ndev) return ctx->fail(MP2V_ERR_ARG, "device ordinal out of range");
+    CK(cudaSetDevice(c.device), "cudaSetDevice");
+    cudaFuncAttributes fa;
+    e = recon_kernel_attributes(c.chroma_format, &fa);   // fails loudly when the sm_100a image cannot load on this device
+    if (e != cudaSuccess) return ctx->cuda_fail(e, "reconstruction kernel image not usable on this device (built for sm_100a only)");
+    CK(cudaStreamCreateWithFlags(&ctx->s_copy, cudaStreamNonBlocking), "stream");
+    CK(cudaStreamCreateWithFlags(&ctx->s_compute, cudaStreamNonBlocking), "stream");
+    CK(cudaStreamCreateWithFlags(&ctx->s_d2h, cudaStreamNonBlocking), "stream");
+    CK(cudaEventCreateWithFlags(&ctx->ev_h2d, cudaEventDisableTiming), "event");
+    // frames: the window staging over-reads one row below and 16 bytes right of a block (always inside
+    // this slack), so every frame carries two luma rows + 256 bytes of tail
+    ctx->frame_alloc = (ctx->lay.bytes + 2 * (size_t)ctx->lay.stride[0] + 256 + 255) & ~(size_t)255;
+    CK(cudaMalloc(&ctx->d_frames, ctx->frame_alloc * c.n_frames), "cudaMalloc frames");
+    CK(cudaMemset(ctx->d_frames, 0, ctx->frame_alloc * c.n_frames), "cudaMemset frames");
+    ctx->h_frames.assign(c.n_frames, nullptr);
+    ctx->frame_ev.assign(c.n_frames, nullptr);
+    ctx->frame_written.assign(c.n_frames, 0);
+    for (auto& ev : ctx->frame_ev) CK(cudaEventCreateWithFlags(&ev, cudaEventDisableTiming), "event");
+    // picture slots
+    const uint32_t worst = (uint32_t)ctx->mb_count * ctx->nblk * 64u;
+    const uint32_t cap = c.coef_capacity ? std::min(c.coef_capacity, worst) : worst;
+    ctx->coef_off = kParamsBytes + (((size_t)ctx->mb_count * sizeof(mp2v_mb_info_t) + 255) & ~(size_t)255);
+    ctx->arena_bytes = ctx->coef_off + (size_t)cap * sizeof(mp2v_coef_t);
+    ctx->slots.resize(c.n_pictures);
+    for (int i = 0; i < c.n_pictures; i++) {
+        slot_t& s = ctx->slots[i];
+        CK(cudaHostAlloc(&s.h_arena, ctx->arena_bytes, cudaHostAllocDefault), "cudaHostAlloc picture arena");
+        CK(cudaMalloc(&s.d_arena, ctx->arena_bytes), "cudaMalloc picture arena");
+        CK(cudaEventCreateWithFlags(&s.done, cudaEventDisableTiming), "event");
+        s.pub.params = reinterpret_cast<mp2v_pic_params_t*>(s.h_arena);
+        s.pub.mb = reinterpret_cast<mp2v_mb_info_t*>(s.h_arena + kParamsBytes);
+        s.pub.coef = reinterpret_cast<mp2v_coef_t*>(s.h_arena + ctx->coef_off);
+        s.pub.mb_count = (uint32_t)ctx->mb_count;
+        s.pub.coef_capacity = cap;
+        s.pub.slot = i;
+    }
+    CK(cudaDeviceSynchronize(), "cudaDeviceSynchronize");
+    return MP2V_OK;
+}
+
+extern "C" MP2V_API int mp2v_recon_create(const mp2v_recon_config_t* cfg, mp2v_recon_t** out) {
+    if (!cfg || !out) return MP2V_ERR_ARG;
+    static_assert(sizeof(mp2v_pic_params_t) <= kParamsBytes, "params block");
+    static_assert(sizeof(mp2v_mb_info_t) == 16, "mb record");
+    mp2v_recon* ctx = new mp2v_recon();
+    ctx->cfg = *cfg;
+    const int rc = create_impl(ctx);
+    if (rc != MP2V_OK) {
+        g_create_error = ctx->err;
+        destroy_ctx(ctx);
+        *out = nullptr;
+        return rc;
+    }
+    *out = ctx;
+    return MP2V_OK;
+}
+
+extern "C" MP2V_API void mp2v_recon_destroy(mp2v_recon_t* ctx) { destroy_ctx(ctx); }
+
+extern "C" MP2V_API const char* mp2v_recon_last_error(mp2v_recon_t* ctx) { return ctx ? ctx->err.c_str() : g_create_error.c_str(); }
+
+// ---------------------------------------------------------------------------------------------
+// launching
+
+static void fill_desc(mp2v_recon* ctx, const slot_t& s, pic_desc_t& d) {
+    const mp2v_pic_params_t& pp = *s.pub.params;
+    d.params = reinterpret_cast<const mp2v_pic_params_t*>(s.d_arena);
+    d.mb = reinterpret_cast<const mp2v_mb_info_t*>(s.d_arena + kParamsBytes);
+    d.coef = reinterpret_cast<const mp2v_coef_t*>(s.d_arena + ctx->coef_off);
+    for (int p = 0; p < 3; p++) {
+        d.dst[p] = ctx->frame_ptr(pp.dst_frame, p);
+        d.l0[p] = pp.l0_frame >= 0 ? ctx->frame_ptr(pp.l0_frame, p) : nullptr;
+        d.l1[p] = pp.l1_frame >= 0 ? ctx->frame_ptr(pp.l1_frame, p) : nullptr;
+    }
+    d.cta_begin = 0; d.pad = 0;
+}
+
+// one launch over `ids` (<= max_batch slots whose records are already on, or on their way to, the device)
+static int launch_slots(mp2v_recon* ctx, const int* ids, int n) {
+    batch_desc_t b{};
+    b.n_pics = n;
+    b.mbw = ctx->mbw; b.mbh = ctx->mbh; b.mb_count = ctx->mb_count;
+    for (int p = 0; p < 3; p++) b.stride[p] = ctx->lay.stride[p];
+    const int g = mbs_per_cta(ctx->cfg.chroma_format);
+    b.ctas_per_pic = (ctx->mb_count + g - 1) / g;
+    for (int i = 0; i < n; i++) fill_desc(ctx, ctx->slots[ids[i]], b.pic[i]);
+    cudaEvent_t t0 = nullptr, t1 = nullptr;
+    if (ctx->timing) {
+        t0 = cudaEvent_t(); t1 = cudaEvent_t();
+        CK(cudaEventCreate(&t0), "event"); CK(cudaEventCreate(&t1), "event");
+        CK(cudaEventRecord(t0, ctx->s_compute), "event record");
+    }
+    CK(launch_recon(ctx->cfg.chroma_format, b, ctx->s_compute), "reconstruction kernel launch");
+    if (ctx->timing) {
+        CK(cudaEventRecord(t1, ctx->s_compute), "event record");
+        ctx->timed.emplace_back(t0, t1);
+    }
+    for (int i = 0; i < n; i++) {
+        slot_t& s = ctx->slots[ids[i]];
+        const int f = s.pub.params->dst_frame;
+        CK(cudaEventRecord(ctx->frame_ev[f], ctx->s_compute), "event record");
+        ctx->frame_written[f] = 1;
+        ctx->stats.algorithmic_bytes += s.alg_bytes;
+    }
+    ctx->stats.pictures += n;
+    ctx->stats.launches += 1;
+    return MP2V_OK;
+}
+
+static int flush_locked(mp2v_recon* ctx) {
+    if (ctx->pending.empty()) return MP2V_OK;
+    CK(cudaSetDevice(ctx->cfg.device), "cudaSetDevice");
+    // H2D of every queued picture: params + macroblock records + the used part of the coefficient arena
+    for (int id : ctx->pending) {
+        slot_t& s = ctx->slots[id];
+        const size_t bytes = ctx->coef_off + (size_t)s.pub.params->n_coef * sizeof(mp2v_coef_t);
+        CK(cudaMemcpyAsync(s.d_arena, s.h_arena, bytes, cudaMemcpyHostToDevice, ctx->s_copy), "H2D picture records");
+        ctx->stats.h2d_bytes += bytes;
+    }
+    CK(cudaEventRecord(ctx->ev_h2d, ctx->s_copy), "event record");
+    CK(cudaStreamWaitEvent(ctx->s_compute, ctx->ev_h2d, 0), "stream wait");
+    const int rc = launch_slots(ctx, ctx->pending.data(), (int)ctx->pending.size());
+    if (rc != MP2V_OK) return rc;
+    for (int id : ctx->pending) {
+        slot_t& s = ctx->slots[id];
+        CK(cudaEventRecord(s.done, ctx->s_compute), "event record");
+        s.state = SLOT_INFLIGHT;
+    }
+    ctx->pending.clear();
+    return MP2V_OK;
+}
+
+// OUT + REF + COEF + META, and (optionally) the host-side validation of the records
+static int account_and_validate(mp2v_recon* ctx, slot_t& s, bool validate) {
+    const mp2v_pic_params_t& pp = *s.pub.params;
+    const int nf = ctx->cfg.n_frames;
+    if (pp.dst_frame < 0 || pp.dst_frame >= nf || pp.l0_frame >= nf || pp.l1_frame >= nf) return ctx->fail(MP2V_ERR_ARG, "frame id out of range");
+    if (pp.n_coef > s.pub.coef_capacity) return ctx->fail(MP2V_ERR_RANGE, "coefficient arena overflow");
+    const uint64_t mb_bytes = ctx->cfg.chroma_format == 1 ? 384 : ctx->cfg.chroma_format == 2 ? 512 : 768;
+    uint64_t out_bytes = 0;
+    for (int p = 0; p < 3; p++) out_bytes += (uint64_t)ctx->lay.width[p] * ctx->lay.height[p];
+    uint64_t ref = 0, coded = 0;
+    const uint32_t cbp_mask = (1u << ctx->nblk) - 1u;
+    const int W = ctx->cfg.width, H = ctx->cfg.height;
+    for (int m = 0; m < ctx->mb_count; m++) {
+        const mp2v_mb_info_t& r = s.pub.mb[m];
+        const uint32_t bits = r.bits;
+        const int ndir = (bits & MP2V_MB_INTRA) ? 0 : ((bits & MP2V_MB_FWD) ? 1 : 0) + ((bits & MP2V_MB_BWD) ? 1 : 0);
+        ref += (uint64_t)ndir * mb_bytes;
+        coded += (uint64_t)__builtin_popcount(MP2V_MB_CBP(bits) & cbp_mask);
+        if (!validate) continue;
+        if (MP2V_MB_CBP(bits) & ~cbp_mask) return ctx->fail(MP2V_ERR_RANGE, "coded_block_pattern names a block this chroma format does not have");
+        if ((uint64_t)r.coef_off + MP2V_MB_NCOEF(bits) > pp.n_coef) return ctx->fail(MP2V_ERR_RANGE, "macroblock coefficient range outside the arena");
+        if (!(bits & MP2V_MB_INTRA)) {
+            if (ndir == 0) return ctx->fail(MP2V_ERR_RANGE, "non-intra macroblock without a prediction direction");
+            const int mbx = m % ctx->mbw, mby = m / ctx->mbw;
+            for (int d = 0; d < 2; d++) {
+                if (!(bits & (d ? MP2V_MB_BWD : MP2V_MB_FWD))) continue;
+                const int fr = d ? pp.l1_frame : pp.l0_frame;
+                if (fr < 0) return ctx->fail(MP2V_ERR_STATE, "prediction from a missing reference frame");
+                const int mvx = r.mv[d][0], mvy = r.mv[d][1];
+                const int x0 = mbx * 16 + (mvx >> 1), y0 = mby * 16 + (mvy >> 1);
+                // the reference does not clamp: a vector leaving the frame is rejected here
+                if (x0 < 0 || y0 < 0 || x0 + 16 + (mvx & 1) > W || y0 + 16 + (mvy & 1) > H)
+                    return ctx->fail(MP2V_ERR_RANGE, "motion vector points outside the reference frame");
+            }
+        }
+    }
+    s.alg_bytes = out_bytes + ref + 128u * coded + 16u * (uint64_t)ctx->mb_count;
+    return MP2V_OK;
+}
+
+extern "C" MP2V_API int mp2v_recon_acquire_picture(mp2v_recon_t* ctx, mp2v_picture_t** out) {
+    if (!ctx || !out) return MP2V_ERR_ARG;
+    std::lock_guard<std::mutex> lk(ctx->mu);
+    for (int attempt = 0; attempt < 2; attempt++) {
+        int best = -1;
+        for (size_t i = 0; i < ctx->slots.size(); i++) {
+            slot_t& s = ctx->slots[i];
+            if (s.state == SLOT_FREE) { best = (int)i; break; }
+        }
+        if (best < 0) {
+            // recycle the oldest in-flight slot (its launch has to finish before the arenas are reused)
+            for (size_t i = 0; i < ctx->slots.size(); i++) {
+                slot_t& s = ctx->slots[i];
+                if (s.state == SLOT_INFLIGHT && (best < 0 || s.seq < ctx->slots[best].seq)) best = (int)i;
+            }
+            if (best >= 0) {
+                CK(cudaSetDevice(ctx->cfg.device), "cudaSetDevice");
+                CK(cudaEventSynchronize(ctx->slots[best].done), "event sync");
+                ctx->slots[best].state = SLOT_FREE;
+            }
+        }
+        if (best >= 0) {
+            slot_t& s = ctx->slots[best];
+            s.state = SLOT_FILLING;
+            memset(s.pub.params, 0, sizeof(mp2v_pic_params_t));
+            s.pub.params->l0_frame = s.pub.params->l1_frame = -1;
+            *out = &s.pub;
+            return MP2V_OK;
+        }
+        if (ctx->pending.empty()) break;
+        const int rc = flush_locked(ctx);   // everything is queued: launch it, then wait for a slot
+        if (rc != MP2V_OK) return rc;
+    }
+    return ctx->fail(MP2V_ERR_STATE, "no picture slot available (all slots are being filled or resident)");
+}
+
+static slot_t* slot_of(mp2v_recon* ctx, mp2v_picture_t* pic) {
+    if (!pic || pic->slot < 0 || pic->slot >= (int)ctx->slots.size() || &ctx->slots[pic->slot].pub != pic) return nullptr;
+    return &ctx->slots[pic->slot];
+}
+
+extern "C" MP2V_API int mp2v_recon_release_picture(mp2v_recon_t* ctx, mp2v_picture_t* pic) {
+    if (!ctx) return MP2V_ERR_ARG;
+    std::lock_guard<std::mutex> lk(ctx->mu);
+    slot_t* s = slot_of(ctx, pic);
+    if (!s) return ctx->fail(MP2V_ERR_ARG, "not a picture of this context");
+    if (s->state == SLOT_QUEUED) { const int rc = flush_locked(ctx); if (rc != MP2V_OK) return rc; }
+    if (s->state == SLOT_INFLIGHT || s->state == SLOT_RESIDENT) {
+        CK(cudaSetDevice(ctx->cfg.device), "cudaSetDevice");
+        CK(cudaStreamSynchronize(ctx->s_compute), "stream sync");
+    }
+    s->state = SLOT_FREE;
+    return MP2V_OK;
+}
+
+extern "C" MP2V_API int mp2v_recon_submit(mp2v_recon_t* ctx, mp2v_picture_t* pic) {
+    if (!ctx) return MP2V_ERR_ARG;
+    std::lock_guard<std::mutex> lk(ctx->mu);
+    slot_t* s = slot_of(ctx, pic);
+    if (!s || s->state != SLOT_FILLING) return ctx->fail(MP2V_ERR_STATE, "submit: picture was not acquired");
+    int rc = account_and_validate(ctx, *s, (ctx->cfg.flags & MP2V_RECON_VALIDATE) != 0);
+    if (rc != MP2V_OK) return rc;
+    const mp2v_pic_params_t& pp = *s->pub.params;
+    // a picture cannot share a launch with a picture it reads from, nor with one touching its destination
+    bool conflict = (int)ctx->pending.size() >= ctx->max_batch;
+    for (int id : ctx->pending) {
+        const mp2v_pic_params_t& q = *ctx->slots[id].pub.params;
+        if (q.dst_frame == pp.l0_frame || q.dst_frame == pp.l1_frame || q.dst_frame == pp.dst_frame ||
+            q.l0_frame == pp.dst_frame || q.l1_frame == pp.dst_frame) conflict = true;
+    }
+    if (conflict) { rc = flush_locked(ctx); if (rc != MP2V_OK) return rc; }
+    for (int d = 0; d < 2; d++) {
+        const int fr = d ? pp.l1_frame : pp.l0_frame;
+        if (fr >= 0 && !ctx->frame_written[fr]) return ctx->fail(MP2V_ERR_STATE, "reference frame has never been written");
+    }
+    s->state = SLOT_QUEUED;
+    s->seq = ++ctx->seq;
+    ctx->pending.push_back(pic->slot);
+    return MP2V_OK;
+}
+
+extern "C" MP2V_API int mp2v_recon_flush(mp2v_recon_t* ctx) {
+    if (!ctx) return MP2V_ERR_ARG;
+    std::lock_guard<std::mutex> lk(ctx->mu);
+    return flush_locked(ctx);
+}
+
+extern "C" MP2V_API int mp2v_recon_sync(mp2v_recon_t* ctx) {
+    if (!ctx) return MP2V_ERR_ARG;
+    std::lock_guard<std::mutex> lk(ctx->mu);
+    const int rc = flush_locked(ctx);
+    if (rc != MP2V_OK) return rc;
+    CK(cudaSetDevice(ctx->cfg.device), "cudaSetDevice");
+    CK(cudaStreamSynchronize(ctx->s_copy), "stream sync");
+    CK(cudaStreamSynchronize(ctx->s_compute), "stream sync");
+    for (auto& s : ctx->slots) if (s.state == SLOT_INFLIGHT) s.state = SLOT_FREE;
+    return MP2V_OK;
+}
+
+// ---------------------------------------------------------------------------------------------
+// device-resident mode
+
+extern "C" MP2V_API int mp2v_recon_upload(mp2v_recon_t* ctx, mp2v_picture_t* pic) {
+    if (!ctx) return MP2V_ERR_ARG;
+    std::lock_guard<std::mutex> lk(ctx->mu);
+    slot_t* s = slot_of(ctx, pic);
+    if (!s || (s->state != SLOT_FILLING && s->state != SLOT_RESIDENT)) return ctx->fail(MP2V_ERR_STATE, "upload: picture was not acquired");
+    const int rc = account_and_validate(ctx, *s, (ctx->cfg.flags & MP2V_RECON_VALIDATE) != 0);
+    if (rc != MP2V_OK) return rc;
+    CK(cudaSetDevice(ctx->cfg.device), "cudaSetDevice");
+    const size_t bytes = ctx->coef_off + (size_t)s->pub.params->n_coef * sizeof(mp2v_coef_t);
+    CK(cudaMemcpyAsync(s->d_arena, s->h_arena, bytes, cudaMemcpyHostToDevice, ctx->s_copy), "H2D picture records");
+    CK(cudaStreamSynchronize(ctx->s_copy), "stream sync");
+    ctx->stats.h2d_bytes += bytes;
+    s->state = SLOT_RESIDENT;
+    return MP2V_OK;
+}
+
+extern "C" MP2V_API int mp2v_recon_run_resident(mp2v_recon_t* ctx, mp2v_picture_t* const* pics, const int32_t* levels, int n) {
+    if (!ctx || !pics || n < 0) return MP2V_ERR_ARG;
+    std::lock_guard<std::mutex> lk(ctx->mu);
+    int rc = flush_locked(ctx);
+    if (rc != MP2V_OK) return rc;
+    CK(cudaSetDevice(ctx->cfg.device), "cudaSetDevice");
+    std::vector<int> order(n);
+    for (int i = 0; i < n; i++) {
+        slot_t* s = slot_of(ctx, pics[i]);
+        if (!s || s->state != SLOT_RESIDENT) return ctx->fail(MP2V_ERR_STATE, "run_resident: picture is not resident");
+        order[i] = i;
+    }
+    if (levels) std::stable_sort(order.begin(), order.end(), [&](int a, int b) { return levels[a] < levels[b]; });
+    int ids[kMaxBatch];
+    int cnt = 0;
+    for (int k = 0; k < n; k++) {
+        const int i = order[k];
+        ids[cnt++] = pics[i]->slot;
+        const bool last_of_level = (k + 1 == n) || !levels || levels[order[k + 1]] != levels[i];
+        if (cnt == ctx->max_batch || last_of_level) {
+            rc = launch_slots(ctx, ids, cnt);
+            if (rc != MP2V_OK) return rc;
+            cnt = 0;
+        }
+    }
+    return MP2V_OK;
+}
+
+// ---------------------------------------------------------------------------------------------
+// frames
+
+static int copy_frame_out(mp2v_recon* ctx, int frame_id, uint8_t* const dst[3], const int32_t dst_stride[3]) {
+    if (frame_id < 0 || frame_id >= ctx->cfg.n_frames) return ctx->fail(MP2V_ERR_ARG, "frame id out of range");
+    int rc = flush_locked(ctx);
+    if (rc != MP2V_OK) return rc;
+    if (!ctx->frame_written[frame_id]) return ctx->fail(MP2V_ERR_STATE, "frame has never been written");
+    CK(cudaSetDevice(ctx->cfg.device), "cudaSetDevice");
+    CK(cudaStreamWaitEvent(ctx->s_d2h, ctx->frame_ev[frame_id], 0), "stream wait");
+    for (int p = 0; p < 3; p++) {
+        CK(cudaMemcpy2DAsync(dst[p], (size_t)dst_stride[p], ctx->frame_ptr(frame_id, p), (size_t)ctx->lay.stride[p],
+                             (size_t)ctx->lay.width[p], (size_t)ctx->lay.height[p], cudaMemcpyDeviceToHost, ctx->s_d2h), "D2H frame");
+        ctx->stats.d2h_bytes += (uint64_t)ctx->lay.width[p] * ctx->lay.height[p];
+    }
+    CK(cudaStreamSynchronize(ctx->s_d2h), "stream sync");
+    return MP2V_OK;
+}
+
+extern "C" MP2V_API int mp2v_recon_download_frame(mp2v_recon_t* ctx, int frame_id, uint8_t* const dst[3], const int32_t dst_stride[3]) {
+    if (!ctx || !dst || !dst_stride) return MP2V_ERR_ARG;
+    std::lock_guard<std::mutex> lk(ctx->mu);
+    return copy_frame_out(ctx, frame_id, dst, dst_stride);
+}
+
+extern "C" MP2V_API int mp2v_recon_map_frame(mp2v_recon_t* ctx, int frame_id, uint8_t* planes[3], int32_t strides[3]) {
+    if (!ctx || !planes || !strides) return MP2V_ERR_ARG;
+    std::lock_guard<std::mutex> lk(ctx->mu);
+    if (frame_id < 0 || frame_id >= ctx->cfg.n_frames) return ctx->fail(MP2V_ERR_ARG, "frame id out of range");
+    if (!ctx->h_frames[frame_id]) {
+        CK(cudaSetDevice(ctx->cfg.device), "cudaSetDevice");
+        CK(cudaHostAlloc(&ctx->h_frames[frame_id], ctx->lay.bytes, cudaHostAllocDefault), "cudaHostAlloc frame mirror");
+    }
+    for (int p = 0; p < 3; p++) { planes[p] = ctx->h_frames[frame_id] + ctx->lay.plane_offset[p]; strides[p] = ctx->lay.stride[p]; }
+    return copy_frame_out(ctx, frame_id, planes, strides);
+}
+
+extern "C" MP2V_API int mp2v_recon_upload_frame(mp2v_recon_t* ctx, int frame_id, const uint8_t* const src[3], const int32_t src_stride[3]) {
+    if (!ctx || !src || !src_stride) return MP2V_ERR_ARG;
+    std::lock_guard<std::mutex> lk(ctx->mu);
+    if (frame_id < 0 || frame_id >= ctx->cfg.n_frames) return ctx->fail(MP2V_ERR_ARG, "frame id out of range");
+    int rc = flush_locked(ctx);
+    if (rc != MP2V_OK) return rc;
+    CK(cudaSetDevice(ctx->cfg.device), "cudaSetDevice");
+    CK(cudaStreamSynchronize(ctx->s_compute), "stream sync");
+    for (int p = 0; p < 3; p++)
+        CK(cudaMemcpy2D(ctx->frame_ptr(frame_id, p), (size_t)ctx->lay.stride[p], src[p], (size_t)src_stride[p],
+                        (size_t)ctx->lay.width[p], (size_t)ctx->lay.height[p], cudaMemcpyHostToDevice), "H2D frame");
+    ctx->frame_written[frame_id] = 1;
+    CK(cudaEventRecord(ctx->frame_ev[frame_id], ctx->s_compute), "event record");
+    return MP2V_OK;
+}
+
+extern "C" MP2V_API int mp2v_recon_frame_device_ptrs(mp2v_recon_t* ctx, int frame_id, void* planes[3], int32_t strides[3]) {
+    if (!ctx || !planes || !strides) return MP2V_ERR_ARG;
+    if (frame_id < 0 || frame_id >= ctx->cfg.n_frames) return ctx->fail(MP2V_ERR_ARG, "frame id out of range");
+    for (int p = 0; p < 3; p++) { planes[p] = ctx->frame_ptr(frame_id, p); strides[p] = ctx->lay.stride[p]; }
+    return MP2V_OK;
+}
+
+// ---------------------------------------------------------------------------------------------
+// statistics
+
+extern "C" MP2V_API int mp2v_recon_set_timing(mp2v_recon_t* ctx, int enable) {
+    if (!ctx) return MP2V_ERR_ARG;
+    std::lock_guard<std::mutex> lk(ctx->mu);
+    ctx->timing = enable != 0;
+    return MP2V_OK;
+}
+
+extern "C" MP2V_API int mp2v_recon_get_stats(mp2v_recon_t* ctx, mp2v_recon_stats_t* out, int reset) {
+    if (!ctx || !out) return MP2V_ERR_ARG;
+    std::lock_guard<std::mutex> lk(ctx->mu);
+    CK(cudaSetDevice(ctx->cfg.device), "cudaSetDevice");
+    if (!ctx->timed.empty()) {
+        CK(cudaStreamSynchronize(ctx->s_compute), "stream sync");
+        for (auto& pr : ctx->timed) {
+            float ms = 0.f;
+            CK(cudaEventElapsedTime(&ms, pr.first, pr.second), "event elapsed");
+            ctx->stats.kernel_ms += ms;
+            cudaEventDestroy(pr.first); cudaEventDestroy(pr.second);
+        }
+        ctx->timed.clear();
+    }
+    *out = ctx->stats;
+    if (reset) ctx->stats = mp2v_recon_stats_t{};
+    return MP2V_OK;
+}

@@ -1,0 +1,188 @@
+"""ctypes binding of the reconstruction C ABI (include/mp2v_recon.h, libmp2v_b200.so).
+
+There is deliberately no fallback: if the library is missing it is built, if it cannot be loaded or
+no sm_100a device is usable every call raises."""
+import ctypes as C
+import os
+
+import numpy as np
+
+from . import build as _build
+from .abi import (OK, FrameLayout, MbInfo, PicParams, Picture, ReconConfig, ReconStats, mb_dtype)
+
+U8P = C.POINTER(C.c_uint8)
+_lib = None
+
+EXPORTS = [
+    "mp2v_frame_layout", "mp2v_recon_create", "mp2v_recon_destroy", "mp2v_recon_last_error",
+    "mp2v_recon_acquire_picture", "mp2v_recon_release_picture", "mp2v_recon_submit", "mp2v_recon_flush",
+    "mp2v_recon_sync", "mp2v_recon_upload", "mp2v_recon_run_resident", "mp2v_recon_download_frame",
+    "mp2v_recon_map_frame", "mp2v_recon_upload_frame", "mp2v_recon_frame_device_ptrs",
+    "mp2v_recon_set_timing", "mp2v_recon_get_stats",
+]
+
+
+class ReconError(RuntimeError):
+    pass
+
+
+def lib():
+    global _lib
+    if _lib is None:
+        path = _build.PRODUCT_LIB
+        if not os.path.exists(path):
+            _build.build_product()
+        L = C.CDLL(path)
+        P = C.POINTER
+        L.mp2v_frame_layout.argtypes = [C.c_int, C.c_int, C.c_int, P(FrameLayout)]
+        L.mp2v_recon_create.argtypes = [P(ReconConfig), P(C.c_void_p)]
+        L.mp2v_recon_destroy.argtypes = [C.c_void_p]
+        L.mp2v_recon_destroy.restype = None
+        L.mp2v_recon_last_error.argtypes = [C.c_void_p]
+        L.mp2v_recon_last_error.restype = C.c_char_p
+        L.mp2v_recon_acquire_picture.argtypes = [C.c_void_p, P(P(Picture))]
+        L.mp2v_recon_release_picture.argtypes = [C.c_void_p, P(Picture)]
+        L.mp2v_recon_submit.argtypes = [C.c_void_p, P(Picture)]
+        L.mp2v_recon_flush.argtypes = [C.c_void_p]
+        L.mp2v_recon_sync.argtypes = [C.c_void_p]
+        L.mp2v_recon_upload.argtypes = [C.c_void_p, P(Picture)]
+        L.mp2v_recon_run_resident.argtypes = [C.c_void_p, P(P(Picture)), P(C.c_int32), C.c_int]
+        L.mp2v_recon_download_frame.argtypes = [C.c_void_p, C.c_int, U8P * 3, C.c_int32 * 3]
+        L.mp2v_recon_map_frame.argtypes = [C.c_void_p, C.c_int, U8P * 3, C.c_int32 * 3]
+        L.mp2v_recon_upload_frame.argtypes = [C.c_void_p, C.c_int, U8P * 3, C.c_int32 * 3]
+        L.mp2v_recon_frame_device_ptrs.argtypes = [C.c_void_p, C.c_int, C.c_void_p * 3, C.c_int32 * 3]
+        L.mp2v_recon_set_timing.argtypes = [C.c_void_p, C.c_int]
+        L.mp2v_recon_get_stats.argtypes = [C.c_void_p, P(ReconStats), C.c_int]
+        _lib = L
+    return _lib
+
+
+def frame_layout(width, height, chroma_format):
+    lay = FrameLayout()
+    if lib().mp2v_frame_layout(width, height, chroma_format, C.byref(lay)) != OK:
+        raise ReconError("bad geometry %dx%d cf=%d" % (width, height, chroma_format))
+    return lay
+
+
+class Recon:
+    """One reconstruction context = one device."""
+
+    def __init__(self, width, height, chroma_format, n_frames=8, n_pictures=8, device=0, max_batch=0, flags=1,
+                 coef_capacity=0):
+        self.L = lib()
+        cfg = ReconConfig(device, width, height, chroma_format, n_frames, n_pictures, max_batch, flags, coef_capacity, 0)
+        h = C.c_void_p()
+        rc = self.L.mp2v_recon_create(C.byref(cfg), C.byref(h))
+        if rc != OK:
+            raise ReconError("mp2v_recon_create failed (%d): %s" % (rc, self.L.mp2v_recon_last_error(None).decode()))
+        self.h = h
+        self.width, self.height, self.chroma_format = width, height, chroma_format
+        self.lay = frame_layout(width, height, chroma_format)
+
+    def close(self):
+        if self.h:
+            self.L.mp2v_recon_destroy(self.h)
+            self.h = None
+
+    def __enter__(self):
+        return self
+
+    def __exit__(self, *a):
+        self.close()
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    def _ck(self, rc):
+        if rc != OK:
+            raise ReconError("mp2v_recon error %d: %s" % (rc, self.L.mp2v_recon_last_error(self.h).decode()))
+
+    # ---- pictures
+    def acquire(self):
+        p = C.POINTER(Picture)()
+        self._ck(self.L.mp2v_recon_acquire_picture(self.h, C.byref(p)))
+        return p
+
+    def fill(self, pic, params, mb, coef, dst, l0=-1, l1=-1):
+        """copy ground-truth / parsed records into an acquired picture's pinned buffers"""
+        p = pic.contents
+        n_mb, n_coef = len(mb), len(coef)
+        assert n_mb == p.mb_count, (n_mb, p.mb_count)
+        if n_coef > p.coef_capacity:
+            raise ReconError("picture needs %d coefficient records, slot holds %d" % (n_coef, p.coef_capacity))
+        C.memmove(p.params, C.byref(params), C.sizeof(PicParams))
+        p.params.contents.dst_frame, p.params.contents.l0_frame, p.params.contents.l1_frame = dst, l0, l1
+        p.params.contents.n_coef = n_coef
+        C.memmove(p.mb, mb.ctypes.data, n_mb * 16)
+        if n_coef:
+            C.memmove(p.coef, np.ascontiguousarray(coef, np.uint32).ctypes.data, n_coef * 4)
+
+    def submit(self, pic):
+        self._ck(self.L.mp2v_recon_submit(self.h, pic))
+
+    def upload(self, pic):
+        self._ck(self.L.mp2v_recon_upload(self.h, pic))
+
+    def release(self, pic):
+        self._ck(self.L.mp2v_recon_release_picture(self.h, pic))
+
+    def run_resident(self, pics, levels=None):
+        n = len(pics)
+        arr = (C.POINTER(Picture) * n)(*pics)
+        lv = (C.c_int32 * n)(*levels) if levels is not None else None
+        self._ck(self.L.mp2v_recon_run_resident(self.h, arr, lv, n))
+
+    def flush(self):
+        self._ck(self.L.mp2v_recon_flush(self.h))
+
+    def sync(self):
+        self._ck(self.L.mp2v_recon_sync(self.h))
+
+    # ---- frames
+    def download(self, frame_id):
+        """-> cropped planar YUV bytes of a frame"""
+        planes = [np.empty((self.lay.height[p], self.lay.width[p]), np.uint8) for p in range(3)]
+        ptrs = (U8P * 3)(*[a.ctypes.data_as(U8P) for a in planes])
+        strides = (C.c_int32 * 3)(*[self.lay.width[p] for p in range(3)])
+        self._ck(self.L.mp2v_recon_download_frame(self.h, frame_id, ptrs, strides))
+        return b"".join(a.tobytes() for a in planes)
+
+    def upload_frame(self, frame_id, planes):
+        planes = [np.ascontiguousarray(a, np.uint8) for a in planes]
+        ptrs = (U8P * 3)(*[a.ctypes.data_as(U8P) for a in planes])
+        strides = (C.c_int32 * 3)(*[a.shape[1] for a in planes])
+        self._ck(self.L.mp2v_recon_upload_frame(self.h, frame_id, ptrs, strides))
+
+    # ---- statistics
+    def set_timing(self, on=True):
+        self._ck(self.L.mp2v_recon_set_timing(self.h, 1 if on else 0))
+
+    def stats(self, reset=False):
+        s = ReconStats()
+        self._ck(self.L.mp2v_recon_get_stats(self.h, C.byref(s), 1 if reset else 0))
+        return s
+
+
+def reconstruct_stream(stream, recon=None, n_frames=None, batch=True):
+    """Reconstruct every picture of a generated Stream from its ground-truth records on the GPU.
+    Frame id = coded index (the pool is sized to hold the whole stream).  Returns cropped planar YUV in
+    display order -- the CUDA counterpart of tests/oracle_lib.oracle_decode_stream."""
+    n = len(stream.pictures)
+    own = recon is None
+    if own:
+        recon = Recon(stream.width, stream.height, stream.chroma_format, n_frames=n_frames or n, n_pictures=min(n, 8))
+    try:
+        for idx, pic in enumerate(stream.pictures):
+            h = recon.acquire()
+            recon.fill(h, pic.params, pic.mb, pic.coef, dst=idx, l0=pic.params.l0_frame, l1=pic.params.l1_frame)
+            recon.submit(h)
+            if not batch:
+                recon.flush()
+        recon.sync()
+        return b"".join(recon.download(i) for i in stream.display_order())
+    finally:
+        if own:
+            recon.close()
