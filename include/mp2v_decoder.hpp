@@ -1,0 +1,93 @@
+// Drop-in C++ decode API of the B200 back end: the same three public types as the reference's
+// src/core/decoder.h -- decoder_config_t (:25-32), frame_c (:34-49), mp2v_decoder_c (:82-131) -- with
+// the same constructor / decode / renderer conventions, implemented on top of the C ABI in
+// mp2v_recon.h (host slice parsing on num_threads threads, reconstruction on the GPU).
+//
+// Conventions kept from the reference:
+//   * the caller owns `buffer` (a whole elementary stream) and pads it with >= 64 readable bytes;
+//     it must stay valid until decode() returns; `len` is int
+//   * decode() is one-shot and blocks until every frame has been rendered
+//   * `renderer` runs on an internal thread, in display order when `reordering`, and receives a
+//     frame_c* exposing HOST plane pointers that are valid only during the call
+//   * geometry and chroma_format come from decoder_config_t, not from the sequence header
+// Differences: decode() returns false (and last_error() says why) instead of undefined behaviour on
+// malformed input; streams without a quant_matrix_extension decode with the sequence-header /
+// default matrices instead of crashing (decoder.cpp:187 dereferences nullptr there).
+#pragma once
+#include <cstdint>
+#include <functional>
+#include <memory>
+#include <string>
+#include <vector>
+
+#if defined(__GNUC__)
+#define MP2V_CXX_API __attribute__((visibility("default")))
+#else
+#define MP2V_CXX_API
+#endif
+
+constexpr int MAX_NUM_THREADS = 256;
+
+struct decoder_config_t {
+    int width;
+    int height;
+    int chroma_format;
+    int pictures_pool_size;
+    int num_threads;
+    bool reordering;
+};
+
+class MP2V_CXX_API frame_c {
+public:
+    frame_c(int width, int height, int chroma_format);   // owning host frame, reference geometry (decoder.cpp:44-87)
+    ~frame_c();
+    frame_c(const frame_c&) = delete;
+    frame_c& operator=(const frame_c&) = delete;
+
+    uint8_t* get_planes (int plane_idx) { return m_planes[plane_idx]; }
+    int      get_strides(int plane_idx) { return (int)m_stride[plane_idx]; }
+    int      get_width  (int plane_idx) { return (int)m_width [plane_idx]; }
+    int      get_height (int plane_idx) { return (int)m_height[plane_idx]; }
+
+    // view over planes owned elsewhere (the decoder's pinned frame mirrors)
+    frame_c(int width, int height, int chroma_format, uint8_t* const planes[3], const int strides[3]);
+private:
+    uint32_t m_width [3] = { 0 };
+    uint32_t m_height[3] = { 0 };
+    uint32_t m_stride[3] = { 0 };
+    uint8_t* m_planes[3] = { 0 };
+    bool m_owner = false;
+};
+
+// Knobs the reference does not have; all optional.
+struct mp2v_b200_options_t {
+    std::vector<int> devices = {0};   // CUDA ordinals; more than one = closed GOPs round-robin over the devices
+    int max_batch = 8;                // pictures fused into one launch
+    int output_lag = 4;               // pictures the display side stays behind the submit side (lets launches batch)
+    bool download_frames = true;      // false: renderer gets frames whose planes were not copied back (benchmarks)
+};
+
+class MP2V_CXX_API mp2v_decoder_c {
+public:
+    mp2v_decoder_c();
+    mp2v_decoder_c(const decoder_config_t& config, std::function<void(frame_c*)> renderer);
+    ~mp2v_decoder_c();
+    bool decoder_init(const decoder_config_t& config, std::function<void(frame_c*)> renderer);
+    bool decode(uint8_t* buffer, int len);
+    void flush();
+
+    // extensions
+    void set_options(const mp2v_b200_options_t& opt);
+    const char* last_error() const;
+    struct stats_t {
+        uint64_t pictures = 0, launches = 0, h2d_bytes = 0, d2h_bytes = 0, algorithmic_bytes = 0;
+        double kernel_ms = 0;          // CUDA-event time of the reconstruction launches
+        double parse_cpu_seconds = 0;  // summed over worker threads: slice parsing only
+        double wall_seconds = 0;       // decode() wall clock
+    };
+    stats_t stats() const;
+
+private:
+    struct impl_t;
+    std::unique_ptr<impl_t> m;
+};

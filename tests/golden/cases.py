@@ -1,0 +1,14 @@
+"""The golden stream set: generator parameters only (streams are regenerated deterministically)."""
+CASES = {
+    "cif420_ipb": (352, 288, 1, dict(seed=101, n_gops=2, gop_n=9, gop_m=3)),
+    "cif422_ipb": (352, 288, 2, dict(seed=102, n_gops=2, gop_n=9, gop_m=3)),
+    "cif444_ipb": (352, 288, 3, dict(seed=103, n_gops=2, gop_n=9, gop_m=3)),
+    "qcif420_stress": (176, 144, 1, dict(seed=104, qscale_code_max=31, pct_big_levels=40, gop_n=12, gop_m=3)),
+    "qcif444_altscan_nonlinear": (176, 144, 3, dict(seed=105, alternate_scan=1, q_scale_type=1, intra_dc_precision=3, qscale_code_max=31, gop_n=9, gop_m=3)),
+    "sd420_intra": (720, 480, 1, dict(seed=106, intra_only=1, gop_n=4)),
+    "sd422_longmv": (720, 480, 2, dict(seed=107, gop_n=7, gop_m=3, mv_range=120, pct_skipped=30)),
+    "tiny420_m1": (48, 32, 1, dict(seed=108, gop_n=10, gop_m=1)),
+    "natural420": (640, 368, 1, dict(seed=109, mode=1, n_gops=2, gop_n=15, gop_m=3)),
+    "hd420_ipb": (1920, 1088, 1, dict(seed=110, gop_n=7, gop_m=3)),
+    "hd422_ipb": (1920, 1088, 2, dict(seed=111, gop_n=4, gop_m=3)),
+}

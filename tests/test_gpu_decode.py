@@ -1,0 +1,90 @@
+"""End to end through the reference-facing API (mp2v_decoder_c via the C ABI): elementary stream in,
+YUV out, against the golden hashes of the real reference and -- when it travelled -- the reference
+itself (oracle/_ref, serial driver)."""
+import numpy as np
+import pytest
+
+import oracle_lib as O
+from helpers import GOLDEN, GOLDEN_CASES, sha
+from tiny_mp2v_dec_b200.decoder import Decoder, frame_bytes
+from tiny_mp2v_dec_b200.streamgen import Stream
+
+pytestmark = pytest.mark.gpu
+
+
+@pytest.mark.parametrize("name", sorted(GOLDEN_CASES))
+def test_decoder_matches_reference_golden(name):
+    w, h, cf, kw = GOLDEN_CASES[name]
+    s = Stream(w, h, cf, **kw)
+    d = Decoder(w, h, cf, num_threads=4)
+    yuv = d.decode(s.padded, s.size)
+    assert d.stats.frames == GOLDEN[name]["frames"]
+    assert sha(yuv) == GOLDEN[name]["yuv_sha256"]
+    assert d.stats.launches >= 1 and d.stats.pictures == GOLDEN[name]["frames"]
+
+
+@pytest.mark.skipif(not O.have_ref(), reason="oracle/_ref (the compiled reference) did not travel")
+@pytest.mark.parametrize("cf", [1, 2, 3])
+def test_decoder_matches_live_reference(cf):
+    s = Stream(320, 192, cf, seed=50 + cf, n_gops=3, gop_n=10, gop_m=3, qscale_code_max=31, pct_big_levels=10)
+    assert Decoder(320, 192, cf, num_threads=3).decode(s.padded, s.size) == O.ref_decode_serial(s)
+
+
+@pytest.mark.parametrize("threads,batch,lag", [(1, 1, 1), (2, 4, 2), (8, 8, 6), (16, 32, 12)])
+def test_threads_and_batching_do_not_change_the_output(threads, batch, lag):
+    s = Stream(352, 288, 1, seed=60, n_gops=4, gop_n=12, gop_m=3)
+    want = O.oracle_decode_stream(s)
+    got = Decoder(352, 288, 1, num_threads=threads, max_batch=batch, output_lag=lag).decode(s.padded, s.size)
+    assert got == want
+
+
+def test_no_reordering_gives_coded_order():
+    s = Stream(176, 144, 1, seed=61, gop_n=7, gop_m=3)
+    got = Decoder(176, 144, 1, num_threads=2, reordering=False).decode(s.padded, s.size)
+    disp = O.oracle_decode_stream(s)
+    fb = frame_bytes(176, 144, 1)
+    frames = {idx: disp[k * fb:(k + 1) * fb] for k, idx in enumerate(s.display_order())}
+    assert got == b"".join(frames[i] for i in range(len(s.pictures)))
+
+
+def test_4k444_decodes():
+    s = Stream(3840, 2160, 3, seed=62, gop_n=4, gop_m=3, mode=1)
+    got = Decoder(3840, 2160, 3, num_threads=8).decode(s.padded, s.size)
+    assert sha(got) == sha(O.oracle_decode_stream(s))
+
+
+def test_decode_without_download_still_reconstructs():
+    s = Stream(352, 288, 1, seed=63, gop_n=9, gop_m=3)
+    d = Decoder(352, 288, 1, num_threads=2)
+    assert d.decode(s.padded, s.size, want_output=False, download=False) is None
+    assert d.stats.frames == 9 and d.stats.d2h_bytes == 0 and d.stats.pictures == 9
+
+
+def test_malformed_stream_is_an_error_not_a_crash():
+    from tiny_mp2v_dec_b200.recon import ReconError
+    s = Stream(176, 144, 1, seed=64, gop_n=4, gop_m=3)
+    bad = s.padded.copy()
+    start = int(np.nonzero((bad[:-3] == 0) & (bad[1:-2] == 0) & (bad[2:-1] == 1) & (bad[3:] == 2))[0][1])
+    bad[start + 6:start + 60] = 0xFF
+    with pytest.raises(ReconError):
+        Decoder(176, 144, 1, num_threads=2).decode(bad, s.size)
+    # the decoder stays usable afterwards
+    assert sha(Decoder(176, 144, 1, num_threads=2).decode(s.padded, s.size)) == sha(O.oracle_decode_stream(s))
+
+
+def test_motion_vector_outside_the_frame_is_rejected():
+    """the reference reads out of bounds here (no clamping); the C ABI validates instead"""
+    from tiny_mp2v_dec_b200.recon import Recon, ReconError
+    s = Stream(64, 48, 1, seed=65, gop_n=2, gop_m=1)
+    p = s.pictures[1]
+    mb = p.mb.copy()
+    k = int(np.nonzero(mb["bits"] & (1 << 30))[0][0])
+    mb["mv"][k, 0, 0] = -400
+    with Recon(64, 48, 1, n_frames=2, n_pictures=2) as r:
+        h0 = r.acquire()
+        r.fill(h0, s.pictures[0].params, s.pictures[0].mb, s.pictures[0].coef, dst=0)
+        r.submit(h0)
+        h1 = r.acquire()
+        r.fill(h1, p.params, mb, p.coef, dst=1, l0=0)
+        with pytest.raises(ReconError):
+            r.submit(h1)

@@ -1,0 +1,64 @@
+"""Host slice parser (product code, runs on the CPU) against the generator's ground truth: every
+macroblock record and every coefficient record must come out exactly as it was encoded."""
+import numpy as np
+import pytest
+
+from tiny_mp2v_dec_b200.abi import mb_ncoef
+from tiny_mp2v_dec_b200.decoder import parse_stream
+from tiny_mp2v_dec_b200.streamgen import Stream
+
+CASES = [
+    (128, 64, 1, dict(seed=1, n_gops=2, gop_n=7, gop_m=3)),
+    (128, 64, 2, dict(seed=2, n_gops=2, gop_n=7, gop_m=3)),
+    (128, 64, 3, dict(seed=3, n_gops=2, gop_n=7, gop_m=3)),
+    (128, 64, 1, dict(seed=11, qscale_code_max=31, pct_big_levels=30)),
+    (128, 64, 2, dict(seed=12, qscale_code_max=31, pct_big_levels=30, alternate_scan=1, q_scale_type=1)),
+    (128, 64, 3, dict(seed=13, qscale_code_max=31, pct_big_levels=50, intra_dc_precision=3)),
+    (320, 240, 1, dict(seed=14, n_gops=2, gop_n=15, gop_m=3, mv_range=60)),
+    (352, 288, 2, dict(seed=15, gop_n=12, gop_m=4, pct_skipped=40)),
+    (64, 48, 1, dict(seed=16, intra_only=1, gop_n=5)),
+    (16, 16, 1, dict(seed=21, gop_n=4, gop_m=2)),
+    (720, 576, 1, dict(seed=23, gop_n=6, gop_m=3, mode=1)),
+    (1920, 1088, 1, dict(seed=18, gop_n=4, gop_m=3)),
+]
+
+
+def check_stream(s, threads):
+    pics, wall, cpu, n = parse_stream(s.padded, s.size, s.width, s.height, s.chroma_format, threads=threads)
+    assert n == len(s.pictures)
+    for i, (got, want) in enumerate(zip(pics, s.pictures)):
+        assert got.params.picture_coding_type == want.params.picture_coding_type, i
+        assert got.params.alternate_scan == want.params.alternate_scan, i
+        assert (got.params.l0_frame, got.params.l1_frame) == (want.params.l0_frame, want.params.l1_frame), i
+        assert got.gop == want.gop, i
+        nsets = 2 if s.chroma_format == 1 else 4
+        assert bytes(got.params.W)[:64 * nsets] == bytes(want.params.W)[:64 * nsets], "W differs in picture %d" % i
+        assert np.array_equal(got.mb["bits"], want.mb["bits"]), "mb bits differ in picture %d at %s" % (
+            i, np.nonzero(got.mb["bits"] != want.mb["bits"])[0][:5])
+        assert np.array_equal(got.mb["mv"], want.mb["mv"]), "motion vectors differ in picture %d" % i
+        # coefficient offsets differ (chunked arena vs dense), the records must not
+        n_coef = mb_ncoef(got.mb["bits"]).astype(np.int64)
+        idx_g = np.repeat(got.mb["coef_off"].astype(np.int64), n_coef) + (np.arange(n_coef.sum()) - np.repeat(np.cumsum(n_coef) - n_coef, n_coef))
+        idx_w = np.repeat(want.mb["coef_off"].astype(np.int64), n_coef) + (np.arange(n_coef.sum()) - np.repeat(np.cumsum(n_coef) - n_coef, n_coef))
+        assert np.array_equal(got.coef[idx_g], want.coef[idx_w]), "coefficient records differ in picture %d" % i
+
+
+@pytest.mark.parametrize("w,h,cf,kw", CASES)
+def test_parser_matches_generator_truth(w, h, cf, kw):
+    check_stream(Stream(w, h, cf, **kw), threads=1)
+
+
+def test_parser_threaded_is_deterministic():
+    s = Stream(352, 288, 1, seed=5, n_gops=2, gop_n=9, gop_m=3)
+    check_stream(s, threads=4)
+
+
+def test_parser_rejects_garbage():
+    from tiny_mp2v_dec_b200.recon import ReconError
+    s = Stream(64, 48, 1, seed=9, gop_n=3, gop_m=1)
+    bad = s.padded.copy()
+    # corrupt the middle of the slice data of the first picture
+    start = int(np.nonzero((bad[:-3] == 0) & (bad[1:-2] == 0) & (bad[2:-1] == 1) & (bad[3:] == 1))[0][0])
+    bad[start + 6:start + 40] = 0xFF
+    with pytest.raises(ReconError):
+        parse_stream(bad, s.size, 64, 48, 1)

@@ -1,0 +1,403 @@
+// mp2v_decoder_c on the B200 back end -- see include/mp2v_decoder.hpp.
+//
+// Reference roles and where they went (src/core/decoder.cpp, threads.cpp):
+//   decode()'s start-code switch          -> index_stream()                       (caller's thread)
+//   task_queue_c ring + busy-spin workers  -> slice queue with condition variables (num_threads workers)
+//   mp2v_picture_c::decode_slice           -> parse_slice(): emits records, no pixel work
+//   picture dependencies (add_dependency)  -> coded-order submission to mp2v_recon; the device stream is the order
+//   decoder_output_scheduler               -> per-device output thread, same I/P/B display reorder
+//   frame_c pool                           -> device frame pool (ids) + pinned host mirrors for the renderer
+// Closed GOPs are independent chains: with several devices they are dealt round-robin to one
+// pipeline per GPU and stitched back in display order; nothing is exchanged between GPUs.
+#include "mp2v_decoder.hpp"
+
+#include <atomic>
+#include <chrono>
+#include <condition_variable>
+#include <cstdlib>
+#include <cstring>
+#include <deque>
+#include <mutex>
+#include <thread>
+
+#include "mp2v_parser.h"
+#include "mp2v_recon.h"
+#include "stream_index.h"
+
+using namespace mp2v;
+
+// ------------------------------------------------------------------------------------------------ frame_c
+
+static void frame_geometry(int width, int height, int cf, uint32_t w[3], uint32_t h[3], uint32_t s[3]) {
+    mp2v_frame_layout_t lay;
+    if (mp2v_frame_layout(width, height, cf, &lay) != MP2V_OK) { for (int p = 0; p < 3; p++) w[p] = h[p] = s[p] = 0; return; }
+    for (int p = 0; p < 3; p++) { w[p] = (uint32_t)lay.width[p]; h[p] = (uint32_t)lay.height[p]; s[p] = (uint32_t)lay.stride[p]; }
+}
+
+frame_c::frame_c(int width, int height, int chroma_format) {
+    frame_geometry(width, height, chroma_format, m_width, m_height, m_stride);
+    for (int p = 0; p < 3; p++) m_planes[p] = (uint8_t*)aligned_alloc(64, ((size_t)m_height[p] * m_stride[p] + 63) & ~(size_t)63);
+    m_owner = true;
+}
+
+frame_c::frame_c(int width, int height, int chroma_format, uint8_t* const planes[3], const int strides[3]) {
+    frame_geometry(width, height, chroma_format, m_width, m_height, m_stride);
+    for (int p = 0; p < 3; p++) { m_planes[p] = planes[p]; m_stride[p] = (uint32_t)strides[p]; }
+}
+
+frame_c::~frame_c() {
+    if (m_owner) for (auto* p : m_planes) free(p);
+}
+
+// ------------------------------------------------------------------------------------------------ internals
+
+namespace {
+
+using clock_t_ = std::chrono::steady_clock;
+
+struct pipeline_t;
+
+struct pic_task_t {
+    const coded_picture_t* src = nullptr;
+    pipeline_t* pipe = nullptr;
+    int local_index = 0;               // position in the pipeline's coded order
+    int dst = -1, l0 = -1, l1 = -1;    // device frame ids
+    mp2v_picture_t* rp = nullptr;
+    coef_arena_t arena;
+    std::atomic<int> remaining{0};
+    std::atomic<bool> ok{true};
+    const char* error = nullptr;
+    bool parsed = false, submitted = false;
+};
+
+struct slice_job_t { pic_task_t* task; int slice; };
+
+struct shared_t {
+    decoder_config_t cfg{};
+    mp2v_b200_options_t opt;
+    std::function<void(frame_c*)> renderer;
+    int mbw = 0, mbh = 0;
+    // slice queue
+    std::mutex qmu;
+    std::condition_variable qcv;
+    std::deque<slice_job_t> queue;
+    bool stop = false;
+    // errors
+    std::atomic<bool> failed{false};
+    std::mutex emu;
+    std::string error;
+    // display order across GOP chains
+    std::mutex gmu;
+    std::condition_variable gcv;
+    int emit_gop = 0;
+    std::vector<int> gop_size, gop_emitted;
+    // statistics
+    std::atomic<int64_t> parse_ns{0};
+    std::vector<pipeline_t*> pipes;
+
+    void fail(const std::string& why);
+};
+
+struct pipeline_t {
+    shared_t* sh = nullptr;
+    int device = 0;
+    mp2v_recon_t* recon = nullptr;
+    std::deque<pic_task_t> tasks;            // coded order, this device's GOP chains only
+    // frame pool: use count = 1 while awaiting display + 1 while it is one of the two live references
+    std::vector<int> frame_use;
+    int n_frames = 0, n_slots = 0, parse_window = 0;
+    std::mutex mu;
+    std::condition_variable cv;
+    int in_parse = 0;                        // acquired, not yet submitted
+    int next_submit = 0;
+    std::thread feeder_thread, output_thread;
+
+    bool create();
+    void feeder();
+    void output();
+    void on_parsed(pic_task_t* t);
+    void release_frame_use(int f) {
+        std::lock_guard<std::mutex> lk(mu);
+        if (f >= 0 && --frame_use[f] == 0) cv.notify_all();
+    }
+    void wake() { { std::lock_guard<std::mutex> lk(mu); } cv.notify_all(); }
+};
+
+void shared_t::fail(const std::string& why) {
+    { std::lock_guard<std::mutex> lk(emu); if (error.empty()) error = why; }
+    failed.store(true);
+    { std::lock_guard<std::mutex> lk(qmu); }
+    qcv.notify_all();
+    { std::lock_guard<std::mutex> lk(gmu); }
+    gcv.notify_all();
+    for (auto* p : pipes) p->cv.notify_all();   // waiters re-check `failed` (they hold p->mu only while testing)
+}
+
+bool pipeline_t::create() {
+    const decoder_config_t& c = sh->cfg;
+    const int lag = sh->opt.output_lag < 0 ? 0 : sh->opt.output_lag;
+    n_frames = (c.pictures_pool_size > 4 ? c.pictures_pool_size : 4) + lag + 2;
+    n_slots = 2 * (sh->opt.max_batch > 0 ? sh->opt.max_batch : 8);
+    if (n_slots < 6) n_slots = 6;
+    parse_window = n_slots / 2;
+    const uint32_t nblk = c.chroma_format == 1 ? 6 : c.chroma_format == 2 ? 8 : 12;
+    const uint64_t worst = (uint64_t)sh->mbw * sh->mbh * nblk * 64u;
+    // a picture needs the worst case only when every coefficient of every block is coded; size the
+    // slots for a quarter of that (at least 1 Mi records) plus one chunk of slack per slice row
+    uint64_t cap = worst < (1u << 20) ? worst : (worst / 4 > (1u << 20) ? worst / 4 : (1u << 20));
+    cap += (uint64_t)(sh->mbh + 8) * coef_arena_t::kChunk;
+    if (worst < (1u << 20)) cap = worst + (uint64_t)(sh->mbh + 8) * ((uint64_t)sh->mbw * nblk * 64u < coef_arena_t::kChunk ? (uint64_t)sh->mbw * nblk * 64u : coef_arena_t::kChunk);
+    mp2v_recon_config_t rc{};
+    rc.device = device; rc.width = c.width; rc.height = c.height; rc.chroma_format = c.chroma_format;
+    rc.n_frames = n_frames; rc.n_pictures = n_slots; rc.max_batch = sh->opt.max_batch; rc.flags = MP2V_RECON_VALIDATE;
+    rc.coef_capacity = (uint32_t)(cap > 0xffffffffull ? 0xffffffffull : cap);
+    if (mp2v_recon_create(&rc, &recon) != MP2V_OK) {
+        sh->fail(std::string("mp2v_recon_create: ") + mp2v_recon_last_error(nullptr));
+        return false;
+    }
+    mp2v_recon_set_timing(recon, 1);
+    frame_use.assign(n_frames, 0);
+    return true;
+}
+
+void pipeline_t::feeder() {
+    int refs[2] = {-1, -1};   // local task indices of the two live references
+    auto unref = [&](int k) { if (k >= 0) release_frame_use(tasks[k].dst); };
+    for (size_t k = 0; k < tasks.size() && !sh->failed.load(); k++) {
+        pic_task_t& t = tasks[k];
+        const picture_info_t& info = t.src->info;
+        {   // a free device frame and room in the parse window
+            std::unique_lock<std::mutex> lk(mu);
+            int f = -1;
+            cv.wait(lk, [&] {
+                if (sh->failed.load()) return true;
+                if (in_parse >= parse_window) return false;
+                for (int i = 0; i < n_frames; i++) if (frame_use[i] == 0) { f = i; return true; }
+                return false;
+            });
+            if (sh->failed.load()) break;
+            t.dst = f;
+            frame_use[f] = 1;               // awaiting display
+            in_parse++;
+        }
+        if (info.picture_coding_type == 3) {                       // B: both references (decoder.cpp:303)
+            t.l0 = refs[0] >= 0 ? tasks[refs[0]].dst : -1;
+            t.l1 = refs[1] >= 0 ? tasks[refs[1]].dst : -1;
+            if (t.l0 < 0 || t.l1 < 0) { sh->fail("B picture without two reference pictures"); break; }
+        } else {                                                   // I/P: previous reference (decoder.cpp:298-302)
+            t.l0 = (info.picture_coding_type == 2 && refs[1] >= 0) ? tasks[refs[1]].dst : -1;
+            if (info.picture_coding_type == 2 && t.l0 < 0) { sh->fail("P picture without a reference picture"); break; }
+            unref(refs[0]);
+            refs[0] = refs[1];
+            refs[1] = (int)k;
+            { std::lock_guard<std::mutex> lk(mu); frame_use[t.dst]++; }
+        }
+        if (mp2v_recon_acquire_picture(recon, &t.rp) != MP2V_OK) { sh->fail(std::string("acquire_picture: ") + mp2v_recon_last_error(recon)); break; }
+        mp2v_pic_params_t& pp = *t.rp->params;
+        build_picture_matrices(info, pp.W);
+        pp.picture_coding_type = info.picture_coding_type;
+        pp.alternate_scan = info.alternate_scan;
+        pp.dst_frame = t.dst; pp.l0_frame = t.l0; pp.l1_frame = t.l1;
+        // macroblocks no slice covers: intra with no coded block (reconstructs to 0); never the case in valid streams
+        const mp2v_mb_info_t blank = {0u, MP2V_MB_BITS(0, 1, 0, MP2V_MB_INTRA), {{0, 0}, {0, 0}}};
+        for (uint32_t i = 0; i < t.rp->mb_count; i++) t.rp->mb[i] = blank;
+        t.arena.base = t.rp->coef;
+        t.arena.capacity = t.rp->coef_capacity;
+        t.arena.next.store(0);
+        t.arena.overflow.store(false);
+        const int ns = (int)t.src->slices.size();
+        if (ns == 0) { on_parsed(&t); continue; }
+        t.remaining.store(ns);
+        {
+            std::lock_guard<std::mutex> lk(sh->qmu);
+            for (int s = 0; s < ns; s++) sh->queue.push_back({&t, s});
+        }
+        sh->qcv.notify_all();
+    }
+    unref(refs[0]);
+    unref(refs[1]);
+}
+
+// called by the worker that finished the last slice of a picture
+void pipeline_t::on_parsed(pic_task_t* t) {
+    std::lock_guard<std::mutex> lk(mu);
+    t->parsed = true;
+    while (next_submit < (int)tasks.size() && tasks[next_submit].parsed && !sh->failed.load()) {
+        pic_task_t& s = tasks[next_submit];
+        if (!s.ok.load() || s.arena.overflow.load()) {
+            sh->fail(std::string("picture ") + std::to_string(next_submit) + ": " + (s.error ? s.error : "coefficient arena exhausted"));
+            break;
+        }
+        s.rp->params->n_coef = s.arena.next.load();
+        if (mp2v_recon_submit(recon, s.rp) != MP2V_OK) { sh->fail(std::string("submit: ") + mp2v_recon_last_error(recon)); break; }
+        s.submitted = true;
+        next_submit++;
+        in_parse--;
+    }
+    cv.notify_all();
+}
+
+void pipeline_t::output() {
+    const int n = (int)tasks.size();
+    const int lag = sh->opt.output_lag < 0 ? 0 : sh->opt.output_lag;
+    auto emit = [&](int k) -> bool {
+        pic_task_t& t = tasks[k];
+        {   // stay `lag` pictures behind the submit side so that launches can batch
+            std::unique_lock<std::mutex> lk(mu);
+            const int need = (k + lag < n - 1 ? k + lag : n - 1) + 1;
+            cv.wait(lk, [&] { return sh->failed.load() || next_submit >= need; });
+            if (sh->failed.load()) return false;
+        }
+        uint8_t* planes[3] = {nullptr, nullptr, nullptr};
+        int32_t strides[3] = {0, 0, 0};
+        if (sh->opt.download_frames) {
+            if (mp2v_recon_map_frame(recon, t.dst, planes, strides) != MP2V_OK) { sh->fail(std::string("map_frame: ") + mp2v_recon_last_error(recon)); return false; }
+        }
+        {   // display order across GOP chains: chain g is shown after chain g-1
+            std::unique_lock<std::mutex> lk(sh->gmu);
+            sh->gcv.wait(lk, [&] { return sh->failed.load() || sh->emit_gop == t.src->gop; });
+            if (sh->failed.load()) return false;
+        }
+        if (sh->renderer) {
+            const int st[3] = {strides[0], strides[1], strides[2]};
+            frame_c view(sh->cfg.width, sh->cfg.height, sh->cfg.chroma_format, planes, st);
+            sh->renderer(&view);
+        }
+        {
+            std::lock_guard<std::mutex> lk(sh->gmu);
+            if (++sh->gop_emitted[t.src->gop] == sh->gop_size[t.src->gop]) { sh->emit_gop++; sh->gcv.notify_all(); }
+        }
+        release_frame_use(t.dst);
+        return true;
+    };
+    // display reorder of decoder_output_scheduler (decoder.cpp:350-378)
+    int held = -1;
+    for (int k = 0; k < n; k++) {
+        // end of a GOP chain: its held reference is the last frame of that chain
+        if (k > 0 && held >= 0 && tasks[k].src->gop != tasks[k - 1].src->gop) { if (!emit(held)) return; held = -1; }
+        const bool is_b = tasks[k].src->info.picture_coding_type == 3;
+        if (is_b || !sh->cfg.reordering) { if (!emit(k)) return; }
+        else {
+            if (held >= 0 && !emit(held)) return;
+            held = k;
+        }
+    }
+    if (held >= 0) emit(held);
+}
+
+void worker_main(shared_t* sh) {
+    for (;;) {
+        slice_job_t job;
+        {
+            std::unique_lock<std::mutex> lk(sh->qmu);
+            sh->qcv.wait(lk, [&] { return sh->stop || !sh->queue.empty(); });
+            if (sh->queue.empty()) return;
+            job = sh->queue.front();
+            sh->queue.pop_front();
+        }
+        pic_task_t* t = job.task;
+        if (!sh->failed.load()) {
+            const auto t0 = clock_t_::now();
+            const slice_ref_t& sr = t->src->slices[job.slice];
+            const slice_result_t r = parse_slice(sr.payload, sr.code, t->src->seq, t->src->info, sh->mbw, sh->mbh, t->rp->mb, t->arena);
+            sh->parse_ns.fetch_add(std::chrono::duration_cast<std::chrono::nanoseconds>(clock_t_::now() - t0).count());
+            if (!r.ok) { t->error = r.error; t->ok.store(false); }
+        }
+        if (t->remaining.fetch_sub(1) == 1) t->pipe->on_parsed(t);
+    }
+}
+
+}  // namespace
+
+// ------------------------------------------------------------------------------------------------ mp2v_decoder_c
+
+struct mp2v_decoder_c::impl_t {
+    decoder_config_t cfg{};
+    mp2v_b200_options_t opt;
+    std::function<void(frame_c*)> renderer;
+    bool initialised = false;
+    std::string error;
+    stats_t stats;
+};
+
+mp2v_decoder_c::mp2v_decoder_c() : m(new impl_t) {
+    if (const char* d = getenv("MP2V_DEVICE")) m->opt.devices = {atoi(d)};
+}
+mp2v_decoder_c::mp2v_decoder_c(const decoder_config_t& config, std::function<void(frame_c*)> renderer) : mp2v_decoder_c() {
+    decoder_init(config, renderer);
+}
+mp2v_decoder_c::~mp2v_decoder_c() = default;
+
+bool mp2v_decoder_c::decoder_init(const decoder_config_t& config, std::function<void(frame_c*)> renderer) {
+    m->cfg = config;
+    m->renderer = renderer;
+    mp2v_frame_layout_t lay;
+    m->initialised = mp2v_frame_layout(config.width, config.height, config.chroma_format, &lay) == MP2V_OK && config.num_threads >= 1;
+    if (!m->initialised) m->error = "bad decoder_config_t (width/height must be multiples of 16, chroma_format 1..3, num_threads >= 1)";
+    return m->initialised;
+}
+
+void mp2v_decoder_c::set_options(const mp2v_b200_options_t& opt) { m->opt = opt; }
+const char* mp2v_decoder_c::last_error() const { return m->error.c_str(); }
+mp2v_decoder_c::stats_t mp2v_decoder_c::stats() const { return m->stats; }
+void mp2v_decoder_c::flush() {}   // decode() is one-shot and drains everything itself (as the reference's always does)
+
+bool mp2v_decoder_c::decode(uint8_t* buffer, int len) {
+    if (!m->initialised) return false;
+    const auto t_begin = clock_t_::now();
+    m->error.clear();
+    stream_index_t index;
+    if (!index_stream(buffer, (size_t)len, index)) { m->error = index.error; return false; }
+    shared_t sh;
+    sh.cfg = m->cfg; sh.opt = m->opt; sh.renderer = m->renderer;
+    sh.mbw = m->cfg.width / 16; sh.mbh = m->cfg.height / 16;
+    for (const auto& pic : index.pictures)
+        if (pic.seq.chroma_format != m->cfg.chroma_format) { m->error = "stream chroma_format differs from decoder_config_t.chroma_format"; return false; }
+    sh.gop_size.assign(index.n_gops > 0 ? index.n_gops : 1, 0);
+    sh.gop_emitted.assign(sh.gop_size.size(), 0);
+    for (const auto& pic : index.pictures) sh.gop_size[pic.gop]++;
+    // one pipeline per device; GOP chain g -> device g mod N
+    std::vector<int> devices = m->opt.devices.empty() ? std::vector<int>{0} : m->opt.devices;
+    std::deque<pipeline_t> pipes(devices.size());
+    for (size_t d = 0; d < pipes.size(); d++) { pipes[d].sh = &sh; pipes[d].device = devices[d]; sh.pipes.push_back(&pipes[d]); }
+    for (const auto& pic : index.pictures) {
+        pipeline_t& p = pipes[(size_t)pic.gop % pipes.size()];
+        p.tasks.emplace_back();
+        pic_task_t& t = p.tasks.back();
+        t.src = &pic; t.pipe = &p; t.local_index = (int)p.tasks.size() - 1;
+    }
+    bool ok = true;
+    for (auto& p : pipes) if (!p.tasks.empty() && !p.create()) { ok = false; break; }
+    std::vector<std::thread> workers;
+    if (ok) {
+        int nthreads = m->cfg.num_threads > MAX_NUM_THREADS ? MAX_NUM_THREADS : m->cfg.num_threads;
+        for (int i = 0; i < nthreads; i++) workers.emplace_back(worker_main, &sh);
+        for (auto& p : pipes) if (!p.tasks.empty()) {
+            p.feeder_thread = std::thread(&pipeline_t::feeder, &p);
+            p.output_thread = std::thread(&pipeline_t::output, &p);
+        }
+        for (auto& p : pipes) {
+            if (p.feeder_thread.joinable()) p.feeder_thread.join();
+            if (p.output_thread.joinable()) p.output_thread.join();
+        }
+        { std::lock_guard<std::mutex> lk(sh.qmu); sh.stop = true; }
+        sh.qcv.notify_all();
+        for (auto& w : workers) w.join();
+    }
+    m->stats = stats_t();
+    for (auto& p : pipes) {
+        if (!p.recon) continue;
+        if (mp2v_recon_sync(p.recon) != MP2V_OK && !sh.failed.load()) sh.fail(std::string("sync: ") + mp2v_recon_last_error(p.recon));
+        mp2v_recon_stats_t st;
+        if (mp2v_recon_get_stats(p.recon, &st, 0) == MP2V_OK) {
+            m->stats.pictures += st.pictures; m->stats.launches += st.launches; m->stats.h2d_bytes += st.h2d_bytes;
+            m->stats.d2h_bytes += st.d2h_bytes; m->stats.algorithmic_bytes += st.algorithmic_bytes; m->stats.kernel_ms += st.kernel_ms;
+        }
+        mp2v_recon_destroy(p.recon);
+        p.recon = nullptr;
+    }
+    m->stats.parse_cpu_seconds = sh.parse_ns.load() * 1e-9;
+    m->stats.wall_seconds = std::chrono::duration<double>(clock_t_::now() - t_begin).count();
+    if (sh.failed.load()) { m->error = sh.error; return false; }
+    return ok;
+}

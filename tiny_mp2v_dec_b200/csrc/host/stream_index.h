@@ -1,0 +1,35 @@
+// One pass over an elementary stream: start codes -> coded pictures with their headers and slice
+// payload pointers.  This is the role of mp2v_decoder_c::decode()'s start-code switch in the
+// reference (decoder.cpp:278-329), separated from scheduling so that the GPU decoder, the host-only
+// parse benchmark and the tests share it.
+#pragma once
+#include <cstdint>
+#include <string>
+#include <vector>
+
+#include "mp2v_parser.h"
+
+namespace mp2v {
+
+struct slice_ref_t {
+    const uint8_t* payload;   // first byte after the 4-byte start code
+    int code;                 // slice_start_code value 0x01..0xAF
+};
+
+struct coded_picture_t {
+    picture_info_t info;
+    sequence_info_t seq;      // sequence state in force for this picture
+    std::vector<slice_ref_t> slices;
+    int gop = 0;              // index of the closed GOP chain this picture belongs to (sharding unit)
+};
+
+struct stream_index_t {
+    std::vector<coded_picture_t> pictures;   // coded order
+    int n_gops = 0;
+    std::string error;
+};
+
+// buffer must be followed by >= 64 readable bytes (decode() contract)
+bool index_stream(const uint8_t* buffer, size_t len, stream_index_t& out);
+
+}  // namespace mp2v

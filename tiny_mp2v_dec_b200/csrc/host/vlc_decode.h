@@ -1,0 +1,103 @@
+// Prefix-indexed decode tables for the Annex B codes, built once from vlc_tables.h.
+//
+// The reference decodes with leading-zero-count tables generated offline (mp2v_luts.hpp,
+// mp2v_vlc_dec.hpp); here every table is a flat "peek N bits -> {length, value}" array generated at
+// start-up from the same bit-strings the stream generator encodes with, so encoder and decoder cannot
+// drift apart.  Run/level codes use a two-level table (8-bit root, 9-bit leaves) to stay L1-resident.
+#pragma once
+#include <cstdint>
+#include <cstring>
+#include <vector>
+
+#include "vlc_tables.h"
+
+namespace mp2v {
+
+struct vlc_entry_t { int8_t len; int8_t pad; int16_t val; };          // len 0 = invalid code
+
+struct coef_entry_t {     // run/level tables
+    uint8_t len;          // code length WITHOUT the sign bit; 0 = invalid; root entries with sub != 0 chain to a leaf table
+    uint8_t run;
+    int16_t level;        // magnitude; kEob / kEscape markers below
+    uint16_t sub;         // root only: 1-based leaf table index
+    uint16_t pad;
+};
+constexpr int16_t kCoefEob = -1;
+constexpr int16_t kCoefEsc = -2;
+
+template <int BITS>
+struct flat_vlc_t {
+    vlc_entry_t e[1 << BITS];
+    flat_vlc_t() { memset(e, 0, sizeof(e)); }
+    void add(const char* bits, int val) {
+        const int len = (int)strlen(bits);
+        uint32_t code = 0;
+        for (int i = 0; i < len; i++) code = (code << 1) | (uint32_t)(bits[i] == '1');
+        const uint32_t lo = code << (BITS - len), n = 1u << (BITS - len);
+        for (uint32_t k = 0; k < n; k++) { e[lo + k].len = (int8_t)len; e[lo + k].val = (int16_t)val; }
+    }
+    inline const vlc_entry_t& look(uint32_t peek_bits) const { return e[peek_bits]; }
+};
+
+struct coef_vlc_t {
+    static constexpr int ROOT = 8, LEAF = 9;                      // longest code is 16 bits (+ sign)
+    coef_entry_t root[1 << ROOT];
+    std::vector<coef_entry_t> leaves;                             // (1 << LEAF) entries per leaf table
+    coef_vlc_t() { memset(root, 0, sizeof(root)); }
+    void add(const char* bits, int run, int level) {
+        const int len = (int)strlen(bits);
+        uint32_t code = 0;
+        for (int i = 0; i < len; i++) code = (code << 1) | (uint32_t)(bits[i] == '1');
+        if (len <= ROOT) {
+            const uint32_t lo = code << (ROOT - len), n = 1u << (ROOT - len);
+            for (uint32_t k = 0; k < n; k++) { root[lo + k].len = (uint8_t)len; root[lo + k].run = (uint8_t)run; root[lo + k].level = (int16_t)level; root[lo + k].sub = 0; }
+        } else {
+            const uint32_t prefix = code >> (len - ROOT);
+            if (!root[prefix].sub) {
+                leaves.resize(leaves.size() + (1u << LEAF));
+                memset(&leaves[leaves.size() - (1u << LEAF)], 0, sizeof(coef_entry_t) << LEAF);
+                root[prefix].sub = (uint16_t)(leaves.size() >> LEAF);
+                root[prefix].len = 0;
+            }
+            coef_entry_t* leaf = &leaves[(size_t)(root[prefix].sub - 1) << LEAF];
+            const int rem = len - ROOT;
+            const uint32_t low = code & ((1u << rem) - 1u);
+            const uint32_t lo = low << (LEAF - rem), n = 1u << (LEAF - rem);
+            for (uint32_t k = 0; k < n; k++) { leaf[lo + k].len = (uint8_t)len; leaf[lo + k].run = (uint8_t)run; leaf[lo + k].level = (int16_t)level; }
+        }
+    }
+    // peek17 = next 17 bits of the stream
+    inline const coef_entry_t& look(uint32_t peek17) const {
+        const coef_entry_t& r = root[peek17 >> (17 - ROOT)];
+        if (!r.sub) return r;
+        return leaves[((size_t)(r.sub - 1) << LEAF) + (peek17 & ((1u << LEAF) - 1u))];
+    }
+};
+
+struct vlc_decode_tables_t {
+    flat_vlc_t<11> mba;            // val = increment, 0 = escape (adds 33)
+    flat_vlc_t<6> mbtype[4];       // per picture_coding_type; val = flag byte
+    flat_vlc_t<9> cbp;
+    flat_vlc_t<10> motion;         // magnitude 0..16 (sign bit follows when != 0)
+    flat_vlc_t<10> dcsize[2];      // 0 luminance, 1 chrominance
+    coef_vlc_t b14, b15;
+
+    vlc_decode_tables_t() {
+        for (int i = 0; i < MP2V_COUNT(kTabMbAddrInc); i++) mba.add(kTabMbAddrInc[i].bits, kTabMbAddrInc[i].a);
+        for (int i = 0; i < MP2V_COUNT(kTabMbType); i++) mbtype[kTabMbType[i].b].add(kTabMbType[i].bits, kTabMbType[i].a);
+        for (int i = 0; i < MP2V_COUNT(kTabCbp); i++) cbp.add(kTabCbp[i].bits, kTabCbp[i].a);
+        for (int i = 0; i < MP2V_COUNT(kTabMotionCode); i++) motion.add(kTabMotionCode[i].bits, kTabMotionCode[i].a);
+        for (int i = 0; i < MP2V_COUNT(kTabDcSize); i++) dcsize[kTabDcSize[i].b].add(kTabDcSize[i].bits, kTabDcSize[i].a);
+        for (int i = 0; i < MP2V_COUNT(kTabCoefB14); i++) b14.add(kTabCoefB14[i].bits, kTabCoefB14[i].a, kTabCoefB14[i].b);
+        for (int i = 0; i < MP2V_COUNT(kTabCoefB15); i++) b15.add(kTabCoefB15[i].bits, kTabCoefB15[i].a, kTabCoefB15[i].b);
+        b14.add(kEobB14, 0, kCoefEob); b15.add(kEobB15, 0, kCoefEob);
+        b14.add(kCoefEscape, 0, kCoefEsc); b15.add(kCoefEscape, 0, kCoefEsc);
+    }
+};
+
+inline const vlc_decode_tables_t& vlc_decode_tables() {
+    static const vlc_decode_tables_t t;
+    return t;
+}
+
+}  // namespace mp2v

@@ -147,7 +147,7 @@ static int create_impl(mp2v_recon* ctx) {
     for (auto& ev : ctx->frame_ev) CK(cudaEventCreateWithFlags(&ev, cudaEventDisableTiming), "event");
     // picture slots
     const uint32_t worst = (uint32_t)ctx->mb_count * ctx->nblk * 64u;
-    const uint32_t cap = c.coef_capacity ? std::min(c.coef_capacity, worst) : worst;
+    const uint32_t cap = c.coef_capacity ? c.coef_capacity : worst;
     ctx->coef_off = kParamsBytes + (((size_t)ctx->mb_count * sizeof(mp2v_mb_info_t) + 255) & ~(size_t)255);
     ctx->arena_bytes = ctx->coef_off + (size_t)cap * sizeof(mp2v_coef_t);
     ctx->slots.resize(c.n_pictures);

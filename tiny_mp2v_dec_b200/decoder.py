@@ -1,0 +1,127 @@
+"""Python mirror of the reference-facing decode API (include/mp2v_decoder.hpp via mp2v_decode_c.h).
+
+`Decoder` mirrors mp2v_decoder_c: construct with the fields of decoder_config_t, call decode() once
+with a whole elementary stream.  `parse_stream` exposes the host-only slice parser (tests, host-parse
+throughput).  No CPU reconstruction exists behind these calls."""
+import ctypes as C
+
+import numpy as np
+
+from .abi import OK, MbInfo, PicParams, mb_dtype
+from .recon import ReconError, lib as _recon_lib
+
+
+class DecodeParams(C.Structure):
+    _fields_ = [("width", C.c_int32), ("height", C.c_int32), ("chroma_format", C.c_int32),
+                ("pictures_pool_size", C.c_int32), ("num_threads", C.c_int32), ("reordering", C.c_int32),
+                ("n_devices", C.c_int32), ("devices", C.c_int32 * 8), ("max_batch", C.c_int32), ("output_lag", C.c_int32),
+                ("download_frames", C.c_int32)]
+
+
+class DecodeStats(C.Structure):
+    _fields_ = [("frames", C.c_uint64), ("pictures", C.c_uint64), ("launches", C.c_uint64), ("h2d_bytes", C.c_uint64),
+                ("d2h_bytes", C.c_uint64), ("algorithmic_bytes", C.c_uint64), ("kernel_ms", C.c_double),
+                ("parse_cpu_seconds", C.c_double), ("wall_seconds", C.c_double), ("hash", C.c_uint64)]
+
+
+DECODE_EXPORTS = ["mp2v_decode_stream", "mp2v_parse_stream", "mp2v_parsed_num_pictures", "mp2v_parsed_picture",
+                  "mp2v_parsed_wall_seconds", "mp2v_parsed_cpu_seconds", "mp2v_parsed_free"]
+
+_bound = False
+
+
+def lib():
+    global _bound
+    L = _recon_lib()
+    if not _bound:
+        P = C.POINTER
+        L.mp2v_decode_stream.argtypes = [P(DecodeParams), C.c_void_p, C.c_int, C.c_void_p, C.c_void_p, C.c_void_p, C.c_size_t,
+                                         P(C.c_size_t), P(DecodeStats), C.c_char_p, C.c_size_t]
+        L.mp2v_parse_stream.argtypes = [C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, P(C.c_void_p), C.c_char_p, C.c_size_t]
+        L.mp2v_parsed_num_pictures.argtypes = [C.c_void_p]
+        L.mp2v_parsed_picture.argtypes = [C.c_void_p, C.c_int, P(PicParams), P(P(MbInfo)), P(P(C.c_uint32)), P(C.c_uint32),
+                                          P(C.c_int32), P(C.c_int32)]
+        L.mp2v_parsed_wall_seconds.argtypes = [C.c_void_p]
+        L.mp2v_parsed_wall_seconds.restype = C.c_double
+        L.mp2v_parsed_cpu_seconds.argtypes = [C.c_void_p]
+        L.mp2v_parsed_cpu_seconds.restype = C.c_double
+        L.mp2v_parsed_free.argtypes = [C.c_void_p]
+        L.mp2v_parsed_free.restype = None
+        _bound = True
+    return L
+
+
+def frame_bytes(width, height, chroma_format):
+    return width * height * {1: 3, 2: 4, 3: 6}[chroma_format] // 2
+
+
+class Decoder:
+    """mp2v_decoder_c(decoder_config_t{width, height, chroma_format, pictures_pool_size, num_threads, reordering})"""
+
+    def __init__(self, width, height, chroma_format, pictures_pool_size=10, num_threads=8, reordering=True,
+                 devices=(0,), max_batch=0, output_lag=0):
+        self.p = DecodeParams(width, height, chroma_format, pictures_pool_size, num_threads, 1 if reordering else 0,
+                              len(devices), (C.c_int32 * 8)(*devices), max_batch, output_lag, 1)
+        self.stats = None
+
+    def decode(self, padded, size, want_output=True, download=True):
+        """padded: uint8 array holding the stream followed by >= 64 bytes of padding; size: stream length.
+        Returns cropped planar YUV (display order) as bytes when want_output, else None; self.stats is filled."""
+        L = lib()
+        buf = np.ascontiguousarray(padded, np.uint8)
+        assert buf.size >= size + 64, "decode(): the stream buffer must be padded with >= 64 bytes"
+        self.p.download_frames = 1 if download else 0
+        st = DecodeStats()
+        err = C.create_string_buffer(512)
+        out = None
+        cap = 0
+        if want_output and download:
+            # upper bound: every picture start code yields one frame
+            n_pics = int(np.count_nonzero((buf[:size - 3] == 0) & (buf[1:size - 2] == 0) & (buf[2:size - 1] == 1) & (buf[3:size] == 0)))
+            cap = n_pics * frame_bytes(self.p.width, self.p.height, self.p.chroma_format)
+            out = np.empty(max(cap, 1), np.uint8)
+        nbytes = C.c_size_t()
+        rc = L.mp2v_decode_stream(C.byref(self.p), buf.ctypes.data, size, None, None, out.ctypes.data if out is not None else None,
+                                  cap, C.byref(nbytes), C.byref(st), err, 512)
+        self.stats = st
+        if rc != OK:
+            raise ReconError("decode failed (%d): %s" % (rc, err.value.decode()))
+        if out is None:
+            return None
+        assert nbytes.value <= cap, (nbytes.value, cap)
+        return out[:nbytes.value].tobytes()
+
+
+class ParsedPicture:
+    def __init__(self, params, mb, coef, temporal_reference, gop):
+        self.params, self.mb, self.coef, self.temporal_reference, self.gop = params, mb, coef, temporal_reference, gop
+
+
+def parse_stream(padded, size, width, height, chroma_format, threads=1, want_records=True):
+    """host-only slice parse -> (pictures, wall_seconds, cpu_seconds)"""
+    L = lib()
+    buf = np.ascontiguousarray(padded, np.uint8)
+    h = C.c_void_p()
+    err = C.create_string_buffer(512)
+    rc = L.mp2v_parse_stream(buf.ctypes.data, size, width, height, chroma_format, threads, C.byref(h), err, 512)
+    if rc != OK:
+        raise ReconError("parse failed (%d): %s" % (rc, err.value.decode()))
+    try:
+        pics = []
+        if want_records:
+            n_mb = (width // 16) * (height // 16)
+            for i in range(L.mp2v_parsed_num_pictures(h)):
+                pp = PicParams()
+                mb = C.POINTER(MbInfo)()
+                coef = C.POINTER(C.c_uint32)()
+                n_coef = C.c_uint32()
+                tr = C.c_int32()
+                gop = C.c_int32()
+                L.mp2v_parsed_picture(h, i, C.byref(pp), C.byref(mb), C.byref(coef), C.byref(n_coef), C.byref(tr), C.byref(gop))
+                mba = np.ctypeslib.as_array(C.cast(mb, C.POINTER(C.c_uint8)), shape=(n_mb * 16,)).copy().view(mb_dtype)
+                ca = np.ctypeslib.as_array(coef, shape=(n_coef.value,)).copy() if n_coef.value else np.zeros(0, np.uint32)
+                pics.append(ParsedPicture(pp, mba, ca, tr.value, gop.value))
+        n = L.mp2v_parsed_num_pictures(h)
+        return pics, L.mp2v_parsed_wall_seconds(h), L.mp2v_parsed_cpu_seconds(h), n
+    finally:
+        L.mp2v_parsed_free(h)
