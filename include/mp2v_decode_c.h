@@ -21,6 +21,7 @@ typedef struct mp2v_decode_params {
     int32_t devices[8];
     int32_t max_batch, output_lag;          /* 0 = defaults                                                 */
     int32_t download_frames;                /* 0: reconstruct only (frames stay on the device)             */
+    int32_t hash_output;                    /* 1: FNV-1a of the output into stats->hash (slow; tests only)  */
 } mp2v_decode_params_t;
 
 typedef struct mp2v_decode_stats {
@@ -40,6 +41,15 @@ typedef void (*mp2v_frame_fn)(void* user, uint8_t* const planes[3], const int32_
 MP2V_API int mp2v_decode_stream(const mp2v_decode_params_t* params, uint8_t* buffer, int len,
                                 mp2v_frame_fn fn, void* user, uint8_t* out, size_t out_cap, size_t* out_bytes,
                                 mp2v_decode_stats_t* stats, char* err, size_t err_len);
+
+/* The same with a decoder that outlives the call: create allocates the device contexts (the
+ * reference allocates its frame pool in the constructor), decode may be called repeatedly. */
+typedef struct mp2v_decoder mp2v_decoder_t;
+MP2V_API int mp2v_decoder_create(const mp2v_decode_params_t* params, mp2v_decoder_t** out, char* err, size_t err_len);
+MP2V_API int mp2v_decoder_decode(mp2v_decoder_t* dec, uint8_t* buffer, int len, mp2v_frame_fn fn, void* user,
+                                 uint8_t* out, size_t out_cap, size_t* out_bytes, mp2v_decode_stats_t* stats,
+                                 char* err, size_t err_len);
+MP2V_API void mp2v_decoder_destroy(mp2v_decoder_t* dec);
 
 /* Host-only: index + slice-parse a stream into reconstruction records on `threads` threads, no GPU
  * involved (parser tests; the "host parse" figure of the benchmark). */

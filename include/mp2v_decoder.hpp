@@ -78,6 +78,7 @@ public:
 
     // extensions
     void set_options(const mp2v_b200_options_t& opt);
+    bool prepare();                   // allocate the device contexts now (otherwise the first decode() does)
     const char* last_error() const;
     struct stats_t {
         uint64_t pictures = 0, launches = 0, h2d_bytes = 0, d2h_bytes = 0, algorithmic_bytes = 0;

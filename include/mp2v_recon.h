@@ -204,6 +204,11 @@ typedef struct mp2v_recon_stats {
                                       timing is enabled)                                          */
 } mp2v_recon_stats_t;
 MP2V_API int  mp2v_recon_set_timing(mp2v_recon_t* ctx, int enable);
+/* CUDA-event stopwatch on the context's compute stream (the stream every kernel is launched on):
+ * start records an event behind the work queued so far, stop records another, waits for it and
+ * returns the elapsed device time in milliseconds. */
+MP2V_API int  mp2v_recon_timer_start(mp2v_recon_t* ctx);
+MP2V_API int  mp2v_recon_timer_stop(mp2v_recon_t* ctx, double* elapsed_ms);
 MP2V_API int  mp2v_recon_get_stats(mp2v_recon_t* ctx, mp2v_recon_stats_t* out, int reset);
 
 #ifdef __cplusplus

@@ -112,7 +112,6 @@ struct pipeline_t {
     int next_submit = 0;
     std::thread feeder_thread, output_thread;
 
-    bool create();
     void feeder();
     void output();
     void on_parsed(pic_task_t* t);
@@ -131,33 +130,6 @@ void shared_t::fail(const std::string& why) {
     { std::lock_guard<std::mutex> lk(gmu); }
     gcv.notify_all();
     for (auto* p : pipes) p->cv.notify_all();   // waiters re-check `failed` (they hold p->mu only while testing)
-}
-
-bool pipeline_t::create() {
-    const decoder_config_t& c = sh->cfg;
-    const int lag = sh->opt.output_lag < 0 ? 0 : sh->opt.output_lag;
-    n_frames = (c.pictures_pool_size > 4 ? c.pictures_pool_size : 4) + lag + 2;
-    n_slots = 2 * (sh->opt.max_batch > 0 ? sh->opt.max_batch : 8);
-    if (n_slots < 6) n_slots = 6;
-    parse_window = n_slots / 2;
-    const uint32_t nblk = c.chroma_format == 1 ? 6 : c.chroma_format == 2 ? 8 : 12;
-    const uint64_t worst = (uint64_t)sh->mbw * sh->mbh * nblk * 64u;
-    // a picture needs the worst case only when every coefficient of every block is coded; size the
-    // slots for a quarter of that (at least 1 Mi records) plus one chunk of slack per slice row
-    uint64_t cap = worst < (1u << 20) ? worst : (worst / 4 > (1u << 20) ? worst / 4 : (1u << 20));
-    cap += (uint64_t)(sh->mbh + 8) * coef_arena_t::kChunk;
-    if (worst < (1u << 20)) cap = worst + (uint64_t)(sh->mbh + 8) * ((uint64_t)sh->mbw * nblk * 64u < coef_arena_t::kChunk ? (uint64_t)sh->mbw * nblk * 64u : coef_arena_t::kChunk);
-    mp2v_recon_config_t rc{};
-    rc.device = device; rc.width = c.width; rc.height = c.height; rc.chroma_format = c.chroma_format;
-    rc.n_frames = n_frames; rc.n_pictures = n_slots; rc.max_batch = sh->opt.max_batch; rc.flags = MP2V_RECON_VALIDATE;
-    rc.coef_capacity = (uint32_t)(cap > 0xffffffffull ? 0xffffffffull : cap);
-    if (mp2v_recon_create(&rc, &recon) != MP2V_OK) {
-        sh->fail(std::string("mp2v_recon_create: ") + mp2v_recon_last_error(nullptr));
-        return false;
-    }
-    mp2v_recon_set_timing(recon, 1);
-    frame_use.assign(n_frames, 0);
-    return true;
 }
 
 void pipeline_t::feeder() {
@@ -311,6 +283,13 @@ void worker_main(shared_t* sh) {
 
 // ------------------------------------------------------------------------------------------------ mp2v_decoder_c
 
+// per-device reconstruction context, created once (prepare) and reused by every decode() call
+struct device_ctx_t {
+    int device = 0;
+    mp2v_recon_t* recon = nullptr;
+    int n_frames = 0, n_slots = 0;
+};
+
 struct mp2v_decoder_c::impl_t {
     decoder_config_t cfg{};
     mp2v_b200_options_t opt;
@@ -318,7 +297,46 @@ struct mp2v_decoder_c::impl_t {
     bool initialised = false;
     std::string error;
     stats_t stats;
+    std::vector<device_ctx_t> devs;
+
+    void release() {
+        for (auto& d : devs) if (d.recon) mp2v_recon_destroy(d.recon);
+        devs.clear();
+    }
+    bool prepare();
 };
+
+bool mp2v_decoder_c::impl_t::prepare() {
+    if (!devs.empty()) return true;
+    const decoder_config_t& c = cfg;
+    const int mbw = c.width / 16, mbh = c.height / 16;
+    const int lag = opt.output_lag < 0 ? 0 : opt.output_lag;
+    const uint32_t nblk = c.chroma_format == 1 ? 6 : c.chroma_format == 2 ? 8 : 12;
+    const uint64_t worst = (uint64_t)mbw * mbh * nblk * 64u;
+    // a picture needs the worst case only when every coefficient of every block is coded: size the
+    // slots for a quarter of it, but never below 1 Mi records (or the worst case itself if smaller)
+    uint64_t cap = worst / 4 > (1u << 20) ? worst / 4 : (worst < (1u << 20) ? worst : (1u << 20));
+    std::vector<int> ids = opt.devices.empty() ? std::vector<int>{0} : opt.devices;
+    for (int id : ids) {
+        device_ctx_t d;
+        d.device = id;
+        d.n_frames = (c.pictures_pool_size > 4 ? c.pictures_pool_size : 4) + lag + 2;
+        d.n_slots = 2 * (opt.max_batch > 0 ? opt.max_batch : 8);
+        if (d.n_slots < 6) d.n_slots = 6;
+        mp2v_recon_config_t rc{};
+        rc.device = id; rc.width = c.width; rc.height = c.height; rc.chroma_format = c.chroma_format;
+        rc.n_frames = d.n_frames; rc.n_pictures = d.n_slots; rc.max_batch = opt.max_batch; rc.flags = MP2V_RECON_VALIDATE;
+        rc.coef_capacity = (uint32_t)(cap > 0xffffffffull ? 0xffffffffull : cap);
+        if (mp2v_recon_create(&rc, &d.recon) != MP2V_OK) {
+            error = std::string("mp2v_recon_create (CUDA device ") + std::to_string(id) + "): " + mp2v_recon_last_error(nullptr);
+            release();
+            return false;
+        }
+        mp2v_recon_set_timing(d.recon, 1);
+        devs.push_back(d);
+    }
+    return true;
+}
 
 mp2v_decoder_c::mp2v_decoder_c() : m(new impl_t) {
     if (const char* d = getenv("MP2V_DEVICE")) m->opt.devices = {atoi(d)};
@@ -326,7 +344,7 @@ mp2v_decoder_c::mp2v_decoder_c() : m(new impl_t) {
 mp2v_decoder_c::mp2v_decoder_c(const decoder_config_t& config, std::function<void(frame_c*)> renderer) : mp2v_decoder_c() {
     decoder_init(config, renderer);
 }
-mp2v_decoder_c::~mp2v_decoder_c() = default;
+mp2v_decoder_c::~mp2v_decoder_c() { m->release(); }
 
 bool mp2v_decoder_c::decoder_init(const decoder_config_t& config, std::function<void(frame_c*)> renderer) {
     m->cfg = config;
@@ -337,7 +355,8 @@ bool mp2v_decoder_c::decoder_init(const decoder_config_t& config, std::function<
     return m->initialised;
 }
 
-void mp2v_decoder_c::set_options(const mp2v_b200_options_t& opt) { m->opt = opt; }
+void mp2v_decoder_c::set_options(const mp2v_b200_options_t& opt) { m->release(); m->opt = opt; }
+bool mp2v_decoder_c::prepare() { return m->initialised && m->prepare(); }
 const char* mp2v_decoder_c::last_error() const { return m->error.c_str(); }
 mp2v_decoder_c::stats_t mp2v_decoder_c::stats() const { return m->stats; }
 void mp2v_decoder_c::flush() {}   // decode() is one-shot and drains everything itself (as the reference's always does)
@@ -357,19 +376,25 @@ bool mp2v_decoder_c::decode(uint8_t* buffer, int len) {
     sh.gop_emitted.assign(sh.gop_size.size(), 0);
     for (const auto& pic : index.pictures) sh.gop_size[pic.gop]++;
     // one pipeline per device; GOP chain g -> device g mod N
-    std::vector<int> devices = m->opt.devices.empty() ? std::vector<int>{0} : m->opt.devices;
-    std::deque<pipeline_t> pipes(devices.size());
-    for (size_t d = 0; d < pipes.size(); d++) { pipes[d].sh = &sh; pipes[d].device = devices[d]; sh.pipes.push_back(&pipes[d]); }
+    if (!m->prepare()) return false;
+    std::deque<pipeline_t> pipes(m->devs.size());
+    for (size_t d = 0; d < pipes.size(); d++) {
+        pipeline_t& p = pipes[d];
+        p.sh = &sh; p.device = m->devs[d].device; p.recon = m->devs[d].recon;
+        p.n_frames = m->devs[d].n_frames; p.n_slots = m->devs[d].n_slots; p.parse_window = p.n_slots / 2;
+        p.frame_use.assign(p.n_frames, 0);
+        sh.pipes.push_back(&p);
+        mp2v_recon_stats_t st;
+        mp2v_recon_get_stats(p.recon, &st, 1);   // statistics are per decode() call
+    }
     for (const auto& pic : index.pictures) {
         pipeline_t& p = pipes[(size_t)pic.gop % pipes.size()];
         p.tasks.emplace_back();
         pic_task_t& t = p.tasks.back();
         t.src = &pic; t.pipe = &p; t.local_index = (int)p.tasks.size() - 1;
     }
-    bool ok = true;
-    for (auto& p : pipes) if (!p.tasks.empty() && !p.create()) { ok = false; break; }
     std::vector<std::thread> workers;
-    if (ok) {
+    {
         int nthreads = m->cfg.num_threads > MAX_NUM_THREADS ? MAX_NUM_THREADS : m->cfg.num_threads;
         for (int i = 0; i < nthreads; i++) workers.emplace_back(worker_main, &sh);
         for (auto& p : pipes) if (!p.tasks.empty()) {
@@ -386,18 +411,20 @@ bool mp2v_decoder_c::decode(uint8_t* buffer, int len) {
     }
     m->stats = stats_t();
     for (auto& p : pipes) {
-        if (!p.recon) continue;
         if (mp2v_recon_sync(p.recon) != MP2V_OK && !sh.failed.load()) sh.fail(std::string("sync: ") + mp2v_recon_last_error(p.recon));
         mp2v_recon_stats_t st;
         if (mp2v_recon_get_stats(p.recon, &st, 0) == MP2V_OK) {
             m->stats.pictures += st.pictures; m->stats.launches += st.launches; m->stats.h2d_bytes += st.h2d_bytes;
             m->stats.d2h_bytes += st.d2h_bytes; m->stats.algorithmic_bytes += st.algorithmic_bytes; m->stats.kernel_ms += st.kernel_ms;
         }
-        mp2v_recon_destroy(p.recon);
-        p.recon = nullptr;
     }
     m->stats.parse_cpu_seconds = sh.parse_ns.load() * 1e-9;
     m->stats.wall_seconds = std::chrono::duration<double>(clock_t_::now() - t_begin).count();
-    if (sh.failed.load()) { m->error = sh.error; return false; }
-    return ok;
+    if (sh.failed.load()) {
+        // pictures may be left acquired / queued inside the contexts: rebuild them on the next call
+        m->release();
+        m->error = sh.error;
+        return false;
+    }
+    return true;
 }

@@ -21,52 +21,89 @@ static void set_err(char* err, size_t n, const std::string& s) {
     if (err && n) { snprintf(err, n, "%s", s.c_str()); }
 }
 
-extern "C" MP2V_API int mp2v_decode_stream(const mp2v_decode_params_t* p, uint8_t* buffer, int len,
-                                           mp2v_frame_fn fn, void* user, uint8_t* out, size_t out_cap, size_t* out_bytes,
-                                           mp2v_decode_stats_t* stats, char* err, size_t err_len) {
-    if (!p || !buffer || len < 0) return MP2V_ERR_ARG;
-    size_t pos = 0;
-    uint64_t hash = 1469598103934665603ull, frames = 0;
-    const bool want_pixels = p->download_frames != 0;
-    auto renderer = [&](frame_c* f) {
+// a decoder that outlives one call: device contexts are allocated at create (as the reference
+// allocates its frame pool in the constructor, decoder.cpp:381-406) and reused by every decode
+struct mp2v_decoder {
+    mp2v_decode_params_t p{};
+    mp2v_decoder_c dec;
+    // per-call sink state, read by the renderer closure
+    mp2v_frame_fn fn = nullptr;
+    void* user = nullptr;
+    uint8_t* out = nullptr;
+    size_t out_cap = 0, pos = 0;
+    uint64_t hash = 0, frames = 0;
+
+    void render(frame_c* f) {
         frames++;
-        if (!want_pixels) return;
+        if (!p.download_frames) return;
         int32_t strides[3], widths[3], heights[3];
         uint8_t* planes[3];
         for (int i = 0; i < 3; i++) { planes[i] = f->get_planes(i); strides[i] = f->get_strides(i); widths[i] = f->get_width(i); heights[i] = f->get_height(i); }
         if (fn) fn(user, planes, strides, widths, heights);
-        if (out || stats) {
-            for (int i = 0; i < 3; i++) {
-                const uint8_t* row = planes[i];
-                for (int y = 0; y < heights[i]; y++, row += strides[i]) {
-                    if (out && pos + (size_t)widths[i] <= out_cap) memcpy(out + pos, row, (size_t)widths[i]);
-                    else if (stats && !out) for (int x = 0; x < widths[i]; x++) { hash ^= row[x]; hash *= 1099511628211ull; }
-                    pos += (size_t)widths[i];
-                }
+        if (!out && !p.hash_output) return;
+        for (int i = 0; i < 3; i++) {
+            const uint8_t* row = planes[i];
+            for (int y = 0; y < heights[i]; y++, row += strides[i]) {
+                if (out && pos + (size_t)widths[i] <= out_cap) memcpy(out + pos, row, (size_t)widths[i]);
+                if (p.hash_output) for (int x = 0; x < widths[i]; x++) { hash ^= row[x]; hash *= 1099511628211ull; }
+                pos += (size_t)widths[i];
             }
         }
-    };
+    }
+};
+
+extern "C" MP2V_API int mp2v_decoder_create(const mp2v_decode_params_t* p, mp2v_decoder_t** out, char* err, size_t err_len) {
+    if (!p || !out) return MP2V_ERR_ARG;
+    std::unique_ptr<mp2v_decoder> d(new mp2v_decoder);
+    d->p = *p;
+    mp2v_decoder* raw = d.get();
     decoder_config_t cfg = {p->width, p->height, p->chroma_format, p->pictures_pool_size > 0 ? p->pictures_pool_size : 10,
                             p->num_threads > 0 ? p->num_threads : 1, p->reordering != 0};
-    mp2v_decoder_c dec;
-    if (!dec.decoder_init(cfg, renderer)) { set_err(err, err_len, dec.last_error()); return MP2V_ERR_ARG; }
+    if (!d->dec.decoder_init(cfg, [raw](frame_c* f) { raw->render(f); })) { set_err(err, err_len, d->dec.last_error()); return MP2V_ERR_ARG; }
     mp2v_b200_options_t opt;
     if (p->n_devices > 0) opt.devices.assign(p->devices, p->devices + (p->n_devices > 8 ? 8 : p->n_devices));
     if (p->max_batch > 0) opt.max_batch = p->max_batch;
     if (p->output_lag > 0) opt.output_lag = p->output_lag;
-    opt.download_frames = want_pixels;
-    dec.set_options(opt);
-    const bool ok = dec.decode(buffer, len);
-    if (out_bytes) *out_bytes = pos;
+    opt.download_frames = p->download_frames != 0;
+    d->dec.set_options(opt);
+    if (!d->dec.prepare()) { set_err(err, err_len, d->dec.last_error()); return MP2V_ERR_CUDA; }
+    *out = d.release();
+    return MP2V_OK;
+}
+
+extern "C" MP2V_API void mp2v_decoder_destroy(mp2v_decoder_t* d) { delete d; }
+
+extern "C" MP2V_API int mp2v_decoder_decode(mp2v_decoder_t* d, uint8_t* buffer, int len, mp2v_frame_fn fn, void* user,
+                                            uint8_t* out, size_t out_cap, size_t* out_bytes, mp2v_decode_stats_t* stats,
+                                            char* err, size_t err_len) {
+    if (!d || !buffer || len < 0) return MP2V_ERR_ARG;
+    d->fn = fn; d->user = user; d->out = out; d->out_cap = out_cap; d->pos = 0;
+    d->hash = 1469598103934665603ull; d->frames = 0;
+    const bool ok = d->dec.decode(buffer, len);
+    if (out_bytes) *out_bytes = d->pos;
     if (stats) {
-        const auto s = dec.stats();
-        stats->frames = frames; stats->pictures = s.pictures; stats->launches = s.launches;
+        const auto s = d->dec.stats();
+        stats->frames = d->frames; stats->pictures = s.pictures; stats->launches = s.launches;
         stats->h2d_bytes = s.h2d_bytes; stats->d2h_bytes = s.d2h_bytes; stats->algorithmic_bytes = s.algorithmic_bytes;
         stats->kernel_ms = s.kernel_ms; stats->parse_cpu_seconds = s.parse_cpu_seconds; stats->wall_seconds = s.wall_seconds;
-        stats->hash = hash;
+        stats->hash = d->hash;
     }
-    if (!ok) { set_err(err, err_len, dec.last_error()); return strstr(dec.last_error(), "CUDA") || strstr(dec.last_error(), "recon_create") ? MP2V_ERR_CUDA : MP2V_ERR_RANGE; }
+    if (!ok) {
+        set_err(err, err_len, d->dec.last_error());
+        return (strstr(d->dec.last_error(), "CUDA") || strstr(d->dec.last_error(), "recon_create")) ? MP2V_ERR_CUDA : MP2V_ERR_RANGE;
+    }
     return MP2V_OK;
+}
+
+extern "C" MP2V_API int mp2v_decode_stream(const mp2v_decode_params_t* p, uint8_t* buffer, int len,
+                                           mp2v_frame_fn fn, void* user, uint8_t* out, size_t out_cap, size_t* out_bytes,
+                                           mp2v_decode_stats_t* stats, char* err, size_t err_len) {
+    mp2v_decoder_t* d = nullptr;
+    int rc = mp2v_decoder_create(p, &d, err, err_len);
+    if (rc != MP2V_OK) return rc;
+    rc = mp2v_decoder_decode(d, buffer, len, fn, user, out, out_cap, out_bytes, stats, err, err_len);
+    mp2v_decoder_destroy(d);
+    return rc;
 }
 
 // ------------------------------------------------------------------------------------------------ host-only parse
@@ -105,9 +142,10 @@ extern "C" MP2V_API int mp2v_parse_stream(const uint8_t* buffer, int len, int wi
             const uint8_t* b = find_start_code(a, buffer + len);
             bytes += (size_t)(b - a);
         }
-        uint64_t chunk = (uint64_t)mbw * nblk * 64u;
-        if (chunk > coef_arena_t::kChunk) chunk = coef_arena_t::kChunk;
-        const uint64_t cap = bytes * 8 / 3 + (src.slices.size() + 2) * chunk + (uint64_t)mbw * mbh * nblk;
+        // bits bound the records: a coefficient costs >= 3 bits, an intra DC + end of block >= 4
+        uint64_t cap = bytes * 8 / 3 + (uint64_t)mbw * mbh * nblk;
+        const uint64_t worst = (uint64_t)mbw * mbh * nblk * 64u;
+        if (cap > worst) cap = worst;
         pic.coef.reset(new mp2v_coef_t[cap]);
         pic.arena.base = pic.coef.get();
         pic.arena.capacity = (uint32_t)cap;

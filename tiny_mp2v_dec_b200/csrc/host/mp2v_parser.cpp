@@ -4,6 +4,7 @@
 #include "mp2v_parser.h"
 
 #include <cstring>
+#include <vector>
 
 #include "bitreader.h"
 #include "scan_tables.h"
@@ -129,21 +130,19 @@ void build_picture_matrices(const picture_info_t& pic, uint8_t W[4][64]) {
 // ------------------------------------------------------------------------------------------------
 namespace {
 
+// slice-local record writer over the thread's scratch buffer (sized for a whole row in the worst case)
 struct coef_writer_t {
-    coef_arena_t& arena;
-    uint32_t cur = 0, end = 0;
-    uint32_t chunk, need;
-    coef_writer_t(coef_arena_t& a, uint32_t chunk_, uint32_t max_per_mb) : arena(a), chunk(chunk_), need(max_per_mb) {}
-    // make room for one whole macroblock; false when the arena is exhausted
-    inline bool begin_mb() {
-        if (end - cur >= need) return true;
-        const uint32_t start = arena.next.fetch_add(chunk, std::memory_order_relaxed);
-        if ((uint64_t)start + chunk > arena.capacity) { arena.overflow.store(true, std::memory_order_relaxed); return false; }
-        cur = start; end = start + chunk;
-        return true;
-    }
-    inline void put(mp2v_coef_t c) { arena.base[cur++] = c; }
+    mp2v_coef_t* buf;
+    uint32_t cur = 0;
+    explicit coef_writer_t(mp2v_coef_t* b) : buf(b) {}
+    inline void put(mp2v_coef_t c) { buf[cur++] = c; }
 };
+
+mp2v_coef_t* thread_scratch(size_t records) {
+    static thread_local std::vector<mp2v_coef_t> scratch;
+    if (scratch.size() < records) scratch.resize(records);
+    return scratch.data();
+}
 
 struct slice_ctx_t {
     bitreader_t br;
@@ -246,10 +245,7 @@ slice_result_t parse_slice(const uint8_t* payload, int slice_start_code, const s
         return fail("only progressive frame pictures with frame prediction are supported (the reference's envelope)");
     const int cf = seq.chroma_format;
     const int nblk = cf == 1 ? 6 : cf == 2 ? 8 : 12;
-    const uint32_t max_per_mb = (uint32_t)nblk * 64u;
-    uint32_t chunk = (uint32_t)mbw * max_per_mb;
-    if (chunk > coef_arena_t::kChunk) chunk = coef_arena_t::kChunk;
-    coef_writer_t w(arena, chunk, max_per_mb);
+    coef_writer_t w(thread_scratch((size_t)mbw * nblk * 64u));
 
     slice_ctx_t c(pic);
     bitreader_t& br = c.br;
@@ -267,7 +263,7 @@ slice_result_t parse_slice(const uint8_t* payload, int slice_start_code, const s
     const int pct = pic.picture_coding_type;
     mp2v_mb_info_t* row = mb + (size_t)mb_row * mbw;
     uint32_t prev_dirs = 0;
-    int mbx = -1;
+    int mbx = -1, first_mbx = 0;
     bool first = true;
     do {
         // ---- macroblock_address_increment (+ escapes)
@@ -284,7 +280,7 @@ slice_result_t parse_slice(const uint8_t* payload, int slice_start_code, const s
         const int target = first ? inc - 1 : mbx + inc;
         if (target >= mbw) return fail("macroblock address past the end of the row");
         const int skipped = first ? 0 : inc - 1;
-        if (first) { mbx = target - 1; first = false; }
+        if (first) { mbx = target - 1; first_mbx = target; first = false; }
         // ---- skipped macroblocks (mb_decoder.cpp:541-550)
         if (skipped > 0) {
             if (pct == 1) return fail("skipped macroblock in an I picture");
@@ -335,7 +331,6 @@ slice_result_t parse_slice(const uint8_t* payload, int slice_start_code, const s
             if (cf == 3) { const uint32_t x = br.peek(6); br.skip(6); for (int i = 0; i < 6; i++) cbp |= ((x >> (5 - i)) & 1u) << (6 + i); }
         }
         // ---- blocks
-        if (!w.begin_mb()) return fail("coefficient arena exhausted");
         const uint32_t off = w.cur;
         for (int b = 0; b < nblk; b++)
             if (cbp & (1u << b))
@@ -354,7 +349,12 @@ slice_result_t parse_slice(const uint8_t* payload, int slice_start_code, const s
         res.mbs++;
         br.refill();
     } while (br.peek(23) != 0 && mbx < mbw - 1);
-    // trailing macroblocks of the row that the slice did not code keep the caller's defaults
+    // trailing macroblocks of the row that the slice did not code keep the caller's defaults.
+    // append the slice's records to the picture arena and rebase the offsets written above
+    const uint32_t base = arena.next.fetch_add(w.cur, std::memory_order_relaxed);
+    if ((uint64_t)base + w.cur > arena.capacity) { arena.overflow.store(true, std::memory_order_relaxed); return fail("coefficient arena exhausted"); }
+    memcpy(arena.base + base, w.buf, (size_t)w.cur * sizeof(mp2v_coef_t));
+    for (int x = first_mbx; x <= mbx; x++) row[x].coef_off += base;
     return res;
 }
 

@@ -47,14 +47,14 @@ bool parse_picture_header(const uint8_t* payload, const sequence_info_t& seq, pi
 // quantiser_matrices of mp2v_picture_c::init() (decoder.cpp:154-192) for all four sets
 void build_picture_matrices(const picture_info_t& pic, uint8_t W[4][64]);
 
-// Coefficient arena of one picture, shared by the slice parsers of that picture (one thread each):
-// slices take chunks with one atomic add; a macroblock's records never straddle a chunk.
+// Coefficient arena of one picture, shared by the slice parsers of that picture (one thread each).
+// A slice is parsed into the calling thread's scratch buffer, then appended with ONE atomic add and
+// one memcpy, so the arena stays dense: its high-water mark is exactly what the H2D copy moves.
 struct coef_arena_t {
     mp2v_coef_t* base = nullptr;
     uint32_t capacity = 0;
     std::atomic<uint32_t> next{0};
     std::atomic<bool> overflow{false};
-    static constexpr uint32_t kChunk = 16384;   // records
 };
 
 struct slice_result_t {

@@ -47,7 +47,7 @@ struct mp2v_recon {
     std::vector<cudaEvent_t> frame_ev;         // last writer of each frame
     std::vector<uint8_t> frame_written;
     cudaStream_t s_copy = nullptr, s_compute = nullptr, s_d2h = nullptr;
-    cudaEvent_t ev_h2d = nullptr;
+    cudaEvent_t ev_h2d = nullptr, ev_t0 = nullptr, ev_t1 = nullptr;
     std::vector<slot_t> slots;
     std::vector<int> pending;                  // queued slots, submit order
     std::mutex mu;
@@ -110,6 +110,8 @@ static void destroy_ctx(mp2v_recon* ctx) {
     for (auto e : ctx->ev_pool) cudaEventDestroy(e);
     for (auto& pr : ctx->timed) { cudaEventDestroy(pr.first); cudaEventDestroy(pr.second); }
     if (ctx->ev_h2d) cudaEventDestroy(ctx->ev_h2d);
+    if (ctx->ev_t0) cudaEventDestroy(ctx->ev_t0);
+    if (ctx->ev_t1) cudaEventDestroy(ctx->ev_t1);
     if (ctx->d_frames) cudaFree(ctx->d_frames);
     if (ctx->s_copy) cudaStreamDestroy(ctx->s_copy);
     if (ctx->s_compute) cudaStreamDestroy(ctx->s_compute);
@@ -136,6 +138,8 @@ static int create_impl(mp2v_recon* ctx) {
     CK(cudaStreamCreateWithFlags(&ctx->s_compute, cudaStreamNonBlocking), "stream");
     CK(cudaStreamCreateWithFlags(&ctx->s_d2h, cudaStreamNonBlocking), "stream");
     CK(cudaEventCreateWithFlags(&ctx->ev_h2d, cudaEventDisableTiming), "event");
+    CK(cudaEventCreate(&ctx->ev_t0), "event");
+    CK(cudaEventCreate(&ctx->ev_t1), "event");
     // frames: the window staging over-reads one row below and 16 bytes right of a block (always inside
     // this slack), so every frame carries two luma rows + 256 bytes of tail
     ctx->frame_alloc = (ctx->lay.bytes + 2 * (size_t)ctx->lay.stride[0] + 256 + 255) & ~(size_t)255;
@@ -531,5 +535,29 @@ extern "C" MP2V_API int mp2v_recon_get_stats(mp2v_recon_t* ctx, mp2v_recon_stats
     }
     *out = ctx->stats;
     if (reset) ctx->stats = mp2v_recon_stats_t{};
+    return MP2V_OK;
+}
+
+extern "C" MP2V_API int mp2v_recon_timer_start(mp2v_recon_t* ctx) {
+    if (!ctx) return MP2V_ERR_ARG;
+    std::lock_guard<std::mutex> lk(ctx->mu);
+    const int rc = flush_locked(ctx);
+    if (rc != MP2V_OK) return rc;
+    CK(cudaSetDevice(ctx->cfg.device), "cudaSetDevice");
+    CK(cudaEventRecord(ctx->ev_t0, ctx->s_compute), "event record");
+    return MP2V_OK;
+}
+
+extern "C" MP2V_API int mp2v_recon_timer_stop(mp2v_recon_t* ctx, double* elapsed_ms) {
+    if (!ctx || !elapsed_ms) return MP2V_ERR_ARG;
+    std::lock_guard<std::mutex> lk(ctx->mu);
+    const int rc = flush_locked(ctx);
+    if (rc != MP2V_OK) return rc;
+    CK(cudaSetDevice(ctx->cfg.device), "cudaSetDevice");
+    CK(cudaEventRecord(ctx->ev_t1, ctx->s_compute), "event record");
+    CK(cudaEventSynchronize(ctx->ev_t1), "event sync");
+    float ms = 0.f;
+    CK(cudaEventElapsedTime(&ms, ctx->ev_t0, ctx->ev_t1), "event elapsed");
+    *elapsed_ms = ms;
     return MP2V_OK;
 }

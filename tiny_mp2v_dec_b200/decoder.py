@@ -15,7 +15,7 @@ class DecodeParams(C.Structure):
     _fields_ = [("width", C.c_int32), ("height", C.c_int32), ("chroma_format", C.c_int32),
                 ("pictures_pool_size", C.c_int32), ("num_threads", C.c_int32), ("reordering", C.c_int32),
                 ("n_devices", C.c_int32), ("devices", C.c_int32 * 8), ("max_batch", C.c_int32), ("output_lag", C.c_int32),
-                ("download_frames", C.c_int32)]
+                ("download_frames", C.c_int32), ("hash_output", C.c_int32)]
 
 
 class DecodeStats(C.Structure):
@@ -24,7 +24,7 @@ class DecodeStats(C.Structure):
                 ("parse_cpu_seconds", C.c_double), ("wall_seconds", C.c_double), ("hash", C.c_uint64)]
 
 
-DECODE_EXPORTS = ["mp2v_decode_stream", "mp2v_parse_stream", "mp2v_parsed_num_pictures", "mp2v_parsed_picture",
+DECODE_EXPORTS = ["mp2v_decode_stream", "mp2v_decoder_create", "mp2v_decoder_decode", "mp2v_decoder_destroy", "mp2v_parse_stream", "mp2v_parsed_num_pictures", "mp2v_parsed_picture",
                   "mp2v_parsed_wall_seconds", "mp2v_parsed_cpu_seconds", "mp2v_parsed_free"]
 
 _bound = False
@@ -37,6 +37,11 @@ def lib():
         P = C.POINTER
         L.mp2v_decode_stream.argtypes = [P(DecodeParams), C.c_void_p, C.c_int, C.c_void_p, C.c_void_p, C.c_void_p, C.c_size_t,
                                          P(C.c_size_t), P(DecodeStats), C.c_char_p, C.c_size_t]
+        L.mp2v_decoder_create.argtypes = [P(DecodeParams), P(C.c_void_p), C.c_char_p, C.c_size_t]
+        L.mp2v_decoder_decode.argtypes = [C.c_void_p, C.c_void_p, C.c_int, C.c_void_p, C.c_void_p, C.c_void_p, C.c_size_t,
+                                          P(C.c_size_t), P(DecodeStats), C.c_char_p, C.c_size_t]
+        L.mp2v_decoder_destroy.argtypes = [C.c_void_p]
+        L.mp2v_decoder_destroy.restype = None
         L.mp2v_parse_stream.argtypes = [C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, P(C.c_void_p), C.c_char_p, C.c_size_t]
         L.mp2v_parsed_num_pictures.argtypes = [C.c_void_p]
         L.mp2v_parsed_picture.argtypes = [C.c_void_p, C.c_int, P(PicParams), P(P(MbInfo)), P(P(C.c_uint32)), P(C.c_uint32),
@@ -61,8 +66,41 @@ class Decoder:
     def __init__(self, width, height, chroma_format, pictures_pool_size=10, num_threads=8, reordering=True,
                  devices=(0,), max_batch=0, output_lag=0):
         self.p = DecodeParams(width, height, chroma_format, pictures_pool_size, num_threads, 1 if reordering else 0,
-                              len(devices), (C.c_int32 * 8)(*devices), max_batch, output_lag, 1)
+                              len(devices), (C.c_int32 * 8)(*devices), max_batch, output_lag, 1, 0)
         self.stats = None
+        self.h = None
+        self._download = None
+
+    def _handle(self, download):
+        """the native decoder (device contexts allocated here, as the reference allocates its frame pool in
+        the constructor); re-created when the download mode changes"""
+        if self.h is not None and self._download == download:
+            return self.h
+        self.close()
+        L = lib()
+        self.p.download_frames = 1 if download else 0
+        h = C.c_void_p()
+        err = C.create_string_buffer(512)
+        rc = L.mp2v_decoder_create(C.byref(self.p), C.byref(h), err, 512)
+        if rc != OK:
+            raise ReconError("decoder create failed (%d): %s" % (rc, err.value.decode()))
+        self.h, self._download = h, download
+        return h
+
+    def prepare(self, download=True):
+        self._handle(download)
+        return self
+
+    def close(self):
+        if self.h is not None:
+            lib().mp2v_decoder_destroy(self.h)
+            self.h = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
 
     def decode(self, padded, size, want_output=True, download=True):
         """padded: uint8 array holding the stream followed by >= 64 bytes of padding; size: stream length.
@@ -70,7 +108,7 @@ class Decoder:
         L = lib()
         buf = np.ascontiguousarray(padded, np.uint8)
         assert buf.size >= size + 64, "decode(): the stream buffer must be padded with >= 64 bytes"
-        self.p.download_frames = 1 if download else 0
+        h = self._handle(download)
         st = DecodeStats()
         err = C.create_string_buffer(512)
         out = None
@@ -81,8 +119,8 @@ class Decoder:
             cap = n_pics * frame_bytes(self.p.width, self.p.height, self.p.chroma_format)
             out = np.empty(max(cap, 1), np.uint8)
         nbytes = C.c_size_t()
-        rc = L.mp2v_decode_stream(C.byref(self.p), buf.ctypes.data, size, None, None, out.ctypes.data if out is not None else None,
-                                  cap, C.byref(nbytes), C.byref(st), err, 512)
+        rc = L.mp2v_decoder_decode(h, buf.ctypes.data, size, None, None, out.ctypes.data if out is not None else None,
+                                   cap, C.byref(nbytes), C.byref(st), err, 512)
         self.stats = st
         if rc != OK:
             raise ReconError("decode failed (%d): %s" % (rc, err.value.decode()))

@@ -18,7 +18,7 @@ EXPORTS = [
     "mp2v_recon_acquire_picture", "mp2v_recon_release_picture", "mp2v_recon_submit", "mp2v_recon_flush",
     "mp2v_recon_sync", "mp2v_recon_upload", "mp2v_recon_run_resident", "mp2v_recon_download_frame",
     "mp2v_recon_map_frame", "mp2v_recon_upload_frame", "mp2v_recon_frame_device_ptrs",
-    "mp2v_recon_set_timing", "mp2v_recon_get_stats",
+    "mp2v_recon_set_timing", "mp2v_recon_get_stats", "mp2v_recon_timer_start", "mp2v_recon_timer_stop",
 ]
 
 
@@ -53,6 +53,8 @@ def lib():
         L.mp2v_recon_frame_device_ptrs.argtypes = [C.c_void_p, C.c_int, C.c_void_p * 3, C.c_int32 * 3]
         L.mp2v_recon_set_timing.argtypes = [C.c_void_p, C.c_int]
         L.mp2v_recon_get_stats.argtypes = [C.c_void_p, P(ReconStats), C.c_int]
+        L.mp2v_recon_timer_start.argtypes = [C.c_void_p]
+        L.mp2v_recon_timer_stop.argtypes = [C.c_void_p, P(C.c_double)]
         _lib = L
     return _lib
 
@@ -159,6 +161,15 @@ class Recon:
     # ---- statistics
     def set_timing(self, on=True):
         self._ck(self.L.mp2v_recon_set_timing(self.h, 1 if on else 0))
+
+    def timer_start(self):
+        self._ck(self.L.mp2v_recon_timer_start(self.h))
+
+    def timer_stop(self):
+        """-> device milliseconds since timer_start() on the compute stream (waits for the work)"""
+        ms = C.c_double()
+        self._ck(self.L.mp2v_recon_timer_stop(self.h, C.byref(ms)))
+        return ms.value
 
     def stats(self, reset=False):
         s = ReconStats()
