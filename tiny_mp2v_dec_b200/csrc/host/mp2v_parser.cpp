@@ -177,10 +177,16 @@ inline bool decode_mv_component(slice_ctx_t& c, int f_code, int& pmv, int& out) 
     return true;
 }
 
-// one block: DC (intra) + run/level list; returns false on a syntax error
+// one block: DC (intra) + run/level list; returns false on a syntax error.
+// The bit reader and the write cursor are copied into locals for the duration of the block so that
+// the run/level loop keeps them in registers (stores through the record pointer could otherwise
+// alias the reader's fields and force reloads on every coefficient).
 inline bool parse_block(slice_ctx_t& c, coef_writer_t& w, int b, bool intra) {
-    bitreader_t& br = c.br;
+    bitreader_t br = c.br;
+    mp2v_coef_t* out = w.buf + w.cur;
+    const uint32_t blk_bits = (uint32_t)b << 22;
     int i = 0;
+    bool ok = false;
     const coef_vlc_t* table = &c.T.b14;
     if (intra) {
         const int comp = b < 4 ? 0 : 1 + (b & 1);
@@ -197,7 +203,7 @@ inline bool parse_block(slice_ctx_t& c, coef_writer_t& w, int b, bool intra) {
         }
         c.dc_pred[comp] = (uint16_t)(c.dc_pred[comp] + diff);
         const int16_t dc = (int16_t)(uint16_t)((uint32_t)c.dc_pred[comp] << (3 - c.pic.intra_dc_precision));
-        w.put(MP2V_COEF(dc, 0, b, MP2V_COEF_RAW));
+        *out++ = MP2V_COEF(dc, 0, b, MP2V_COEF_RAW);
         i = 1;
         if (c.pic.intra_vlc_format) table = &c.T.b15;
     } else {
@@ -205,34 +211,43 @@ inline bool parse_block(slice_ctx_t& c, coef_writer_t& w, int b, bool intra) {
         if (br.peek(1)) {                                    // first coefficient "1s" (mb_decoder.cpp:79-88)
             const int neg = (int)br.peek(2) & 1;
             br.skip(2);
-            w.put(MP2V_COEF(neg ? -1 : 1, 0, b, MP2V_COEF_FIRST));
+            *out++ = MP2V_COEF(neg ? -1 : 1, 0, b, MP2V_COEF_FIRST);
             i = 1;
         }
     }
+    const coef_entry_t* root = table->root;
+    const coef_entry_t* leaves = table->leaves.data();
     for (;;) {
         br.refill();
-        const coef_entry_t& e = table->look(br.peek(17));
+        const uint32_t p17 = br.peek(17);
+        const coef_entry_t* e = &root[p17 >> 9];
+        if (__builtin_expect(e->sub != 0, 0)) e = &leaves[((size_t)(e->sub - 1) << coef_vlc_t::LEAF) + (p17 & 511u)];
         int run, level;
-        if (e.level > 0) {
-            br.skip(e.len);
+        if (__builtin_expect(e->level > 0, 1)) {
+            br.skip(e->len);
             const int neg = (int)br.peek(1);
             br.skip(1);
-            run = e.run; level = neg ? -e.level : e.level;
-        } else if (e.level == kCoefEob && e.len) {
-            br.skip(e.len);
-            return true;
-        } else if (e.level == kCoefEsc && e.len) {           // 6-bit run, 12-bit two's complement level
+            run = e->run;
+            level = (e->level ^ -neg) + neg;
+        } else if (e->level == kCoefEob && e->len) {
+            br.skip(e->len);
+            ok = true;
+            break;
+        } else if (e->level == kCoefEsc && e->len) {         // 6-bit run, 12-bit two's complement level
             br.skip(6);
             run = (int)br.peek(6); br.skip(6);
             level = ((int)br.peek(12) ^ 0x800) - 0x800; br.skip(12);
         } else {
-            return false;
+            break;
         }
         i += run;
-        if (i > 63) return false;
-        w.put(MP2V_COEF(level, i, b, 0));
+        if (__builtin_expect(i > 63, 0)) break;
+        *out++ = (uint32_t)(uint16_t)level | ((uint32_t)i << 16) | blk_bits;
         i++;
     }
+    c.br = br;
+    w.cur = (uint32_t)(out - w.buf);
+    return ok;
 }
 
 }  // namespace

@@ -68,7 +68,7 @@ struct mp2v_recon {
     cudaEvent_t get_event() {
         if (!ev_pool.empty()) { cudaEvent_t e = ev_pool.back(); ev_pool.pop_back(); return e; }
         cudaEvent_t e = nullptr;
-        cudaEventCreate(&e);
+        cudaEventCreateWithFlags(&e, cudaEventDisableTiming);
         return e;
     }
 };
@@ -264,11 +264,12 @@ static int flush_locked(mp2v_recon* ctx) {
 }
 
 // OUT + REF + COEF + META, and (optionally) the host-side validation of the records
-static int account_and_validate(mp2v_recon* ctx, slot_t& s, bool validate) {
+static int account_and_validate(mp2v_recon* ctx, slot_t& s, bool validate, std::string* why) {
+    auto bad = [&](int code, const char* msg) { *why = msg; return code; };
     const mp2v_pic_params_t& pp = *s.pub.params;
     const int nf = ctx->cfg.n_frames;
-    if (pp.dst_frame < 0 || pp.dst_frame >= nf || pp.l0_frame >= nf || pp.l1_frame >= nf) return ctx->fail(MP2V_ERR_ARG, "frame id out of range");
-    if (pp.n_coef > s.pub.coef_capacity) return ctx->fail(MP2V_ERR_RANGE, "coefficient arena overflow");
+    if (pp.dst_frame < 0 || pp.dst_frame >= nf || pp.l0_frame >= nf || pp.l1_frame >= nf) return bad(MP2V_ERR_ARG, "frame id out of range");
+    if (pp.n_coef > s.pub.coef_capacity) return bad(MP2V_ERR_RANGE, "coefficient arena overflow");
     const uint64_t mb_bytes = ctx->cfg.chroma_format == 1 ? 384 : ctx->cfg.chroma_format == 2 ? 512 : 768;
     uint64_t out_bytes = 0;
     for (int p = 0; p < 3; p++) out_bytes += (uint64_t)ctx->lay.width[p] * ctx->lay.height[p];
@@ -282,20 +283,20 @@ static int account_and_validate(mp2v_recon* ctx, slot_t& s, bool validate) {
         ref += (uint64_t)ndir * mb_bytes;
         coded += (uint64_t)__builtin_popcount(MP2V_MB_CBP(bits) & cbp_mask);
         if (!validate) continue;
-        if (MP2V_MB_CBP(bits) & ~cbp_mask) return ctx->fail(MP2V_ERR_RANGE, "coded_block_pattern names a block this chroma format does not have");
-        if ((uint64_t)r.coef_off + MP2V_MB_NCOEF(bits) > pp.n_coef) return ctx->fail(MP2V_ERR_RANGE, "macroblock coefficient range outside the arena");
+        if (MP2V_MB_CBP(bits) & ~cbp_mask) return bad(MP2V_ERR_RANGE, "coded_block_pattern names a block this chroma format does not have");
+        if ((uint64_t)r.coef_off + MP2V_MB_NCOEF(bits) > pp.n_coef) return bad(MP2V_ERR_RANGE, "macroblock coefficient range outside the arena");
         if (!(bits & MP2V_MB_INTRA)) {
-            if (ndir == 0) return ctx->fail(MP2V_ERR_RANGE, "non-intra macroblock without a prediction direction");
+            if (ndir == 0) return bad(MP2V_ERR_RANGE, "non-intra macroblock without a prediction direction");
             const int mbx = m % ctx->mbw, mby = m / ctx->mbw;
             for (int d = 0; d < 2; d++) {
                 if (!(bits & (d ? MP2V_MB_BWD : MP2V_MB_FWD))) continue;
                 const int fr = d ? pp.l1_frame : pp.l0_frame;
-                if (fr < 0) return ctx->fail(MP2V_ERR_STATE, "prediction from a missing reference frame");
+                if (fr < 0) return bad(MP2V_ERR_STATE, "prediction from a missing reference frame");
                 const int mvx = r.mv[d][0], mvy = r.mv[d][1];
                 const int x0 = mbx * 16 + (mvx >> 1), y0 = mby * 16 + (mvy >> 1);
                 // the reference does not clamp: a vector leaving the frame is rejected here
                 if (x0 < 0 || y0 < 0 || x0 + 16 + (mvx & 1) > W || y0 + 16 + (mvy & 1) > H)
-                    return ctx->fail(MP2V_ERR_RANGE, "motion vector points outside the reference frame");
+                    return bad(MP2V_ERR_RANGE, "motion vector points outside the reference frame");
             }
         }
     }
@@ -305,38 +306,45 @@ static int account_and_validate(mp2v_recon* ctx, slot_t& s, bool validate) {
 
 extern "C" MP2V_API int mp2v_recon_acquire_picture(mp2v_recon_t* ctx, mp2v_picture_t** out) {
     if (!ctx || !out) return MP2V_ERR_ARG;
-    std::lock_guard<std::mutex> lk(ctx->mu);
-    for (int attempt = 0; attempt < 2; attempt++) {
-        int best = -1;
-        for (size_t i = 0; i < ctx->slots.size(); i++) {
-            slot_t& s = ctx->slots[i];
-            if (s.state == SLOT_FREE) { best = (int)i; break; }
-        }
-        if (best < 0) {
-            // recycle the oldest in-flight slot (its launch has to finish before the arenas are reused)
-            for (size_t i = 0; i < ctx->slots.size(); i++) {
-                slot_t& s = ctx->slots[i];
-                if (s.state == SLOT_INFLIGHT && (best < 0 || s.seq < ctx->slots[best].seq)) best = (int)i;
+    for (int attempt = 0; attempt < 4; attempt++) {
+        cudaEvent_t wait_for = nullptr;
+        int candidate = -1;
+        {
+            std::lock_guard<std::mutex> lk(ctx->mu);
+            int best = -1;
+            for (size_t i = 0; i < ctx->slots.size(); i++)
+                if (ctx->slots[i].state == SLOT_FREE) { best = (int)i; break; }
+            if (best < 0) {
+                // an in-flight slot whose launch already finished is as good as a free one
+                for (size_t i = 0; i < ctx->slots.size() && best < 0; i++)
+                    if (ctx->slots[i].state == SLOT_INFLIGHT && cudaEventQuery(ctx->slots[i].done) == cudaSuccess) best = (int)i;
             }
             if (best >= 0) {
-                CK(cudaSetDevice(ctx->cfg.device), "cudaSetDevice");
-                CK(cudaEventSynchronize(ctx->slots[best].done), "event sync");
-                ctx->slots[best].state = SLOT_FREE;
+                slot_t& s = ctx->slots[best];
+                s.state = SLOT_FILLING;
+                memset(s.pub.params, 0, sizeof(mp2v_pic_params_t));
+                s.pub.params->l0_frame = s.pub.params->l1_frame = -1;
+                *out = &s.pub;
+                return MP2V_OK;
             }
+            // otherwise wait (outside the lock) for the oldest in-flight slot; launch queued work first
+            for (size_t i = 0; i < ctx->slots.size(); i++) {
+                slot_t& s = ctx->slots[i];
+                if (s.state == SLOT_INFLIGHT && (candidate < 0 || s.seq < ctx->slots[candidate].seq)) candidate = (int)i;
+            }
+            if (candidate < 0) {
+                if (ctx->pending.empty()) return ctx->fail(MP2V_ERR_STATE, "no picture slot available (all slots are being filled or resident)");
+                const int rc = flush_locked(ctx);
+                if (rc != MP2V_OK) return rc;
+                continue;
+            }
+            wait_for = ctx->slots[candidate].done;
         }
-        if (best >= 0) {
-            slot_t& s = ctx->slots[best];
-            s.state = SLOT_FILLING;
-            memset(s.pub.params, 0, sizeof(mp2v_pic_params_t));
-            s.pub.params->l0_frame = s.pub.params->l1_frame = -1;
-            *out = &s.pub;
-            return MP2V_OK;
-        }
-        if (ctx->pending.empty()) break;
-        const int rc = flush_locked(ctx);   // everything is queued: launch it, then wait for a slot
-        if (rc != MP2V_OK) return rc;
+        const cudaError_t e = cudaEventSynchronize(wait_for);
+        if (e != cudaSuccess) { std::lock_guard<std::mutex> lk(ctx->mu); return ctx->cuda_fail(e, "event sync"); }
     }
-    return ctx->fail(MP2V_ERR_STATE, "no picture slot available (all slots are being filled or resident)");
+    std::lock_guard<std::mutex> lk(ctx->mu);
+    return ctx->fail(MP2V_ERR_STATE, "no picture slot became available");
 }
 
 static slot_t* slot_of(mp2v_recon* ctx, mp2v_picture_t* pic) {
@@ -360,11 +368,13 @@ extern "C" MP2V_API int mp2v_recon_release_picture(mp2v_recon_t* ctx, mp2v_pictu
 
 extern "C" MP2V_API int mp2v_recon_submit(mp2v_recon_t* ctx, mp2v_picture_t* pic) {
     if (!ctx) return MP2V_ERR_ARG;
-    std::lock_guard<std::mutex> lk(ctx->mu);
     slot_t* s = slot_of(ctx, pic);
-    if (!s || s->state != SLOT_FILLING) return ctx->fail(MP2V_ERR_STATE, "submit: picture was not acquired");
-    int rc = account_and_validate(ctx, *s, (ctx->cfg.flags & MP2V_RECON_VALIDATE) != 0);
-    if (rc != MP2V_OK) return rc;
+    if (!s || s->state != SLOT_FILLING) { std::lock_guard<std::mutex> lk(ctx->mu); return ctx->fail(MP2V_ERR_STATE, "submit: picture was not acquired"); }
+    // the slot belongs to the caller until it is queued: validate its records without holding the lock
+    std::string why;
+    int rc = account_and_validate(ctx, *s, (ctx->cfg.flags & MP2V_RECON_VALIDATE) != 0, &why);
+    std::lock_guard<std::mutex> lk(ctx->mu);
+    if (rc != MP2V_OK) return ctx->fail(rc, why);
     const mp2v_pic_params_t& pp = *s->pub.params;
     // a picture cannot share a launch with a picture it reads from, nor with one touching its destination
     bool conflict = (int)ctx->pending.size() >= ctx->max_batch;
@@ -410,8 +420,9 @@ extern "C" MP2V_API int mp2v_recon_upload(mp2v_recon_t* ctx, mp2v_picture_t* pic
     std::lock_guard<std::mutex> lk(ctx->mu);
     slot_t* s = slot_of(ctx, pic);
     if (!s || (s->state != SLOT_FILLING && s->state != SLOT_RESIDENT)) return ctx->fail(MP2V_ERR_STATE, "upload: picture was not acquired");
-    const int rc = account_and_validate(ctx, *s, (ctx->cfg.flags & MP2V_RECON_VALIDATE) != 0);
-    if (rc != MP2V_OK) return rc;
+    std::string why;
+    const int rc = account_and_validate(ctx, *s, (ctx->cfg.flags & MP2V_RECON_VALIDATE) != 0, &why);
+    if (rc != MP2V_OK) return ctx->fail(rc, why);
     CK(cudaSetDevice(ctx->cfg.device), "cudaSetDevice");
     const size_t bytes = ctx->coef_off + (size_t)s->pub.params->n_coef * sizeof(mp2v_coef_t);
     CK(cudaMemcpyAsync(s->d_arena, s->h_arena, bytes, cudaMemcpyHostToDevice, ctx->s_copy), "H2D picture records");
@@ -452,7 +463,9 @@ extern "C" MP2V_API int mp2v_recon_run_resident(mp2v_recon_t* ctx, mp2v_picture_
 // ---------------------------------------------------------------------------------------------
 // frames
 
-static int copy_frame_out(mp2v_recon* ctx, int frame_id, uint8_t* const dst[3], const int32_t dst_stride[3]) {
+// Enqueue the D2H copies of a frame behind its last writer (call with ctx->mu held); the caller waits
+// for *done outside the lock so that submissions and launches keep flowing while the copy runs.
+static int enqueue_frame_copy(mp2v_recon* ctx, int frame_id, uint8_t* const dst[3], const int32_t dst_stride[3], cudaEvent_t* done) {
     if (frame_id < 0 || frame_id >= ctx->cfg.n_frames) return ctx->fail(MP2V_ERR_ARG, "frame id out of range");
     int rc = flush_locked(ctx);
     if (rc != MP2V_OK) return rc;
@@ -464,26 +477,45 @@ static int copy_frame_out(mp2v_recon* ctx, int frame_id, uint8_t* const dst[3], 
                              (size_t)ctx->lay.width[p], (size_t)ctx->lay.height[p], cudaMemcpyDeviceToHost, ctx->s_d2h), "D2H frame");
         ctx->stats.d2h_bytes += (uint64_t)ctx->lay.width[p] * ctx->lay.height[p];
     }
-    CK(cudaStreamSynchronize(ctx->s_d2h), "stream sync");
+    *done = ctx->get_event();
+    CK(cudaEventRecord(*done, ctx->s_d2h), "event record");
+    return MP2V_OK;
+}
+
+static int wait_frame_copy(mp2v_recon* ctx, cudaEvent_t done) {
+    const cudaError_t e = cudaEventSynchronize(done);
+    std::lock_guard<std::mutex> lk(ctx->mu);
+    ctx->ev_pool.push_back(done);
+    if (e != cudaSuccess) return ctx->cuda_fail(e, "D2H frame");
     return MP2V_OK;
 }
 
 extern "C" MP2V_API int mp2v_recon_download_frame(mp2v_recon_t* ctx, int frame_id, uint8_t* const dst[3], const int32_t dst_stride[3]) {
     if (!ctx || !dst || !dst_stride) return MP2V_ERR_ARG;
-    std::lock_guard<std::mutex> lk(ctx->mu);
-    return copy_frame_out(ctx, frame_id, dst, dst_stride);
+    cudaEvent_t done = nullptr;
+    {
+        std::lock_guard<std::mutex> lk(ctx->mu);
+        const int rc = enqueue_frame_copy(ctx, frame_id, dst, dst_stride, &done);
+        if (rc != MP2V_OK) return rc;
+    }
+    return wait_frame_copy(ctx, done);
 }
 
 extern "C" MP2V_API int mp2v_recon_map_frame(mp2v_recon_t* ctx, int frame_id, uint8_t* planes[3], int32_t strides[3]) {
     if (!ctx || !planes || !strides) return MP2V_ERR_ARG;
-    std::lock_guard<std::mutex> lk(ctx->mu);
-    if (frame_id < 0 || frame_id >= ctx->cfg.n_frames) return ctx->fail(MP2V_ERR_ARG, "frame id out of range");
-    if (!ctx->h_frames[frame_id]) {
-        CK(cudaSetDevice(ctx->cfg.device), "cudaSetDevice");
-        CK(cudaHostAlloc(&ctx->h_frames[frame_id], ctx->lay.bytes, cudaHostAllocDefault), "cudaHostAlloc frame mirror");
+    cudaEvent_t done = nullptr;
+    {
+        std::lock_guard<std::mutex> lk(ctx->mu);
+        if (frame_id < 0 || frame_id >= ctx->cfg.n_frames) return ctx->fail(MP2V_ERR_ARG, "frame id out of range");
+        if (!ctx->h_frames[frame_id]) {
+            CK(cudaSetDevice(ctx->cfg.device), "cudaSetDevice");
+            CK(cudaHostAlloc(&ctx->h_frames[frame_id], ctx->lay.bytes, cudaHostAllocDefault), "cudaHostAlloc frame mirror");
+        }
+        for (int p = 0; p < 3; p++) { planes[p] = ctx->h_frames[frame_id] + ctx->lay.plane_offset[p]; strides[p] = ctx->lay.stride[p]; }
+        const int rc = enqueue_frame_copy(ctx, frame_id, planes, strides, &done);
+        if (rc != MP2V_OK) return rc;
     }
-    for (int p = 0; p < 3; p++) { planes[p] = ctx->h_frames[frame_id] + ctx->lay.plane_offset[p]; strides[p] = ctx->lay.stride[p]; }
-    return copy_frame_out(ctx, frame_id, planes, strides);
+    return wait_frame_copy(ctx, done);
 }
 
 extern "C" MP2V_API int mp2v_recon_upload_frame(mp2v_recon_t* ctx, int frame_id, const uint8_t* const src[3], const int32_t src_stride[3]) {
