@@ -15,6 +15,7 @@
 // default matrices instead of crashing (decoder.cpp:187 dereferences nullptr there).
 #pragma once
 #include <cstdint>
+#include <fstream>      // the reference's decoder.h pulls this in (bitstream.h:3); its sample relies on it
 #include <functional>
 #include <memory>
 #include <string>

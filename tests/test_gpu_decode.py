@@ -88,3 +88,23 @@ def test_motion_vector_outside_the_frame_is_rejected():
         r.fill(h1, p.params, mb, p.coef, dst=1, l0=0)
         with pytest.raises(ReconError):
             r.submit(h1)
+
+
+def test_reference_sample_recompiled_against_this_library():
+    """drop-in proof: the reference's unmodified sample source (tiny_decoder/tiny_mp2v_dec.cpp), compiled
+    against include/core/decoder.h and linked with libmp2v_b200.so by oracle/Makefile, writes the same
+    YUV as the reference's own build of it (golden hd422_ipb: hard-wired 1920x1088 4:2:2)."""
+    import os
+    import subprocess
+    import tempfile
+    exe = os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "oracle", "_ref", "tiny_mp2v_dec_sample_b200")
+    if not os.path.exists(exe):
+        pytest.skip("oracle/_ref/tiny_mp2v_dec_sample_b200 was not built (needs the reference sources at build time)")
+    w, h, cf, kw = GOLDEN_CASES["hd422_ipb"]
+    s = Stream(w, h, cf, **kw)
+    with tempfile.TemporaryDirectory() as d:
+        m2v, yuv = os.path.join(d, "in.m2v"), os.path.join(d, "out.yuv")
+        s.padded[:s.size + 64].tofile(m2v)      # the sample pads to 16 bytes only; keep the zero tail in the file
+        subprocess.check_call([exe, "-v", m2v, "-o", yuv], stdout=subprocess.DEVNULL, timeout=300)
+        got = open(yuv, "rb").read()
+    assert sha(got) == GOLDEN["hd422_ipb"]["sample_yuv_sha256"]

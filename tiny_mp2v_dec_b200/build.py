@@ -91,8 +91,8 @@ def build_oracle(force=False):
 
 def build_all(force=False, verbose=False):
     build_streamgen(force)
-    build_oracle(force)
     build_product(force, verbose)
+    build_oracle(force)      # after the product: oracle/_ref also holds the reference sample linked against it
 
 
 if __name__ == "__main__":
