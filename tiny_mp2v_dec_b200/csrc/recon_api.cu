@@ -214,7 +214,8 @@ static int launch_slots(mp2v_recon* ctx, const int* ids, int n) {
     b.n_pics = n;
     b.mbw = ctx->mbw; b.mbh = ctx->mbh; b.mb_count = ctx->mb_count;
     for (int p = 0; p < 3; p++) b.stride[p] = ctx->lay.stride[p];
-    const int g = mbs_per_cta(ctx->cfg.chroma_format);
+    b.mbs_per_warp = choose_mbs_per_warp(ctx->cfg.chroma_format, (long long)n * ctx->mb_count);
+    const int g = b.mbs_per_warp * (kCtaThreads / 32);
     b.ctas_per_pic = (ctx->mb_count + g - 1) / g;
     for (int i = 0; i < n; i++) fill_desc(ctx, ctx->slots[ids[i]], b.pic[i]);
     cudaEvent_t t0 = nullptr, t1 = nullptr;

@@ -4,24 +4,32 @@
 // back (the CPU reference writes it with mc_pred*/mc_bidir* and re-reads it in
 // inverse_dct_template<true>, idct_sse2.hpp:110-114).
 //
-// One CTA (128 threads) owns a group of consecutive macroblocks of one picture and walks four phases
-// separated by __syncthreads():
-//   0  stage W[4][64], the scan table and the group's macroblock records in shared memory;
-//      exclusive scan of popc(cbp) assigns every coded block a 144-byte slot of the residual tile
-//   1  zero the used slots
-//   2  dequantise: a warp streams one macroblock's coefficient records with coalesced 32-bit loads,
-//      applies parse_block's arithmetic (mb_decoder.cpp:139-146) and scatters int16 values to
-//      tile[slot][g_scan_trans[pos]]; the mismatch parity of all (<= 12) blocks of the macroblock is
-//      one REDUX.XOR per 32 records
-//   3  IDCT: one thread per coded block, all 64 values in registers, so the 8x8 transpose between
-//      the two passes (transpose_8x8_sse2, idct_sse2.hpp:67-94) is register renaming; every SSE2
-//      lane operation is reproduced on sign-extended int32: adds/subs = VIADDMNMX+VIMNMX,
-//      mulhi = one IMAD.HI against (c << 16), slli = SHF + sign-extending PRMT
-//   4  prediction: a warp takes one macroblock at a time, copies the (w+1)x(h+1) reference windows
-//      of all planes / directions into shared memory as aligned 16-byte chunks (one L1 wavefront
-//      per window row), then every lane produces one output row: funnel-shift realignment,
-//      __vavgu4 rounding averages in the reference's order (mc_c.hpp:3-17), residual add and
-//      unsigned saturation as VIADDMNMX.S16x2.RELU, one 128-bit (or 64-bit) store.
+// Work decomposition (v2, "warp-autonomous"): a warp owns a run of consecutive macroblocks of one
+// picture and walks it in batches of <= 32 coded blocks.  There is ONE __syncthreads() per CTA (after
+// the picture tables are staged); everything else is __syncwarp(), so warps of a CTA drift apart and
+// the memory latency of one overlaps the integer work of the others.  Per batch:
+//   1  lanes load the macroblock records (one 16-byte record per lane); a warp scan of popc(cbp)
+//      assigns every coded block one of 32 residual-tile slots (144 B each) -- and one IDCT lane
+//   2  the first macroblock's reference windows start flowing into shared memory (cp.async)
+//   3  dequantise: the warp streams each macroblock's coefficient records with coalesced 32-bit
+//      loads, applies parse_block's arithmetic (mb_decoder.cpp:139-146) and scatters int16 values to
+//      tile[slot][g_scan_trans[pos]]; mismatch parity of all (<= 12) blocks of a macroblock is one
+//      REDUX.XOR per 32 records; a weighted L1 norm per block feeds the saturation bound below
+//   4  IDCT: four lanes per coded block, 8 blocks per round, values as packed int16 pairs in the
+//      tile (the 8x8 transpose between the passes, idct_sse2.hpp:67-94, is the conflict-free shared
+//      memory round trip).  Three bit-exact variants of the lane arithmetic, chosen per round of 8
+//      blocks from rigorous range bounds (tools/dev/idct_bounds.py):
+//        pass 1  dequantised inputs (|F| <= 2048, first coefficient <= 3036) cannot saturate or wrap
+//                anywhere except in the last 8 additions -> plain int32 ops + 8 saturating adds
+//        pass 2  if sum |F[k][c]| * Omax[k] * G[c] of every block in the warp stays below the
+//                threshold no intermediate can leave int16 -> plain int32 ops; otherwise the exact form
+//        exact   every SSE2 lane op reproduced: adds/subs = VIADDMNMX+VIMNMX, mulhi = IMAD+SHF,
+//                slli = shift pair with 16-bit wrap
+//   5  prediction: per macroblock the (w+1)x(h+1) reference windows of all planes / directions are
+//      staged as aligned 16-byte chunks (cp.async, double buffered: the next macroblock's windows load
+//      while this one is computed), then every lane produces one output row: funnel-shift
+//      realignment, __vavgu4 rounding averages in the reference's order (mc_c.hpp:3-17), residual
+//      add + unsigned saturation as VIADDMNMX.S16x2.RELU, one 128-bit (or 64-bit) store.
 //
 // The roofline that bounds this kernel and the byte counts are in DESIGN.md.
 #include "recon_kernels.cuh"
@@ -32,11 +40,23 @@ namespace mp2v {
 
 __constant__ uint8_t c_scan_trans[2][64];
 
+// Saturation bound weights, 16 * Omax[k] * G[c] rounded up (tools/dev/idct_bounds.py):
+// G[c]   = largest |coefficient| input c has in ANY intermediate of one idct_1d_sse2 lane,
+// Omax[k] = largest |coefficient| input k has in any OUTPUT of a lane.
+// For the second pass: max |intermediate| <= sum_c G[c] * |y_c| + E and |y_c| <= sum_k Omax[k] * |F[k][c]| + E.
+__constant__ uint16_t c_bound_w[64] = {
+    129, 329, 238, 279, 129, 187, 168, 179,  179, 456, 329, 387, 179, 259, 233, 247,
+    168, 430, 310, 364, 168, 244, 220, 233,  179, 456, 329, 387, 179, 259, 233, 247,
+    129, 329, 238, 279, 129, 187, 168, 179,  179, 456, 329, 387, 179, 259, 233, 247,
+    168, 430, 310, 364, 168, 244, 220, 233,  179, 456, 329, 387, 179, 259, 233, 247 };
+// 16 * (32767 - sum(G) * E - E), E = 56.3 (max accumulated mulhi rounding error), sum(G) = 36.0; kept below
+constexpr int kBoundLimit = 16 * 30000;
+constexpr int kBoundWild = 1 << 28;       // added when a block must take the fully exact path
+constexpr int kMaxFirstCoef = 3036;       // (3 * 255 * 127) >> 5: largest unclamped pass-1 input the analysis covers
+
 template <int CF>
 struct fmt_t {
     static constexpr int NBLK = CF == 1 ? 6 : CF == 2 ? 8 : 12;
-    static constexpr int MBG = mbs_per_cta(CF);
-    static constexpr int NSLOT = MBG * NBLK;
     static constexpr int CW = CF == 3 ? 16 : 8;     // chroma macroblock width
     static constexpr int CH = CF == 1 ? 8 : 16;     // chroma macroblock height
     static constexpr int WIN_LUMA = 17 * 32;        // 17 rows x 2 aligned 16-byte chunks
@@ -47,23 +67,29 @@ struct fmt_t {
 };
 
 constexpr int kTilePitch = 72;   // int16 per slot: 64 + 8 pad -> 144 B, conflict-free 128-bit row access
+constexpr int kSlots = 32;       // coded blocks per batch = IDCT lanes
+constexpr int kWarps = kCtaThreads / 32;
+
+template <int CF>
+struct warp_smem_t {
+    alignas(16) int16_t tile[kSlots][kTilePitch];
+    alignas(16) uint8_t win[2][2][fmt_t<CF>::WIN_DIR];   // [buffer][direction]
+    int bound[kSlots];
+};
 
 template <int CF>
 struct smem_t {
-    alignas(16) int16_t tile[fmt_t<CF>::NSLOT][kTilePitch];
-    alignas(16) uint8_t win[kCtaThreads / 32][2][fmt_t<CF>::WIN_DIR];
-    alignas(16) uint4 mb[fmt_t<CF>::MBG];
+    warp_smem_t<CF> w[kWarps];
     alignas(16) uint8_t W[4][64];
     alignas(16) uint8_t scan[64];
-    int prefix[fmt_t<CF>::MBG + 1];
+    alignas(16) uint16_t bw[64];
 };
 
 // ------------------------------------------------------------------------------------------------
-// The reference's 16-bit lane arithmetic on sign-extended int32 (idct_sse2.hpp:7-21 helpers).
-// Written as inline PTX on purpose: given C++ min/max on values the compiler knows to be
-// sign-extended int16, LLVM canonicalises the clamp into sadd.sat.i16 and the NVPTX back end then
-// legalises that into ~10 instructions (PRMT sign extensions + ISETP/LOP3 overflow logic).  ptxas
-// turns the PTX below into VIADDMNMX + VIMNMX (2 ALU ops), IMAD + SHF, and SHF/LEA pairs.
+// Exact 16-bit lane arithmetic on sign-extended int32 (idct_sse2.hpp:7-21 helpers).
+// Inline PTX on purpose: given C++ min/max on values the compiler knows to be sign-extended int16,
+// LLVM canonicalises the clamp into sadd.sat.i16 and the NVPTX back end legalises that into ~10
+// instructions.  ptxas turns the PTX below into VIADDMNMX + VIMNMX, IMAD + SHF and SHF/LEA pairs.
 __device__ __forceinline__ int adds16(int a, int b) {   // _mm_adds_epi16
     int r;
     asm("{\n\t.reg .s32 t;\n\tadd.s32 t, %1, %2;\n\tmin.s32 t, t, 32767;\n\tmax.s32 %0, t, -32768;\n\t}" : "=r"(r) : "r"(a), "r"(b));
@@ -85,66 +111,124 @@ template <int N> __device__ __forceinline__ int slli16(int a) {   // _mm_slli_ep
     return r;
 }
 
-// one lane of idct_1d_sse2 (idct_sse2.hpp:23-65), op for op
+// One lane of idct_1d_sse2 (idct_sse2.hpp:23-65), op for op.
+//   MODE 0  exact: every add saturates, every shift wraps
+//   MODE 1  steps 0-2 in plain int32 (proven in range), the 8 output additions saturate   (pass 1)
+//   MODE 2  plain int32 throughout (proven in range by the per-block bound)                (pass 2)
+template <int MODE>
 __device__ __forceinline__ void idct_lane(int& x0, int& x1, int& x2, int& x3, int& x4, int& x5, int& x6, int& x7) {
-    const int v15 = adds16(slli16<1>(mulhi16<27145>(x0)), slli16<1>(x0));
-    const int v26 = adds16(mulhi16<-5037>(x1), slli16<2>(x1));
-    const int v21 = adds16(mulhi16<-19954>(x2), slli16<2>(x2));
-    const int v28 = adds16(slli16<1>(mulhi16<-22089>(x3)), slli16<2>(x3));
-    const int v16 = adds16(slli16<1>(mulhi16<27145>(x4)), slli16<1>(x4));
-    const int v25 = adds16(mulhi16<14567>(x5), slli16<1>(x5));
-    const int v22 = adds16(slli16<1>(mulhi16<17391>(x6)), x6);
-    const int v27 = slli16<1>(mulhi16<25570>(x7));
-    const int v19 = subs16(v25, v28), v20 = subs16(v26, v27), v23 = adds16(v26, v27), v24 = adds16(v25, v28);
-    const int v7 = adds16(v23, v24), v11 = adds16(v21, v22), v13 = subs16(v23, v24), v17 = subs16(v21, v22);
-    const int v8 = adds16(v15, v16), v9 = subs16(v15, v16);
-    const int v18 = mulhi16<25079>(subs16(v19, v20));
-    const int v12 = subs16(v18, adds16(v19, mulhi16<20090>(v19)));
-    const int v14 = subs16(subs16(v20, mulhi16<30068>(v20)), v18);
-    const int v6 = subs16(slli16<1>(v14), v7);
-    const int v5 = subs16(adds16(v13, mulhi16<27145>(v13)), v6);
-    const int v4 = adds16(v5, slli16<1>(v12));
-    const int v10 = subs16(adds16(v17, mulhi16<27145>(v17)), v11);
-    const int v0 = adds16(v8, v11), v1 = adds16(v9, v10), v2 = subs16(v9, v10), v3 = subs16(v8, v11);
-    x0 = adds16(v0, v7); x1 = adds16(v1, v6); x2 = adds16(v2, v5); x3 = subs16(v3, v4);
-    x4 = adds16(v3, v4); x5 = subs16(v2, v5); x6 = subs16(v1, v6); x7 = subs16(v0, v7);
+    if (MODE == 0) {
+        const int v15 = adds16(slli16<1>(mulhi16<27145>(x0)), slli16<1>(x0));
+        const int v26 = adds16(mulhi16<-5037>(x1), slli16<2>(x1));
+        const int v21 = adds16(mulhi16<-19954>(x2), slli16<2>(x2));
+        const int v28 = adds16(slli16<1>(mulhi16<-22089>(x3)), slli16<2>(x3));
+        const int v16 = adds16(slli16<1>(mulhi16<27145>(x4)), slli16<1>(x4));
+        const int v25 = adds16(mulhi16<14567>(x5), slli16<1>(x5));
+        const int v22 = adds16(slli16<1>(mulhi16<17391>(x6)), x6);
+        const int v27 = slli16<1>(mulhi16<25570>(x7));
+        const int v19 = subs16(v25, v28), v20 = subs16(v26, v27), v23 = adds16(v26, v27), v24 = adds16(v25, v28);
+        const int v7 = adds16(v23, v24), v11 = adds16(v21, v22), v13 = subs16(v23, v24), v17 = subs16(v21, v22);
+        const int v8 = adds16(v15, v16), v9 = subs16(v15, v16);
+        const int v18 = mulhi16<25079>(subs16(v19, v20));
+        const int v12 = subs16(v18, adds16(v19, mulhi16<20090>(v19)));
+        const int v14 = subs16(subs16(v20, mulhi16<30068>(v20)), v18);
+        const int v6 = subs16(slli16<1>(v14), v7);
+        const int v5 = subs16(adds16(v13, mulhi16<27145>(v13)), v6);
+        const int v4 = adds16(v5, slli16<1>(v12));
+        const int v10 = subs16(adds16(v17, mulhi16<27145>(v17)), v11);
+        const int v0 = adds16(v8, v11), v1 = adds16(v9, v10), v2 = subs16(v9, v10), v3 = subs16(v8, v11);
+        x0 = adds16(v0, v7); x1 = adds16(v1, v6); x2 = adds16(v2, v5); x3 = subs16(v3, v4);
+        x4 = adds16(v3, v4); x5 = subs16(v2, v5); x6 = subs16(v1, v6); x7 = subs16(v0, v7);
+    } else {
+#define MH(a, c) (((a) * (c)) >> 16)
+        const int v15 = (MH(x0, 27145) << 1) + (x0 << 1);
+        const int v26 = MH(x1, -5037) + (x1 << 2);
+        const int v21 = MH(x2, -19954) + (x2 << 2);
+        const int v28 = (MH(x3, -22089) << 1) + (x3 << 2);
+        const int v16 = (MH(x4, 27145) << 1) + (x4 << 1);
+        const int v25 = MH(x5, 14567) + (x5 << 1);
+        const int v22 = (MH(x6, 17391) << 1) + x6;
+        const int v27 = MH(x7, 25570) << 1;
+        const int v19 = v25 - v28, v20 = v26 - v27, v23 = v26 + v27, v24 = v25 + v28;
+        const int v7 = v23 + v24, v11 = v21 + v22, v13 = v23 - v24, v17 = v21 - v22;
+        const int v8 = v15 + v16, v9 = v15 - v16;
+        const int v18 = MH(v19 - v20, 25079);
+        const int v12 = v18 - (v19 + MH(v19, 20090));
+        const int v14 = (v20 - MH(v20, 30068)) - v18;
+        const int v6 = (v14 << 1) - v7;
+        const int v5 = (v13 + MH(v13, 27145)) - v6;
+        const int v4 = v5 + (v12 << 1);
+        const int v10 = (v17 + MH(v17, 27145)) - v11;
+        const int v0 = v8 + v11, v1 = v9 + v10, v2 = v9 - v10, v3 = v8 - v11;
+#undef MH
+        if (MODE == 1) {
+            x0 = adds16(v0, v7); x1 = adds16(v1, v6); x2 = adds16(v2, v5); x3 = subs16(v3, v4);
+            x4 = adds16(v3, v4); x5 = subs16(v2, v5); x6 = subs16(v1, v6); x7 = subs16(v0, v7);
+        } else {
+            x0 = v0 + v7; x1 = v1 + v6; x2 = v2 + v5; x3 = v3 - v4;
+            x4 = v3 + v4; x5 = v2 - v5; x6 = v1 - v6; x7 = v0 - v7;
+        }
+    }
 }
 
-// inverse_dct_template up to the >>6 (idct_sse2.hpp:96-107), in place on one tile slot:
-// in  F[k*8+c] (the transposed-raster layout parse_block writes), out res[r*8+c]
-__device__ __forceinline__ void idct_block(int16_t* slot) {
-    int v[64];
-    uint4* q = reinterpret_cast<uint4*>(slot);
+// inverse_dct_template up to the >>6 (idct_sse2.hpp:96-107) for 8 tile slots at a time, in place:
+// in  F[k*8+c] (the transposed-raster layout parse_block writes), out res[r*8+c].
+// FOUR lanes share a block; lane j owns columns 2j,2j+1 in pass 1 and rows 2j,2j+1 in pass 2, always
+// as packed int16 pairs (one 32-bit word), so a lane holds 16 values, the 8x8 transpose between the
+// passes (transpose_8x8_sse2, idct_sse2.hpp:67-94) is the shared-memory round trip, and with the
+// 36-word slot pitch every access pattern below is bank-conflict free:
+//   word k*4+j of 8 slots x 4 lanes -> banks 4*slot + 4*k + j, all distinct;
+//   128-bit rows 2j, 2j+1           -> quarter-warps cover 8 disjoint 4-bank groups.
+// p1_exact / p2_exact are uniform over the warp.
+__device__ __forceinline__ void idct_round(int16_t* slot_base, int j, bool active, bool p1_exact, bool p2_exact) {
+    uint32_t* t = reinterpret_cast<uint32_t*>(slot_base);
+    int a[8], b[8];
+    // ---- pass 1: the transform runs across the vector index k for columns 2j and 2j+1
+    if (active) {
 #pragma unroll
-    for (int k = 0; k < 8; k++) {
-        const uint4 w = q[k];
-        v[k * 8 + 0] = (int)(short)(w.x & 0xffff); v[k * 8 + 1] = (int)w.x >> 16;
-        v[k * 8 + 2] = (int)(short)(w.y & 0xffff); v[k * 8 + 3] = (int)w.y >> 16;
-        v[k * 8 + 4] = (int)(short)(w.z & 0xffff); v[k * 8 + 5] = (int)w.z >> 16;
-        v[k * 8 + 6] = (int)(short)(w.w & 0xffff); v[k * 8 + 7] = (int)w.w >> 16;
+        for (int k = 0; k < 8; k++) { const uint32_t w = t[k * 4 + j]; a[k] = (int)(short)(w & 0xffffu); b[k] = (int)w >> 16; }
+    } else {
+#pragma unroll
+        for (int k = 0; k < 8; k++) a[k] = b[k] = 0;
     }
-    // pass 1: the transform runs across the vector index k for every lane c
+    if (p1_exact) {
+        idct_lane<0>(a[0], a[1], a[2], a[3], a[4], a[5], a[6], a[7]);
+        idct_lane<0>(b[0], b[1], b[2], b[3], b[4], b[5], b[6], b[7]);
+    } else {
+        idct_lane<1>(a[0], a[1], a[2], a[3], a[4], a[5], a[6], a[7]);
+        idct_lane<1>(b[0], b[1], b[2], b[3], b[4], b[5], b[6], b[7]);
+    }
+    if (active) {
 #pragma unroll
-    for (int c = 0; c < 8; c++)
-        idct_lane(v[c], v[8 + c], v[16 + c], v[24 + c], v[32 + c], v[40 + c], v[48 + c], v[56 + c]);
-    // transpose + pass 2: lane c of the transposed block is row c; results land in v[c*8 + r] = res[r][c]
+        for (int k = 0; k < 8; k++) t[k * 4 + j] = __byte_perm(a[k], b[k], 0x5410);
+    }
+    __syncwarp();
+    // ---- pass 2: rows 2j and 2j+1 of the first-pass result are lanes 2j, 2j+1 of the transposed block
+    if (active) {
+        const uint4 r0 = reinterpret_cast<const uint4*>(t)[2 * j], r1 = reinterpret_cast<const uint4*>(t)[2 * j + 1];
+        a[0] = (int)(short)(r0.x & 0xffffu); a[1] = (int)r0.x >> 16; a[2] = (int)(short)(r0.y & 0xffffu); a[3] = (int)r0.y >> 16;
+        a[4] = (int)(short)(r0.z & 0xffffu); a[5] = (int)r0.z >> 16; a[6] = (int)(short)(r0.w & 0xffffu); a[7] = (int)r0.w >> 16;
+        b[0] = (int)(short)(r1.x & 0xffffu); b[1] = (int)r1.x >> 16; b[2] = (int)(short)(r1.y & 0xffffu); b[3] = (int)r1.y >> 16;
+        b[4] = (int)(short)(r1.z & 0xffffu); b[5] = (int)r1.z >> 16; b[6] = (int)(short)(r1.w & 0xffffu); b[7] = (int)r1.w >> 16;
+    }
+    __syncwarp();      // every lane has its rows in registers before anyone overwrites the slot
+    if (p2_exact) {
+        idct_lane<0>(a[0], a[1], a[2], a[3], a[4], a[5], a[6], a[7]);
+        idct_lane<0>(b[0], b[1], b[2], b[3], b[4], b[5], b[6], b[7]);
+    } else {
+        idct_lane<2>(a[0], a[1], a[2], a[3], a[4], a[5], a[6], a[7]);
+        idct_lane<2>(b[0], b[1], b[2], b[3], b[4], b[5], b[6], b[7]);
+    }
+    // output r of row k is res[r][k]: rows 2j, 2j+1 give the adjacent columns 2j, 2j+1 of every result row
+    if (active) {
 #pragma unroll
-    for (int c = 0; c < 8; c++)
-        idct_lane(v[c * 8 + 0], v[c * 8 + 1], v[c * 8 + 2], v[c * 8 + 3], v[c * 8 + 4], v[c * 8 + 5], v[c * 8 + 6], v[c * 8 + 7]);
-#pragma unroll
-    for (int r = 0; r < 8; r++) {
-        uint4 w;
-        w.x = __byte_perm(v[0 * 8 + r] >> 6, v[1 * 8 + r] >> 6, 0x5410);
-        w.y = __byte_perm(v[2 * 8 + r] >> 6, v[3 * 8 + r] >> 6, 0x5410);
-        w.z = __byte_perm(v[4 * 8 + r] >> 6, v[5 * 8 + r] >> 6, 0x5410);
-        w.w = __byte_perm(v[6 * 8 + r] >> 6, v[7 * 8 + r] >> 6, 0x5410);
-        q[r] = w;
+        for (int r = 0; r < 8; r++) t[r * 4 + j] = __byte_perm(a[r] >> 6, b[r] >> 6, 0x5410);   // _mm_srai_epi16(.,6)
     }
 }
 
 // ------------------------------------------------------------------------------------------------
-// prediction row: NW words (4 pixels each) of plane row `row` of a staged window, realigned from
-// byte offset o, with the reference's half-pel averaging order (mc_c.hpp:3-17)
+// prediction row: NW words (4 pixels each) of one row of a staged window, realigned from byte offset
+// o, with the reference's half-pel averaging order (mc_c.hpp:3-17)
 template <int NW>
 __device__ __forceinline__ void pred_row(const uint8_t* win_row, int o, int hx, int hy, uint32_t (&out)[NW]) {
     const int sh = (o & 3) * 8;
@@ -182,140 +266,58 @@ __device__ __forceinline__ uint32_t add_clip4(uint32_t pred, uint32_t r01, uint3
 
 __device__ __forceinline__ int chroma_mv(int mv, bool halve) { return halve ? (mv >> 1) : mv; }   // floor, mb_decoder.cpp:198-206
 
+__device__ __forceinline__ void cp_async16(void* smem, const void* gmem) {
+    const unsigned s = (unsigned)__cvta_generic_to_shared(smem);
+    asm volatile("cp.async.ca.shared.global [%0], [%1], 16;\n" ::"r"(s), "l"(gmem) : "memory");
+}
+__device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;\n" ::: "memory"); }
+template <int N> __device__ __forceinline__ void cp_async_wait() { asm volatile("cp.async.wait_group %0;\n" ::"n"(N) : "memory"); }
+
+// stage the reference windows of one macroblock: aligned 16-byte chunks, 2 per row, (h+1) rows per plane
 template <int CF>
-__global__ void __launch_bounds__(kCtaThreads, 4) recon_kernel(const __grid_constant__ batch_desc_t batch) {
+__device__ __forceinline__ void stage_windows(const pic_desc_t& pd, const batch_desc_t& batch, uint4 m, int mbx, int mby,
+                                              uint8_t* win /* [2][WIN_DIR] */, int lane) {
     using F = fmt_t<CF>;
-    __shared__ smem_t<CF> s;
-
-    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-    const int pi = blockIdx.x / batch.ctas_per_pic;
-    const int grp = blockIdx.x - pi * batch.ctas_per_pic;
-    const pic_desc_t& pd = batch.pic[pi];
-    const int mb0 = grp * F::MBG;
-    const int nmb = min(F::MBG, batch.mb_count - mb0);
-
-    // ---- phase 0: stage tables and macroblock records
-    if (tid < 64) {
-        reinterpret_cast<uint32_t*>(&s.W[0][0])[tid] = reinterpret_cast<const uint32_t*>(&pd.params->W[0][0])[tid];
-    } else if (tid < 80) {
-        const int alt = pd.params->alternate_scan ? 1 : 0;
-        reinterpret_cast<uint32_t*>(s.scan)[tid - 64] = reinterpret_cast<const uint32_t*>(c_scan_trans[alt])[tid - 64];
-    } else if (tid >= 96 && tid < 96 + F::MBG) {
-        const int i = tid - 96;
-        s.mb[i] = i < nmb ? reinterpret_cast<const uint4*>(pd.mb)[mb0 + i] : make_uint4(0, 0, 0, 0);
-    }
-    __syncthreads();
-    if (warp == 0) {
-        int c = lane < F::MBG ? __popc(MP2V_MB_CBP(s.mb[lane < F::MBG ? lane : 0].y)) : 0;
-        int incl = c;
+    if (m.y & MP2V_MB_INTRA) return;
 #pragma unroll
-        for (int d = 1; d < 32; d <<= 1) {
-            const int t = __shfl_up_sync(0xffffffffu, incl, d);
-            if (lane >= d) incl += t;
-        }
-        if (lane < F::MBG) s.prefix[lane + 1] = incl;
-        if (lane == 0) s.prefix[0] = 0;
-    }
-    __syncthreads();
-    const int nslots = s.prefix[nmb];
-
-    // ---- phase 1: zero the used slots (QFS[64] = {0}, mb_decoder.cpp:159)
-    for (int i = tid; i < nslots * 8; i += kCtaThreads)
-        reinterpret_cast<uint4*>(&s.tile[i >> 3][0])[i & 7] = make_uint4(0, 0, 0, 0);
-    __syncthreads();
-
-    // ---- phase 2: dequantise + saturate + mismatch (mb_decoder.cpp:74-155)
-    for (int i = warp; i < nmb; i += kCtaThreads / 32) {
-        const uint4 m = s.mb[i];
-        const int n = MP2V_MB_NCOEF(m.y);
-        const int qs = MP2V_MB_QSCALE(m.y);
-        const uint32_t cbp = MP2V_MB_CBP(m.y);
-        const bool intra = (m.y & MP2V_MB_INTRA) != 0;
-        const int base = s.prefix[i];
-        const mp2v_coef_t* cp = pd.coef + m.x;
-        uint32_t parity = 0;
-        for (int k0 = 0; k0 < n; k0 += 32) {
-            const int k = k0 + lane;
-            uint32_t pbit = 0;
-            const uint32_t c = k < n ? cp[k] : 0u;
-            if (k < n && (cbp >> ((c >> 22) & 15) & 1)) {   // a record naming an uncoded block is ignored (memory safety)
-                const int level = (int)(short)(c & 0xffffu);
-                const int pos = (c >> 16) & 63, blk = (c >> 22) & 15;
-                const int slot = base + __popc(cbp & ((1u << blk) - 1u));
-                int val, idx;
-                if (c & MP2V_COEF_RAW) { val = level; idx = 0; }                        // intra DC, not summed (:160)
-                else {
-                    const int w = s.W[(blk < 6 ? 0 : 2) + (intra ? 0 : 1)][pos];        // luma matrices for blocks 4,5 (:184-185)
-                    const int mag = abs(level);
-                    if (c & MP2V_COEF_FIRST) { val = (3 * w * qs) >> 5; idx = 0; }      // first coefficient "1s": no clamp (:84)
-                    else {
-                        val = intra ? (mag * w * qs) >> 4 : ((2 * mag + 1) * w * qs) >> 5;   // :142-143
-                        idx = s.scan[pos];
-                    }
-                    if (level < 0) val = -val;                                          // :144
-                    if (!(c & MP2V_COEF_FIRST)) val = max(min((int)(short)val, 2047), -2048);   // int16 wrap, then clamp (:146)
-                    pbit = (uint32_t)(val & 1) << blk;
-                }
-                s.tile[slot][idx] = (int16_t)val;
-            }
-            parity ^= __reduce_xor_sync(0xffffffffu, pbit);
-        }
-        __syncwarp();
-        // qfs[63] ^= (sum & 1) ^ 1 for every coded block (:150-152)
-        if (lane < F::NBLK && (cbp >> lane & 1)) {
-            const int slot = base + __popc(cbp & ((1u << lane) - 1u));
-            s.tile[slot][63] ^= (int16_t)(((parity >> lane) & 1u) ^ 1u);
-        }
-    }
-    __syncthreads();
-
-    // ---- phase 3: IDCT, one thread per coded block
-    for (int slot = tid; slot < nslots; slot += kCtaThreads) idct_block(&s.tile[slot][0]);
-    __syncthreads();
-
-    // ---- phase 4: prediction + residual + clip + store, one macroblock per warp at a time
-    const int mbw = batch.mbw;
-    for (int i = warp; i < nmb; i += kCtaThreads / 32) {
-        const uint4 m = s.mb[i];
-        const int mbi = mb0 + i;
-        const int mby = mbi / mbw, mbx = mbi - mby * mbw;
-        const uint32_t cbp = MP2V_MB_CBP(m.y);
-        const bool fwd = (m.y & MP2V_MB_FWD) != 0, bwd = (m.y & MP2V_MB_BWD) != 0;
-        const int base = s.prefix[i];
-        uint8_t* win = &s.win[warp][0][0];
-
-        // stage the reference windows: aligned 16-byte chunks, 2 per row, (h+1) rows per plane
-#pragma unroll
-        for (int d = 0; d < 2; d++) {
-            if (!(d ? bwd : fwd)) continue;
-            const uint32_t mvw = d ? m.w : m.z;
-            const int mvx = (int)(short)(mvw & 0xffffu), mvy = (int)mvw >> 16;
-            const uint8_t* const* ref = d ? pd.l1 : pd.l0;
-            for (int j = lane; j < F::N_ITEMS; j += 32) {
-                int p, jj;
-                if (j < 34) { p = 0; jj = j; }
-                else if (j < 34 + 2 * (F::CH + 1)) { p = 1; jj = j - 34; }
-                else { p = 2; jj = j - 34 - 2 * (F::CH + 1); }
-                const int r = jj >> 1, ch = jj & 1;
-                const int cx = p ? chroma_mv(mvx, CF < 3) : mvx, cy = p ? chroma_mv(mvy, CF < 2) : mvy;
-                const int pw = p ? F::CW : 16, ph = p ? F::CH : 16;
-                const int x0 = mbx * pw + (cx >> 1), y0 = mby * ph + (cy >> 1);
-                const uint8_t* src = ref[p] + (size_t)(y0 + r) * batch.stride[p] + (x0 & ~15) + 16 * ch;
-                const int woff = d * F::WIN_DIR + (p == 0 ? 0 : F::WIN_LUMA + (p - 1) * F::WIN_CHROMA) + r * 32 + 16 * ch;
-                *reinterpret_cast<uint4*>(win + woff) = __ldg(reinterpret_cast<const uint4*>(src));
-            }
-        }
-        __syncwarp();
-
-        for (int u = lane; u < F::N_UNITS; u += 32) {
-            int p, r;
-            if (u < 16) { p = 0; r = u; }
-            else if (u < 16 + F::CH) { p = 1; r = u - 16; }
-            else { p = 2; r = u - 16 - F::CH; }
-            const bool wide = (p == 0) || (CF == 3);
+    for (int d = 0; d < 2; d++) {
+        if (!(m.y & (d ? MP2V_MB_BWD : MP2V_MB_FWD))) continue;
+        const uint32_t mvw = d ? m.w : m.z;
+        const int mvx = (int)(short)(mvw & 0xffffu), mvy = (int)mvw >> 16;
+        const uint8_t* const* ref = d ? pd.l1 : pd.l0;
+        for (int j = lane; j < F::N_ITEMS; j += 32) {
+            int p, jj;
+            if (j < 34) { p = 0; jj = j; }
+            else if (j < 34 + 2 * (F::CH + 1)) { p = 1; jj = j - 34; }
+            else { p = 2; jj = j - 34 - 2 * (F::CH + 1); }
+            const int r = jj >> 1, ch = jj & 1;
+            const int cx = p ? chroma_mv(mvx, CF < 3) : mvx, cy = p ? chroma_mv(mvy, CF < 2) : mvy;
             const int pw = p ? F::CW : 16, ph = p ? F::CH : 16;
-            uint32_t pred[4] = {0, 0, 0, 0};
-            bool have = false;
+            const int x0 = mbx * pw + (cx >> 1), y0 = mby * ph + (cy >> 1);
+            const uint8_t* src = ref[p] + (size_t)(y0 + r) * batch.stride[p] + (x0 & ~15) + 16 * ch;
+            const int woff = d * F::WIN_DIR + (p == 0 ? 0 : F::WIN_LUMA + (p - 1) * F::WIN_CHROMA) + r * 32 + 16 * ch;
+            cp_async16(win + woff, src);
+        }
+    }
+}
+
+// prediction + residual + clip + store of one macroblock; windows already staged in `win`
+template <int CF>
+__device__ __forceinline__ void reconstruct_mb(const pic_desc_t& pd, const batch_desc_t& batch, uint4 m, int mbx, int mby, int base,
+                                               const uint8_t* win, const int16_t (*tile)[kTilePitch], int lane) {
+    using F = fmt_t<CF>;
+    const uint32_t cbp = MP2V_MB_CBP(m.y);
+    const bool fwd = (m.y & MP2V_MB_FWD) != 0, bwd = (m.y & MP2V_MB_BWD) != 0, intra = (m.y & MP2V_MB_INTRA) != 0;
+    for (int u = lane; u < F::N_UNITS; u += 32) {
+        int p, r;
+        if (u < 16) { p = 0; r = u; }
+        else if (u < 16 + F::CH) { p = 1; r = u - 16; }
+        else { p = 2; r = u - 16 - F::CH; }
+        const bool wide = (p == 0) || (CF == 3);
+        const int pw = p ? F::CW : 16, ph = p ? F::CH : 16;
+        uint32_t pred[4] = {0, 0, 0, 0};
+        bool have = false;
+        if (!intra) {
 #pragma unroll
             for (int d = 0; d < 2; d++) {
                 if (!(d ? bwd : fwd)) continue;
@@ -336,32 +338,171 @@ __global__ void __launch_bounds__(kCtaThreads, 4) recon_kernel(const __grid_cons
                 }
                 have = true;
             }
-            // residual blocks covering this row (block geometry: mb_decoder.cpp:177-195)
-            int bl, br = -1;
-            if (p == 0) { bl = (r >> 3) * 2; br = bl + 1; }
-            else if (CF == 1) bl = 3 + p;
-            else if (CF == 2) bl = 3 + p + ((r >> 3) << 1);
-            else { bl = 3 + p + ((r >> 3) << 1); br = bl + 4; }
-            const int rr = r & 7;
-            uint32_t out[4];
-            {
-                uint4 res = make_uint4(0, 0, 0, 0);
-                if (cbp >> bl & 1) res = *reinterpret_cast<const uint4*>(&s.tile[base + __popc(cbp & ((1u << bl) - 1u))][rr * 8]);
-                out[0] = add_clip4(pred[0], res.x, res.y);
-                out[1] = add_clip4(pred[1], res.z, res.w);
+        }
+        // residual blocks covering this row (block geometry: mb_decoder.cpp:177-195)
+        int bl, br = -1;
+        if (p == 0) { bl = (r >> 3) * 2; br = bl + 1; }
+        else if (CF == 1) bl = 3 + p;
+        else if (CF == 2) bl = 3 + p + ((r >> 3) << 1);
+        else { bl = 3 + p + ((r >> 3) << 1); br = bl + 4; }
+        const int rr = r & 7;
+        uint32_t out[4];
+        {
+            uint4 res = make_uint4(0, 0, 0, 0);
+            if (cbp >> bl & 1) res = *reinterpret_cast<const uint4*>(&tile[base + __popc(cbp & ((1u << bl) - 1u))][rr * 8]);
+            out[0] = add_clip4(pred[0], res.x, res.y);
+            out[1] = add_clip4(pred[1], res.z, res.w);
+        }
+        uint8_t* drow = pd.dst[p] + (size_t)(mby * ph + r) * batch.stride[p] + mbx * pw;
+        if (wide) {
+            uint4 res = make_uint4(0, 0, 0, 0);
+            if (cbp >> br & 1) res = *reinterpret_cast<const uint4*>(&tile[base + __popc(cbp & ((1u << br) - 1u))][rr * 8]);
+            out[2] = add_clip4(pred[2], res.x, res.y);
+            out[3] = add_clip4(pred[3], res.z, res.w);
+            *reinterpret_cast<uint4*>(drow) = make_uint4(out[0], out[1], out[2], out[3]);
+        } else {
+            *reinterpret_cast<uint2*>(drow) = make_uint2(out[0], out[1]);
+        }
+    }
+}
+
+template <int CF>
+__global__ void __launch_bounds__(kCtaThreads, 4) recon_kernel(const __grid_constant__ batch_desc_t batch) {
+    using F = fmt_t<CF>;
+    __shared__ smem_t<CF> s;
+
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const int pi = blockIdx.x / batch.ctas_per_pic;
+    const int grp = blockIdx.x - pi * batch.ctas_per_pic;
+    const pic_desc_t& pd = batch.pic[pi];
+
+    // ---- picture tables (the only CTA-wide barrier)
+    if (tid < 64) {
+        reinterpret_cast<uint32_t*>(&s.W[0][0])[tid] = reinterpret_cast<const uint32_t*>(&pd.params->W[0][0])[tid];
+    } else if (tid < 80) {
+        const int alt = pd.params->alternate_scan ? 1 : 0;
+        reinterpret_cast<uint32_t*>(s.scan)[tid - 64] = reinterpret_cast<const uint32_t*>(c_scan_trans[alt])[tid - 64];
+    } else if (tid < 112) {
+        reinterpret_cast<uint32_t*>(s.bw)[tid - 80] = reinterpret_cast<const uint32_t*>(c_bound_w)[tid - 80];
+    }
+    __syncthreads();
+
+    warp_smem_t<CF>& ws = s.w[warp];
+    const int mbw = batch.mbw;
+    const int run = batch.mbs_per_warp;
+    const int mb_begin = (grp * kWarps + warp) * run;
+    const int mb_end = min(mb_begin + run, batch.mb_count);
+
+    for (int first = mb_begin; first < mb_end;) {
+        // ---- 1. macroblock records of the batch: as many as fit 32 coded blocks
+        const int idx = first + lane;
+        const bool have = idx < mb_end;
+        uint4 rec = have ? __ldg(reinterpret_cast<const uint4*>(pd.mb) + idx) : make_uint4(0, 0, 0, 0);
+        const int cnt = have ? __popc(MP2V_MB_CBP(rec.y)) : 0;
+        int incl = cnt;
+#pragma unroll
+        for (int d = 1; d < 32; d <<= 1) {
+            const int t = __shfl_up_sync(0xffffffffu, incl, d);
+            if (lane >= d) incl += t;
+        }
+        const int nb = max(__popc(__ballot_sync(0xffffffffu, have && incl <= kSlots)), 1);
+        const int base = incl - cnt;
+        const int nslots = __shfl_sync(0xffffffffu, incl, nb - 1);
+
+        // ---- 2. first macroblock's windows start loading now; they land while we dequantise and transform
+        {
+            const int mby0 = first / mbw, mbx0 = first - mby0 * mbw;
+            const uint4 m0 = make_uint4(__shfl_sync(0xffffffffu, rec.x, 0), __shfl_sync(0xffffffffu, rec.y, 0),
+                                        __shfl_sync(0xffffffffu, rec.z, 0), __shfl_sync(0xffffffffu, rec.w, 0));
+            stage_windows<CF>(pd, batch, m0, mbx0, mby0, &ws.win[0][0][0], lane);
+            cp_async_commit();
+        }
+
+        // ---- 3. zero the used slots (QFS[64] = {0}, mb_decoder.cpp:159), then dequantise + saturate + mismatch
+        for (int i = lane; i < nslots * 8; i += 32)
+            reinterpret_cast<uint4*>(&ws.tile[i >> 3][0])[i & 7] = make_uint4(0, 0, 0, 0);
+        ws.bound[lane] = 0;
+        __syncwarp();
+        for (int mi = 0; mi < nb; mi++) {
+            const uint32_t m_off = __shfl_sync(0xffffffffu, rec.x, mi), m_bits = __shfl_sync(0xffffffffu, rec.y, mi);
+            const int mbase = __shfl_sync(0xffffffffu, base, mi);
+            const int n = MP2V_MB_NCOEF(m_bits);
+            const int qs = MP2V_MB_QSCALE(m_bits);
+            const uint32_t cbp = MP2V_MB_CBP(m_bits);
+            const bool intra = (m_bits & MP2V_MB_INTRA) != 0;
+            const mp2v_coef_t* cp = pd.coef + m_off;
+            uint32_t parity = 0;
+            for (int k0 = 0; k0 < n; k0 += 32) {
+                const int k = k0 + lane;
+                uint32_t pbit = 0;
+                const uint32_t c = k < n ? __ldg(cp + k) : 0u;
+                if (k < n && (cbp >> ((c >> 22) & 15) & 1)) {   // a record naming an uncoded block is ignored (memory safety)
+                    const int level = (int)(short)(c & 0xffffu);
+                    const int pos = (c >> 16) & 63, blk = (c >> 22) & 15;
+                    const int slot = mbase + __popc(cbp & ((1u << blk) - 1u));
+                    int val, idx2, wsum;
+                    if (c & MP2V_COEF_RAW) {                                                // intra DC, not summed (:160)
+                        val = level; idx2 = 0;
+                        wsum = abs(val) <= kMaxFirstCoef ? abs(val) * (int)s.bw[0] : kBoundWild;
+                    } else {
+                        const int w = s.W[(blk < 6 ? 0 : 2) + (intra ? 0 : 1)][pos];        // luma matrices for blocks 4,5 (:184-185)
+                        const int mag = abs(level);
+                        if (c & MP2V_COEF_FIRST) { val = (3 * w * qs) >> 5; idx2 = 0; }     // first coefficient "1s": no clamp (:84)
+                        else {
+                            val = intra ? (mag * w * qs) >> 4 : ((2 * mag + 1) * w * qs) >> 5;   // :142-143
+                            idx2 = s.scan[pos];
+                        }
+                        if (level < 0) val = -val;                                          // :144
+                        if (!(c & MP2V_COEF_FIRST)) val = max(min((int)(short)val, 2047), -2048);   // int16 wrap, then clamp (:146)
+                        pbit = (uint32_t)(val & 1) << blk;
+                        wsum = (abs(val) + 1) * (int)s.bw[idx2];     // +1: the mismatch toggle may change |F[63]| by one
+                    }
+                    ws.tile[slot][idx2] = (int16_t)val;
+                    atomicAdd(&ws.bound[slot], wsum);
+                }
+                parity ^= __reduce_xor_sync(0xffffffffu, pbit);
             }
-            uint8_t* drow = pd.dst[p] + (size_t)(mby * ph + r) * batch.stride[p] + mbx * pw;
-            if (wide) {
-                uint4 res = make_uint4(0, 0, 0, 0);
-                if (cbp >> br & 1) res = *reinterpret_cast<const uint4*>(&s.tile[base + __popc(cbp & ((1u << br) - 1u))][rr * 8]);
-                out[2] = add_clip4(pred[2], res.x, res.y);
-                out[3] = add_clip4(pred[3], res.z, res.w);
-                *reinterpret_cast<uint4*>(drow) = make_uint4(out[0], out[1], out[2], out[3]);
-            } else {
-                *reinterpret_cast<uint2*>(drow) = make_uint2(out[0], out[1]);
+            __syncwarp();
+            // qfs[63] ^= (sum & 1) ^ 1 for every coded block (:150-152)
+            if (lane < F::NBLK && (cbp >> lane & 1)) {
+                const int slot = mbase + __popc(cbp & ((1u << lane) - 1u));
+                ws.tile[slot][63] ^= (int16_t)(((parity >> lane) & 1u) ^ 1u);
             }
         }
         __syncwarp();
+
+        // ---- 4. IDCT, four lanes per coded block, 8 blocks per round; arithmetic variant chosen per round
+        for (int r0 = 0; r0 < nslots; r0 += 8) {
+            const int slot = r0 + (lane >> 2);
+            const bool active = slot < nslots;
+            const int bnd = active ? ws.bound[slot] + (int)s.bw[63] : 0;    // a toggled-in F[63] = 1 counts too
+            const bool p1_exact = __any_sync(0xffffffffu, bnd >= kBoundWild);
+            const bool p2_exact = __any_sync(0xffffffffu, bnd > kBoundLimit);
+            idct_round(&ws.tile[active ? slot : 0][0], lane & 3, active, p1_exact, p2_exact);
+        }
+        __syncwarp();
+
+        // ---- 5. prediction + residual + clip + store; the next macroblock's windows load meanwhile
+        for (int mi = 0; mi < nb; mi++) {
+            const uint4 m = make_uint4(__shfl_sync(0xffffffffu, rec.x, mi), __shfl_sync(0xffffffffu, rec.y, mi),
+                                       __shfl_sync(0xffffffffu, rec.z, mi), __shfl_sync(0xffffffffu, rec.w, mi));
+            const int mbase = __shfl_sync(0xffffffffu, base, mi);
+            const int mbi = first + mi;
+            const int mby = mbi / mbw, mbx = mbi - mby * mbw;
+            if (mi + 1 < nb) {
+                const uint4 mn = make_uint4(__shfl_sync(0xffffffffu, rec.x, mi + 1), __shfl_sync(0xffffffffu, rec.y, mi + 1),
+                                            __shfl_sync(0xffffffffu, rec.z, mi + 1), __shfl_sync(0xffffffffu, rec.w, mi + 1));
+                const int nby = (mbi + 1) / mbw, nbx = (mbi + 1) - nby * mbw;
+                stage_windows<CF>(pd, batch, mn, nbx, nby, &ws.win[(mi + 1) & 1][0][0], lane);
+            }
+            cp_async_commit();
+            cp_async_wait<1>();      // everything but the group just committed has landed: this macroblock's windows
+            __syncwarp();
+            reconstruct_mb<CF>(pd, batch, m, mbx, mby, mbase, &ws.win[mi & 1][0][0], ws.tile, lane);
+            __syncwarp();
+        }
+        cp_async_wait<0>();
+        first += nb;
     }
 }
 

@@ -9,9 +9,17 @@ namespace mp2v {
 constexpr int kMaxBatch = 32;        // pictures fused into one launch (descriptors travel as kernel arguments)
 constexpr int kCtaThreads = 128;
 
-// macroblocks per CTA, chosen so that an all-coded group fills the 128 IDCT threads:
-// 4:2:0 20*6 = 120 blocks, 4:2:2 16*8 = 128, 4:4:4 10*12 = 120
-__host__ __device__ constexpr int mbs_per_cta(int cf) { return cf == 1 ? 20 : cf == 2 ? 16 : 10; }
+// A warp owns `mbs_per_warp` consecutive macroblocks and walks them in batches of <= 32 coded blocks
+// (one IDCT lane per block).  The run length is a multiple of the all-coded batch size
+// (4:2:0 5 MBs = 30 blocks, 4:2:2 4 MBs = 32, 4:4:4 2 MBs = 24) and is chosen per launch so that the
+// grid is about two waves of the resident warps (148 SMs x 4 CTAs x 4 warps).
+inline int choose_mbs_per_warp(int cf, long long total_mbs) {
+    const int unit = cf == 1 ? 5 : cf == 2 ? 4 : 2;
+    long long run = total_mbs / (2LL * 148 * 4 * 4);
+    if (run > 60) run = 60;
+    if (run < 2 * unit) run = 2 * unit;
+    return (int)(run / unit * unit);
+}
 
 struct pic_desc_t {
     const mp2v_pic_params_t* params;   // device copy of the picture parameters (W, alternate_scan)
@@ -30,6 +38,7 @@ struct batch_desc_t {
     int32_t mbw, mbh, mb_count;
     int32_t stride[3];
     int32_t ctas_per_pic;
+    int32_t mbs_per_warp;
 };
 
 // grid = n_pics * ctas_per_pic; returns the CUDA error of the launch
