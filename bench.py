@@ -29,23 +29,32 @@ import time
 ROOT = os.path.dirname(os.path.abspath(__file__))
 sys.path.insert(0, ROOT)
 
-# BASELINE.json configs -> generator parameters.  seed = stream_id*1000 + config_id
+# BASELINE.json configs -> generator parameters.  seed = stream_id*1000 + config_id.
+# Throughput runs use the generator's natural-like mode (decaying run/level statistics, default
+# matrices, quantiser_scale_code 1..12) at about 40 Mbit/s for 1080p IPB, as SURVEY.md 8(d) asks;
+# the random-syntax fuzz mode is what the parity tests use.
+NATURAL = dict(mode=1, pct_coded=70)
 WORKLOADS = {
     # configs[1]: 1080p 4:2:0 intra-only, every block coded (IQ + IDCT path)
     "1080p420_intra": dict(width=1920, height=1088, chroma_format=1, config_id=2,
-                           gen=dict(n_gops=4, gop_n=15, gop_m=1, intra_only=1)),
+                           gen=dict(n_gops=4, gop_n=15, gop_m=1, intra_only=1, natural_mean_coefs=6, **NATURAL)),
     # configs[2]: 1080p 4:2:0 IPB, GOP N=15 M=3, half-pel bidirectional MC
     "1080p420_ipb": dict(width=1920, height=1088, chroma_format=1, config_id=3,
-                         gen=dict(n_gops=4, gop_n=15, gop_m=3)),
+                         gen=dict(n_gops=4, gop_n=15, gop_m=3, natural_mean_coefs=5, **NATURAL)),
     # configs[0]: 1080p 4:2:2 IPB (the reference sample's hard-wired geometry)
     "1080p422_ipb": dict(width=1920, height=1088, chroma_format=2, config_id=1,
-                         gen=dict(n_gops=4, gop_n=15, gop_m=3)),
+                         gen=dict(n_gops=4, gop_n=15, gop_m=3, natural_mean_coefs=5, **NATURAL)),
     # configs[3]: 4K 4:4:4 IPB
     "2160p444_ipb": dict(width=3840, height=2160, chroma_format=3, config_id=4,
-                         gen=dict(n_gops=2, gop_n=15, gop_m=3)),
+                         gen=dict(n_gops=2, gop_n=15, gop_m=3, natural_mean_coefs=5, **NATURAL)),
     # configs[4]: 720p 4:2:0 streams (per-GPU share of the 64-stream batch is run as consecutive GOP chains)
     "720p420_ipb": dict(width=1280, height=720, chroma_format=1, config_id=5,
-                        gen=dict(n_gops=8, gop_n=15, gop_m=3)),
+                        gen=dict(n_gops=8, gop_n=15, gop_m=3, natural_mean_coefs=5, **NATURAL)),
+    # the same two 1080p shapes in random-syntax fuzz mode (stress: escapes, saturating levels)
+    "1080p420_intra_fuzz": dict(width=1920, height=1088, chroma_format=1, config_id=2,
+                                gen=dict(n_gops=4, gop_n=15, gop_m=1, intra_only=1)),
+    "1080p420_ipb_fuzz": dict(width=1920, height=1088, chroma_format=1, config_id=3,
+                              gen=dict(n_gops=4, gop_n=15, gop_m=3)),
 }
 DEFAULT_WORKLOAD = "1080p420_intra"
 
@@ -365,7 +374,7 @@ def main():
 
     # ---- e2e: the reference-facing decode API from a host buffer (parse + H2D + kernels + D2H)
     from tiny_mp2v_dec_b200.decoder import Decoder
-    threads = host_threads(world)
+    threads = max(1, host_threads(world) - 2)      # two cores stay free for the decoder's feeder and output threads
     dec = Decoder(wl["width"], wl["height"], wl["chroma_format"], pictures_pool_size=10, num_threads=threads,
                   devices=(local,), max_batch=8, output_lag=6).prepare(download=True)
     for _ in range(2):

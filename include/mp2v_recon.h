@@ -171,6 +171,9 @@ MP2V_API int  mp2v_recon_release_picture(mp2v_recon_t* ctx, mp2v_picture_t* pic)
  * coded order (references before the pictures that use them).  Asynchronous; consecutive
  * submissions that do not depend on one another are fused into one launch. */
 MP2V_API int  mp2v_recon_submit(mp2v_recon_t* ctx, mp2v_picture_t* pic);
+/* Optional: run submit's record validation + byte accounting now, from any thread, without taking the
+ * context lock (the picture still belongs to the caller); submit then skips it. */
+MP2V_API int  mp2v_recon_precheck(mp2v_recon_t* ctx, mp2v_picture_t* pic);
 MP2V_API int  mp2v_recon_flush(mp2v_recon_t* ctx);               /* launch whatever is queued       */
 MP2V_API int  mp2v_recon_sync(mp2v_recon_t* ctx);                /* flush + wait for the device     */
 

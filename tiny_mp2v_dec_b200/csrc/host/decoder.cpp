@@ -64,23 +64,23 @@ struct pic_task_t {
     int dst = -1, l0 = -1, l1 = -1;    // device frame ids
     mp2v_picture_t* rp = nullptr;
     coef_arena_t arena;
+    std::atomic<int> next_slice{0};    // next slice index a worker may claim
     std::atomic<int> remaining{0};
     std::atomic<bool> ok{true};
     const char* error = nullptr;
     bool parsed = false, submitted = false;
 };
 
-struct slice_job_t { pic_task_t* task; int slice; };
-
 struct shared_t {
     decoder_config_t cfg{};
     mp2v_b200_options_t opt;
     std::function<void(frame_c*)> renderer;
     int mbw = 0, mbh = 0;
-    // slice queue
+    // work distribution: pictures whose slices may be claimed (an atomic index per picture); workers
+    // only take the lock to move on to the next picture or to sleep
     std::mutex qmu;
     std::condition_variable qcv;
-    std::deque<slice_job_t> queue;
+    std::deque<pic_task_t*> queue;
     bool stop = false;
     // errors
     std::atomic<bool> failed{false};
@@ -180,9 +180,10 @@ void pipeline_t::feeder() {
         const int ns = (int)t.src->slices.size();
         if (ns == 0) { on_parsed(&t); continue; }
         t.remaining.store(ns);
+        t.next_slice.store(0);
         {
             std::lock_guard<std::mutex> lk(sh->qmu);
-            for (int s = 0; s < ns; s++) sh->queue.push_back({&t, s});
+            sh->queue.push_back(&t);
         }
         sh->qcv.notify_all();
     }
@@ -192,6 +193,11 @@ void pipeline_t::feeder() {
 
 // called by the worker that finished the last slice of a picture
 void pipeline_t::on_parsed(pic_task_t* t) {
+    // record validation / byte accounting is per picture: do it before taking the submission lock
+    if (t->ok.load() && !t->arena.overflow.load() && t->rp) {
+        t->rp->params->n_coef = t->arena.next.load();
+        if (mp2v_recon_precheck(recon, t->rp) != MP2V_OK) { t->error = "records failed validation (motion vector outside the frame or bad offsets)"; t->ok.store(false); }
+    }
     std::lock_guard<std::mutex> lk(mu);
     t->parsed = true;
     while (next_submit < (int)tasks.size() && tasks[next_submit].parsed && !sh->failed.load()) {
@@ -259,23 +265,31 @@ void pipeline_t::output() {
 
 void worker_main(shared_t* sh) {
     for (;;) {
-        slice_job_t job;
+        pic_task_t* t = nullptr;
+        int slice = -1;
         {
             std::unique_lock<std::mutex> lk(sh->qmu);
-            sh->qcv.wait(lk, [&] { return sh->stop || !sh->queue.empty(); });
-            if (sh->queue.empty()) return;
-            job = sh->queue.front();
-            sh->queue.pop_front();
+            for (;;) {
+                // drop pictures whose slices have all been claimed, claim one from the first that has any
+                while (!sh->queue.empty() && sh->queue.front()->next_slice.load(std::memory_order_relaxed) >= (int)sh->queue.front()->src->slices.size())
+                    sh->queue.pop_front();
+                if (!sh->queue.empty()) { t = sh->queue.front(); break; }
+                if (sh->stop) return;
+                sh->qcv.wait(lk);
+            }
         }
-        pic_task_t* t = job.task;
-        if (!sh->failed.load()) {
-            const auto t0 = clock_t_::now();
-            const slice_ref_t& sr = t->src->slices[job.slice];
-            const slice_result_t r = parse_slice(sr.payload, sr.code, t->src->seq, t->src->info, sh->mbw, sh->mbh, t->rp->mb, t->arena);
-            sh->parse_ns.fetch_add(std::chrono::duration_cast<std::chrono::nanoseconds>(clock_t_::now() - t0).count());
-            if (!r.ok) { t->error = r.error; t->ok.store(false); }
+        // claim slices of this picture without the lock until it runs dry
+        const int ns = (int)t->src->slices.size();
+        while ((slice = t->next_slice.fetch_add(1, std::memory_order_relaxed)) < ns) {
+            if (!sh->failed.load(std::memory_order_relaxed)) {
+                const auto t0 = clock_t_::now();
+                const slice_ref_t& sr = t->src->slices[slice];
+                const slice_result_t r = parse_slice(sr.payload, sr.code, t->src->seq, t->src->info, sh->mbw, sh->mbh, t->rp->mb, t->arena);
+                sh->parse_ns.fetch_add(std::chrono::duration_cast<std::chrono::nanoseconds>(clock_t_::now() - t0).count(), std::memory_order_relaxed);
+                if (!r.ok) { t->error = r.error; t->ok.store(false); }
+            }
+            if (t->remaining.fetch_sub(1) == 1) { t->pipe->on_parsed(t); break; }   // t may be recycled after this
         }
-        if (t->remaining.fetch_sub(1) == 1) t->pipe->on_parsed(t);
     }
 }
 

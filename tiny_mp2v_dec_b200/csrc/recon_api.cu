@@ -30,6 +30,7 @@ struct slot_t {
     slot_state_t state = SLOT_FREE;
     cudaEvent_t done = nullptr;        // recorded on the compute stream after the launch that consumed the slot
     uint64_t alg_bytes = 0;
+    bool prechecked = false;           // account_and_validate already ran for the records now in the slot
     uint64_t seq = 0;                  // submission order, to recycle the oldest in-flight slot first
 };
 
@@ -323,6 +324,7 @@ extern "C" MP2V_API int mp2v_recon_acquire_picture(mp2v_recon_t* ctx, mp2v_pictu
             if (best >= 0) {
                 slot_t& s = ctx->slots[best];
                 s.state = SLOT_FILLING;
+                s.prechecked = false;
                 memset(s.pub.params, 0, sizeof(mp2v_pic_params_t));
                 s.pub.params->l0_frame = s.pub.params->l1_frame = -1;
                 *out = &s.pub;
@@ -373,7 +375,7 @@ extern "C" MP2V_API int mp2v_recon_submit(mp2v_recon_t* ctx, mp2v_picture_t* pic
     if (!s || s->state != SLOT_FILLING) { std::lock_guard<std::mutex> lk(ctx->mu); return ctx->fail(MP2V_ERR_STATE, "submit: picture was not acquired"); }
     // the slot belongs to the caller until it is queued: validate its records without holding the lock
     std::string why;
-    int rc = account_and_validate(ctx, *s, (ctx->cfg.flags & MP2V_RECON_VALIDATE) != 0, &why);
+    int rc = s->prechecked ? MP2V_OK : account_and_validate(ctx, *s, (ctx->cfg.flags & MP2V_RECON_VALIDATE) != 0, &why);
     std::lock_guard<std::mutex> lk(ctx->mu);
     if (rc != MP2V_OK) return ctx->fail(rc, why);
     const mp2v_pic_params_t& pp = *s->pub.params;
@@ -392,6 +394,17 @@ extern "C" MP2V_API int mp2v_recon_submit(mp2v_recon_t* ctx, mp2v_picture_t* pic
     s->state = SLOT_QUEUED;
     s->seq = ++ctx->seq;
     ctx->pending.push_back(pic->slot);
+    return MP2V_OK;
+}
+
+extern "C" MP2V_API int mp2v_recon_precheck(mp2v_recon_t* ctx, mp2v_picture_t* pic) {
+    if (!ctx) return MP2V_ERR_ARG;
+    slot_t* s = slot_of(ctx, pic);
+    if (!s || s->state != SLOT_FILLING) { std::lock_guard<std::mutex> lk(ctx->mu); return ctx->fail(MP2V_ERR_STATE, "precheck: picture was not acquired"); }
+    std::string why;
+    const int rc = account_and_validate(ctx, *s, (ctx->cfg.flags & MP2V_RECON_VALIDATE) != 0, &why);
+    if (rc != MP2V_OK) { std::lock_guard<std::mutex> lk(ctx->mu); return ctx->fail(rc, why); }
+    s->prechecked = true;
     return MP2V_OK;
 }
 
@@ -473,10 +486,19 @@ static int enqueue_frame_copy(mp2v_recon* ctx, int frame_id, uint8_t* const dst[
     if (!ctx->frame_written[frame_id]) return ctx->fail(MP2V_ERR_STATE, "frame has never been written");
     CK(cudaSetDevice(ctx->cfg.device), "cudaSetDevice");
     CK(cudaStreamWaitEvent(ctx->s_d2h, ctx->frame_ev[frame_id], 0), "stream wait");
-    for (int p = 0; p < 3; p++) {
-        CK(cudaMemcpy2DAsync(dst[p], (size_t)dst_stride[p], ctx->frame_ptr(frame_id, p), (size_t)ctx->lay.stride[p],
-                             (size_t)ctx->lay.width[p], (size_t)ctx->lay.height[p], cudaMemcpyDeviceToHost, ctx->s_d2h), "D2H frame");
-        ctx->stats.d2h_bytes += (uint64_t)ctx->lay.width[p] * ctx->lay.height[p];
+    // destination laid out exactly like the device frame (the pinned mirrors are): one copy for all planes
+    bool same = true;
+    for (int p = 0; p < 3; p++)
+        same = same && dst_stride[p] == ctx->lay.stride[p] && dst[p] == dst[0] + ctx->lay.plane_offset[p];
+    if (same) {
+        CK(cudaMemcpyAsync(dst[0], ctx->frame_ptr(frame_id, 0), ctx->lay.bytes, cudaMemcpyDeviceToHost, ctx->s_d2h), "D2H frame");
+        ctx->stats.d2h_bytes += ctx->lay.bytes;
+    } else {
+        for (int p = 0; p < 3; p++) {
+            CK(cudaMemcpy2DAsync(dst[p], (size_t)dst_stride[p], ctx->frame_ptr(frame_id, p), (size_t)ctx->lay.stride[p],
+                                 (size_t)ctx->lay.width[p], (size_t)ctx->lay.height[p], cudaMemcpyDeviceToHost, ctx->s_d2h), "D2H frame");
+            ctx->stats.d2h_bytes += (uint64_t)ctx->lay.width[p] * ctx->lay.height[p];
+        }
     }
     *done = ctx->get_event();
     CK(cudaEventRecord(*done, ctx->s_d2h), "event record");

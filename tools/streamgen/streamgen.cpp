@@ -184,7 +184,12 @@ struct mp2v_gen {
     }
     int draw_count(bool at_least_one) {
         int n;
-        if (p.mode == 1) { n = 0; while (n < 20 && rng.pct(72)) n++; }
+        if (p.mode == 1) {
+            const int m = p.natural_mean_coefs;                  // geometric with mean m (default: continue 72 % -> 2.6)
+            const int cont = m > 0 ? 100 * m / (m + 1) : 72;
+            n = 0;
+            while (n < (m > 0 ? 40 : 20) && rng.pct(cont)) n++;
+        }
         else { static const int k[9] = {0, 0, 1, 1, 2, 3, 5, 8, 12}; n = k[rng.below(9)]; }
         return (at_least_one && n == 0) ? 1 : n;
     }
