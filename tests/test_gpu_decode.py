@@ -108,3 +108,17 @@ def test_reference_sample_recompiled_against_this_library():
         subprocess.check_call([exe, "-v", m2v, "-o", yuv], stdout=subprocess.DEVNULL, timeout=300)
         got = open(yuv, "rb").read()
     assert sha(got) == GOLDEN["hd422_ipb"]["sample_yuv_sha256"]
+
+
+def test_gop_sharding_over_two_devices():
+    """closed GOPs dealt round-robin to one pipeline per GPU, frames stitched back in display order;
+    no collective, no peer traffic"""
+    import torch
+    if torch.cuda.device_count() < 2:
+        pytest.skip("needs two GPUs")
+    s = Stream(352, 288, 1, seed=70, n_gops=5, gop_n=9, gop_m=3)
+    want = O.oracle_decode_stream(s)
+    got = Decoder(352, 288, 1, num_threads=4, devices=(0, 1)).decode(s.padded, s.size)
+    assert got == want
+    one = Decoder(352, 288, 1, num_threads=4, devices=(1,)).decode(s.padded, s.size)
+    assert one == want
