@@ -28,6 +28,7 @@ public:
     // n in 1..32; valid after refill() as long as no more than 56 bits were consumed since
     inline uint32_t peek(int n) const { return (uint32_t)(buf_ >> (64 - n)); }
     inline uint32_t peek32() const { return (uint32_t)(buf_ >> 32); }
+    inline int bits_left() const { return cnt_; }
     inline void skip(int n) { buf_ <<= n; cnt_ -= n; }
     inline uint32_t get(int n) { refill(); const uint32_t v = peek(n); skip(n); return v; }
     inline uint32_t get1() { refill(); const uint32_t v = (uint32_t)(buf_ >> 63); skip(1); return v; }

@@ -130,43 +130,30 @@ void build_picture_matrices(const picture_info_t& pic, uint8_t W[4][64]) {
 // ------------------------------------------------------------------------------------------------
 namespace {
 
-// slice-local record writer over the thread's scratch buffer (sized for a whole row in the worst case)
-struct coef_writer_t {
-    mp2v_coef_t* buf;
-    uint32_t cur = 0;
-    explicit coef_writer_t(mp2v_coef_t* b) : buf(b) {}
-    inline void put(mp2v_coef_t c) { buf[cur++] = c; }
-};
-
 mp2v_coef_t* thread_scratch(size_t records) {
     static thread_local std::vector<mp2v_coef_t> scratch;
     if (scratch.size() < records) scratch.resize(records);
     return scratch.data();
 }
 
-struct slice_ctx_t {
-    bitreader_t br;
-    const vlc_decode_tables_t& T;
-    const picture_info_t& pic;
-    int pmv[2][2];
-    uint16_t dc_pred[3];
-    explicit slice_ctx_t(const picture_info_t& p) : T(vlc_decode_tables()), pic(p) {}
-    void reset_dc() { for (auto& d : dc_pred) d = (uint16_t)(1u << (pic.intra_dc_precision + 7)); }
-};
+#define MP2V_INLINE inline __attribute__((always_inline))
+
+// Everything below works on the slice parser's LOCAL bit reader and write cursor, passed by reference
+// into always-inlined helpers, so that both live in registers for the whole slice.
 
 // one motion vector component, mb_decoder.cpp:447-503
-inline bool decode_mv_component(slice_ctx_t& c, int f_code, int& pmv, int& out) {
-    c.br.refill();
-    const vlc_entry_t& e = c.T.motion.look(c.br.peek(10));
+MP2V_INLINE bool decode_mv_component(bitreader_t& br, const vlc_decode_tables_t& T, int f_code, int& pmv, int& out) {
+    br.refill();
+    const vlc_entry_t& e = T.motion.look(br.peek(10));
     if (!e.len) return false;
-    c.br.skip(e.len);
+    br.skip(e.len);
     int delta = 0;
     if (e.val) {
-        const int neg = (int)c.br.peek(1);
-        c.br.skip(1);
+        const int neg = (int)br.peek(1);
+        br.skip(1);
         const int r_size = f_code - 1;
         delta = e.val;
-        if (r_size) { delta = ((e.val - 1) << r_size) + (int)c.br.peek(r_size) + 1; c.br.skip(r_size); }
+        if (r_size) { delta = ((e.val - 1) << r_size) + (int)br.peek(r_size) + 1; br.skip(r_size); }
         if (neg) delta = -delta;
     }
     const int f16 = 16 << (f_code - 1);
@@ -177,77 +164,79 @@ inline bool decode_mv_component(slice_ctx_t& c, int f_code, int& pmv, int& out) 
     return true;
 }
 
-// one block: DC (intra) + run/level list; returns false on a syntax error.
-// The bit reader and the write cursor are copied into locals for the duration of the block so that
-// the run/level loop keeps them in registers (stores through the record pointer could otherwise
-// alias the reader's fields and force reloads on every coefficient).
-inline bool parse_block(slice_ctx_t& c, coef_writer_t& w, int b, bool intra) {
-    bitreader_t br = c.br;
-    mp2v_coef_t* out = w.buf + w.cur;
+// one block: DC (intra) + run/level list; returns false on a syntax error
+MP2V_INLINE bool parse_block(bitreader_t& br, mp2v_coef_t*& out, const vlc_decode_tables_t& T, const picture_info_t& pic,
+                             uint16_t (&dc_pred)[3], int b, bool intra) {
     const uint32_t blk_bits = (uint32_t)b << 22;
     int i = 0;
-    bool ok = false;
-    const coef_vlc_t* table = &c.T.b14;
+    const coef_vlc_t* table = &T.b14;
+    br.refill();
     if (intra) {
         const int comp = b < 4 ? 0 : 1 + (b & 1);
-        br.refill();
-        const vlc_entry_t& e = c.T.dcsize[comp ? 1 : 0].look(br.peek(10));
-        if (!e.len) return false;
-        br.skip(e.len);
-        int diff = 0;
-        if (e.val) {                                         // mb_decoder.cpp:59-68
-            const int v = (int)br.peek(e.val);
+        int diff;
+        const dc_fast_t f = T.dc_fast[comp ? 1 : 0][br.peek(kDcFastBits)];
+        if (__builtin_expect(f.len != 0, 1)) { br.skip(f.len); diff = f.diff; }
+        else {
+            const vlc_entry_t& e = T.dcsize[comp ? 1 : 0].look(br.peek(10));
+            if (!e.len) return false;
+            br.skip(e.len);
+            const int v = (int)br.peek(e.val);                 // here size >= 1 (size 0 always fits the fast table)
             br.skip(e.val);
             const int half = 1 << (e.val - 1);
-            diff = v >= half ? v : v + 1 - 2 * half;
+            diff = v >= half ? v : v + 1 - 2 * half;           // mb_decoder.cpp:59-68
         }
-        c.dc_pred[comp] = (uint16_t)(c.dc_pred[comp] + diff);
-        const int16_t dc = (int16_t)(uint16_t)((uint32_t)c.dc_pred[comp] << (3 - c.pic.intra_dc_precision));
+        dc_pred[comp] = (uint16_t)(dc_pred[comp] + diff);
+        const int16_t dc = (int16_t)(uint16_t)((uint32_t)dc_pred[comp] << (3 - pic.intra_dc_precision));
         *out++ = MP2V_COEF(dc, 0, b, MP2V_COEF_RAW);
         i = 1;
-        if (c.pic.intra_vlc_format) table = &c.T.b15;
-    } else {
+        if (pic.intra_vlc_format) table = &T.b15;
         br.refill();
-        if (br.peek(1)) {                                    // first coefficient "1s" (mb_decoder.cpp:79-88)
-            const int neg = (int)br.peek(2) & 1;
-            br.skip(2);
-            *out++ = MP2V_COEF(neg ? -1 : 1, 0, b, MP2V_COEF_FIRST);
-            i = 1;
-        }
+    } else if (br.peek(1)) {                                   // first coefficient "1s" (mb_decoder.cpp:79-88)
+        const int neg = (int)br.peek(2) & 1;
+        br.skip(2);
+        *out++ = MP2V_COEF(neg ? -1 : 1, 0, b, MP2V_COEF_FIRST);
+        i = 1;
     }
-    const coef_entry_t* root = table->root;
-    const coef_entry_t* leaves = table->leaves.data();
+    const coef_fast_t* fast = table->fast;
     for (;;) {
-        br.refill();
-        const uint32_t p17 = br.peek(17);
-        const coef_entry_t* e = &root[p17 >> 9];
-        if (__builtin_expect(e->sub != 0, 0)) e = &leaves[((size_t)(e->sub - 1) << coef_vlc_t::LEAF) + (p17 & 511u)];
-        int run, level;
-        if (__builtin_expect(e->level > 0, 1)) {
-            br.skip(e->len);
-            const int neg = (int)br.peek(1);
-            br.skip(1);
-            run = e->run;
-            level = (e->level ^ -neg) + neg;
-        } else if (e->level == kCoefEob && e->len) {
-            br.skip(e->len);
-            ok = true;
-            break;
-        } else if (e->level == kCoefEsc && e->len) {         // 6-bit run, 12-bit two's complement level
-            br.skip(6);
-            run = (int)br.peek(6); br.skip(6);
-            level = ((int)br.peek(12) ^ 0x800) - 0x800; br.skip(12);
-        } else {
-            break;
+        // one refill (>= 56 bits) covers two symbols of any kind (escape = 24 bits); the first round
+        // reuses the refill above (at most 22 bits were consumed since)
+#pragma GCC unroll 2
+        for (int rep = 0; rep < 2; rep++) {
+            const coef_fast_t f = fast[br.peek(kFastBits)];
+            int run, level;
+            if (__builtin_expect(f.run < kFastEob, 1)) {
+                br.skip(f.len);
+                run = f.run; level = f.level;
+            } else if (f.run == kFastEob) {
+                br.skip(f.len);
+                return true;
+            } else {
+                const coef_entry_t& e = table->look(br.peek(17));
+                if (e.level > 0) {
+                    br.skip(e.len);
+                    const int neg = (int)br.peek(1);
+                    br.skip(1);
+                    run = e.run;
+                    level = (e.level ^ -neg) + neg;
+                } else if (e.level == kCoefEob && e.len) {
+                    br.skip(e.len);
+                    return true;
+                } else if (e.level == kCoefEsc && e.len) {     // 6-bit run, 12-bit two's complement level
+                    br.skip(6);
+                    run = (int)br.peek(6); br.skip(6);
+                    level = ((int)br.peek(12) ^ 0x800) - 0x800; br.skip(12);
+                } else {
+                    return false;
+                }
+            }
+            i += run;
+            if (__builtin_expect(i > 63, 0)) return false;
+            *out++ = (uint32_t)(uint16_t)level | ((uint32_t)i << 16) | blk_bits;
+            i++;
         }
-        i += run;
-        if (__builtin_expect(i > 63, 0)) break;
-        *out++ = (uint32_t)(uint16_t)level | ((uint32_t)i << 16) | blk_bits;
-        i++;
+        br.refill();
     }
-    c.br = br;
-    w.cur = (uint32_t)(out - w.buf);
-    return ok;
 }
 
 }  // namespace
@@ -260,11 +249,13 @@ slice_result_t parse_slice(const uint8_t* payload, int slice_start_code, const s
         return fail("only progressive frame pictures with frame prediction are supported (the reference's envelope)");
     const int cf = seq.chroma_format;
     const int nblk = cf == 1 ? 6 : cf == 2 ? 8 : 12;
-    coef_writer_t w(thread_scratch((size_t)mbw * nblk * 64u));
-
-    slice_ctx_t c(pic);
-    bitreader_t& br = c.br;
-    br.reset(payload);
+    mp2v_coef_t* const scratch = thread_scratch((size_t)mbw * nblk * 64u);
+    mp2v_coef_t* out = scratch;
+    const vlc_decode_tables_t& T = vlc_decode_tables();
+    bitreader_t br(payload);
+    int pmv[2][2];
+    uint16_t dc_pred[3];
+    auto reset_dc = [&] { for (auto& d : dc_pred) d = (uint16_t)(1u << (pic.intra_dc_precision + 7)); };
     int mb_row = slice_start_code - 1;
     if (seq.vertical_size > 2800) mb_row += (int)br.get(3) << 7;        // slice_vertical_position_extension
     if (mb_row < 0 || mb_row >= mbh) return fail("slice row outside the picture");
@@ -273,8 +264,8 @@ slice_result_t parse_slice(const uint8_t* payload, int slice_start_code, const s
         br.get(8);
         while (br.get1()) br.get(8);
     }
-    memset(c.pmv, 0, sizeof(c.pmv));
-    c.reset_dc();
+    memset(pmv, 0, sizeof(pmv));
+    reset_dc();
     const int pct = pic.picture_coding_type;
     mp2v_mb_info_t* row = mb + (size_t)mb_row * mbw;
     uint32_t prev_dirs = 0;
@@ -285,7 +276,7 @@ slice_result_t parse_slice(const uint8_t* payload, int slice_start_code, const s
         int inc = 0;
         for (;;) {
             br.refill();
-            const vlc_entry_t& e = c.T.mba.look(br.peek(11));
+            const vlc_entry_t& e = T.mba.look(br.peek(11));
             if (!e.len) return fail("bad macroblock_address_increment");
             br.skip(e.len);
             if (e.val) { inc += e.val; break; }
@@ -299,23 +290,23 @@ slice_result_t parse_slice(const uint8_t* payload, int slice_start_code, const s
         // ---- skipped macroblocks (mb_decoder.cpp:541-550)
         if (skipped > 0) {
             if (pct == 1) return fail("skipped macroblock in an I picture");
-            if (pct == 2) memset(c.pmv, 0, sizeof(c.pmv));
+            if (pct == 2) memset(pmv, 0, sizeof(pmv));
             uint32_t dirs = pct == 2 ? MP2V_MB_FWD : prev_dirs;
             if (!dirs) dirs = MP2V_MB_FWD;                              // after an intra macroblock the reference predicts forward
             for (int k = 0; k < skipped; k++) {
                 mp2v_mb_info_t& r = row[++mbx];
-                r.coef_off = w.cur;
+                r.coef_off = (uint32_t)(out - scratch);
                 r.bits = MP2V_MB_BITS(0, qscale, 0, dirs);
                 for (int s = 0; s < 2; s++) for (int t = 0; t < 2; t++)
-                    r.mv[s][t] = (int16_t)((dirs & (s ? MP2V_MB_BWD : MP2V_MB_FWD)) ? c.pmv[s][t] : 0);
+                    r.mv[s][t] = (int16_t)((dirs & (s ? MP2V_MB_BWD : MP2V_MB_FWD)) ? pmv[s][t] : 0);
                 res.mbs++;
             }
-            c.reset_dc();
+            reset_dc();
         }
         mp2v_mb_info_t& r = row[++mbx];
         // ---- macroblock_type
         br.refill();
-        const vlc_entry_t& te = c.T.mbtype[pct].look(br.peek(6));
+        const vlc_entry_t& te = T.mbtype[pct].look(br.peek(6));
         if (!te.len) return fail("bad macroblock_type");
         br.skip(te.len);
         const int type = te.val;
@@ -328,17 +319,17 @@ slice_result_t parse_slice(const uint8_t* payload, int slice_start_code, const s
             for (int t = 0; t < 2; t++) {
                 const int fc = pic.f_code[s][t];
                 if (fc < 1 || fc > 9) return fail("f_code out of range");
-                if (!decode_mv_component(c, fc, c.pmv[s][t], mv[s][t])) return fail("bad motion_code");
+                if (!decode_mv_component(br, T, fc, pmv[s][t], mv[s][t])) return fail("bad motion_code");
             }
         }
-        if (intra || (pct == 2 && !fwd)) memset(c.pmv, 0, sizeof(c.pmv));   // mb_decoder.cpp:599-603
-        if (!intra) c.reset_dc();                                           // mb_decoder.cpp:623-626
+        if (intra || (pct == 2 && !fwd)) memset(pmv, 0, sizeof(pmv));   // mb_decoder.cpp:599-603
+        if (!intra) reset_dc();                                           // mb_decoder.cpp:623-626
         // ---- coded_block_pattern
         uint32_t cbp = 0;
         if (intra) cbp = (1u << nblk) - 1u;
         else if (pattern) {
             br.refill();
-            const vlc_entry_t& ce = c.T.cbp.look(br.peek(9));
+            const vlc_entry_t& ce = T.cbp.look(br.peek(9));
             if (!ce.len) return fail("bad coded_block_pattern");
             br.skip(ce.len);
             for (int i = 0; i < 6; i++) if (ce.val & (1 << (5 - i))) cbp |= 1u << i;          // mb_decoder.cpp:435-436
@@ -346,10 +337,10 @@ slice_result_t parse_slice(const uint8_t* payload, int slice_start_code, const s
             if (cf == 3) { const uint32_t x = br.peek(6); br.skip(6); for (int i = 0; i < 6; i++) cbp |= ((x >> (5 - i)) & 1u) << (6 + i); }
         }
         // ---- blocks
-        const uint32_t off = w.cur;
+        const uint32_t off = (uint32_t)(out - scratch);
         for (int b = 0; b < nblk; b++)
             if (cbp & (1u << b))
-                if (!parse_block(c, w, b, intra)) return fail("bad DCT coefficient syntax");
+                if (!parse_block(br, out, T, pic, dc_pred, b, intra)) return fail("bad DCT coefficient syntax");
         uint32_t flags = 0;
         if (intra) flags = MP2V_MB_INTRA;
         else {
@@ -358,7 +349,7 @@ slice_result_t parse_slice(const uint8_t* payload, int slice_start_code, const s
             if (!flags) flags = MP2V_MB_FWD;        // P picture "no MC": forward prediction with a zero vector (mb_decoder.cpp:329-338)
         }
         r.coef_off = off;
-        r.bits = MP2V_MB_BITS(w.cur - off, qscale, cbp, flags);
+        r.bits = MP2V_MB_BITS((uint32_t)(out - scratch) - off, qscale, cbp, flags);
         for (int s = 0; s < 2; s++) for (int t = 0; t < 2; t++) r.mv[s][t] = (int16_t)(intra ? 0 : mv[s][t]);
         prev_dirs = flags & (MP2V_MB_FWD | MP2V_MB_BWD);
         res.mbs++;
@@ -366,9 +357,10 @@ slice_result_t parse_slice(const uint8_t* payload, int slice_start_code, const s
     } while (br.peek(23) != 0 && mbx < mbw - 1);
     // trailing macroblocks of the row that the slice did not code keep the caller's defaults.
     // append the slice's records to the picture arena and rebase the offsets written above
-    const uint32_t base = arena.next.fetch_add(w.cur, std::memory_order_relaxed);
-    if ((uint64_t)base + w.cur > arena.capacity) { arena.overflow.store(true, std::memory_order_relaxed); return fail("coefficient arena exhausted"); }
-    memcpy(arena.base + base, w.buf, (size_t)w.cur * sizeof(mp2v_coef_t));
+    const uint32_t total = (uint32_t)(out - scratch);
+    const uint32_t base = arena.next.fetch_add(total, std::memory_order_relaxed);
+    if ((uint64_t)base + total > arena.capacity) { arena.overflow.store(true, std::memory_order_relaxed); return fail("coefficient arena exhausted"); }
+    memcpy(arena.base + base, scratch, (size_t)total * sizeof(mp2v_coef_t));
     for (int x = first_mbx; x <= mbx; x++) row[x].coef_off += base;
     return res;
 }

@@ -39,8 +39,33 @@ struct flat_vlc_t {
     inline const vlc_entry_t& look(uint32_t peek_bits) const { return e[peek_bits]; }
 };
 
+// Fast path of the run/level decoder: one lookup on the next 11 bits resolves code AND sign for
+// every symbol whose code + sign bit fit (all the frequent ones); anything else falls back to the
+// two-level table.  4 bytes per entry, 8 KB per table.
+struct coef_fast_t {
+    int16_t level;     // signed level (fast symbols); unused otherwise
+    uint8_t run;       // 0..63 fast symbol; kFastEob / kFastSlow markers
+    uint8_t len;       // bits consumed including the sign bit (fast symbols and end of block)
+};
+constexpr uint8_t kFastEob = 64, kFastSlow = 65;
+constexpr int kFastBits = 11;
+
 struct coef_vlc_t {
     static constexpr int ROOT = 8, LEAF = 9;                      // longest code is 16 bits (+ sign)
+    coef_fast_t fast[1 << kFastBits];
+    void build_fast() {
+        for (uint32_t i = 0; i < (1u << kFastBits); i++) {
+            const coef_entry_t& e = look(i << (17 - kFastBits));
+            coef_fast_t f{0, kFastSlow, 0};
+            if (e.len && e.level > 0 && e.len + 1 <= kFastBits) {
+                const int neg = (int)(i >> (kFastBits - 1 - e.len)) & 1;
+                f.level = (int16_t)(neg ? -e.level : e.level); f.run = e.run; f.len = (uint8_t)(e.len + 1);
+            } else if (e.len && e.level == kCoefEob && e.len <= kFastBits) {
+                f.run = kFastEob; f.len = e.len;
+            }
+            fast[i] = f;
+        }
+    }
     coef_entry_t root[1 << ROOT];
     std::vector<coef_entry_t> leaves;                             // (1 << LEAF) entries per leaf table
     coef_vlc_t() { memset(root, 0, sizeof(root)); }
@@ -74,7 +99,13 @@ struct coef_vlc_t {
     }
 };
 
+// dct_dc_size + dct_dc_differential in one lookup on the next 12 bits (covers sizes whose code and
+// differential bits fit together -- every small differential); len == 0 -> take the two-step path
+struct dc_fast_t { int16_t diff; uint8_t len; uint8_t pad; };
+constexpr int kDcFastBits = 12;
+
 struct vlc_decode_tables_t {
+    dc_fast_t dc_fast[2][1 << kDcFastBits];
     flat_vlc_t<11> mba;            // val = increment, 0 = escape (adds 33)
     flat_vlc_t<6> mbtype[4];       // per picture_coding_type; val = flag byte
     flat_vlc_t<9> cbp;
@@ -92,6 +123,22 @@ struct vlc_decode_tables_t {
         for (int i = 0; i < MP2V_COUNT(kTabCoefB15); i++) b15.add(kTabCoefB15[i].bits, kTabCoefB15[i].a, kTabCoefB15[i].b);
         b14.add(kEobB14, 0, kCoefEob); b15.add(kEobB15, 0, kCoefEob);
         b14.add(kCoefEscape, 0, kCoefEsc); b15.add(kCoefEscape, 0, kCoefEsc);
+        b14.build_fast(); b15.build_fast();
+        for (int lc = 0; lc < 2; lc++)
+            for (uint32_t i = 0; i < (1u << kDcFastBits); i++) {
+                const vlc_entry_t& e = dcsize[lc].look(i >> (kDcFastBits - 10));
+                dc_fast_t f{0, 0, 0};
+                if (e.len && e.len + e.val <= kDcFastBits) {
+                    int diff = 0;
+                    if (e.val) {                                   // mb_decoder.cpp:59-68
+                        const int v = (int)(i >> (kDcFastBits - e.len - e.val)) & ((1 << e.val) - 1);
+                        const int half = 1 << (e.val - 1);
+                        diff = v >= half ? v : v + 1 - 2 * half;
+                    }
+                    f.diff = (int16_t)diff; f.len = (uint8_t)(e.len + e.val);
+                }
+                dc_fast[lc][i] = f;
+            }
     }
 };
 
