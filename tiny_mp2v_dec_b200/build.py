@@ -49,9 +49,21 @@ def _deps(*dirs):
     return out
 
 
-def build_product(force=False, verbose=False):
-    """nvcc -gencode arch=compute_100a,code=sm_100a -lineinfo: cross-compiles without a GPU."""
+def build_product(force=False, verbose=False, defines=(), out=None):
+    """nvcc -gencode arch=compute_100a,code=sm_100a -lineinfo: cross-compiles without a GPU.
+    `defines` / `out` build kernel-tuning variants next to the product (tools/dev only)."""
     os.makedirs(LIB, exist_ok=True)
+    if out is not None:
+        srcs = [os.path.join(CSRC, s) for s in CUDA_SOURCES + HOST_SOURCES]
+        cmd = [NVCC, "-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-O3", "-std=c++17", "--shared",
+               "-Xcompiler", "-fPIC,-fvisibility=hidden,-Wall,-pthread", "-I", os.path.join(ROOT, "include"), "-I", CSRC,
+               "-I", os.path.join(CSRC, "host"), "-o", out] + ["-D" + d for d in defines] + srcs + ["-lpthread"]
+        if verbose:
+            cmd.insert(1, "-Xptxas=-v")
+        o = _run(cmd)
+        if verbose:
+            print(o)
+        return out
     srcs = [os.path.join(CSRC, s) for s in CUDA_SOURCES + HOST_SOURCES if os.path.exists(os.path.join(CSRC, s))]
     deps = _deps(CSRC, os.path.join(ROOT, "include"))
     if not force and not _stale(PRODUCT_LIB, deps):

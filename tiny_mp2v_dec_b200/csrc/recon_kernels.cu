@@ -67,14 +67,28 @@ struct fmt_t {
 };
 
 constexpr int kTilePitch = 72;   // int16 per slot: 64 + 8 pad -> 144 B, conflict-free 128-bit row access
-constexpr int kSlots = 32;       // coded blocks per batch = IDCT lanes
+#ifndef MP2V_SLOTS
+#define MP2V_SLOTS 24      // measured best: 24 slots (4:2:0 4 MBs, 4:2:2 3, 4:4:4 2 all-coded macroblocks fill it exactly)
+#endif
+#ifndef MP2V_WINBUF
+#define MP2V_WINBUF 1      // one window buffer: 29 KB / CTA -> 8 CTAs per SM; two buffers measured 3-6 % slower
+#endif
+#ifndef MP2V_MINCTAS
+#define MP2V_MINCTAS 8
+#endif
+constexpr int kSlots = MP2V_SLOTS;   // coded blocks per batch (multiple of 8: the IDCT runs 8 blocks per round)
+constexpr int kWinBuf = MP2V_WINBUF; // 2: the next macroblock's windows load while this one is computed
 constexpr int kWarps = kCtaThreads / 32;
 
 template <int CF>
 struct warp_smem_t {
     alignas(16) int16_t tile[kSlots][kTilePitch];
-    alignas(16) uint8_t win[2][2][fmt_t<CF>::WIN_DIR];   // [buffer][direction]
+    alignas(16) uint8_t win[kWinBuf][2][fmt_t<CF>::WIN_DIR];   // [buffer][direction]
     int bound[kSlots];
+    // per-batch macroblock context for the flat dequantisation loop
+    uint32_t mb_pre[33];             // (first record index in the batch << 8) | first tile slot
+    uint32_t mb_bits[32];
+    uint32_t mb_off[32];
 };
 
 template <int CF>
@@ -367,7 +381,7 @@ __device__ __forceinline__ void reconstruct_mb(const pic_desc_t& pd, const batch
 }
 
 template <int CF>
-__global__ void __launch_bounds__(kCtaThreads, 4) recon_kernel(const __grid_constant__ batch_desc_t batch) {
+__global__ void __launch_bounds__(kCtaThreads, MP2V_MINCTAS) recon_kernel(const __grid_constant__ batch_desc_t batch) {
     using F = fmt_t<CF>;
     __shared__ smem_t<CF> s;
 
@@ -418,57 +432,70 @@ __global__ void __launch_bounds__(kCtaThreads, 4) recon_kernel(const __grid_cons
             cp_async_commit();
         }
 
-        // ---- 3. zero the used slots (QFS[64] = {0}, mb_decoder.cpp:159), then dequantise + saturate + mismatch
+        // ---- 3. zero the used slots (QFS[64] = {0}, mb_decoder.cpp:159), then dequantise + saturate + mismatch.
+        // All records of the batch are walked as ONE flat index space (lane = record): a lane finds its
+        // macroblock by binary search over the per-batch record prefix, so sparse P/B macroblocks do not
+        // cost a loop trip each.
         for (int i = lane; i < nslots * 8; i += 32)
             reinterpret_cast<uint4*>(&ws.tile[i >> 3][0])[i & 7] = make_uint4(0, 0, 0, 0);
-        ws.bound[lane] = 0;
+        if (lane < kSlots) ws.bound[lane] = 0;
+        const int ncoef = lane < nb ? (int)MP2V_MB_NCOEF(rec.y) : 0;
+        int cincl = ncoef;
+#pragma unroll
+        for (int d = 1; d < 32; d <<= 1) {
+            const int t = __shfl_up_sync(0xffffffffu, cincl, d);
+            if (lane >= d) cincl += t;
+        }
+        const int total = __shfl_sync(0xffffffffu, cincl, 31);
+        ws.mb_pre[lane] = ((uint32_t)(cincl - ncoef) << 8) | (uint32_t)(lane < nb ? base : nslots);
+        ws.mb_bits[lane] = rec.y;
+        ws.mb_off[lane] = rec.x;
+        if (lane == 0) ws.mb_pre[32] = (uint32_t)total << 8;
         __syncwarp();
-        for (int mi = 0; mi < nb; mi++) {
-            const uint32_t m_off = __shfl_sync(0xffffffffu, rec.x, mi), m_bits = __shfl_sync(0xffffffffu, rec.y, mi);
-            const int mbase = __shfl_sync(0xffffffffu, base, mi);
-            const int n = MP2V_MB_NCOEF(m_bits);
-            const int qs = MP2V_MB_QSCALE(m_bits);
-            const uint32_t cbp = MP2V_MB_CBP(m_bits);
-            const bool intra = (m_bits & MP2V_MB_INTRA) != 0;
-            const mp2v_coef_t* cp = pd.coef + m_off;
-            uint32_t parity = 0;
-            for (int k0 = 0; k0 < n; k0 += 32) {
-                const int k = k0 + lane;
-                uint32_t pbit = 0;
-                const uint32_t c = k < n ? __ldg(cp + k) : 0u;
-                if (k < n && (cbp >> ((c >> 22) & 15) & 1)) {   // a record naming an uncoded block is ignored (memory safety)
+        uint32_t parity = 0;                 // bit s = parity of the coefficient sum of tile slot s
+        for (int f0 = 0; f0 < total; f0 += 32) {
+            const int f = f0 + lane;
+            uint32_t pbit = 0;
+            if (f < total) {
+                int lo = 0, hi = nb;         // last macroblock whose first record index is <= f
+#pragma unroll
+                for (int st = 0; st < 5; st++) {
+                    const int mid = (lo + hi) >> 1;
+                    const bool ge = (int)(ws.mb_pre[mid] >> 8) <= f;
+                    lo = ge ? mid : lo; hi = ge ? hi : mid;
+                }
+                const uint32_t pre = ws.mb_pre[lo], m_bits = ws.mb_bits[lo];
+                const uint32_t c = __ldg(pd.coef + ws.mb_off[lo] + (f - (int)(pre >> 8)));
+                const uint32_t cbp = MP2V_MB_CBP(m_bits);
+                const int blk = (c >> 22) & 15;
+                if (cbp >> blk & 1) {        // a record naming an uncoded block is ignored (memory safety)
+                    const bool intra = (m_bits & MP2V_MB_INTRA) != 0;
+                    const int qs = MP2V_MB_QSCALE(m_bits);
                     const int level = (int)(short)(c & 0xffffu);
-                    const int pos = (c >> 16) & 63, blk = (c >> 22) & 15;
-                    const int slot = mbase + __popc(cbp & ((1u << blk) - 1u));
-                    int val, idx2, wsum;
-                    if (c & MP2V_COEF_RAW) {                                                // intra DC, not summed (:160)
-                        val = level; idx2 = 0;
-                        wsum = abs(val) <= kMaxFirstCoef ? abs(val) * (int)s.bw[0] : kBoundWild;
-                    } else {
-                        const int w = s.W[(blk < 6 ? 0 : 2) + (intra ? 0 : 1)][pos];        // luma matrices for blocks 4,5 (:184-185)
-                        const int mag = abs(level);
-                        if (c & MP2V_COEF_FIRST) { val = (3 * w * qs) >> 5; idx2 = 0; }     // first coefficient "1s": no clamp (:84)
-                        else {
-                            val = intra ? (mag * w * qs) >> 4 : ((2 * mag + 1) * w * qs) >> 5;   // :142-143
-                            idx2 = s.scan[pos];
-                        }
-                        if (level < 0) val = -val;                                          // :144
-                        if (!(c & MP2V_COEF_FIRST)) val = max(min((int)(short)val, 2047), -2048);   // int16 wrap, then clamp (:146)
-                        pbit = (uint32_t)(val & 1) << blk;
-                        wsum = (abs(val) + 1) * (int)s.bw[idx2];     // +1: the mismatch toggle may change |F[63]| by one
-                    }
+                    const int pos = (c >> 16) & 63;
+                    const int slot = (int)(pre & 0xffu) + __popc(cbp & ((1u << blk) - 1u));
+                    const bool raw = (c & MP2V_COEF_RAW) != 0, first = (c & MP2V_COEF_FIRST) != 0;
+                    const int w = s.W[(blk < 6 ? 0 : 2) + (intra ? 0 : 1)][pos];            // luma matrices for blocks 4,5 (:184-185)
+                    const int mag = abs(level);
+                    // intra (level*W*qs)>>4, non-intra ((2*level+1)*W*qs)>>5 (:142-143); "1s" is the latter with level 1 (:84)
+                    int val = ((intra ? mag : 2 * mag + 1) * w * qs) >> (intra ? 4 : 5);
+                    val = level < 0 ? -val : val;                                           // :144
+                    const int clamped = max(min((int)(short)val, 2047), -2048);             // int16 wrap, then clamp (:146)
+                    val = raw ? level : first ? val : clamped;                              // DC as is (:160); "1s" unclamped (:84)
+                    const int idx2 = s.scan[pos];                                           // pos 0 -> 0 for DC / "1s"
+                    const int av = abs(val);
+                    const int wsum = raw ? (av <= kMaxFirstCoef ? av * (int)s.bw[0] : kBoundWild)
+                                         : (av + 1) * (int)s.bw[idx2];   // +1: the mismatch toggle may change |F[63]| by one
+                    pbit = raw ? 0u : (uint32_t)(val & 1) << slot;                          // DC is not part of the sum (:160)
                     ws.tile[slot][idx2] = (int16_t)val;
                     atomicAdd(&ws.bound[slot], wsum);
                 }
-                parity ^= __reduce_xor_sync(0xffffffffu, pbit);
             }
-            __syncwarp();
-            // qfs[63] ^= (sum & 1) ^ 1 for every coded block (:150-152)
-            if (lane < F::NBLK && (cbp >> lane & 1)) {
-                const int slot = mbase + __popc(cbp & ((1u << lane) - 1u));
-                ws.tile[slot][63] ^= (int16_t)(((parity >> lane) & 1u) ^ 1u);
-            }
+            parity ^= __reduce_xor_sync(0xffffffffu, pbit);
         }
+        __syncwarp();
+        // qfs[63] ^= (sum & 1) ^ 1 for every coded block (:150-152)
+        if (lane < nslots) ws.tile[lane][63] ^= (int16_t)(((parity >> lane) & 1u) ^ 1u);
         __syncwarp();
 
         // ---- 4. IDCT, four lanes per coded block, 8 blocks per round; arithmetic variant chosen per round
@@ -482,23 +509,29 @@ __global__ void __launch_bounds__(kCtaThreads, 4) recon_kernel(const __grid_cons
         }
         __syncwarp();
 
-        // ---- 5. prediction + residual + clip + store; the next macroblock's windows load meanwhile
+        // ---- 5. prediction + residual + clip + store; with two window buffers the next macroblock's
+        // windows load while this one is computed
         for (int mi = 0; mi < nb; mi++) {
             const uint4 m = make_uint4(__shfl_sync(0xffffffffu, rec.x, mi), __shfl_sync(0xffffffffu, rec.y, mi),
                                        __shfl_sync(0xffffffffu, rec.z, mi), __shfl_sync(0xffffffffu, rec.w, mi));
             const int mbase = __shfl_sync(0xffffffffu, base, mi);
             const int mbi = first + mi;
             const int mby = mbi / mbw, mbx = mbi - mby * mbw;
-            if (mi + 1 < nb) {
-                const uint4 mn = make_uint4(__shfl_sync(0xffffffffu, rec.x, mi + 1), __shfl_sync(0xffffffffu, rec.y, mi + 1),
-                                            __shfl_sync(0xffffffffu, rec.z, mi + 1), __shfl_sync(0xffffffffu, rec.w, mi + 1));
-                const int nby = (mbi + 1) / mbw, nbx = (mbi + 1) - nby * mbw;
-                stage_windows<CF>(pd, batch, mn, nbx, nby, &ws.win[(mi + 1) & 1][0][0], lane);
+            if (kWinBuf == 2) {
+                if (mi + 1 < nb) {
+                    const uint4 mn = make_uint4(__shfl_sync(0xffffffffu, rec.x, mi + 1), __shfl_sync(0xffffffffu, rec.y, mi + 1),
+                                                __shfl_sync(0xffffffffu, rec.z, mi + 1), __shfl_sync(0xffffffffu, rec.w, mi + 1));
+                    const int nby = (mbi + 1) / mbw, nbx = (mbi + 1) - nby * mbw;
+                    stage_windows<CF>(pd, batch, mn, nbx, nby, &ws.win[(mi + 1) & (kWinBuf - 1)][0][0], lane);
+                }
+                cp_async_commit();
+                cp_async_wait<1>();      // everything but the group just committed has landed: this macroblock's windows
+            } else {
+                if (mi > 0) { stage_windows<CF>(pd, batch, m, mbx, mby, &ws.win[0][0][0], lane); cp_async_commit(); }
+                cp_async_wait<0>();
             }
-            cp_async_commit();
-            cp_async_wait<1>();      // everything but the group just committed has landed: this macroblock's windows
             __syncwarp();
-            reconstruct_mb<CF>(pd, batch, m, mbx, mby, mbase, &ws.win[mi & 1][0][0], ws.tile, lane);
+            reconstruct_mb<CF>(pd, batch, m, mbx, mby, mbase, &ws.win[mi & (kWinBuf - 1)][0][0], ws.tile, lane);
             __syncwarp();
         }
         cp_async_wait<0>();

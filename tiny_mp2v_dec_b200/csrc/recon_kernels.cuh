@@ -9,13 +9,19 @@ namespace mp2v {
 constexpr int kMaxBatch = 32;        // pictures fused into one launch (descriptors travel as kernel arguments)
 constexpr int kCtaThreads = 128;
 
-// A warp owns `mbs_per_warp` consecutive macroblocks and walks them in batches of <= 32 coded blocks
-// (one IDCT lane per block).  The run length is a multiple of the all-coded batch size
-// (4:2:0 5 MBs = 30 blocks, 4:2:2 4 MBs = 32, 4:4:4 2 MBs = 24) and is chosen per launch so that the
-// grid is about two waves of the resident warps (148 SMs x 4 CTAs x 4 warps).
+// A warp owns `mbs_per_warp` consecutive macroblocks and walks them in batches of <= MP2V_SLOTS coded
+// blocks.  The run length is a multiple of the all-coded batch size (24 slots: 4:2:0 4 MBs, 4:2:2 3,
+// 4:4:4 2) and is chosen per launch so that the grid is at least ~6 waves of the resident warps
+// (148 SMs x 8 CTAs x 4 warps): a grid of 1.1 waves costs two, which measured as a 40 % loss.
+#ifndef MP2V_SLOTS
+#define MP2V_SLOTS 24
+#endif
+#ifndef MP2V_WAVES
+#define MP2V_WAVES 6
+#endif
 inline int choose_mbs_per_warp(int cf, long long total_mbs) {
-    const int unit = cf == 1 ? 5 : cf == 2 ? 4 : 2;
-    long long run = total_mbs / (2LL * 148 * 4 * 4);
+    const int unit = MP2V_SLOTS / (cf == 1 ? 6 : cf == 2 ? 8 : 12);
+    long long run = total_mbs / ((long long)MP2V_WAVES * 148 * 8 * 4);
     if (run > 60) run = 60;
     if (run < 2 * unit) run = 2 * unit;
     return (int)(run / unit * unit);

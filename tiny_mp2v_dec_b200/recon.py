@@ -29,7 +29,7 @@ class ReconError(RuntimeError):
 def lib():
     global _lib
     if _lib is None:
-        path = _build.PRODUCT_LIB
+        path = os.environ.get("MP2V_B200_LIB", _build.PRODUCT_LIB)     # dev knob: kernel-tuning variants (tools/dev)
         if not os.path.exists(path):
             _build.build_product()
         L = C.CDLL(path)

@@ -40,10 +40,14 @@ def run(name, w, h, cf, reps=20, max_batch=32, **kw):
     r.close()
 
 
+NAT = dict(mode=1, pct_coded=70)
+
 if __name__ == "__main__":
-    run("1080p420 intra x30", 1920, 1088, 1, seed=2, intra_only=1, gop_n=30, n_gops=1)
-    run("1080p420 IPB 4gops", 1920, 1088, 1, seed=3, gop_n=15, gop_m=3, n_gops=4)
-    run("1080p420 IPB natural", 1920, 1088, 1, seed=3, gop_n=15, gop_m=3, n_gops=4, mode=1)
-    run("1080p422 IPB 4gops", 1920, 1088, 2, seed=1, gop_n=15, gop_m=3, n_gops=4)
-    run("720p420 IPB 8gops", 1280, 720, 1, seed=5, gop_n=15, gop_m=3, n_gops=8)
-    run("4k444 IPB 2gops", 3840, 2160, 3, seed=4, gop_n=15, gop_m=3, n_gops=2)
+    run("1080p420 intra natural", 1920, 1088, 1, seed=2, intra_only=1, gop_n=15, n_gops=2, gop_m=1, natural_mean_coefs=6, **NAT)
+    run("1080p420 IPB natural", 1920, 1088, 1, seed=3, gop_n=15, gop_m=3, n_gops=4, natural_mean_coefs=5, **NAT)
+    run("1080p420 intra fuzz", 1920, 1088, 1, seed=2, intra_only=1, gop_n=15, n_gops=2, gop_m=1)
+    run("1080p420 IPB fuzz", 1920, 1088, 1, seed=3, gop_n=15, gop_m=3, n_gops=4)
+    if "--all" in sys.argv:
+        run("1080p422 IPB natural", 1920, 1088, 2, seed=1, gop_n=15, gop_m=3, n_gops=4, natural_mean_coefs=5, **NAT)
+        run("720p420 IPB natural", 1280, 720, 1, seed=5, gop_n=15, gop_m=3, n_gops=8, natural_mean_coefs=5, **NAT)
+        run("4k444 IPB natural", 3840, 2160, 3, seed=4, gop_n=15, gop_m=3, n_gops=2, natural_mean_coefs=5, **NAT)
