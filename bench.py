@@ -37,10 +37,10 @@ NATURAL = dict(mode=1, pct_coded=70)
 WORKLOADS = {
     # configs[1]: 1080p 4:2:0 intra-only, every block coded (IQ + IDCT path)
     "1080p420_intra": dict(width=1920, height=1088, chroma_format=1, config_id=2,
-                           gen=dict(n_gops=4, gop_n=15, gop_m=1, intra_only=1, natural_mean_coefs=6, **NATURAL)),
+                           gen=dict(n_gops=8, gop_n=15, gop_m=1, intra_only=1, natural_mean_coefs=6, **NATURAL)),
     # configs[2]: 1080p 4:2:0 IPB, GOP N=15 M=3, half-pel bidirectional MC
     "1080p420_ipb": dict(width=1920, height=1088, chroma_format=1, config_id=3,
-                         gen=dict(n_gops=4, gop_n=15, gop_m=3, natural_mean_coefs=5, **NATURAL)),
+                         gen=dict(n_gops=8, gop_n=15, gop_m=3, natural_mean_coefs=5, **NATURAL)),
     # configs[0]: 1080p 4:2:2 IPB (the reference sample's hard-wired geometry)
     "1080p422_ipb": dict(width=1920, height=1088, chroma_format=2, config_id=1,
                          gen=dict(n_gops=4, gop_n=15, gop_m=3, natural_mean_coefs=5, **NATURAL)),

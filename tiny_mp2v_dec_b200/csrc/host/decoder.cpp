@@ -14,6 +14,7 @@
 #include <atomic>
 #include <chrono>
 #include <condition_variable>
+#include <cstdio>
 #include <cstdlib>
 #include <cstring>
 #include <deque>
@@ -91,8 +92,9 @@ struct shared_t {
     std::condition_variable gcv;
     int emit_gop = 0;
     std::vector<int> gop_size, gop_emitted;
-    // statistics
+    // statistics (nanoseconds, summed over threads)
     std::atomic<int64_t> parse_ns{0};
+    std::atomic<int64_t> feeder_wait_ns{0}, feeder_work_ns{0}, submit_ns{0}, precheck_ns{0}, out_wait_ns{0}, out_map_ns{0}, worker_idle_ns{0};
     std::vector<pipeline_t*> pipes;
 
     void fail(const std::string& why);
@@ -138,6 +140,7 @@ void pipeline_t::feeder() {
     for (size_t k = 0; k < tasks.size() && !sh->failed.load(); k++) {
         pic_task_t& t = tasks[k];
         const picture_info_t& info = t.src->info;
+        const auto tf0 = clock_t_::now();
         {   // a free device frame and room in the parse window
             std::unique_lock<std::mutex> lk(mu);
             int f = -1;
@@ -152,6 +155,8 @@ void pipeline_t::feeder() {
             frame_use[f] = 1;               // awaiting display
             in_parse++;
         }
+        const auto tf1 = clock_t_::now();
+        sh->feeder_wait_ns.fetch_add(std::chrono::duration_cast<std::chrono::nanoseconds>(tf1 - tf0).count(), std::memory_order_relaxed);
         if (info.picture_coding_type == 3) {                       // B: both references (decoder.cpp:303)
             t.l0 = refs[0] >= 0 ? tasks[refs[0]].dst : -1;
             t.l1 = refs[1] >= 0 ? tasks[refs[1]].dst : -1;
@@ -186,6 +191,7 @@ void pipeline_t::feeder() {
             sh->queue.push_back(&t);
         }
         sh->qcv.notify_all();
+        sh->feeder_work_ns.fetch_add(std::chrono::duration_cast<std::chrono::nanoseconds>(clock_t_::now() - tf1).count(), std::memory_order_relaxed);
     }
     unref(refs[0]);
     unref(refs[1]);
@@ -194,10 +200,14 @@ void pipeline_t::feeder() {
 // called by the worker that finished the last slice of a picture
 void pipeline_t::on_parsed(pic_task_t* t) {
     // record validation / byte accounting is per picture: do it before taking the submission lock
+    const auto ts0 = clock_t_::now();
     if (t->ok.load() && !t->arena.overflow.load() && t->rp) {
         t->rp->params->n_coef = t->arena.next.load();
         if (mp2v_recon_precheck(recon, t->rp) != MP2V_OK) { t->error = "records failed validation (motion vector outside the frame or bad offsets)"; t->ok.store(false); }
     }
+    const auto ts1 = clock_t_::now();
+    sh->precheck_ns.fetch_add(std::chrono::duration_cast<std::chrono::nanoseconds>(ts1 - ts0).count(), std::memory_order_relaxed);
+    struct submit_timer_t { shared_t* sh; clock_t_::time_point t0; ~submit_timer_t() { sh->submit_ns.fetch_add(std::chrono::duration_cast<std::chrono::nanoseconds>(clock_t_::now() - t0).count(), std::memory_order_relaxed); } } submit_timer{sh, ts1};
     std::lock_guard<std::mutex> lk(mu);
     t->parsed = true;
     while (next_submit < (int)tasks.size() && tasks[next_submit].parsed && !sh->failed.load()) {
@@ -220,6 +230,7 @@ void pipeline_t::output() {
     const int lag = sh->opt.output_lag < 0 ? 0 : sh->opt.output_lag;
     auto emit = [&](int k) -> bool {
         pic_task_t& t = tasks[k];
+        const auto to0 = clock_t_::now();
         {   // stay `lag` pictures behind the submit side so that launches can batch
             std::unique_lock<std::mutex> lk(mu);
             const int need = (k + lag < n - 1 ? k + lag : n - 1) + 1;
@@ -228,9 +239,12 @@ void pipeline_t::output() {
         }
         uint8_t* planes[3] = {nullptr, nullptr, nullptr};
         int32_t strides[3] = {0, 0, 0};
+        const auto to1 = clock_t_::now();
+        sh->out_wait_ns.fetch_add(std::chrono::duration_cast<std::chrono::nanoseconds>(to1 - to0).count(), std::memory_order_relaxed);
         if (sh->opt.download_frames) {
             if (mp2v_recon_map_frame(recon, t.dst, planes, strides) != MP2V_OK) { sh->fail(std::string("map_frame: ") + mp2v_recon_last_error(recon)); return false; }
         }
+        sh->out_map_ns.fetch_add(std::chrono::duration_cast<std::chrono::nanoseconds>(clock_t_::now() - to1).count(), std::memory_order_relaxed);
         {   // display order across GOP chains: chain g is shown after chain g-1
             std::unique_lock<std::mutex> lk(sh->gmu);
             sh->gcv.wait(lk, [&] { return sh->failed.load() || sh->emit_gop == t.src->gop; });
@@ -275,7 +289,9 @@ void worker_main(shared_t* sh) {
                     sh->queue.pop_front();
                 if (!sh->queue.empty()) { t = sh->queue.front(); break; }
                 if (sh->stop) return;
+                const auto ti0 = clock_t_::now();
                 sh->qcv.wait(lk);
+                sh->worker_idle_ns.fetch_add(std::chrono::duration_cast<std::chrono::nanoseconds>(clock_t_::now() - ti0).count(), std::memory_order_relaxed);
             }
         }
         // claim slices of this picture without the lock until it runs dry
@@ -380,7 +396,8 @@ bool mp2v_decoder_c::decode(uint8_t* buffer, int len) {
     const auto t_begin = clock_t_::now();
     m->error.clear();
     stream_index_t index;
-    if (!index_stream(buffer, (size_t)len, index)) { m->error = index.error; return false; }
+    if (!index_stream(buffer, (size_t)len, index, m->cfg.num_threads)) { m->error = index.error; return false; }
+    const auto t_indexed = clock_t_::now();
     shared_t sh;
     sh.cfg = m->cfg; sh.opt = m->opt; sh.renderer = m->renderer;
     sh.mbw = m->cfg.width / 16; sh.mbh = m->cfg.height / 16;
@@ -407,6 +424,7 @@ bool mp2v_decoder_c::decode(uint8_t* buffer, int len) {
         pic_task_t& t = p.tasks.back();
         t.src = &pic; t.pipe = &p; t.local_index = (int)p.tasks.size() - 1;
     }
+    const auto t_setup = clock_t_::now();
     std::vector<std::thread> workers;
     {
         int nthreads = m->cfg.num_threads > MAX_NUM_THREADS ? MAX_NUM_THREADS : m->cfg.num_threads;
@@ -423,6 +441,7 @@ bool mp2v_decoder_c::decode(uint8_t* buffer, int len) {
         sh.qcv.notify_all();
         for (auto& w : workers) w.join();
     }
+    const auto t_joined = clock_t_::now();
     m->stats = stats_t();
     for (auto& p : pipes) {
         if (mp2v_recon_sync(p.recon) != MP2V_OK && !sh.failed.load()) sh.fail(std::string("sync: ") + mp2v_recon_last_error(p.recon));
@@ -433,6 +452,15 @@ bool mp2v_decoder_c::decode(uint8_t* buffer, int len) {
         }
     }
     m->stats.parse_cpu_seconds = sh.parse_ns.load() * 1e-9;
+    if (getenv("MP2V_PROFILE")) {
+        auto ms = [](clock_t_::time_point a, clock_t_::time_point b) { return std::chrono::duration<double, std::milli>(b - a).count(); };
+        fprintf(stderr, "[mp2v profile] index %.2f ms  setup %.2f ms  pipeline %.2f ms  drain+stats %.2f ms\n", ms(t_begin, t_indexed), ms(t_indexed, t_setup),
+                ms(t_setup, t_joined), ms(t_joined, clock_t_::now()));
+    }
+    if (getenv("MP2V_PROFILE"))
+        fprintf(stderr, "[mp2v profile] pictures %zu  parse %.1f ms(cpu)  worker idle %.1f ms(sum)  feeder wait %.1f work %.1f ms  precheck %.1f ms  submit(+lock) %.1f ms  output wait %.1f map %.1f ms\n",
+                index.pictures.size(), sh.parse_ns.load() * 1e-6, sh.worker_idle_ns.load() * 1e-6, sh.feeder_wait_ns.load() * 1e-6, sh.feeder_work_ns.load() * 1e-6,
+                sh.precheck_ns.load() * 1e-6, sh.submit_ns.load() * 1e-6, sh.out_wait_ns.load() * 1e-6, sh.out_map_ns.load() * 1e-6);
     m->stats.wall_seconds = std::chrono::duration<double>(clock_t_::now() - t_begin).count();
     if (sh.failed.load()) {
         // pictures may be left acquired / queued inside the contexts: rebuild them on the next call

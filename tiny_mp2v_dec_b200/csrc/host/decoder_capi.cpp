@@ -124,7 +124,7 @@ extern "C" MP2V_API int mp2v_parse_stream(const uint8_t* buffer, int len, int wi
                                           mp2v_parsed_t** out, char* err, size_t err_len) {
     if (!buffer || !out || width <= 0 || height <= 0 || (width & 15) || (height & 15) || cf < 1 || cf > 3) return MP2V_ERR_ARG;
     std::unique_ptr<mp2v_parsed> P(new mp2v_parsed);
-    if (!index_stream(buffer, (size_t)len, P->index)) { set_err(err, err_len, P->index.error); return MP2V_ERR_RANGE; }
+    if (!index_stream(buffer, (size_t)len, P->index, threads)) { set_err(err, err_len, P->index.error); return MP2V_ERR_RANGE; }
     const int mbw = width / 16, mbh = height / 16, nblk = cf == 1 ? 6 : cf == 2 ? 8 : 12;
     struct job_t { int pic, slice; };
     std::vector<job_t> jobs;

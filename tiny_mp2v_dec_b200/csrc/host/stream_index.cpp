@@ -1,19 +1,48 @@
 #include "stream_index.h"
 
+#include <thread>
+
 #include "bitreader.h"
 
 namespace mp2v {
 
-bool index_stream(const uint8_t* buffer, size_t len, stream_index_t& out) {
+// offsets of every start code prefix in [buffer, buffer+len), ascending
+static std::vector<uint32_t> scan_start_codes(const uint8_t* buffer, size_t len, int threads) {
+    const size_t kMinChunk = 256 * 1024;
+    size_t n = threads < 1 ? 1 : (size_t)threads;
+    if (len / kMinChunk + 1 < n) n = len / kMinChunk + 1;
+    std::vector<std::vector<uint32_t>> found(n);
+    auto scan = [&](size_t part) {
+        const size_t lo = len * part / n, hi = len * (part + 1) / n;
+        // a prefix starting in [lo, hi) may extend two bytes past hi; one starting before lo belongs to the previous part
+        const uint8_t* end = buffer + (hi + 2 < len ? hi + 2 : len);
+        for (const uint8_t* p = find_start_code(buffer + lo, end); p + 3 <= end && p < buffer + hi; p = find_start_code(p + 3, end))
+            found[part].push_back((uint32_t)(p - buffer));
+    };
+    std::vector<std::thread> th;
+    for (size_t i = 1; i < n; i++) th.emplace_back(scan, i);
+    scan(0);
+    for (auto& t : th) t.join();
+    std::vector<uint32_t> all;
+    size_t total = 0;
+    for (auto& f : found) total += f.size();
+    all.reserve(total);
+    for (auto& f : found) all.insert(all.end(), f.begin(), f.end());
+    return all;
+}
+
+bool index_stream(const uint8_t* buffer, size_t len, stream_index_t& out, int threads) {
     out.pictures.clear();
     out.error.clear();
     const uint8_t* end = buffer + len;
+    const std::vector<uint32_t> codes = scan_start_codes(buffer, len, threads);
     sequence_info_t seq;
     coded_picture_t* cur = nullptr;
     int gop = 0;
     bool have_picture = false;      // a picture has been seen since the last chain boundary
-    const uint8_t* p = find_start_code(buffer, end);
-    while (p + 4 <= end) {
+    for (size_t ci = 0; ci < codes.size(); ci++) {
+        const uint8_t* p = buffer + codes[ci];
+        if (p + 4 > end) break;
         const int code = p[3];
         const uint8_t* payload = p + 4;
         if (code == 0xB3) {                              // sequence_header
@@ -45,7 +74,6 @@ bool index_stream(const uint8_t* buffer, size_t len, stream_index_t& out) {
         } else if (code == 0xB7 || code == 0xB4) {       // sequence_end / sequence_error
             cur = nullptr;
         }
-        p = find_start_code(p + 3, end);
     }
     out.n_gops = out.pictures.empty() ? 0 : gop + 1;
     for (auto& pic : out.pictures)

@@ -29,7 +29,8 @@ struct stream_index_t {
     std::string error;
 };
 
-// buffer must be followed by >= 64 readable bytes (decode() contract)
-bool index_stream(const uint8_t* buffer, size_t len, stream_index_t& out);
+// buffer must be followed by >= 64 readable bytes (decode() contract).  The start-code scan (the only
+// part that touches every byte) is split over `threads` threads; header parsing stays serial.
+bool index_stream(const uint8_t* buffer, size_t len, stream_index_t& out, int threads = 1);
 
 }  // namespace mp2v
