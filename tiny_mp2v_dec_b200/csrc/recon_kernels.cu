@@ -154,7 +154,7 @@ __device__ __forceinline__ void idct_lane(int& x0, int& x1, int& x2, int& x3, in
         x0 = adds16(v0, v7); x1 = adds16(v1, v6); x2 = adds16(v2, v5); x3 = subs16(v3, v4);
         x4 = adds16(v3, v4); x5 = subs16(v2, v5); x6 = subs16(v1, v6); x7 = subs16(v0, v7);
     } else {
-#define MH(a, c) (((a) * (c)) >> 16)
+#define MH(a, c) __mulhi((a), (c) * 65536)      // (a*c)>>16 as ONE IMAD.HI on the FMA pipe (frees an ALU-pipe shift)
         const int v15 = (MH(x0, 27145) << 1) + (x0 << 1);
         const int v26 = MH(x1, -5037) + (x1 << 2);
         const int v21 = MH(x2, -19954) + (x2 << 2);
@@ -407,11 +407,13 @@ __global__ void __launch_bounds__(kCtaThreads, MP2V_MINCTAS) recon_kernel(const 
     const int mb_begin = (grp * kWarps + warp) * run;
     const int mb_end = min(mb_begin + run, batch.mb_count);
 
+    uint4 rec_next = (mb_begin + lane < mb_end) ? __ldg(reinterpret_cast<const uint4*>(pd.mb) + mb_begin + lane) : make_uint4(0, 0, 0, 0);
     for (int first = mb_begin; first < mb_end;) {
-        // ---- 1. macroblock records of the batch: as many as fit 32 coded blocks
+        // ---- 1. macroblock records of the batch: as many as fit the tile's coded-block slots
+        // (lane i holds macroblock first+i; the records were requested during the previous batch)
         const int idx = first + lane;
         const bool have = idx < mb_end;
-        uint4 rec = have ? __ldg(reinterpret_cast<const uint4*>(pd.mb) + idx) : make_uint4(0, 0, 0, 0);
+        uint4 rec = rec_next;
         const int cnt = have ? __popc(MP2V_MB_CBP(rec.y)) : 0;
         int incl = cnt;
 #pragma unroll
@@ -422,6 +424,8 @@ __global__ void __launch_bounds__(kCtaThreads, MP2V_MINCTAS) recon_kernel(const 
         const int nb = max(__popc(__ballot_sync(0xffffffffu, have && incl <= kSlots)), 1);
         const int base = incl - cnt;
         const int nslots = __shfl_sync(0xffffffffu, incl, nb - 1);
+        // request the next batch's records now; they arrive while this batch is processed
+        rec_next = (idx + nb < mb_end) ? __ldg(reinterpret_cast<const uint4*>(pd.mb) + idx + nb) : make_uint4(0, 0, 0, 0);
 
         // ---- 2. first macroblock's windows start loading now; they land while we dequantise and transform
         {
@@ -453,9 +457,10 @@ __global__ void __launch_bounds__(kCtaThreads, MP2V_MINCTAS) recon_kernel(const 
         if (lane == 0) ws.mb_pre[32] = (uint32_t)total << 8;
         __syncwarp();
         uint32_t parity = 0;                 // bit s = parity of the coefficient sum of tile slot s
-        for (int f0 = 0; f0 < total; f0 += 32) {
-            const int f = f0 + lane;
-            uint32_t pbit = 0;
+        // software pipelined: the record of the NEXT trip is located (binary search) and requested
+        // before the current one is processed, so its global-memory latency is off the critical path
+        auto fetch = [&](int f, uint32_t& c, uint32_t& pre, uint32_t& m_bits) {
+            c = 0; pre = 0; m_bits = 0;
             if (f < total) {
                 int lo = 0, hi = nb;         // last macroblock whose first record index is <= f
 #pragma unroll
@@ -464,8 +469,18 @@ __global__ void __launch_bounds__(kCtaThreads, MP2V_MINCTAS) recon_kernel(const 
                     const bool ge = (int)(ws.mb_pre[mid] >> 8) <= f;
                     lo = ge ? mid : lo; hi = ge ? hi : mid;
                 }
-                const uint32_t pre = ws.mb_pre[lo], m_bits = ws.mb_bits[lo];
-                const uint32_t c = __ldg(pd.coef + ws.mb_off[lo] + (f - (int)(pre >> 8)));
+                pre = ws.mb_pre[lo]; m_bits = ws.mb_bits[lo];
+                c = __ldg(pd.coef + ws.mb_off[lo] + (f - (int)(pre >> 8)));
+            }
+        };
+        uint32_t c_nx, pre_nx, bits_nx;
+        fetch(lane, c_nx, pre_nx, bits_nx);
+        for (int f0 = 0; f0 < total; f0 += 32) {
+            const int f = f0 + lane;
+            const uint32_t c = c_nx, pre = pre_nx, m_bits = bits_nx;
+            fetch(f + 32, c_nx, pre_nx, bits_nx);
+            uint32_t pbit = 0;
+            if (f < total) {
                 const uint32_t cbp = MP2V_MB_CBP(m_bits);
                 const int blk = (c >> 22) & 15;
                 if (cbp >> blk & 1) {        // a record naming an uncoded block is ignored (memory safety)

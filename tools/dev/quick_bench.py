@@ -51,3 +51,8 @@ if __name__ == "__main__":
         run("1080p422 IPB natural", 1920, 1088, 2, seed=1, gop_n=15, gop_m=3, n_gops=4, natural_mean_coefs=5, **NAT)
         run("720p420 IPB natural", 1280, 720, 1, seed=5, gop_n=15, gop_m=3, n_gops=8, natural_mean_coefs=5, **NAT)
         run("4k444 IPB natural", 3840, 2160, 3, seed=4, gop_n=15, gop_m=3, n_gops=2, natural_mean_coefs=5, **NAT)
+    if "--density" in sys.argv:
+        # roofline fraction vs coded-block density (prediction-dominated ... transform-dominated)
+        for pc in (0, 10, 30, 70, 100):
+            run("1080p420 IPB natural coded=%d%%" % pc, 1920, 1088, 1, seed=3, gop_n=15, gop_m=3, n_gops=8, natural_mean_coefs=5, mode=1,
+                pct_coded=pc, pct_intra_in_pb=0 if pc == 0 else 8)
