@@ -54,13 +54,18 @@ constexpr int kBoundLimit = 16 * 30000;
 constexpr int kBoundWild = 1 << 28;       // added when a block must take the fully exact path
 constexpr int kMaxFirstCoef = 3036;       // (3 * 255 * 127) >> 5: largest unclamped pass-1 input the analysis covers
 
+// Window row pitch: 2 data chunks + 1 chunk of padding.  With 48 bytes the 128-bit row reads of 8
+// consecutive rows (a quarter warp) fall into 8 disjoint 4-bank groups (12*r mod 32), i.e. they are
+// bank-conflict free; the natural 32-byte pitch measured 4.1 wavefronts per shared load.
+constexpr int kWinPitch = 48;
+
 template <int CF>
 struct fmt_t {
     static constexpr int NBLK = CF == 1 ? 6 : CF == 2 ? 8 : 12;
     static constexpr int CW = CF == 3 ? 16 : 8;     // chroma macroblock width
     static constexpr int CH = CF == 1 ? 8 : 16;     // chroma macroblock height
-    static constexpr int WIN_LUMA = 17 * 32;        // 17 rows x 2 aligned 16-byte chunks
-    static constexpr int WIN_CHROMA = (CH + 1) * 32;
+    static constexpr int WIN_LUMA = 17 * kWinPitch; // 17 rows x 2 aligned 16-byte chunks (+ 16 B of pitch padding)
+    static constexpr int WIN_CHROMA = (CH + 1) * kWinPitch;
     static constexpr int WIN_DIR = WIN_LUMA + 2 * WIN_CHROMA;
     static constexpr int N_ITEMS = 2 * 17 + 2 * 2 * (CH + 1);   // 16-byte chunks per direction
     static constexpr int N_UNITS = 16 + 2 * CH;                 // output rows per macroblock
@@ -74,7 +79,7 @@ constexpr int kTilePitch = 72;   // int16 per slot: 64 + 8 pad -> 144 B, conflic
 #define MP2V_WINBUF 1      // one window buffer: 29 KB / CTA -> 8 CTAs per SM; two buffers measured 3-6 % slower
 #endif
 #ifndef MP2V_MINCTAS
-#define MP2V_MINCTAS 8
+#define MP2V_MINCTAS 6
 #endif
 constexpr int kSlots = MP2V_SLOTS;   // coded blocks per batch (multiple of 8: the IDCT runs 8 blocks per round)
 constexpr int kWinBuf = MP2V_WINBUF; // 2: the next macroblock's windows load while this one is computed
@@ -242,14 +247,25 @@ __device__ __forceinline__ void idct_round(int16_t* slot_base, int j, bool activ
 
 // ------------------------------------------------------------------------------------------------
 // prediction row: NW words (4 pixels each) of one row of a staged window, realigned from byte offset
-// o, with the reference's half-pel averaging order (mc_c.hpp:3-17)
+// o, with the reference's half-pel averaging order (mc_c.hpp:3-17).  The 32 data bytes of a row come
+// in as two conflict-free 128-bit loads; the word offset (o >> 2) is resolved by a two-level
+// register mux, the byte offset by funnel shifts.
+template <int NW>
+__device__ __forceinline__ void window_words(const uint8_t* win_row, int k, uint32_t (&u)[NW + 1]) {
+    const uint4 a = *reinterpret_cast<const uint4*>(win_row), b = *reinterpret_cast<const uint4*>(win_row + 16);
+    const uint32_t w[8] = {a.x, a.y, a.z, a.w, b.x, b.y, b.z, b.w};
+    uint32_t t[NW + 2];
+#pragma unroll
+    for (int i = 0; i < NW + 2; i++) t[i] = (k & 2) ? w[i + 2] : w[i];
+#pragma unroll
+    for (int i = 0; i <= NW; i++) u[i] = (k & 1) ? t[i + 1] : t[i];
+}
+
 template <int NW>
 __device__ __forceinline__ void pred_row(const uint8_t* win_row, int o, int hx, int hy, uint32_t (&out)[NW]) {
     const int sh = (o & 3) * 8;
-    const uint32_t* p = reinterpret_cast<const uint32_t*>(win_row) + (o >> 2);
     uint32_t w[NW + 1];
-#pragma unroll
-    for (int j = 0; j <= NW; j++) w[j] = p[j];
+    window_words<NW>(win_row, o >> 2, w);
 #pragma unroll
     for (int j = 0; j < NW; j++) out[j] = __funnelshift_rc(w[j], w[j + 1], sh);
     if (hx) {
@@ -258,8 +274,7 @@ __device__ __forceinline__ void pred_row(const uint8_t* win_row, int o, int hx, 
     }
     if (hy) {
         uint32_t b[NW];
-#pragma unroll
-        for (int j = 0; j <= NW; j++) w[j] = p[j + 8];   // next window row (32-byte pitch)
+        window_words<NW>(win_row + kWinPitch, o >> 2, w);   // next window row
 #pragma unroll
         for (int j = 0; j < NW; j++) b[j] = __funnelshift_rc(w[j], w[j + 1], sh);
         if (hx) {
@@ -282,15 +297,21 @@ __device__ __forceinline__ int chroma_mv(int mv, bool halve) { return halve ? (m
 
 __device__ __forceinline__ void cp_async16(void* smem, const void* gmem) {
     const unsigned s = (unsigned)__cvta_generic_to_shared(smem);
-    asm volatile("cp.async.ca.shared.global [%0], [%1], 16;\n" ::"r"(s), "l"(gmem) : "memory");
+    asm volatile("cp.async.cg.shared.global [%0], [%1], 16;\n" ::"r"(s), "l"(gmem) : "memory");   // L2 only: window chunks are not re-read through L1
 }
 __device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;\n" ::: "memory"); }
 template <int N> __device__ __forceinline__ void cp_async_wait() { asm volatile("cp.async.wait_group %0;\n" ::"n"(N) : "memory"); }
 
-// stage the reference windows of one macroblock: aligned 16-byte chunks, 2 per row, (h+1) rows per plane
+// Stage the reference windows of one macroblock: aligned 16-byte chunks, 2 per row, (h+1) rows per
+// plane.  Lane l always copies chunk (l & 1) of row (l >> 1) of some plane, so its source offset inside
+// a plane (lane_off = row * stride + 16 * chunk) is a per-kernel constant and a trip is just
+// "plane base + lane_off -> window + 16 * lane".  Trips: luma rows 0-15; chroma rows 0-15 (4:2:0: Cb
+// rows 0-7 on lanes 0-15, Cr on lanes 16-31); and, only for vertical half-pel vectors, the extra
+// bottom rows.
 template <int CF>
 __device__ __forceinline__ void stage_windows(const pic_desc_t& pd, const batch_desc_t& batch, uint4 m, int mbx, int mby,
-                                              uint8_t* win /* [2][WIN_DIR] */, int lane) {
+                                              uint8_t* win /* [2][WIN_DIR] */, int lane, int lane_off_y, int lane_off_c) {
+    const int lane_woff = (lane >> 1) * kWinPitch + (lane & 1) * 16;      // window position of this lane's chunk
     using F = fmt_t<CF>;
     if (m.y & MP2V_MB_INTRA) return;
 #pragma unroll
@@ -298,19 +319,28 @@ __device__ __forceinline__ void stage_windows(const pic_desc_t& pd, const batch_
         if (!(m.y & (d ? MP2V_MB_BWD : MP2V_MB_FWD))) continue;
         const uint32_t mvw = d ? m.w : m.z;
         const int mvx = (int)(short)(mvw & 0xffffu), mvy = (int)mvw >> 16;
+        const int cx = chroma_mv(mvx, CF < 3), cy = chroma_mv(mvy, CF < 2);
         const uint8_t* const* ref = d ? pd.l1 : pd.l0;
-        for (int j = lane; j < F::N_ITEMS; j += 32) {
-            int p, jj;
-            if (j < 34) { p = 0; jj = j; }
-            else if (j < 34 + 2 * (F::CH + 1)) { p = 1; jj = j - 34; }
-            else { p = 2; jj = j - 34 - 2 * (F::CH + 1); }
-            const int r = jj >> 1, ch = jj & 1;
-            const int cx = p ? chroma_mv(mvx, CF < 3) : mvx, cy = p ? chroma_mv(mvy, CF < 2) : mvy;
-            const int pw = p ? F::CW : 16, ph = p ? F::CH : 16;
-            const int x0 = mbx * pw + (cx >> 1), y0 = mby * ph + (cy >> 1);
-            const uint8_t* src = ref[p] + (size_t)(y0 + r) * batch.stride[p] + (x0 & ~15) + 16 * ch;
-            const int woff = d * F::WIN_DIR + (p == 0 ? 0 : F::WIN_LUMA + (p - 1) * F::WIN_CHROMA) + r * 32 + 16 * ch;
-            cp_async16(win + woff, src);
+        uint8_t* w = win + d * F::WIN_DIR;
+        const int x0 = mbx * 16 + (mvx >> 1), y0 = mby * 16 + (mvy >> 1);
+        const int cx0 = mbx * F::CW + (cx >> 1), cy0 = mby * F::CH + (cy >> 1);
+        const uint8_t* by = ref[0] + (size_t)y0 * batch.stride[0] + (x0 & ~15);
+        const size_t coff = (size_t)cy0 * batch.stride[1] + (cx0 & ~15);
+        const uint8_t* bcb = ref[1] + coff;
+        const uint8_t* bcr = ref[2] + coff;
+        cp_async16(w + lane_woff, by + lane_off_y);                                   // luma rows 0..15
+        if (CF == 1) {
+            const int l = lane & 15;                                                   // Cb rows 0..7 | Cr rows 0..7
+            cp_async16(w + F::WIN_LUMA + (lane >> 4) * F::WIN_CHROMA + (l >> 1) * kWinPitch + (l & 1) * 16, (lane < 16 ? bcb : bcr) + (l >> 1) * batch.stride[1] + (l & 1) * 16);
+        } else {
+            cp_async16(w + F::WIN_LUMA + lane_woff, bcb + lane_off_c);                 // Cb rows 0..15
+            cp_async16(w + F::WIN_LUMA + F::WIN_CHROMA + lane_woff, bcr + lane_off_c); // Cr rows 0..15
+        }
+        if (((mvy | cy) & 1) && lane < 6) {                                            // bottom rows for vertical half-pel
+            const int pl = lane >> 1, ch = lane & 1;
+            const uint8_t* src = pl == 0 ? by + (size_t)16 * batch.stride[0] : (pl == 1 ? bcb : bcr) + (size_t)F::CH * batch.stride[1];
+            uint8_t* dst = w + (pl == 0 ? 16 * kWinPitch : F::WIN_LUMA + (pl - 1) * F::WIN_CHROMA + F::CH * kWinPitch);
+            cp_async16(dst + 16 * ch, src + 16 * ch);
         }
     }
 }
@@ -339,7 +369,7 @@ __device__ __forceinline__ void reconstruct_mb(const pic_desc_t& pd, const batch
                 const int mvx = (int)(short)(mvw & 0xffffu), mvy = (int)mvw >> 16;
                 const int cx = p ? chroma_mv(mvx, CF < 3) : mvx, cy = p ? chroma_mv(mvy, CF < 2) : mvy;
                 const int o = (mbx * pw + (cx >> 1)) & 15;
-                const uint8_t* row = win + d * F::WIN_DIR + (p == 0 ? 0 : F::WIN_LUMA + (p - 1) * F::WIN_CHROMA) + r * 32;
+                const uint8_t* row = win + d * F::WIN_DIR + (p == 0 ? 0 : F::WIN_LUMA + (p - 1) * F::WIN_CHROMA) + r * kWinPitch;
                 uint32_t q[4] = {0, 0, 0, 0};
                 if (wide) pred_row<4>(row, o, cx & 1, cy & 1, q);
                 else { uint32_t q2[2]; pred_row<2>(row, o, cx & 1, cy & 1, q2); q[0] = q2[0]; q[1] = q2[1]; }
@@ -360,19 +390,19 @@ __device__ __forceinline__ void reconstruct_mb(const pic_desc_t& pd, const batch
         else if (CF == 2) bl = 3 + p + ((r >> 3) << 1);
         else { bl = 3 + p + ((r >> 3) << 1); br = bl + 4; }
         const int rr = r & 7;
-        uint32_t out[4];
-        {
-            uint4 res = make_uint4(0, 0, 0, 0);
-            if (cbp >> bl & 1) res = *reinterpret_cast<const uint4*>(&tile[base + __popc(cbp & ((1u << bl) - 1u))][rr * 8]);
+        uint32_t out[4] = {pred[0], pred[1], pred[2], pred[3]};
+        if (cbp >> bl & 1) {
+            const uint4 res = *reinterpret_cast<const uint4*>(&tile[base + __popc(cbp & ((1u << bl) - 1u))][rr * 8]);
             out[0] = add_clip4(pred[0], res.x, res.y);
             out[1] = add_clip4(pred[1], res.z, res.w);
         }
         uint8_t* drow = pd.dst[p] + (size_t)(mby * ph + r) * batch.stride[p] + mbx * pw;
         if (wide) {
-            uint4 res = make_uint4(0, 0, 0, 0);
-            if (cbp >> br & 1) res = *reinterpret_cast<const uint4*>(&tile[base + __popc(cbp & ((1u << br) - 1u))][rr * 8]);
-            out[2] = add_clip4(pred[2], res.x, res.y);
-            out[3] = add_clip4(pred[3], res.z, res.w);
+            if (cbp >> br & 1) {
+                const uint4 res = *reinterpret_cast<const uint4*>(&tile[base + __popc(cbp & ((1u << br) - 1u))][rr * 8]);
+                out[2] = add_clip4(pred[2], res.x, res.y);
+                out[3] = add_clip4(pred[3], res.z, res.w);
+            }
             *reinterpret_cast<uint4*>(drow) = make_uint4(out[0], out[1], out[2], out[3]);
         } else {
             *reinterpret_cast<uint2*>(drow) = make_uint2(out[0], out[1]);
@@ -403,6 +433,8 @@ __global__ void __launch_bounds__(kCtaThreads, MP2V_MINCTAS) recon_kernel(const 
 
     warp_smem_t<CF>& ws = s.w[warp];
     const int mbw = batch.mbw;
+    const int lane_off_y = (lane >> 1) * batch.stride[0] + (lane & 1) * 16;     // window staging: row lane/2, chunk lane&1
+    const int lane_off_c = (lane >> 1) * batch.stride[1] + (lane & 1) * 16;
     const int run = batch.mbs_per_warp;
     const int mb_begin = (grp * kWarps + warp) * run;
     const int mb_end = min(mb_begin + run, batch.mb_count);
@@ -428,11 +460,11 @@ __global__ void __launch_bounds__(kCtaThreads, MP2V_MINCTAS) recon_kernel(const 
         rec_next = (idx + nb < mb_end) ? __ldg(reinterpret_cast<const uint4*>(pd.mb) + idx + nb) : make_uint4(0, 0, 0, 0);
 
         // ---- 2. first macroblock's windows start loading now; they land while we dequantise and transform
+        const int mby0 = first / mbw, mbx0 = first - mby0 * mbw;      // the only division per batch
         {
-            const int mby0 = first / mbw, mbx0 = first - mby0 * mbw;
             const uint4 m0 = make_uint4(__shfl_sync(0xffffffffu, rec.x, 0), __shfl_sync(0xffffffffu, rec.y, 0),
                                         __shfl_sync(0xffffffffu, rec.z, 0), __shfl_sync(0xffffffffu, rec.w, 0));
-            stage_windows<CF>(pd, batch, m0, mbx0, mby0, &ws.win[0][0][0], lane);
+            stage_windows<CF>(pd, batch, m0, mbx0, mby0, &ws.win[0][0][0], lane, lane_off_y, lane_off_c);
             cp_async_commit();
         }
 
@@ -526,28 +558,28 @@ __global__ void __launch_bounds__(kCtaThreads, MP2V_MINCTAS) recon_kernel(const 
 
         // ---- 5. prediction + residual + clip + store; with two window buffers the next macroblock's
         // windows load while this one is computed
+        int mbx = mbx0, mby = mby0;
         for (int mi = 0; mi < nb; mi++) {
             const uint4 m = make_uint4(__shfl_sync(0xffffffffu, rec.x, mi), __shfl_sync(0xffffffffu, rec.y, mi),
                                        __shfl_sync(0xffffffffu, rec.z, mi), __shfl_sync(0xffffffffu, rec.w, mi));
             const int mbase = __shfl_sync(0xffffffffu, base, mi);
-            const int mbi = first + mi;
-            const int mby = mbi / mbw, mbx = mbi - mby * mbw;
             if (kWinBuf == 2) {
                 if (mi + 1 < nb) {
                     const uint4 mn = make_uint4(__shfl_sync(0xffffffffu, rec.x, mi + 1), __shfl_sync(0xffffffffu, rec.y, mi + 1),
                                                 __shfl_sync(0xffffffffu, rec.z, mi + 1), __shfl_sync(0xffffffffu, rec.w, mi + 1));
-                    const int nby = (mbi + 1) / mbw, nbx = (mbi + 1) - nby * mbw;
-                    stage_windows<CF>(pd, batch, mn, nbx, nby, &ws.win[(mi + 1) & (kWinBuf - 1)][0][0], lane);
+                    const int nbx = mbx + 1 == mbw ? 0 : mbx + 1, nby = mbx + 1 == mbw ? mby + 1 : mby;
+                    stage_windows<CF>(pd, batch, mn, nbx, nby, &ws.win[(mi + 1) & (kWinBuf - 1)][0][0], lane, lane_off_y, lane_off_c);
                 }
                 cp_async_commit();
                 cp_async_wait<1>();      // everything but the group just committed has landed: this macroblock's windows
             } else {
-                if (mi > 0) { stage_windows<CF>(pd, batch, m, mbx, mby, &ws.win[0][0][0], lane); cp_async_commit(); }
+                if (mi > 0) { stage_windows<CF>(pd, batch, m, mbx, mby, &ws.win[0][0][0], lane, lane_off_y, lane_off_c); cp_async_commit(); }
                 cp_async_wait<0>();
             }
             __syncwarp();
             reconstruct_mb<CF>(pd, batch, m, mbx, mby, mbase, &ws.win[mi & (kWinBuf - 1)][0][0], ws.tile, lane);
             __syncwarp();
+            if (++mbx == mbw) { mbx = 0; mby++; }
         }
         cp_async_wait<0>();
         first += nb;
