@@ -250,8 +250,24 @@ __device__ __forceinline__ void idct_round(int16_t* slot_base, int j, bool activ
 // o, with the reference's half-pel averaging order (mc_c.hpp:3-17).  The 32 data bytes of a row come
 // in as two conflict-free 128-bit loads; the word offset (o >> 2) is resolved by a two-level
 // register mux, the byte offset by funnel shifts.
+// _mm_avg_epu8 on 4 packed bytes: (a + b + 1) >> 1 = (a | b) - (((a ^ b) & 0xfe..) >> 1), 4 ops (LOP3 fuses xor+and)
+__device__ __forceinline__ uint32_t avg4(uint32_t a, uint32_t b) {
+    uint32_t t;
+    asm("lop3.b32 %0, %1, %2, 0xfefefefe, 0x28;" : "=r"(t) : "r"(a), "r"(b));    // (a ^ b) & c
+    return (a | b) - (t >> 1);
+}
+
+#ifndef MP2V_WINREAD128
+#define MP2V_WINREAD128 0
+#endif
 template <int NW>
 __device__ __forceinline__ void window_words(const uint8_t* win_row, int k, uint32_t (&u)[NW + 1]) {
+    if (!MP2V_WINREAD128) {     // NW+1 32-bit loads at the dynamic word offset (at most 2-way conflicts with the 48-byte pitch)
+        const uint32_t* p = reinterpret_cast<const uint32_t*>(win_row) + k;
+#pragma unroll
+        for (int i = 0; i <= NW; i++) u[i] = p[i];
+        return;
+    }
     const uint4 a = *reinterpret_cast<const uint4*>(win_row), b = *reinterpret_cast<const uint4*>(win_row + 16);
     const uint32_t w[8] = {a.x, a.y, a.z, a.w, b.x, b.y, b.z, b.w};
     uint32_t t[NW + 2];
@@ -270,7 +286,7 @@ __device__ __forceinline__ void pred_row(const uint8_t* win_row, int o, int hx, 
     for (int j = 0; j < NW; j++) out[j] = __funnelshift_rc(w[j], w[j + 1], sh);
     if (hx) {
 #pragma unroll
-        for (int j = 0; j < NW; j++) out[j] = __vavgu4(out[j], __funnelshift_rc(w[j], w[j + 1], sh + 8));
+        for (int j = 0; j < NW; j++) out[j] = avg4(out[j], __funnelshift_rc(w[j], w[j + 1], sh + 8));
     }
     if (hy) {
         uint32_t b[NW];
@@ -279,10 +295,10 @@ __device__ __forceinline__ void pred_row(const uint8_t* win_row, int o, int hx, 
         for (int j = 0; j < NW; j++) b[j] = __funnelshift_rc(w[j], w[j + 1], sh);
         if (hx) {
 #pragma unroll
-            for (int j = 0; j < NW; j++) b[j] = __vavgu4(b[j], __funnelshift_rc(w[j], w[j + 1], sh + 8));
+            for (int j = 0; j < NW; j++) b[j] = avg4(b[j], __funnelshift_rc(w[j], w[j + 1], sh + 8));
         }
 #pragma unroll
-        for (int j = 0; j < NW; j++) out[j] = __vavgu4(out[j], b[j]);
+        for (int j = 0; j < NW; j++) out[j] = avg4(out[j], b[j]);
     }
 }
 
@@ -375,7 +391,7 @@ __device__ __forceinline__ void reconstruct_mb(const pic_desc_t& pd, const batch
                 else { uint32_t q2[2]; pred_row<2>(row, o, cx & 1, cy & 1, q2); q[0] = q2[0]; q[1] = q2[1]; }
                 if (have) {
 #pragma unroll
-                    for (int j = 0; j < 4; j++) pred[j] = __vavgu4(q[j], pred[j]);   // bidirectional rounding average
+                    for (int j = 0; j < 4; j++) pred[j] = avg4(q[j], pred[j]);   // bidirectional rounding average
                 } else {
 #pragma unroll
                     for (int j = 0; j < 4; j++) pred[j] = q[j];
