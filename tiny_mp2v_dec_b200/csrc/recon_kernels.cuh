@@ -23,7 +23,7 @@ inline int choose_mbs_per_warp(int cf, long long total_mbs) {
     const int unit = MP2V_SLOTS / (cf == 1 ? 6 : cf == 2 ? 8 : 12);
     long long run = total_mbs / ((long long)MP2V_WAVES * 148 * 8 * 4);
     if (run > 60) run = 60;
-    if (run < 2 * unit) run = 2 * unit;
+    if (run < unit) run = unit;          // small launches (one picture): as many CTAs as possible
     return (int)(run / unit * unit);
 }
 
