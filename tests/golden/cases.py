@@ -9,6 +9,7 @@ CASES = {
     "sd422_longmv": (720, 480, 2, dict(seed=107, gop_n=7, gop_m=3, mv_range=120, pct_skipped=30)),
     "tiny420_m1": (48, 32, 1, dict(seed=108, gop_n=10, gop_m=1)),
     "natural420": (640, 368, 1, dict(seed=109, mode=1, n_gops=2, gop_n=15, gop_m=3)),
+    "tall420_vpos_ext": (32, 2816, 1, dict(seed=112, gop_n=4, gop_m=3)),
     "hd420_ipb": (1920, 1088, 1, dict(seed=110, gop_n=7, gop_m=3)),
     "hd422_ipb": (1920, 1088, 2, dict(seed=111, gop_n=4, gop_m=3)),
 }

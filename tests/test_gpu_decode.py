@@ -122,3 +122,20 @@ def test_gop_sharding_over_two_devices():
     assert got == want
     one = Decoder(352, 288, 1, num_threads=4, devices=(1,)).decode(s.padded, s.size)
     assert one == want
+
+
+def test_empty_stream_decodes_to_nothing():
+    d = Decoder(64, 48, 1, num_threads=2)
+    assert d.decode(np.zeros(512, np.uint8), 0) == b""
+    assert d.stats.frames == 0 and d.stats.launches == 0
+    s = Stream(64, 48, 1, seed=66, gop_n=1, gop_m=1)     # a single I picture right after
+    assert d.decode(s.padded, s.size) == O.oracle_decode_stream(s)
+
+
+def test_decoder_is_reusable_and_deterministic():
+    s1 = Stream(176, 144, 2, seed=67, gop_n=6, gop_m=3)
+    s2 = Stream(176, 144, 2, seed=68, n_gops=2, gop_n=5, gop_m=2)
+    d = Decoder(176, 144, 2, num_threads=3)
+    a1, a2, a3 = d.decode(s1.padded, s1.size), d.decode(s2.padded, s2.size), d.decode(s1.padded, s1.size)
+    assert a1 == a3 == O.oracle_decode_stream(s1)
+    assert a2 == O.oracle_decode_stream(s2)

@@ -62,3 +62,31 @@ def test_parser_rejects_garbage():
     bad[start + 6:start + 40] = 0xFF
     with pytest.raises(ReconError):
         parse_stream(bad, s.size, 64, 48, 1)
+
+
+def test_empty_and_header_only_streams():
+    """ragged inputs: nothing, padding only, headers without pictures -> zero pictures, no error"""
+    s = Stream(64, 48, 1, seed=9, gop_n=2, gop_m=1)
+    for blob in (np.zeros(0, np.uint8), np.zeros(100, np.uint8), s.padded[:int(np.nonzero(s.padded[3:] == 0x00)[0][0])][:40]):
+        padded = np.concatenate([np.asarray(blob, np.uint8), np.zeros(256, np.uint8)])
+        pics, _, _, n = parse_stream(padded, len(blob), 64, 48, 1)
+        assert n == 0 and pics == []
+
+
+def test_truncated_stream_is_an_error_or_a_prefix():
+    """a stream cut in the middle of a slice must not crash: either the cut slice is rejected or the
+    pictures before it come out intact"""
+    from tiny_mp2v_dec_b200.recon import ReconError
+    s = Stream(176, 144, 1, seed=10, gop_n=4, gop_m=1)
+    cut = s.size * 2 // 3
+    padded = np.concatenate([s.padded[:cut], np.zeros(256, np.uint8)])
+    try:
+        pics, _, _, n = parse_stream(padded, cut, 176, 144, 1)
+        assert 1 <= n <= 4
+    except ReconError:
+        pass
+
+
+def test_tall_picture_uses_slice_vertical_position_extension():
+    """vertical_size > 2800: slices carry slice_vertical_position_extension (mp2v_hdr.h:347-348)"""
+    check_stream(Stream(32, 2816, 1, seed=12, gop_n=3, gop_m=3), threads=2)
