@@ -249,12 +249,12 @@ def oracle_port_fps(stream, n=4):
 
 # ------------------------------------------------------------------------------------------------ our arm
 
-def measure_resident(wl, stream, steps, warmup, device):
+def measure_resident(wl, stream, steps, warmup, device, world=1):
     """value + roofline: records parsed by the product's host parser, uploaded once, reconstructed K times"""
     from tiny_mp2v_dec_b200.decoder import parse_stream
     from tiny_mp2v_dec_b200.recon import Recon
     w, h, cf = wl["width"], wl["height"], wl["chroma_format"]
-    pics, parse_wall, parse_cpu, n = parse_stream(stream.padded, stream.size, w, h, cf, threads=host_threads(1))
+    pics, parse_wall, parse_cpu, n = parse_stream(stream.padded, stream.size, w, h, cf, threads=host_threads(world))
     r = Recon(w, h, cf, n_frames=n, n_pictures=n, device=device, max_batch=32, flags=1)
     hnds = []
     for i, p in enumerate(pics):
@@ -350,7 +350,7 @@ def main():
     # every rank decodes its own shard: the N-GPU job is N x the GOPs (closed GOPs g = rank mod N)
     stream = make_stream(wl, rank)
     n_frames = len(stream.pictures)
-    r, hnds, levels, n, parse_info = measure_resident(wl, stream, args.steps, args.warmup, local)
+    r, hnds, levels, n, parse_info = measure_resident(wl, stream, args.steps, args.warmup, local, world)
 
     # ---- value: K steps, device time on the launching stream
     sampler = ClockSampler(local)

@@ -115,7 +115,7 @@ class Decoder:
         cap = 0
         if want_output and download:
             # upper bound: every picture start code yields one frame
-            n_pics = int(np.count_nonzero((buf[:size - 3] == 0) & (buf[1:size - 2] == 0) & (buf[2:size - 1] == 1) & (buf[3:size] == 0)))
+            n_pics = 0 if size < 4 else int(np.count_nonzero((buf[:size - 3] == 0) & (buf[1:size - 2] == 0) & (buf[2:size - 1] == 1) & (buf[3:size] == 0)))
             cap = n_pics * frame_bytes(self.p.width, self.p.height, self.p.chroma_format)
             out = np.empty(max(cap, 1), np.uint8)
         nbytes = C.c_size_t()
