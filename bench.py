@@ -63,6 +63,17 @@ def log(*a):
     print(*a, file=sys.stderr, flush=True)
 
 
+def measured_traffic(workload, pictures_per_launch):
+    """DRAM bytes per launch of the dominant kernel from the committed ncu --set full capture
+    (profiles/r1_traffic.json), scaled to this run's average launch size; None when no capture exists."""
+    try:
+        t = json.load(open(os.path.join(ROOT, "profiles", "r1_traffic.json")))[workload]
+        per_picture = (t["dram_read_bytes"] + t["dram_write_bytes"]) / t["pictures_in_launch"]
+        return round(per_picture * pictures_per_launch)
+    except Exception:
+        return None
+
+
 def measured_peak():
     try:
         d = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))
@@ -361,7 +372,6 @@ def main():
         r.run_resident(hnds, levels)
     dev_ms = r.timer_stop()
     barrier()
-    clocks = sampler.stop()
     st = r.stats()
     t_ms = max_over_ranks(dev_ms)
     total_frames = sum_over_ranks(float(n_frames)) * args.steps
@@ -388,6 +398,7 @@ def main():
     torch.cuda.synchronize()
     e2e_s = max_over_ranks(time.perf_counter() - t0)
     barrier()
+    clocks = sampler.stop()          # sampled across both timed regions (the resident steps alone last a few ms)
     e2e_value = total_frames / e2e_s
     h2d = sum(s[0] for s in e2e_stats) / len(e2e_stats)
     d2h = sum(s[1] for s in e2e_stats) / len(e2e_stats)
@@ -434,7 +445,7 @@ def main():
                            (n_frames * (wl["width"] * wl["height"] * {1: 1.5, 2: 2, 3: 3}[wl["chroma_format"]]) + parse_info["record_bytes"]) / 1e6)},
             "mpixel_per_s": round(value * wl["width"] * wl["height"] / 1e6, 1),
             "roofline": {"bound": "hbm", "achieved": round(achieved, 1), "peak": peak, "unit": "GB/s", "frac": round(achieved / peak, 4),
-                         "traffic": None, "peak_source": peak_src, "kernel": "recon_kernel<%d>" % wl["chroma_format"],
+                         "traffic": measured_traffic(args.workload, n_frames * args.steps / launches), "peak_source": peak_src, "kernel": "recon_kernel<%d>" % wl["chroma_format"],
                          "algorithmic_bytes_per_launch": round(alg_per_launch), "launch_ms": round(kernel_ms / launches, 4)},
             "e2e": {"value": round(e2e_value, 1), "unit": "frames/s", "h2d_bytes_per_step": int(h2d), "d2h_bytes_per_step": int(d2h),
                     "host_threads": threads, "host_parse_cpu_s_per_step": round(parse_cpu, 4),

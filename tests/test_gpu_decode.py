@@ -139,3 +139,29 @@ def test_decoder_is_reusable_and_deterministic():
     a1, a2, a3 = d.decode(s1.padded, s1.size), d.decode(s2.padded, s2.size), d.decode(s1.padded, s1.size)
     assert a1 == a3 == O.oracle_decode_stream(s1)
     assert a2 == O.oracle_decode_stream(s2)
+
+
+def test_bench_workload_full_size_consistency():
+    """BASELINE.json full size (1080p, the bench's own stream parameters, 2 GOPs of each workload): the two
+    product paths -- records reconstructed resident on the device, and the whole decoder from the
+    elementary stream -- must agree frame for frame (a checksum of per-frame checksums), and both must equal
+    the oracle on the first GOP."""
+    import hashlib
+    import os
+    import sys
+    sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+    import bench
+    from tiny_mp2v_dec_b200.recon import reconstruct_stream
+    for name in ("1080p420_intra", "1080p420_ipb"):
+        wl = bench.WORKLOADS[name]
+        g = dict(wl["gen"], n_gops=2)
+        s = Stream(wl["width"], wl["height"], wl["chroma_format"], seed=wl["config_id"], **g)
+        fb = frame_bytes(wl["width"], wl["height"], wl["chroma_format"])
+        a = Decoder(wl["width"], wl["height"], wl["chroma_format"], num_threads=8).decode(s.padded, s.size)
+        b = reconstruct_stream(s)
+        sums = lambda y: hashlib.sha256(b"".join(hashlib.sha256(y[i:i + fb]).digest() for i in range(0, len(y), fb))).hexdigest()
+        assert len(a) == len(b) == fb * len(s.pictures)
+        assert sums(a) == sums(b)
+        first = Stream(wl["width"], wl["height"], wl["chroma_format"], seed=wl["config_id"], **dict(g, n_gops=1))
+        want = O.oracle_decode_stream(first)
+        assert a[:len(want)] == want
