@@ -7,16 +7,29 @@
 #include <cstdint>
 #include <cstring>
 
+#ifdef __CUDACC__
+#define MP2V_HD __host__ __device__
+#else
+#define MP2V_HD
+#endif
+
 namespace mp2v {
 
 class bitreader_t {
 public:
     bitreader_t() = default;
-    explicit bitreader_t(const uint8_t* p) { reset(p); }
-    void reset(const uint8_t* p) { ptr_ = p; buf_ = 0; cnt_ = 0; refill(); }
+    MP2V_HD explicit bitreader_t(const uint8_t* p) { reset(p); }
+    MP2V_HD void reset(const uint8_t* p) { ptr_ = p; buf_ = 0; cnt_ = 0; refill(); }
 
     // make at least 56 bits available
-    inline void refill() {
+    MP2V_HD inline void refill() {
+#ifdef __CUDA_ARCH__
+        // device: byte loads through the read-only path (a thread walks its own slice; lines stay in L1)
+        while (cnt_ <= 56) {
+            buf_ |= (uint64_t)__ldg(ptr_++) << (56 - cnt_);
+            cnt_ += 8;
+        }
+#else
         uint64_t w;
         memcpy(&w, ptr_, 8);
         w = __builtin_bswap64(w);
@@ -24,16 +37,17 @@ public:
         const int adv = (63 - cnt_) >> 3;
         ptr_ += adv;
         cnt_ += adv << 3;
+#endif
     }
     // n in 1..32; valid after refill() as long as no more than 56 bits were consumed since
-    inline uint32_t peek(int n) const { return (uint32_t)(buf_ >> (64 - n)); }
-    inline uint32_t peek32() const { return (uint32_t)(buf_ >> 32); }
-    inline int bits_left() const { return cnt_; }
-    inline void skip(int n) { buf_ <<= n; cnt_ -= n; }
-    inline uint32_t get(int n) { refill(); const uint32_t v = peek(n); skip(n); return v; }
-    inline uint32_t get1() { refill(); const uint32_t v = (uint32_t)(buf_ >> 63); skip(1); return v; }
+    MP2V_HD inline uint32_t peek(int n) const { return (uint32_t)(buf_ >> (64 - n)); }
+    MP2V_HD inline uint32_t peek32() const { return (uint32_t)(buf_ >> 32); }
+    MP2V_HD inline int bits_left() const { return cnt_; }
+    MP2V_HD inline void skip(int n) { buf_ <<= n; cnt_ -= n; }
+    MP2V_HD inline uint32_t get(int n) { refill(); const uint32_t v = peek(n); skip(n); return v; }
+    MP2V_HD inline uint32_t get1() { refill(); const uint32_t v = (uint32_t)(buf_ >> 63); skip(1); return v; }
     // position of the next unread bit, in bytes from `base` (rounded down)
-    inline const uint8_t* byte_pos() const { return ptr_ - ((cnt_ + 7) >> 3); }
+    MP2V_HD inline const uint8_t* byte_pos() const { return ptr_ - ((cnt_ + 7) >> 3); }
 
 private:
     const uint8_t* ptr_ = nullptr;

@@ -69,6 +69,11 @@ struct slice_result_t {
 slice_result_t parse_slice(const uint8_t* payload, int slice_start_code, const sequence_info_t& seq, const picture_info_t& pic,
                            int mbw, int mbh, mp2v_mb_info_t* mb, coef_arena_t& arena);
 
+// the POD view of the headers that the shared slice core (slice_core.h) and the GPU-side parser take
+struct slice_syntax_t;
+slice_syntax_t make_slice_syntax(const sequence_info_t& seq, const picture_info_t& pic, int mbw, int mbh);
+bool picture_in_envelope(const picture_info_t& pic);
+
 // locate the next start code prefix (00 00 01) in [p, end); returns end if none
 const uint8_t* find_start_code(const uint8_t* p, const uint8_t* end);
 

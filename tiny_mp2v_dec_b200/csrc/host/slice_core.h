@@ -1,0 +1,293 @@
+// Slice-layer syntax parser shared by the host (mp2v_parser.cpp) and the device (csrc/vlc_kernel.cu).
+//
+// One function, parse_slice_core(), walks one slice (ISO/IEC 13818-2 6.2.4-6.2.6, frame pictures with
+// frame prediction: the reference's envelope) and writes reconstruction records (include/mp2v_recon.h):
+// a macroblock record per macroblock of the slice's row and the coefficient records behind `out`.
+// It is the re-cut of the reference's parse_macroblock_template / parse_block (mb_decoder.cpp:74-155,
+// 521-641): everything that is serial inside a slice -- VLC decoding, intra DC prediction
+// (mb_decoder.cpp:46-72), motion vector prediction (:447-519, 580-604), quantiser_scale tracking
+// (:555-563), skipped-macroblock resolution (:541-550) -- and nothing that touches pixels.
+// The same source compiled for both sides is what keeps the two parsers bit-identical.
+#pragma once
+#include <cstdint>
+#include <cstring>
+
+#include "bitreader.h"
+#include "mp2v_recon.h"
+#include "vlc_decode.h"
+
+namespace mp2v {
+
+// what the slice layer needs of the picture / sequence headers (POD: also passed to the GPU)
+struct slice_syntax_t {
+    int32_t picture_coding_type;      // 1 I, 2 P, 3 B
+    int32_t f_code[2][2];
+    int32_t intra_dc_precision;
+    int32_t q_scale_type;
+    int32_t intra_vlc_format;
+    int32_t chroma_format;            // 1, 2, 3
+    int32_t vertical_size;            // > 2800: slices carry slice_vertical_position_extension
+    int32_t mbw, mbh;
+};
+
+enum slice_error_t {
+    SLICE_OK = 0, SLICE_ERR_ROW, SLICE_ERR_MBA, SLICE_ERR_ADDRESS, SLICE_ERR_SKIP_IN_I, SLICE_ERR_MBTYPE, SLICE_ERR_FCODE,
+    SLICE_ERR_MOTION, SLICE_ERR_CBP, SLICE_ERR_COEF, SLICE_ERR_CAPACITY, SLICE_ERR_MV_RANGE
+};
+
+inline const char* slice_error_string(int e) {
+    switch (e) {
+        case SLICE_OK: return "ok";
+        case SLICE_ERR_ROW: return "slice row outside the picture";
+        case SLICE_ERR_MBA: return "bad macroblock_address_increment";
+        case SLICE_ERR_ADDRESS: return "macroblock address past the end of the row";
+        case SLICE_ERR_SKIP_IN_I: return "skipped macroblock in an I picture";
+        case SLICE_ERR_MBTYPE: return "bad macroblock_type";
+        case SLICE_ERR_FCODE: return "f_code out of range";
+        case SLICE_ERR_MOTION: return "bad motion_code";
+        case SLICE_ERR_CBP: return "bad coded_block_pattern";
+        case SLICE_ERR_COEF: return "bad DCT coefficient syntax";
+        case SLICE_ERR_CAPACITY: return "coefficient arena exhausted";
+        case SLICE_ERR_MV_RANGE: return "motion vector points outside the reference frame";
+        default: return "slice parse error";
+    }
+}
+
+#if defined(__CUDACC__)
+#define MP2V_HDI __host__ __device__ __forceinline__
+#else
+#define MP2V_HDI inline __attribute__((always_inline))
+#endif
+
+MP2V_HDI int quantiser_scale_of(int code, int q_scale_type) {   // decoder.cpp:140-145, mb_decoder.cpp:555-563
+    if (!q_scale_type) return code << 1;
+    if (code < 9) return code;
+    if (code < 17) return (code - 4) << 1;
+    if (code < 25) return (code - 10) << 2;
+    return (code - 17) << 3;
+}
+
+// Everything below works on the caller's LOCAL bit reader and write cursor, passed by reference into
+// always-inlined helpers, so that both live in registers for the whole slice.
+
+// one motion vector component, mb_decoder.cpp:447-503
+MP2V_HDI bool decode_mv_component(bitreader_t& br, const vlc_decode_tables_t& T, int f_code, int& pmv, int& out) {
+    br.refill();
+    const vlc_entry_t e = T.motion.look(br.peek(10));
+    if (!e.len) return false;
+    br.skip(e.len);
+    int delta = 0;
+    if (e.val) {
+        const int neg = (int)br.peek(1);
+        br.skip(1);
+        const int r_size = f_code - 1;
+        delta = e.val;
+        if (r_size) { delta = ((e.val - 1) << r_size) + (int)br.peek(r_size) + 1; br.skip(r_size); }
+        if (neg) delta = -delta;
+    }
+    const int f16 = 16 << (f_code - 1);
+    int v = pmv + delta;
+    if (v < -f16) v += 2 * f16;
+    if (v > f16 - 1) v -= 2 * f16;
+    pmv = v; out = v;
+    return true;
+}
+
+// one block: DC (intra) + run/level list; returns false on a syntax error
+MP2V_HDI bool parse_block(bitreader_t& br, mp2v_coef_t*& out, const vlc_decode_tables_t& T, const slice_syntax_t& sx,
+                          uint16_t (&dc_pred)[3], int b, bool intra) {
+    const uint32_t blk_bits = (uint32_t)b << 22;
+    int i = 0;
+    const coef_vlc_t* table = &T.b14;
+    br.refill();
+    if (intra) {
+        const int comp = b < 4 ? 0 : 1 + (b & 1);
+        int diff;
+        const dc_fast_t f = T.dc_fast[comp ? 1 : 0][br.peek(kDcFastBits)];
+        if (f.len != 0) { br.skip(f.len); diff = f.diff; }
+        else {
+            const vlc_entry_t e = T.dcsize[comp ? 1 : 0].look(br.peek(10));
+            if (!e.len) return false;
+            br.skip(e.len);
+            const int v = (int)br.peek(e.val);                 // here size >= 1 (size 0 always fits the fast table)
+            br.skip(e.val);
+            const int half = 1 << (e.val - 1);
+            diff = v >= half ? v : v + 1 - 2 * half;           // mb_decoder.cpp:59-68
+        }
+        dc_pred[comp] = (uint16_t)(dc_pred[comp] + diff);
+        const int16_t dc = (int16_t)(uint16_t)((uint32_t)dc_pred[comp] << (3 - sx.intra_dc_precision));
+        *out++ = MP2V_COEF(dc, 0, b, MP2V_COEF_RAW);
+        i = 1;
+        if (sx.intra_vlc_format) table = &T.b15;
+        br.refill();
+    } else if (br.peek(1)) {                                   // first coefficient "1s" (mb_decoder.cpp:79-88)
+        const int neg = (int)br.peek(2) & 1;
+        br.skip(2);
+        *out++ = MP2V_COEF(neg ? -1 : 1, 0, b, MP2V_COEF_FIRST);
+        i = 1;
+    }
+    const coef_fast_t* fast = table->fast;
+    for (;;) {
+        // one refill (>= 56 bits) covers two symbols of any kind (escape = 24 bits); the first round
+        // reuses the refill above (at most 22 bits were consumed since)
+#pragma unroll 2
+        for (int rep = 0; rep < 2; rep++) {
+            const coef_fast_t f = fast[br.peek(kFastBits)];
+            int run, level;
+            if (f.run < kFastEob) {
+                br.skip(f.len);
+                run = f.run; level = f.level;
+            } else if (f.run == kFastEob) {
+                br.skip(f.len);
+                return true;
+            } else {
+                const coef_entry_t e = table->look(br.peek(17));
+                if (e.level > 0) {
+                    br.skip(e.len);
+                    const int neg = (int)br.peek(1);
+                    br.skip(1);
+                    run = e.run;
+                    level = (e.level ^ -neg) + neg;
+                } else if (e.level == kCoefEob && e.len) {
+                    br.skip(e.len);
+                    return true;
+                } else if (e.level == kCoefEsc && e.len) {     // 6-bit run, 12-bit two's complement level
+                    br.skip(6);
+                    run = (int)br.peek(6); br.skip(6);
+                    level = ((int)br.peek(12) ^ 0x800) - 0x800; br.skip(12);
+                } else {
+                    return false;
+                }
+            }
+            i += run;
+            if (i > 63) return false;
+            *out++ = (uint32_t)(uint16_t)level | ((uint32_t)i << 16) | blk_bits;
+            i++;
+        }
+        br.refill();
+    }
+}
+
+// Parse one slice.  payload = first byte after the 4-byte start code.  Macroblock records go to
+// mb[row * mbw + x]; coefficient records to out_base[0 ...] with coef_off = coef_off_base + index.
+// Returns a slice_error_t; *n_out = coefficient records written, [*first_mbx, *last_mbx] = the
+// macroblocks of the row this slice wrote.
+MP2V_HDI int parse_slice_core(const uint8_t* payload, int slice_start_code, const slice_syntax_t& sx, const vlc_decode_tables_t& T,
+                              mp2v_mb_info_t* mb, mp2v_coef_t* out_base, uint32_t coef_off_base,
+                              uint32_t* n_out, int* first_mbx_out, int* last_mbx_out, int* mb_row_out) {
+    const int cf = sx.chroma_format, mbw = sx.mbw;
+    const int nblk = cf == 1 ? 6 : cf == 2 ? 8 : 12;
+    mp2v_coef_t* out = out_base;
+    bitreader_t br(payload);
+    int pmv[2][2] = {{0, 0}, {0, 0}};
+    uint16_t dc_pred[3];
+    const uint16_t dc_reset = (uint16_t)(1u << (sx.intra_dc_precision + 7));
+    dc_pred[0] = dc_pred[1] = dc_pred[2] = dc_reset;
+    int mb_row = slice_start_code - 1;
+    if (sx.vertical_size > 2800) mb_row += (int)br.get(3) << 7;        // slice_vertical_position_extension
+    *n_out = 0; *first_mbx_out = 0; *last_mbx_out = -1; *mb_row_out = mb_row;
+    if (mb_row < 0 || mb_row >= sx.mbh) return SLICE_ERR_ROW;
+    int qscale = quantiser_scale_of((int)br.get(5), sx.q_scale_type);
+    if (br.get1()) {                                                    // intra_slice_flag (mp2v_hdr.h:352-360)
+        br.get(8);
+        while (br.get1()) br.get(8);
+    }
+    const int pct = sx.picture_coding_type;
+    mp2v_mb_info_t* row = mb + (size_t)mb_row * mbw;
+    uint32_t prev_dirs = 0;
+    int mbx = -1, first_mbx = 0;
+    bool first = true;
+    int err = SLICE_OK;
+    do {
+        // ---- macroblock_address_increment (+ escapes)
+        int inc = 0;
+        for (;;) {
+            br.refill();
+            const vlc_entry_t e = T.mba.look(br.peek(11));
+            if (!e.len) { err = SLICE_ERR_MBA; break; }
+            br.skip(e.len);
+            if (e.val) { inc += e.val; break; }
+            inc += 33;
+        }
+        if (err) break;
+        // first macroblock of a slice: the increment is its column (6.3.16); later ones: inc-1 skipped
+        const int target = first ? inc - 1 : mbx + inc;
+        if (target >= mbw) { err = SLICE_ERR_ADDRESS; break; }
+        const int skipped = first ? 0 : inc - 1;
+        if (first) { mbx = target - 1; first_mbx = target; first = false; }
+        // ---- skipped macroblocks (mb_decoder.cpp:541-550)
+        if (skipped > 0) {
+            if (pct == 1) { err = SLICE_ERR_SKIP_IN_I; break; }
+            if (pct == 2) { pmv[0][0] = pmv[0][1] = pmv[1][0] = pmv[1][1] = 0; }
+            uint32_t dirs = pct == 2 ? MP2V_MB_FWD : prev_dirs;
+            if (!dirs) dirs = MP2V_MB_FWD;                              // after an intra macroblock the reference predicts forward
+            for (int k = 0; k < skipped; k++) {
+                mp2v_mb_info_t& r = row[++mbx];
+                r.coef_off = coef_off_base + (uint32_t)(out - out_base);
+                r.bits = MP2V_MB_BITS(0, qscale, 0, dirs);
+                for (int s = 0; s < 2; s++) for (int t = 0; t < 2; t++)
+                    r.mv[s][t] = (int16_t)((dirs & (s ? MP2V_MB_BWD : MP2V_MB_FWD)) ? pmv[s][t] : 0);
+            }
+            dc_pred[0] = dc_pred[1] = dc_pred[2] = dc_reset;
+        }
+        mp2v_mb_info_t& r = row[++mbx];
+        // ---- macroblock_type
+        br.refill();
+        const vlc_entry_t te = T.mbtype[pct].look(br.peek(6));
+        if (!te.len) { err = SLICE_ERR_MBTYPE; break; }
+        br.skip(te.len);
+        const int type = te.val;
+        const bool intra = type & 0x02, fwd = type & 0x10, bwd = type & 0x08, pattern = type & 0x04;
+        if (type & 0x20) { qscale = quantiser_scale_of((int)br.peek(5), sx.q_scale_type); br.skip(5); }
+        // ---- motion vectors (frame prediction: one vector per direction)
+        int mv[2][2] = {{0, 0}, {0, 0}};
+        for (int s = 0; s < 2 && !err; s++) {
+            if (!(s ? bwd : fwd)) continue;
+            for (int t = 0; t < 2; t++) {
+                const int fc = sx.f_code[s][t];
+                if (fc < 1 || fc > 9) { err = SLICE_ERR_FCODE; break; }
+                if (!decode_mv_component(br, T, fc, pmv[s][t], mv[s][t])) { err = SLICE_ERR_MOTION; break; }
+            }
+        }
+        if (err) break;
+        if (intra || (pct == 2 && !fwd)) { pmv[0][0] = pmv[0][1] = pmv[1][0] = pmv[1][1] = 0; }   // mb_decoder.cpp:599-603
+        if (!intra) dc_pred[0] = dc_pred[1] = dc_pred[2] = dc_reset;                                // mb_decoder.cpp:623-626
+        // ---- coded_block_pattern
+        uint32_t cbp = 0;
+        if (intra) cbp = (1u << nblk) - 1u;
+        else if (pattern) {
+            br.refill();
+            const vlc_entry_t ce = T.cbp.look(br.peek(9));
+            if (!ce.len) { err = SLICE_ERR_CBP; break; }
+            br.skip(ce.len);
+            for (int i = 0; i < 6; i++) if (ce.val & (1 << (5 - i))) cbp |= 1u << i;          // mb_decoder.cpp:435-436
+            if (cf == 2) { const uint32_t x = br.peek(2); br.skip(2); cbp |= ((x >> 1) & 1u) << 6 | (x & 1u) << 7; }
+            if (cf == 3) { const uint32_t x = br.peek(6); br.skip(6); for (int i = 0; i < 6; i++) cbp |= ((x >> (5 - i)) & 1u) << (6 + i); }
+        }
+        // ---- blocks
+        const uint32_t off = (uint32_t)(out - out_base);
+        for (int b = 0; b < nblk; b++)
+            if (cbp & (1u << b))
+                if (!parse_block(br, out, T, sx, dc_pred, b, intra)) { err = SLICE_ERR_COEF; break; }
+        if (err) break;
+        uint32_t flags = 0;
+        if (intra) flags = MP2V_MB_INTRA;
+        else {
+            if (fwd) flags |= MP2V_MB_FWD;
+            if (bwd) flags |= MP2V_MB_BWD;
+            if (!flags) flags = MP2V_MB_FWD;        // P picture "no MC": forward prediction with a zero vector (mb_decoder.cpp:329-338)
+        }
+        r.coef_off = coef_off_base + off;
+        r.bits = MP2V_MB_BITS((uint32_t)(out - out_base) - off, qscale, cbp, flags);
+        for (int s = 0; s < 2; s++) for (int t = 0; t < 2; t++) r.mv[s][t] = (int16_t)(intra ? 0 : mv[s][t]);
+        prev_dirs = flags & (MP2V_MB_FWD | MP2V_MB_BWD);
+        br.refill();
+    } while (br.peek(23) != 0 && mbx < mbw - 1);
+    // trailing macroblocks of the row that the slice did not code keep the caller's defaults
+    *n_out = (uint32_t)(out - out_base);
+    *first_mbx_out = first_mbx;
+    *last_mbx_out = err ? first_mbx - 1 : mbx;
+    return err;
+}
+
+}  // namespace mp2v

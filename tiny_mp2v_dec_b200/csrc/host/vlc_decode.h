@@ -7,9 +7,17 @@
 #pragma once
 #include <cstdint>
 #include <cstring>
-#include <vector>
 
 #include "vlc_tables.h"
+
+// The lookup side of these tables is shared by the host slice parser and the device-side one
+// (csrc/vlc_kernel.cu): everything is pointer-free so that the whole vlc_decode_tables_t object can be
+// copied to the GPU byte for byte.
+#ifdef __CUDACC__
+#define MP2V_HD __host__ __device__
+#else
+#define MP2V_HD
+#endif
 
 namespace mp2v {
 
@@ -36,7 +44,7 @@ struct flat_vlc_t {
         const uint32_t lo = code << (BITS - len), n = 1u << (BITS - len);
         for (uint32_t k = 0; k < n; k++) { e[lo + k].len = (int8_t)len; e[lo + k].val = (int16_t)val; }
     }
-    inline const vlc_entry_t& look(uint32_t peek_bits) const { return e[peek_bits]; }
+    MP2V_HD inline const vlc_entry_t& look(uint32_t peek_bits) const { return e[peek_bits]; }
 };
 
 // Fast path of the run/level decoder: one lookup on the next 11 bits resolves code AND sign for
@@ -66,9 +74,11 @@ struct coef_vlc_t {
             fast[i] = f;
         }
     }
+    static constexpr int MAX_LEAVES = 8;                          // distinct 8-bit prefixes with longer codes (B.14/B.15 need 6)
     coef_entry_t root[1 << ROOT];
-    std::vector<coef_entry_t> leaves;                             // (1 << LEAF) entries per leaf table
-    coef_vlc_t() { memset(root, 0, sizeof(root)); }
+    coef_entry_t leaves[MAX_LEAVES << LEAF];                      // (1 << LEAF) entries per leaf table
+    int n_leaves = 0;
+    coef_vlc_t() { memset(root, 0, sizeof(root)); memset(leaves, 0, sizeof(leaves)); }
     void add(const char* bits, int run, int level) {
         const int len = (int)strlen(bits);
         uint32_t code = 0;
@@ -79,9 +89,8 @@ struct coef_vlc_t {
         } else {
             const uint32_t prefix = code >> (len - ROOT);
             if (!root[prefix].sub) {
-                leaves.resize(leaves.size() + (1u << LEAF));
-                memset(&leaves[leaves.size() - (1u << LEAF)], 0, sizeof(coef_entry_t) << LEAF);
-                root[prefix].sub = (uint16_t)(leaves.size() >> LEAF);
+                if (n_leaves >= MAX_LEAVES) return;               // cannot happen with the Annex B tables (checked in tests)
+                root[prefix].sub = (uint16_t)(++n_leaves);
                 root[prefix].len = 0;
             }
             coef_entry_t* leaf = &leaves[(size_t)(root[prefix].sub - 1) << LEAF];
@@ -92,7 +101,7 @@ struct coef_vlc_t {
         }
     }
     // peek17 = next 17 bits of the stream
-    inline const coef_entry_t& look(uint32_t peek17) const {
+    MP2V_HD inline const coef_entry_t& look(uint32_t peek17) const {
         const coef_entry_t& r = root[peek17 >> (17 - ROOT)];
         if (!r.sub) return r;
         return leaves[((size_t)(r.sub - 1) << LEAF) + (peek17 & ((1u << LEAF) - 1u))];
