@@ -22,12 +22,15 @@ typedef struct mp2v_decode_params {
     int32_t max_batch, output_lag;          /* 0 = defaults                                                 */
     int32_t download_frames;                /* 0: reconstruct only (frames stay on the device)             */
     int32_t hash_output;                    /* 1: FNV-1a of the output into stats->hash (slow; tests only)  */
+    int32_t host_parser;                    /* 1: parse slices on the host (mp2v_b200_options_t.gpu_vlc = false);
+                                               0: on the device whenever the stream is inside its envelope   */
 } mp2v_decode_params_t;
 
 typedef struct mp2v_decode_stats {
     uint64_t frames, pictures, launches, h2d_bytes, d2h_bytes, algorithmic_bytes;
     double kernel_ms, parse_cpu_seconds, wall_seconds;
     uint64_t hash;                          /* FNV-1a 64 of the cropped planar output, display order        */
+    uint64_t vlc_launches;                  /* slice parser kernel launches (0: the host parser was used)   */
 } mp2v_decode_stats_t;
 
 /* per-frame callback, invoked on the decoder's output thread in display order */

@@ -66,6 +66,10 @@ struct mp2v_b200_options_t {
     int max_batch = 8;                // pictures fused into one launch
     int output_lag = 4;               // pictures the display side stays behind the submit side (lets launches batch)
     bool download_frames = true;      // false: renderer gets frames whose planes were not copied back (benchmarks)
+    bool gpu_vlc = true;              // slices are parsed on the device (mp2v_recon_submit_slices): the host only finds
+                                      // start codes and parses headers.  Streams outside the device parser's envelope
+                                      // (several slices in one macroblock row, oversized pictures) and gpu_vlc = false
+                                      // take the host slice parser on num_threads worker threads instead.
 };
 
 class MP2V_CXX_API mp2v_decoder_c {
@@ -84,6 +88,7 @@ public:
     struct stats_t {
         uint64_t pictures = 0, launches = 0, h2d_bytes = 0, d2h_bytes = 0, algorithmic_bytes = 0;
         double kernel_ms = 0;          // CUDA-event time of the reconstruction launches
+        uint64_t vlc_launches = 0;     // slice parser kernel launches (0: the host parser was used)
         double parse_cpu_seconds = 0;  // summed over worker threads: slice parsing only
         double wall_seconds = 0;       // decode() wall clock
     };

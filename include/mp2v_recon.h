@@ -142,10 +142,19 @@ typedef struct mp2v_recon_config {
     uint32_t coef_capacity;        /* coefficient records per picture slot; 0 = worst case
                                       (mb_count * blocks * 64).  submit fails with MP2V_ERR_RANGE
                                       when a picture needs more.                                 */
-    uint32_t reserved;
+    uint32_t bitstream_capacity;   /* MP2V_RECON_DEVICE_VLC: bytes of coded slice data one picture
+                                      may carry; 0 = max(2 MiB, 128 bytes per macroblock)         */
 } mp2v_recon_config_t;
 
 #define MP2V_RECON_VALIDATE   1    /* check vectors / offsets on the host before launch          */
+#define MP2V_RECON_DEVICE_VLC 2    /* pictures are handed over as coded slices
+                                      (mp2v_recon_submit_slices) and parsed on the device; every
+                                      slot's device arena then has the worst-case capacity and
+                                      mp2v_picture_t.coef is NULL (no host-side coefficient arena) */
+#define MP2V_RECON_AUTO_DOWNLOAD 4 /* queue the copy of every submitted picture's frame into its
+                                      pinned mirror right behind the picture's launch, so that the
+                                      copies overlap later launches; mp2v_recon_map_frame then only
+                                      waits for that copy (for decoders that show every frame)     */
 
 typedef struct mp2v_recon mp2v_recon_t;
 
@@ -174,6 +183,33 @@ MP2V_API int  mp2v_recon_submit(mp2v_recon_t* ctx, mp2v_picture_t* pic);
 /* Optional: run submit's record validation + byte accounting now, from any thread, without taking the
  * context lock (the picture still belongs to the caller); submit then skips it. */
 MP2V_API int  mp2v_recon_precheck(mp2v_recon_t* ctx, mp2v_picture_t* pic);
+
+/* ---- device-side slice parsing (contexts created with MP2V_RECON_DEVICE_VLC) ------------------
+ * Instead of filling mb[] / coef[] on the host, hand over the picture's coded slices: the library
+ * copies the bytes to the device and a kernel does what the reference's parse_macroblock /
+ * parse_block do up to (not including) dequantisation (mb_decoder.cpp:74-155, 521-641) -- one
+ * thread per slice, all slices of all pictures in flight at once -- writing the same records the
+ * host parser would.  The caller fills params (W, picture_coding_type, alternate_scan, frame ids)
+ * as for mp2v_recon_submit and passes what the slice layer needs of picture_coding_extension.
+ * Envelope: frame pictures with frame prediction, at most one slice per macroblock row.
+ * Asynchronous like submit; a syntax error inside a slice (or a vector leaving the frame) is
+ * reported by the next sync / map_frame / download_frame / acquire as MP2V_ERR_RANGE, and the
+ * macroblocks after the error reconstruct as blank intra macroblocks.                            */
+typedef struct mp2v_pic_syntax {
+    int32_t f_code[2][2];          /* [forward, backward][horizontal, vertical]                   */
+    int32_t intra_dc_precision;    /* 0..3                                                        */
+    int32_t q_scale_type;
+    int32_t intra_vlc_format;
+    int32_t reserved;
+} mp2v_pic_syntax_t;
+typedef struct mp2v_slice_ref {
+    const uint8_t* payload;        /* first byte after the 4-byte slice start code               */
+    uint32_t bytes;                /* up to the next start code prefix                            */
+    int32_t  code;                 /* slice_start_code value 0x01..0xAF                           */
+} mp2v_slice_ref_t;
+MP2V_API int  mp2v_recon_submit_slices(mp2v_recon_t* ctx, mp2v_picture_t* pic, const mp2v_pic_syntax_t* syntax,
+                                       const mp2v_slice_ref_t* slices, int n_slices);
+
 MP2V_API int  mp2v_recon_flush(mp2v_recon_t* ctx);               /* launch whatever is queued       */
 MP2V_API int  mp2v_recon_sync(mp2v_recon_t* ctx);                /* flush + wait for the device     */
 
@@ -205,6 +241,9 @@ typedef struct mp2v_recon_stats {
     uint64_t algorithmic_bytes;    /* OUT + REF + COEF(128 B/coded block) + META   */
     double   kernel_ms;            /* CUDA-event time of the reconstruction launches (when
                                       timing is enabled)                                          */
+    uint64_t vlc_launches;         /* slice parser kernel launches (one per picture)              */
+    uint64_t vlc_slices;           /* slices handed to the device parser                          */
+    uint64_t vlc_coefs;            /* coefficient records it wrote (parses completed so far)      */
 } mp2v_recon_stats_t;
 MP2V_API int  mp2v_recon_set_timing(mp2v_recon_t* ctx, int enable);
 /* CUDA-event stopwatch on the context's compute stream (the stream every kernel is launched on):

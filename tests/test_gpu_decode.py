@@ -12,64 +12,72 @@ from tiny_mp2v_dec_b200.streamgen import Stream
 pytestmark = pytest.mark.gpu
 
 
+@pytest.fixture(params=[True, False], ids=["device_parser", "host_parser"])
+def gpu_vlc(request):
+    """both slice parsers behind mp2v_decoder_c: the CUDA one (default) and the host one"""
+    return request.param
+
+
 @pytest.mark.parametrize("name", sorted(GOLDEN_CASES))
-def test_decoder_matches_reference_golden(name):
+def test_decoder_matches_reference_golden(name, gpu_vlc):
     w, h, cf, kw = GOLDEN_CASES[name]
     s = Stream(w, h, cf, **kw)
-    d = Decoder(w, h, cf, num_threads=4)
+    d = Decoder(w, h, cf, num_threads=4, gpu_vlc=gpu_vlc)
     yuv = d.decode(s.padded, s.size)
     assert d.stats.frames == GOLDEN[name]["frames"]
     assert sha(yuv) == GOLDEN[name]["yuv_sha256"]
     assert d.stats.launches >= 1 and d.stats.pictures == GOLDEN[name]["frames"]
+    # the parser that was asked for is the one that ran
+    assert (d.stats.vlc_launches == GOLDEN[name]["frames"] and d.stats.parse_cpu_seconds == 0.0) if gpu_vlc else (d.stats.vlc_launches == 0 and d.stats.parse_cpu_seconds > 0.0)
 
 
 @pytest.mark.skipif(not O.have_ref(), reason="oracle/_ref (the compiled reference) did not travel")
 @pytest.mark.parametrize("cf", [1, 2, 3])
-def test_decoder_matches_live_reference(cf):
+def test_decoder_matches_live_reference(cf, gpu_vlc):
     s = Stream(320, 192, cf, seed=50 + cf, n_gops=3, gop_n=10, gop_m=3, qscale_code_max=31, pct_big_levels=10)
-    assert Decoder(320, 192, cf, num_threads=3).decode(s.padded, s.size) == O.ref_decode_serial(s)
+    assert Decoder(320, 192, cf, num_threads=3, gpu_vlc=gpu_vlc).decode(s.padded, s.size) == O.ref_decode_serial(s)
 
 
 @pytest.mark.parametrize("threads,batch,lag", [(1, 1, 1), (2, 4, 2), (8, 8, 6), (16, 32, 12)])
-def test_threads_and_batching_do_not_change_the_output(threads, batch, lag):
+def test_threads_and_batching_do_not_change_the_output(threads, batch, lag, gpu_vlc):
     s = Stream(352, 288, 1, seed=60, n_gops=4, gop_n=12, gop_m=3)
     want = O.oracle_decode_stream(s)
-    got = Decoder(352, 288, 1, num_threads=threads, max_batch=batch, output_lag=lag).decode(s.padded, s.size)
+    got = Decoder(352, 288, 1, num_threads=threads, max_batch=batch, output_lag=lag, gpu_vlc=gpu_vlc).decode(s.padded, s.size)
     assert got == want
 
 
-def test_no_reordering_gives_coded_order():
+def test_no_reordering_gives_coded_order(gpu_vlc):
     s = Stream(176, 144, 1, seed=61, gop_n=7, gop_m=3)
-    got = Decoder(176, 144, 1, num_threads=2, reordering=False).decode(s.padded, s.size)
+    got = Decoder(176, 144, 1, num_threads=2, reordering=False, gpu_vlc=gpu_vlc).decode(s.padded, s.size)
     disp = O.oracle_decode_stream(s)
     fb = frame_bytes(176, 144, 1)
     frames = {idx: disp[k * fb:(k + 1) * fb] for k, idx in enumerate(s.display_order())}
     assert got == b"".join(frames[i] for i in range(len(s.pictures)))
 
 
-def test_4k444_decodes():
+def test_4k444_decodes(gpu_vlc):
     s = Stream(3840, 2160, 3, seed=62, gop_n=4, gop_m=3, mode=1)
-    got = Decoder(3840, 2160, 3, num_threads=8).decode(s.padded, s.size)
+    got = Decoder(3840, 2160, 3, num_threads=8, gpu_vlc=gpu_vlc).decode(s.padded, s.size)
     assert sha(got) == sha(O.oracle_decode_stream(s))
 
 
-def test_decode_without_download_still_reconstructs():
+def test_decode_without_download_still_reconstructs(gpu_vlc):
     s = Stream(352, 288, 1, seed=63, gop_n=9, gop_m=3)
-    d = Decoder(352, 288, 1, num_threads=2)
+    d = Decoder(352, 288, 1, num_threads=2, gpu_vlc=gpu_vlc)
     assert d.decode(s.padded, s.size, want_output=False, download=False) is None
     assert d.stats.frames == 9 and d.stats.d2h_bytes == 0 and d.stats.pictures == 9
 
 
-def test_malformed_stream_is_an_error_not_a_crash():
+def test_malformed_stream_is_an_error_not_a_crash(gpu_vlc):
     from tiny_mp2v_dec_b200.recon import ReconError
     s = Stream(176, 144, 1, seed=64, gop_n=4, gop_m=3)
     bad = s.padded.copy()
     start = int(np.nonzero((bad[:-3] == 0) & (bad[1:-2] == 0) & (bad[2:-1] == 1) & (bad[3:] == 2))[0][1])
     bad[start + 6:start + 60] = 0xFF
     with pytest.raises(ReconError):
-        Decoder(176, 144, 1, num_threads=2).decode(bad, s.size)
+        Decoder(176, 144, 1, num_threads=2, gpu_vlc=gpu_vlc).decode(bad, s.size)
     # the decoder stays usable afterwards
-    assert sha(Decoder(176, 144, 1, num_threads=2).decode(s.padded, s.size)) == sha(O.oracle_decode_stream(s))
+    assert sha(Decoder(176, 144, 1, num_threads=2, gpu_vlc=gpu_vlc).decode(s.padded, s.size)) == sha(O.oracle_decode_stream(s))
 
 
 def test_motion_vector_outside_the_frame_is_rejected():
@@ -110,7 +118,7 @@ def test_reference_sample_recompiled_against_this_library():
     assert sha(got) == GOLDEN["hd422_ipb"]["sample_yuv_sha256"]
 
 
-def test_gop_sharding_over_two_devices():
+def test_gop_sharding_over_two_devices(gpu_vlc):
     """closed GOPs dealt round-robin to one pipeline per GPU, frames stitched back in display order;
     no collective, no peer traffic"""
     import torch
@@ -124,24 +132,24 @@ def test_gop_sharding_over_two_devices():
     assert one == want
 
 
-def test_empty_stream_decodes_to_nothing():
-    d = Decoder(64, 48, 1, num_threads=2)
+def test_empty_stream_decodes_to_nothing(gpu_vlc):
+    d = Decoder(64, 48, 1, num_threads=2, gpu_vlc=gpu_vlc)
     assert d.decode(np.zeros(512, np.uint8), 0) == b""
     assert d.stats.frames == 0 and d.stats.launches == 0
     s = Stream(64, 48, 1, seed=66, gop_n=1, gop_m=1)     # a single I picture right after
     assert d.decode(s.padded, s.size) == O.oracle_decode_stream(s)
 
 
-def test_decoder_is_reusable_and_deterministic():
+def test_decoder_is_reusable_and_deterministic(gpu_vlc):
     s1 = Stream(176, 144, 2, seed=67, gop_n=6, gop_m=3)
     s2 = Stream(176, 144, 2, seed=68, n_gops=2, gop_n=5, gop_m=2)
-    d = Decoder(176, 144, 2, num_threads=3)
+    d = Decoder(176, 144, 2, num_threads=3, gpu_vlc=gpu_vlc)
     a1, a2, a3 = d.decode(s1.padded, s1.size), d.decode(s2.padded, s2.size), d.decode(s1.padded, s1.size)
     assert a1 == a3 == O.oracle_decode_stream(s1)
     assert a2 == O.oracle_decode_stream(s2)
 
 
-def test_bench_workload_full_size_consistency():
+def test_bench_workload_full_size_consistency(gpu_vlc):
     """BASELINE.json full size (1080p, the bench's own stream parameters, 2 GOPs of each workload): the two
     product paths -- records reconstructed resident on the device, and the whole decoder from the
     elementary stream -- must agree frame for frame (a checksum of per-frame checksums), and both must equal
@@ -157,7 +165,7 @@ def test_bench_workload_full_size_consistency():
         g = dict(wl["gen"], n_gops=2)
         s = Stream(wl["width"], wl["height"], wl["chroma_format"], seed=wl["config_id"], **g)
         fb = frame_bytes(wl["width"], wl["height"], wl["chroma_format"])
-        a = Decoder(wl["width"], wl["height"], wl["chroma_format"], num_threads=8).decode(s.padded, s.size)
+        a = Decoder(wl["width"], wl["height"], wl["chroma_format"], num_threads=8, gpu_vlc=gpu_vlc).decode(s.padded, s.size)
         b = reconstruct_stream(s)
         sums = lambda y: hashlib.sha256(b"".join(hashlib.sha256(y[i:i + fb]).digest() for i in range(0, len(y), fb))).hexdigest()
         assert len(a) == len(b) == fb * len(s.pictures)

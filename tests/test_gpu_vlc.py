@@ -1,0 +1,109 @@
+"""Device-side slice parsing (mp2v_b200_options_t.gpu_vlc / mp2v_recon_submit_slices), what is specific to
+it: agreement with the host parser on every syntax knob, error reporting, the envelope and the fall-back.
+(tests/test_gpu_decode.py runs the golden vectors and the API tests through BOTH parsers.)"""
+import numpy as np
+import pytest
+
+import oracle_lib as O
+from helpers import sha
+from tiny_mp2v_dec_b200.abi import RECON_DEVICE_VLC, RECON_VALIDATE, PicParams
+from tiny_mp2v_dec_b200.decoder import Decoder
+from tiny_mp2v_dec_b200.recon import Recon, ReconError
+from tiny_mp2v_dec_b200.streamgen import Stream
+
+pytestmark = pytest.mark.gpu
+
+
+@pytest.mark.parametrize("cf,mode", [(1, 0), (2, 0), (3, 0), (1, 1), (3, 1)])
+def test_device_parser_matches_host_parser_and_oracle(cf, mode):
+    s = Stream(352, 288, cf, seed=300 + 10 * cf + mode, n_gops=3, gop_n=12, gop_m=3, mode=mode, qscale_code_max=31,
+               pct_big_levels=8, q_scale_type=cf & 1, intra_dc_precision=cf - 1, alternate_scan=mode)
+    want = O.oracle_decode_stream(s)
+    assert Decoder(352, 288, cf, num_threads=4).decode(s.padded, s.size) == want
+    assert Decoder(352, 288, cf, num_threads=4, gpu_vlc=True).decode(s.padded, s.size) == want
+
+
+def test_device_parser_1080p_and_reuse():
+    s = Stream(1920, 1088, 1, seed=301, n_gops=2, gop_n=6, gop_m=3, mode=1, pct_coded=70)
+    want = sha(O.oracle_decode_stream(s))
+    d = Decoder(1920, 1088, 1, num_threads=4, gpu_vlc=True)
+    assert sha(d.decode(s.padded, s.size)) == want
+    assert sha(d.decode(s.padded, s.size)) == want     # same handle, second stream
+
+
+def test_device_parser_reports_slice_errors():
+    s = Stream(352, 288, 1, seed=302, gop_n=6, gop_m=3)
+    buf = s.padded.copy()
+    # overwrite the middle of the stream with a pattern that is no valid macroblock syntax
+    mid = s.size // 2
+    buf[mid:mid + 64] = 0x00
+    buf[mid + 64:mid + 96] = 0xFF
+    with pytest.raises(ReconError, match="slice"):
+        Decoder(352, 288, 1, num_threads=2, gpu_vlc=True).decode(buf, s.size)
+    # the decoder object survives: a good stream decodes afterwards
+    d = Decoder(352, 288, 1, num_threads=2, gpu_vlc=True)
+    with pytest.raises(ReconError):
+        d.decode(buf, s.size)
+    assert d.decode(s.padded, s.size) == O.oracle_decode_stream(s)
+
+
+def test_device_parser_rejects_vectors_outside_the_frame():
+    # generator knob: no frame clamp on the vectors -> some leave the frame (the reference would read out of bounds)
+    s = Stream(176, 144, 1, seed=303, gop_n=9, gop_m=3, mv_range=40, unclamped_mv=1)
+    with pytest.raises(ReconError, match="outside the reference frame"):
+        Decoder(176, 144, 1, num_threads=2, gpu_vlc=True).decode(s.padded, s.size)
+    with pytest.raises(ReconError):
+        Decoder(176, 144, 1, num_threads=2).decode(s.padded, s.size)          # the host path rejects it too
+
+
+def test_submit_slices_needs_a_vlc_context():
+    with Recon(176, 144, 1, n_frames=2, n_pictures=2, flags=RECON_VALIDATE) as r:
+        pic = r.acquire()
+        with pytest.raises(ReconError, match="MP2V_RECON_DEVICE_VLC"):
+            r.submit_slices(pic, PicParams(picture_coding_type=1), np.zeros(64, np.uint8), [(0, 8, 1)], ((1, 1), (1, 1)))
+        r.release(pic)
+
+
+def test_submit_slices_checks_its_arguments():
+    with Recon(176, 144, 1, n_frames=2, n_pictures=2, flags=RECON_VALIDATE | RECON_DEVICE_VLC) as r:
+        data = np.zeros(256, np.uint8)
+        pic = r.acquire()
+        assert not pic.contents.coef and pic.contents.coef_capacity == 0      # no host coefficient arena in this mode
+        with pytest.raises(ReconError, match="picture_coding_type"):
+            r.submit_slices(pic, PicParams(picture_coding_type=4), data, [(0, 8, 1)], ((1, 1), (1, 1)))
+        with pytest.raises(ReconError, match="missing reference"):
+            r.submit_slices(pic, PicParams(picture_coding_type=2), data, [(0, 8, 1)], ((1, 1), (1, 1)))
+        with pytest.raises(ReconError, match="one slice per macroblock row"):
+            r.submit_slices(pic, PicParams(picture_coding_type=1), data, [(0, 8, 1), (16, 8, 1)], ((1, 1), (1, 1)))
+        with pytest.raises(ReconError, match="row outside"):
+            r.submit_slices(pic, PicParams(picture_coding_type=1), data, [(0, 8, 40)], ((1, 1), (1, 1)))
+        # a picture without slices reconstructs to blank macroblocks
+        r.submit_slices(pic, PicParams(picture_coding_type=1), data, [], ((1, 1), (1, 1)), dst=0)
+        r.sync()
+        assert set(r.download(0)) == {0}
+
+
+def _start_codes(buf, size):
+    b = buf[:size]
+    return np.nonzero((b[:-3] == 0) & (b[1:-2] == 0) & (b[2:-1] == 1))[0]
+
+
+def test_stream_outside_the_device_envelope_takes_the_host_parser():
+    """two slices in one macroblock row (legal MPEG-2, handled by the reference): the device parser's
+    one-slice-per-row envelope does not hold, so the decoder parses this stream on the host"""
+    s = Stream(352, 288, 1, seed=304, gop_n=6, gop_m=3)
+    want = O.oracle_decode_stream(s)
+    sc = _start_codes(s.padded, s.size)
+    # duplicate one slice of the third picture (decoding a slice twice reconstructs the same pixels twice)
+    pics = [int(o) for o in sc if s.padded[o + 3] == 0x00]
+    k = int(np.searchsorted(sc, pics[2])) + 3
+    while not (1 <= s.padded[sc[k] + 3] <= 0xAF):
+        k += 1
+    a, b = int(sc[k]), int(sc[k + 1])
+    buf = np.concatenate([s.padded[:b], s.padded[a:b], s.padded[b:]])
+    d = Decoder(352, 288, 1, num_threads=3)
+    assert d.decode(buf, s.size + (b - a)) == want
+    assert d.stats.vlc_launches == 0 and d.stats.parse_cpu_seconds > 0.0
+    # the same decoder object goes back to the device parser for a stream inside the envelope
+    assert d.decode(s.padded, s.size) == want
+    assert d.stats.vlc_launches == len(s.pictures)

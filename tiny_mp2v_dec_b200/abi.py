@@ -41,7 +41,7 @@ class Picture(C.Structure):
 class ReconConfig(C.Structure):
     _fields_ = [("device", C.c_int32), ("width", C.c_int32), ("height", C.c_int32), ("chroma_format", C.c_int32),
                 ("n_frames", C.c_int32), ("n_pictures", C.c_int32), ("max_batch", C.c_int32), ("flags", C.c_int32),
-                ("coef_capacity", C.c_uint32), ("reserved", C.c_uint32)]
+                ("coef_capacity", C.c_uint32), ("bitstream_capacity", C.c_uint32)]
 
 
 class FrameLayout(C.Structure):
@@ -51,8 +51,20 @@ class FrameLayout(C.Structure):
 
 class ReconStats(C.Structure):
     _fields_ = [("pictures", C.c_uint64), ("launches", C.c_uint64), ("h2d_bytes", C.c_uint64), ("d2h_bytes", C.c_uint64),
-                ("algorithmic_bytes", C.c_uint64), ("kernel_ms", C.c_double)]
+                ("algorithmic_bytes", C.c_uint64), ("kernel_ms", C.c_double),
+                ("vlc_launches", C.c_uint64), ("vlc_slices", C.c_uint64), ("vlc_coefs", C.c_uint64)]
+
+
+class PicSyntax(C.Structure):
+    _fields_ = [("f_code", (C.c_int32 * 2) * 2), ("intra_dc_precision", C.c_int32), ("q_scale_type", C.c_int32),
+                ("intra_vlc_format", C.c_int32), ("reserved", C.c_int32)]
+
+
+class SliceRef(C.Structure):
+    _fields_ = [("payload", C.c_void_p), ("bytes", C.c_uint32), ("code", C.c_int32)]
 
 
 RECON_VALIDATE = 1
+RECON_DEVICE_VLC = 2
+RECON_AUTO_DOWNLOAD = 4
 OK, ERR_ARG, ERR_CUDA, ERR_NOMEM, ERR_STATE, ERR_RANGE = 0, -1, -2, -3, -4, -5

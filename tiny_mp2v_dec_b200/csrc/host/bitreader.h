@@ -23,21 +23,23 @@ public:
 
     // make at least 56 bits available
     MP2V_HD inline void refill() {
-#ifdef __CUDA_ARCH__
-        // device: byte loads through the read-only path (a thread walks its own slice; lines stay in L1)
-        while (cnt_ <= 56) {
-            buf_ |= (uint64_t)__ldg(ptr_++) << (56 - cnt_);
-            cnt_ += 8;
-        }
-#else
         uint64_t w;
+#ifdef __CUDA_ARCH__
+        // device: 8 bytes from an arbitrary address = three aligned words + two byte permutes
+        // (reads at most 11 bytes past ptr_; the staged bitstream carries 16 bytes of padding)
+        const uintptr_t a = (uintptr_t)ptr_;
+        const uint32_t* p32 = (const uint32_t*)(a & ~(uintptr_t)3);
+        const uint32_t sel = 0x0123u + 0x1111u * ((uint32_t)a & 3u);
+        const uint32_t w0 = __ldg(p32), w1 = __ldg(p32 + 1), w2 = __ldg(p32 + 2);
+        w = ((uint64_t)__byte_perm(w0, w1, sel) << 32) | __byte_perm(w1, w2, sel);
+#else
         memcpy(&w, ptr_, 8);
         w = __builtin_bswap64(w);
+#endif
         buf_ |= w >> cnt_;
         const int adv = (63 - cnt_) >> 3;
         ptr_ += adv;
         cnt_ += adv << 3;
-#endif
     }
     // n in 1..32; valid after refill() as long as no more than 56 bits were consumed since
     MP2V_HD inline uint32_t peek(int n) const { return (uint32_t)(buf_ >> (64 - n)); }

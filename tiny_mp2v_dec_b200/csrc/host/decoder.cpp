@@ -11,6 +11,7 @@
 // pipeline per GPU and stitched back in display order; nothing is exchanged between GPUs.
 #include "mp2v_decoder.hpp"
 
+#include <algorithm>
 #include <atomic>
 #include <chrono>
 #include <condition_variable>
@@ -136,6 +137,7 @@ void shared_t::fail(const std::string& why) {
 
 void pipeline_t::feeder() {
     int refs[2] = {-1, -1};   // local task indices of the two live references
+    std::vector<mp2v_slice_ref_t> slice_refs;
     auto unref = [&](int k) { if (k >= 0) release_frame_use(tasks[k].dst); };
     for (size_t k = 0; k < tasks.size() && !sh->failed.load(); k++) {
         pic_task_t& t = tasks[k];
@@ -175,6 +177,30 @@ void pipeline_t::feeder() {
         pp.picture_coding_type = info.picture_coding_type;
         pp.alternate_scan = info.alternate_scan;
         pp.dst_frame = t.dst; pp.l0_frame = t.l0; pp.l1_frame = t.l1;
+        if (sh->opt.gpu_vlc) {
+            // device-side parsing: hand the coded slices over; submission is in coded order by construction
+            if (!picture_in_envelope(info)) { sh->fail("only progressive frame pictures with frame prediction are supported (the reference's envelope)"); break; }
+            mp2v_pic_syntax_t sy{};
+            for (int a = 0; a < 2; a++) for (int b = 0; b < 2; b++) sy.f_code[a][b] = info.f_code[a][b];
+            sy.intra_dc_precision = info.intra_dc_precision;
+            sy.q_scale_type = info.q_scale_type;
+            sy.intra_vlc_format = info.intra_vlc_format;
+            slice_refs.clear();
+            for (const slice_ref_t& sr : t.src->slices) slice_refs.push_back({sr.payload, sr.bytes, sr.code});
+            if (mp2v_recon_submit_slices(recon, t.rp, &sy, slice_refs.data(), (int)slice_refs.size()) != MP2V_OK) {
+                sh->fail(std::string("picture ") + std::to_string(k) + ": " + mp2v_recon_last_error(recon));
+                break;
+            }
+            {
+                std::lock_guard<std::mutex> lk(mu);
+                t.parsed = t.submitted = true;
+                next_submit++;
+                in_parse--;
+            }
+            cv.notify_all();
+            sh->feeder_work_ns.fetch_add(std::chrono::duration_cast<std::chrono::nanoseconds>(clock_t_::now() - tf1).count(), std::memory_order_relaxed);
+            continue;
+        }
         // macroblocks no slice covers: intra with no coded block (reconstructs to 0); never the case in valid streams
         const mp2v_mb_info_t blank = {0u, MP2V_MB_BITS(0, 1, 0, MP2V_MB_INTRA), {{0, 0}, {0, 0}}};
         for (uint32_t i = 0; i < t.rp->mb_count; i++) t.rp->mb[i] = blank;
@@ -327,16 +353,47 @@ struct mp2v_decoder_c::impl_t {
     bool initialised = false;
     std::string error;
     stats_t stats;
-    std::vector<device_ctx_t> devs;
+    // [0] contexts fed by the host slice parser, [1] contexts that parse on the device; each set is
+    // created when first needed (a stream outside the device parser's envelope takes the host parser)
+    std::vector<device_ctx_t> dev_sets[2];
 
     void release() {
-        for (auto& d : devs) if (d.recon) mp2v_recon_destroy(d.recon);
-        devs.clear();
+        for (auto& devs : dev_sets) {
+            for (auto& d : devs) if (d.recon) mp2v_recon_destroy(d.recon);
+            devs.clear();
+        }
     }
-    bool prepare();
+    bool prepare(bool gpu_vlc);
+    bool device_parser_can_take(const stream_index_t& index) const;
 };
 
-bool mp2v_decoder_c::impl_t::prepare() {
+// mp2v_recon_submit_slices' envelope: at most one slice per macroblock row, coded picture within the staging capacity
+bool mp2v_decoder_c::impl_t::device_parser_can_take(const stream_index_t& index) const {
+    const int mbh = cfg.height / 16;
+    const size_t cap = std::max<size_t>(2u << 20, (size_t)(cfg.width / 16) * mbh * 128u);   // the library's default bitstream_capacity
+    std::vector<uint8_t> seen((size_t)mbh);
+    for (const auto& pic : index.pictures) {
+        if ((int)pic.slices.size() > mbh) return false;
+        if (pic.slices.empty()) continue;
+        std::fill(seen.begin(), seen.end(), 0);
+        const uint8_t* lo = pic.slices[0].payload;
+        const uint8_t* hi = lo;
+        for (const auto& sl : pic.slices) {
+            int row = sl.code - 1;
+            if (cfg.height > 2800 && sl.bytes > 0) row += (sl.payload[0] >> 5) << 7;
+            if (row < 0 || row >= mbh) continue;          // reported as an error by either parser
+            if (seen[row]) return false;
+            seen[row] = 1;
+            lo = std::min(lo, sl.payload);
+            hi = std::max(hi, sl.payload + sl.bytes);
+        }
+        if ((size_t)(hi - lo) + 64 > cap) return false;
+    }
+    return true;
+}
+
+bool mp2v_decoder_c::impl_t::prepare(bool gpu_vlc) {
+    std::vector<device_ctx_t>& devs = dev_sets[gpu_vlc ? 1 : 0];
     if (!devs.empty()) return true;
     const decoder_config_t& c = cfg;
     const int mbw = c.width / 16, mbh = c.height / 16;
@@ -353,13 +410,16 @@ bool mp2v_decoder_c::impl_t::prepare() {
         d.n_frames = (c.pictures_pool_size > 4 ? c.pictures_pool_size : 4) + lag + 2;
         d.n_slots = 2 * (opt.max_batch > 0 ? opt.max_batch : 8);
         if (d.n_slots < 6) d.n_slots = 6;
+        // a slice parses at the speed of one GPU thread: throughput comes from the number of pictures in flight
+        if (gpu_vlc) { d.n_frames += 24; if (d.n_slots < 32) d.n_slots = 32; }
         mp2v_recon_config_t rc{};
         rc.device = id; rc.width = c.width; rc.height = c.height; rc.chroma_format = c.chroma_format;
-        rc.n_frames = d.n_frames; rc.n_pictures = d.n_slots; rc.max_batch = opt.max_batch; rc.flags = MP2V_RECON_VALIDATE;
+        rc.n_frames = d.n_frames; rc.n_pictures = d.n_slots; rc.max_batch = opt.max_batch; rc.flags = MP2V_RECON_VALIDATE | (gpu_vlc ? MP2V_RECON_DEVICE_VLC : 0) | (opt.download_frames ? MP2V_RECON_AUTO_DOWNLOAD : 0);
         rc.coef_capacity = (uint32_t)(cap > 0xffffffffull ? 0xffffffffull : cap);
         if (mp2v_recon_create(&rc, &d.recon) != MP2V_OK) {
             error = std::string("mp2v_recon_create (CUDA device ") + std::to_string(id) + "): " + mp2v_recon_last_error(nullptr);
-            release();
+            for (auto& x : devs) if (x.recon) mp2v_recon_destroy(x.recon);
+            devs.clear();
             return false;
         }
         mp2v_recon_set_timing(d.recon, 1);
@@ -370,6 +430,7 @@ bool mp2v_decoder_c::impl_t::prepare() {
 
 mp2v_decoder_c::mp2v_decoder_c() : m(new impl_t) {
     if (const char* d = getenv("MP2V_DEVICE")) m->opt.devices = {atoi(d)};
+    if (const char* v = getenv("MP2V_GPU_VLC")) m->opt.gpu_vlc = atoi(v) != 0;
 }
 mp2v_decoder_c::mp2v_decoder_c(const decoder_config_t& config, std::function<void(frame_c*)> renderer) : mp2v_decoder_c() {
     decoder_init(config, renderer);
@@ -386,7 +447,7 @@ bool mp2v_decoder_c::decoder_init(const decoder_config_t& config, std::function<
 }
 
 void mp2v_decoder_c::set_options(const mp2v_b200_options_t& opt) { m->release(); m->opt = opt; }
-bool mp2v_decoder_c::prepare() { return m->initialised && m->prepare(); }
+bool mp2v_decoder_c::prepare() { return m->initialised && m->prepare(m->opt.gpu_vlc); }
 const char* mp2v_decoder_c::last_error() const { return m->error.c_str(); }
 mp2v_decoder_c::stats_t mp2v_decoder_c::stats() const { return m->stats; }
 void mp2v_decoder_c::flush() {}   // decode() is one-shot and drains everything itself (as the reference's always does)
@@ -407,12 +468,14 @@ bool mp2v_decoder_c::decode(uint8_t* buffer, int len) {
     sh.gop_emitted.assign(sh.gop_size.size(), 0);
     for (const auto& pic : index.pictures) sh.gop_size[pic.gop]++;
     // one pipeline per device; GOP chain g -> device g mod N
-    if (!m->prepare()) return false;
-    std::deque<pipeline_t> pipes(m->devs.size());
+    sh.opt.gpu_vlc = m->opt.gpu_vlc && m->device_parser_can_take(index);
+    if (!m->prepare(sh.opt.gpu_vlc)) return false;
+    const std::vector<device_ctx_t>& devs = m->dev_sets[sh.opt.gpu_vlc ? 1 : 0];
+    std::deque<pipeline_t> pipes(devs.size());
     for (size_t d = 0; d < pipes.size(); d++) {
         pipeline_t& p = pipes[d];
-        p.sh = &sh; p.device = m->devs[d].device; p.recon = m->devs[d].recon;
-        p.n_frames = m->devs[d].n_frames; p.n_slots = m->devs[d].n_slots; p.parse_window = p.n_slots / 2;
+        p.sh = &sh; p.device = devs[d].device; p.recon = devs[d].recon;
+        p.n_frames = devs[d].n_frames; p.n_slots = devs[d].n_slots; p.parse_window = p.n_slots / 2;
         p.frame_use.assign(p.n_frames, 0);
         sh.pipes.push_back(&p);
         mp2v_recon_stats_t st;
@@ -428,6 +491,7 @@ bool mp2v_decoder_c::decode(uint8_t* buffer, int len) {
     std::vector<std::thread> workers;
     {
         int nthreads = m->cfg.num_threads > MAX_NUM_THREADS ? MAX_NUM_THREADS : m->cfg.num_threads;
+        if (sh.opt.gpu_vlc) nthreads = 0;        // no host slice parsing
         for (int i = 0; i < nthreads; i++) workers.emplace_back(worker_main, &sh);
         for (auto& p : pipes) if (!p.tasks.empty()) {
             p.feeder_thread = std::thread(&pipeline_t::feeder, &p);
@@ -449,6 +513,7 @@ bool mp2v_decoder_c::decode(uint8_t* buffer, int len) {
         if (mp2v_recon_get_stats(p.recon, &st, 0) == MP2V_OK) {
             m->stats.pictures += st.pictures; m->stats.launches += st.launches; m->stats.h2d_bytes += st.h2d_bytes;
             m->stats.d2h_bytes += st.d2h_bytes; m->stats.algorithmic_bytes += st.algorithmic_bytes; m->stats.kernel_ms += st.kernel_ms;
+            m->stats.vlc_launches += st.vlc_launches;
         }
     }
     m->stats.parse_cpu_seconds = sh.parse_ns.load() * 1e-9;

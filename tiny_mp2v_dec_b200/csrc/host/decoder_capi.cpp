@@ -65,6 +65,7 @@ extern "C" MP2V_API int mp2v_decoder_create(const mp2v_decode_params_t* p, mp2v_
     if (p->max_batch > 0) opt.max_batch = p->max_batch;
     if (p->output_lag > 0) opt.output_lag = p->output_lag;
     opt.download_frames = p->download_frames != 0;
+    opt.gpu_vlc = p->host_parser == 0;
     d->dec.set_options(opt);
     if (!d->dec.prepare()) { set_err(err, err_len, d->dec.last_error()); return MP2V_ERR_CUDA; }
     *out = d.release();
@@ -87,6 +88,7 @@ extern "C" MP2V_API int mp2v_decoder_decode(mp2v_decoder_t* d, uint8_t* buffer, 
         stats->h2d_bytes = s.h2d_bytes; stats->d2h_bytes = s.d2h_bytes; stats->algorithmic_bytes = s.algorithmic_bytes;
         stats->kernel_ms = s.kernel_ms; stats->parse_cpu_seconds = s.parse_cpu_seconds; stats->wall_seconds = s.wall_seconds;
         stats->hash = d->hash;
+        stats->vlc_launches = s.vlc_launches;
     }
     if (!ok) {
         set_err(err, err_len, d->dec.last_error());

@@ -161,7 +161,7 @@ slice_result_t parse_slice(const uint8_t* payload, int slice_start_code, const s
     mp2v_coef_t* const scratch = thread_scratch((size_t)mbw * nblk * 64u);
     uint32_t total = 0;
     int first_mbx = 0, last_mbx = -1, mb_row = 0;
-    const int err = parse_slice_core(payload, slice_start_code, sx, vlc_decode_tables(), mb, scratch, 0u, &total, &first_mbx, &last_mbx, &mb_row);
+    const int err = parse_slice_core<false>(payload, slice_start_code, sx, vlc_decode_tables(), mb, scratch, 0u, &total, &first_mbx, &last_mbx, &mb_row);
     if (err != SLICE_OK) return fail(slice_error_string(err));
     res.mbs = last_mbx - first_mbx + 1;
     const uint32_t base = arena.next.fetch_add(total, std::memory_order_relaxed);

@@ -53,6 +53,14 @@ inline const char* slice_error_string(int e) {
     }
 }
 
+#if defined(__CUDA_ARCH__)
+#define MP2V_UNROLL2 _Pragma("unroll 2")
+#elif defined(__CUDACC__)
+#define MP2V_UNROLL2                       /* host pass of a .cu file: the host copy is never called from there */
+#else
+#define MP2V_UNROLL2 _Pragma("GCC unroll 2")
+#endif
+
 #if defined(__CUDACC__)
 #define MP2V_HDI __host__ __device__ __forceinline__
 #else
@@ -130,7 +138,7 @@ MP2V_HDI bool parse_block(bitreader_t& br, mp2v_coef_t*& out, const vlc_decode_t
     for (;;) {
         // one refill (>= 56 bits) covers two symbols of any kind (escape = 24 bits); the first round
         // reuses the refill above (at most 22 bits were consumed since)
-#pragma unroll 2
+        MP2V_UNROLL2
         for (int rep = 0; rep < 2; rep++) {
             const coef_fast_t f = fast[br.peek(kFastBits)];
             int run, level;
@@ -168,10 +176,18 @@ MP2V_HDI bool parse_block(bitreader_t& br, mp2v_coef_t*& out, const vlc_decode_t
     }
 }
 
+// the reference does not clamp vectors: one that leaves the frame is an error here
+MP2V_HDI bool mv_inside(int mbx, int mby, int mvx, int mvy, int width, int height) {
+    const int x0 = mbx * 16 + (mvx >> 1), y0 = mby * 16 + (mvy >> 1);
+    return x0 >= 0 && y0 >= 0 && x0 + 16 + (mvx & 1) <= width && y0 + 16 + (mvy & 1) <= height;
+}
+
 // Parse one slice.  payload = first byte after the 4-byte start code.  Macroblock records go to
 // mb[row * mbw + x]; coefficient records to out_base[0 ...] with coef_off = coef_off_base + index.
 // Returns a slice_error_t; *n_out = coefficient records written, [*first_mbx, *last_mbx] = the
-// macroblocks of the row this slice wrote.
+// macroblocks of the row this slice wrote.  CHECK_MV: reject vectors that leave the frame while
+// parsing (the device-side parser; the host path validates whole pictures in mp2v_recon_precheck).
+template <bool CHECK_MV>
 MP2V_HDI int parse_slice_core(const uint8_t* payload, int slice_start_code, const slice_syntax_t& sx, const vlc_decode_tables_t& T,
                               mp2v_mb_info_t* mb, mp2v_coef_t* out_base, uint32_t coef_off_base,
                               uint32_t* n_out, int* first_mbx_out, int* last_mbx_out, int* mb_row_out) {
@@ -195,7 +211,7 @@ MP2V_HDI int parse_slice_core(const uint8_t* payload, int slice_start_code, cons
     const int pct = sx.picture_coding_type;
     mp2v_mb_info_t* row = mb + (size_t)mb_row * mbw;
     uint32_t prev_dirs = 0;
-    int mbx = -1, first_mbx = 0;
+    int mbx = -1, first_mbx = 0, done_mbx = -1;      // done_mbx: last macroblock whose record is complete
     bool first = true;
     int err = SLICE_OK;
     do {
@@ -214,20 +230,26 @@ MP2V_HDI int parse_slice_core(const uint8_t* payload, int slice_start_code, cons
         const int target = first ? inc - 1 : mbx + inc;
         if (target >= mbw) { err = SLICE_ERR_ADDRESS; break; }
         const int skipped = first ? 0 : inc - 1;
-        if (first) { mbx = target - 1; first_mbx = target; first = false; }
+        if (first) { mbx = target - 1; first_mbx = target; done_mbx = target - 1; first = false; }
         // ---- skipped macroblocks (mb_decoder.cpp:541-550)
         if (skipped > 0) {
             if (pct == 1) { err = SLICE_ERR_SKIP_IN_I; break; }
             if (pct == 2) { pmv[0][0] = pmv[0][1] = pmv[1][0] = pmv[1][1] = 0; }
             uint32_t dirs = pct == 2 ? MP2V_MB_FWD : prev_dirs;
             if (!dirs) dirs = MP2V_MB_FWD;                              // after an intra macroblock the reference predicts forward
-            for (int k = 0; k < skipped; k++) {
+            for (int k = 0; k < skipped && !err; k++) {
+                if (CHECK_MV)
+                    for (int s = 0; s < 2; s++)
+                        if ((dirs & (s ? MP2V_MB_BWD : MP2V_MB_FWD)) && !mv_inside(mbx + 1, mb_row, pmv[s][0], pmv[s][1], mbw * 16, sx.mbh * 16)) err = SLICE_ERR_MV_RANGE;
+                if (err) break;
                 mp2v_mb_info_t& r = row[++mbx];
                 r.coef_off = coef_off_base + (uint32_t)(out - out_base);
                 r.bits = MP2V_MB_BITS(0, qscale, 0, dirs);
                 for (int s = 0; s < 2; s++) for (int t = 0; t < 2; t++)
                     r.mv[s][t] = (int16_t)((dirs & (s ? MP2V_MB_BWD : MP2V_MB_FWD)) ? pmv[s][t] : 0);
+                done_mbx = mbx;
             }
+            if (err) break;
             dc_pred[0] = dc_pred[1] = dc_pred[2] = dc_reset;
         }
         mp2v_mb_info_t& r = row[++mbx];
@@ -276,17 +298,22 @@ MP2V_HDI int parse_slice_core(const uint8_t* payload, int slice_start_code, cons
             if (fwd) flags |= MP2V_MB_FWD;
             if (bwd) flags |= MP2V_MB_BWD;
             if (!flags) flags = MP2V_MB_FWD;        // P picture "no MC": forward prediction with a zero vector (mb_decoder.cpp:329-338)
+            if (CHECK_MV)
+                for (int s = 0; s < 2; s++)
+                    if ((flags & (s ? MP2V_MB_BWD : MP2V_MB_FWD)) && !mv_inside(mbx, mb_row, mv[s][0], mv[s][1], mbw * 16, sx.mbh * 16)) err = SLICE_ERR_MV_RANGE;
+            if (err) break;
         }
         r.coef_off = coef_off_base + off;
         r.bits = MP2V_MB_BITS((uint32_t)(out - out_base) - off, qscale, cbp, flags);
         for (int s = 0; s < 2; s++) for (int t = 0; t < 2; t++) r.mv[s][t] = (int16_t)(intra ? 0 : mv[s][t]);
         prev_dirs = flags & (MP2V_MB_FWD | MP2V_MB_BWD);
+        done_mbx = mbx;
         br.refill();
     } while (br.peek(23) != 0 && mbx < mbw - 1);
     // trailing macroblocks of the row that the slice did not code keep the caller's defaults
     *n_out = (uint32_t)(out - out_base);
     *first_mbx_out = first_mbx;
-    *last_mbx_out = err ? first_mbx - 1 : mbx;
+    *last_mbx_out = done_mbx;
     return err;
 }
 

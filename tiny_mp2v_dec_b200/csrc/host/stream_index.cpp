@@ -70,7 +70,8 @@ bool index_stream(const uint8_t* buffer, size_t len, stream_index_t& out, int th
             have_picture = true;
         } else if (code >= 0x01 && code <= 0xAF) {       // slice
             if (!cur) { out.error = "slice before any picture header"; return false; }
-            cur->slices.push_back({payload, code});
+            const uint8_t* next = ci + 1 < codes.size() ? buffer + codes[ci + 1] : end;
+            cur->slices.push_back({payload, code, (uint32_t)(next - payload)});
         } else if (code == 0xB7 || code == 0xB4) {       // sequence_end / sequence_error
             cur = nullptr;
         }

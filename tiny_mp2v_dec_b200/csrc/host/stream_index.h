@@ -14,6 +14,7 @@ namespace mp2v {
 struct slice_ref_t {
     const uint8_t* payload;   // first byte after the 4-byte start code
     int code;                 // slice_start_code value 0x01..0xAF
+    uint32_t bytes;           // payload length: up to the next start code prefix (or the end of the buffer)
 };
 
 struct coded_picture_t {

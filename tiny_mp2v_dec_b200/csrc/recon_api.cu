@@ -14,6 +14,7 @@
 
 #include "mp2v_recon.h"
 #include "recon_kernels.cuh"
+#include "vlc_kernel.cuh"
 
 using namespace mp2v;
 
@@ -32,6 +33,17 @@ struct slot_t {
     uint64_t alg_bytes = 0;
     bool prechecked = false;           // account_and_validate already ran for the records now in the slot
     uint64_t seq = 0;                  // submission order, to recycle the oldest in-flight slot first
+    // device-side slice parsing (MP2V_RECON_DEVICE_VLC): staged bitstream, own stream, parse result
+    uint8_t* h_staged = nullptr;
+    uint8_t* d_staged = nullptr;
+    vlc_slice_status_t* h_status = nullptr;   // pinned + mapped: one entry per slice, written by the kernel
+    vlc_slice_status_t* d_status = nullptr;   // the device's address of h_status
+    int n_slices = 0;
+    cudaStream_t s_vlc = nullptr;
+    cudaEvent_t vlc_done = nullptr;    // H2D + parse + status read-back of the picture now in the slot
+    bool vlc = false;                  // the slot's records come from the device parser
+    bool status_pending = false;       // h_status not yet folded into the statistics / error state
+    uint64_t picture_no = 0;
 };
 
 constexpr size_t kParamsBytes = 512;   // sizeof(mp2v_pic_params_t) rounded up; mb records follow
@@ -47,6 +59,10 @@ struct mp2v_recon {
     std::vector<uint8_t*> h_frames;            // pinned mirrors, allocated on first map
     std::vector<cudaEvent_t> frame_ev;         // last writer of each frame
     std::vector<uint8_t> frame_written;
+    // MP2V_RECON_AUTO_DOWNLOAD: every submitted picture's frame is copied to its pinned mirror right behind its launch
+    bool auto_dl = false;
+    std::vector<cudaEvent_t> mirror_ev;        // the mirror copy of each frame
+    std::vector<uint8_t> mirror_valid;         // mirror_ev covers the frame's current content
     cudaStream_t s_copy = nullptr, s_compute = nullptr, s_d2h = nullptr;
     cudaEvent_t ev_h2d = nullptr, ev_t0 = nullptr, ev_t1 = nullptr;
     std::vector<slot_t> slots;
@@ -59,6 +75,15 @@ struct mp2v_recon {
     bool timing = false;
     std::vector<std::pair<cudaEvent_t, cudaEvent_t>> timed;   // (start, stop) of launches not yet summed
     std::vector<cudaEvent_t> ev_pool;
+    // device-side slice parsing
+    bool vlc = false;
+    int vlc_lanes = 1;
+    size_t staged_bytes = 0;                   // per-slot staging capacity (header + slice table + bitstream)
+    uint32_t slice_region = 0;
+    void* d_tables = nullptr;
+    uint8_t* d_blank_mb = nullptr;             // mb_count blank records, copied over a slot's records before each parse
+    std::string vlc_error;                     // sticky: first slice error reported by the device parser
+    uint64_t pictures_submitted = 0;
 
     int fail(int code, const std::string& what) { err = what; return code; }
     int cuda_fail(cudaError_t e, const char* what) {
@@ -105,9 +130,17 @@ static void destroy_ctx(mp2v_recon* ctx) {
         if (s.h_arena) cudaFreeHost(s.h_arena);
         if (s.d_arena) cudaFree(s.d_arena);
         if (s.done) cudaEventDestroy(s.done);
+        if (s.s_vlc) { cudaStreamSynchronize(s.s_vlc); cudaStreamDestroy(s.s_vlc); }
+        if (s.vlc_done) cudaEventDestroy(s.vlc_done);
+        if (s.h_staged) cudaFreeHost(s.h_staged);
+        if (s.d_staged) cudaFree(s.d_staged);
+        if (s.h_status) cudaFreeHost(s.h_status);
     }
+    if (ctx->d_tables) cudaFree(ctx->d_tables);
+    if (ctx->d_blank_mb) cudaFree(ctx->d_blank_mb);
     for (auto* h : ctx->h_frames) if (h) cudaFreeHost(h);
     for (auto e : ctx->frame_ev) if (e) cudaEventDestroy(e);
+    for (auto e : ctx->mirror_ev) if (e) cudaEventDestroy(e);
     for (auto e : ctx->ev_pool) cudaEventDestroy(e);
     for (auto& pr : ctx->timed) { cudaEventDestroy(pr.first); cudaEventDestroy(pr.second); }
     if (ctx->ev_h2d) cudaEventDestroy(ctx->ev_h2d);
@@ -150,23 +183,60 @@ static int create_impl(mp2v_recon* ctx) {
     ctx->frame_ev.assign(c.n_frames, nullptr);
     ctx->frame_written.assign(c.n_frames, 0);
     for (auto& ev : ctx->frame_ev) CK(cudaEventCreateWithFlags(&ev, cudaEventDisableTiming), "event");
+    ctx->auto_dl = (c.flags & MP2V_RECON_AUTO_DOWNLOAD) != 0;
+    ctx->mirror_valid.assign(c.n_frames, 0);
+    if (ctx->auto_dl) {
+        ctx->mirror_ev.assign(c.n_frames, nullptr);
+        for (auto& ev : ctx->mirror_ev) CK(cudaEventCreateWithFlags(&ev, cudaEventDisableTiming), "event");
+        for (auto& h : ctx->h_frames) CK(cudaHostAlloc(&h, ctx->lay.bytes, cudaHostAllocDefault), "cudaHostAlloc frame mirror");
+    }
     // picture slots
-    const uint32_t worst = (uint32_t)ctx->mb_count * ctx->nblk * 64u;
-    const uint32_t cap = c.coef_capacity ? c.coef_capacity : worst;
+    const uint64_t worst = (uint64_t)ctx->mb_count * ctx->nblk * 64u;
+    if (worst > 0xffffffffull) return ctx->fail(MP2V_ERR_ARG, "picture too large");
+    ctx->vlc = (c.flags & MP2V_RECON_DEVICE_VLC) != 0;
+    // With the device parser every slice owns a worst-case region of the device arena (sparse use of
+    // plentiful HBM instead of a second counting pass), and the host side of a slot holds no
+    // coefficient records at all.
+    const uint32_t cap = ctx->vlc ? (uint32_t)worst : (c.coef_capacity ? c.coef_capacity : (uint32_t)worst);
+    const uint32_t host_cap = ctx->vlc ? 0u : cap;
     ctx->coef_off = kParamsBytes + (((size_t)ctx->mb_count * sizeof(mp2v_mb_info_t) + 255) & ~(size_t)255);
     ctx->arena_bytes = ctx->coef_off + (size_t)cap * sizeof(mp2v_coef_t);
+    const size_t host_arena_bytes = ctx->coef_off + (size_t)host_cap * sizeof(mp2v_coef_t);
+    if (ctx->vlc) {
+        cudaFuncAttributes va;
+        e = vlc_kernel_attributes(&va);
+        if (e != cudaSuccess) return ctx->cuda_fail(e, "slice parser kernel image not usable on this device (built for sm_100a only)");
+        CK(vlc_upload_tables(&ctx->d_tables), "slice parser tables");
+        ctx->slice_region = (uint32_t)ctx->mbw * ctx->nblk * 64u;
+        const size_t bits_cap = c.bitstream_capacity ? c.bitstream_capacity : std::max<size_t>(2u << 20, (size_t)ctx->mb_count * 128u);
+        ctx->staged_bytes = kVlcParamsBytes + sizeof(vlc_pic_header_t) + (size_t)ctx->mbh * sizeof(vlc_slice_t) + 16 + bits_cap + 16;
+        if (const char* v = getenv("MP2V_VLC_LANES")) { const int l = atoi(v); if (l >= 1 && l <= 32) ctx->vlc_lanes = l; }
+        std::vector<mp2v_mb_info_t> blank((size_t)ctx->mb_count, mp2v_mb_info_t{0u, MP2V_MB_BITS(0, 1, 0, MP2V_MB_INTRA), {{0, 0}, {0, 0}}});
+        CK(cudaMalloc(&ctx->d_blank_mb, blank.size() * sizeof(mp2v_mb_info_t)), "cudaMalloc blank records");
+        CK(cudaMemcpy(ctx->d_blank_mb, blank.data(), blank.size() * sizeof(mp2v_mb_info_t), cudaMemcpyHostToDevice), "H2D blank records");
+    }
     ctx->slots.resize(c.n_pictures);
     for (int i = 0; i < c.n_pictures; i++) {
         slot_t& s = ctx->slots[i];
-        CK(cudaHostAlloc(&s.h_arena, ctx->arena_bytes, cudaHostAllocDefault), "cudaHostAlloc picture arena");
+        CK(cudaHostAlloc(&s.h_arena, host_arena_bytes, cudaHostAllocDefault), "cudaHostAlloc picture arena");
         CK(cudaMalloc(&s.d_arena, ctx->arena_bytes), "cudaMalloc picture arena");
         CK(cudaEventCreateWithFlags(&s.done, cudaEventDisableTiming), "event");
         s.pub.params = reinterpret_cast<mp2v_pic_params_t*>(s.h_arena);
         s.pub.mb = reinterpret_cast<mp2v_mb_info_t*>(s.h_arena + kParamsBytes);
-        s.pub.coef = reinterpret_cast<mp2v_coef_t*>(s.h_arena + ctx->coef_off);
+        s.pub.coef = host_cap ? reinterpret_cast<mp2v_coef_t*>(s.h_arena + ctx->coef_off) : nullptr;
         s.pub.mb_count = (uint32_t)ctx->mb_count;
-        s.pub.coef_capacity = cap;
+        s.pub.coef_capacity = host_cap;
         s.pub.slot = i;
+        if (ctx->vlc) {
+            // the parameters travel with the staged bitstream: one H2D per picture
+            CK(cudaHostAlloc(&s.h_staged, ctx->staged_bytes, cudaHostAllocDefault), "cudaHostAlloc bitstream staging");
+            CK(cudaMalloc(&s.d_staged, ctx->staged_bytes), "cudaMalloc bitstream staging");
+            s.pub.params = reinterpret_cast<mp2v_pic_params_t*>(s.h_staged);
+            CK(cudaHostAlloc(&s.h_status, (size_t)ctx->mbh * sizeof(vlc_slice_status_t), cudaHostAllocMapped), "cudaHostAlloc parse status");
+            CK(cudaHostGetDevicePointer(&s.d_status, s.h_status, 0), "cudaHostGetDevicePointer");
+            CK(cudaStreamCreateWithFlags(&s.s_vlc, cudaStreamNonBlocking), "stream");
+            CK(cudaEventCreateWithFlags(&s.vlc_done, cudaEventDisableTiming), "event");
+        }
     }
     CK(cudaDeviceSynchronize(), "cudaDeviceSynchronize");
     return MP2V_OK;
@@ -174,7 +244,7 @@ static int create_impl(mp2v_recon* ctx) {
 
 extern "C" MP2V_API int mp2v_recon_create(const mp2v_recon_config_t* cfg, mp2v_recon_t** out) {
     if (!cfg || !out) return MP2V_ERR_ARG;
-    static_assert(sizeof(mp2v_pic_params_t) <= kParamsBytes, "params block");
+    static_assert(sizeof(mp2v_pic_params_t) <= kParamsBytes && kVlcParamsBytes == kParamsBytes, "params block");
     static_assert(sizeof(mp2v_mb_info_t) == 16, "mb record");
     mp2v_recon* ctx = new mp2v_recon();
     ctx->cfg = *cfg;
@@ -198,7 +268,7 @@ extern "C" MP2V_API const char* mp2v_recon_last_error(mp2v_recon_t* ctx) { retur
 
 static void fill_desc(mp2v_recon* ctx, const slot_t& s, pic_desc_t& d) {
     const mp2v_pic_params_t& pp = *s.pub.params;
-    d.params = reinterpret_cast<const mp2v_pic_params_t*>(s.d_arena);
+    d.params = reinterpret_cast<const mp2v_pic_params_t*>(ctx->vlc ? s.d_staged : s.d_arena);
     d.mb = reinterpret_cast<const mp2v_mb_info_t*>(s.d_arena + kParamsBytes);
     d.coef = reinterpret_cast<const mp2v_coef_t*>(s.d_arena + ctx->coef_off);
     for (int p = 0; p < 3; p++) {
@@ -210,7 +280,7 @@ static void fill_desc(mp2v_recon* ctx, const slot_t& s, pic_desc_t& d) {
 }
 
 // one launch over `ids` (<= max_batch slots whose records are already on, or on their way to, the device)
-static int launch_slots(mp2v_recon* ctx, const int* ids, int n) {
+static int launch_slots(mp2v_recon* ctx, const int* ids, int n, bool download = false) {
     batch_desc_t b{};
     b.n_pics = n;
     b.mbw = ctx->mbw; b.mbh = ctx->mbh; b.mb_count = ctx->mb_count;
@@ -235,7 +305,19 @@ static int launch_slots(mp2v_recon* ctx, const int* ids, int n) {
         const int f = s.pub.params->dst_frame;
         CK(cudaEventRecord(ctx->frame_ev[f], ctx->s_compute), "event record");
         ctx->frame_written[f] = 1;
+        ctx->mirror_valid[f] = 0;
         ctx->stats.algorithmic_bytes += s.alg_bytes;
+    }
+    if (download) {
+        // the copies queue up on the D2H stream behind this launch and overlap the launches that follow
+        CK(cudaStreamWaitEvent(ctx->s_d2h, ctx->frame_ev[ctx->slots[ids[n - 1]].pub.params->dst_frame], 0), "stream wait");
+        for (int i = 0; i < n; i++) {
+            const int f = ctx->slots[ids[i]].pub.params->dst_frame;
+            CK(cudaMemcpyAsync(ctx->h_frames[f], ctx->frame_ptr(f, 0), ctx->lay.bytes, cudaMemcpyDeviceToHost, ctx->s_d2h), "D2H frame");
+            CK(cudaEventRecord(ctx->mirror_ev[f], ctx->s_d2h), "event record");
+            ctx->mirror_valid[f] = 1;
+            ctx->stats.d2h_bytes += ctx->lay.bytes;
+        }
     }
     ctx->stats.pictures += n;
     ctx->stats.launches += 1;
@@ -246,15 +328,21 @@ static int flush_locked(mp2v_recon* ctx) {
     if (ctx->pending.empty()) return MP2V_OK;
     CK(cudaSetDevice(ctx->cfg.device), "cudaSetDevice");
     // H2D of every queued picture: params + macroblock records + the used part of the coefficient arena
+    // (pictures parsed on the device already have them there: the launch waits for their parse instead)
+    bool any_h2d = false;
     for (int id : ctx->pending) {
         slot_t& s = ctx->slots[id];
+        if (s.vlc) { CK(cudaStreamWaitEvent(ctx->s_compute, s.vlc_done, 0), "stream wait"); continue; }
         const size_t bytes = ctx->coef_off + (size_t)s.pub.params->n_coef * sizeof(mp2v_coef_t);
         CK(cudaMemcpyAsync(s.d_arena, s.h_arena, bytes, cudaMemcpyHostToDevice, ctx->s_copy), "H2D picture records");
         ctx->stats.h2d_bytes += bytes;
+        any_h2d = true;
     }
-    CK(cudaEventRecord(ctx->ev_h2d, ctx->s_copy), "event record");
-    CK(cudaStreamWaitEvent(ctx->s_compute, ctx->ev_h2d, 0), "stream wait");
-    const int rc = launch_slots(ctx, ctx->pending.data(), (int)ctx->pending.size());
+    if (any_h2d) {
+        CK(cudaEventRecord(ctx->ev_h2d, ctx->s_copy), "event record");
+        CK(cudaStreamWaitEvent(ctx->s_compute, ctx->ev_h2d, 0), "stream wait");
+    }
+    const int rc = launch_slots(ctx, ctx->pending.data(), (int)ctx->pending.size(), ctx->auto_dl);
     if (rc != MP2V_OK) return rc;
     for (int id : ctx->pending) {
         slot_t& s = ctx->slots[id];
@@ -306,6 +394,29 @@ static int account_and_validate(mp2v_recon* ctx, slot_t& s, bool validate, std::
     return MP2V_OK;
 }
 
+// ---------------------------------------------------------------------------------------------
+// device-side slice parsing
+
+// Fold the parse results that have arrived into the statistics and the sticky error (ctx->mu held).
+static void harvest_status(mp2v_recon* ctx, slot_t& s) {
+    if (!s.status_pending || cudaEventQuery(s.vlc_done) != cudaSuccess) return;
+    s.status_pending = false;
+    uint64_t n_coef = 0, coded = 0, dirs = 0;
+    for (int i = 0; i < s.n_slices; i++) {
+        const vlc_slice_status_t& st = s.h_status[i];
+        n_coef += st.n_coef; coded += st.coded_blocks; dirs += st.ref_dirs;
+        if (st.error && ctx->vlc_error.empty())
+            ctx->vlc_error = "picture " + std::to_string(s.picture_no) + " slice " + std::to_string(i) + ": " + slice_error_string((int)st.error);
+    }
+    const uint64_t mb_bytes = ctx->cfg.chroma_format == 1 ? 384 : ctx->cfg.chroma_format == 2 ? 512 : 768;
+    uint64_t out_bytes = 0;
+    for (int p = 0; p < 3; p++) out_bytes += (uint64_t)ctx->lay.width[p] * ctx->lay.height[p];
+    ctx->stats.algorithmic_bytes += out_bytes + dirs * mb_bytes + 128u * coded + 16u * (uint64_t)ctx->mb_count;
+    ctx->stats.vlc_coefs += n_coef;
+}
+static void harvest_all(mp2v_recon* ctx) { if (ctx->vlc) for (auto& s : ctx->slots) harvest_status(ctx, s); }
+#define CHECK_VLC_ERROR() do { if (!ctx->vlc_error.empty()) return ctx->fail(MP2V_ERR_RANGE, ctx->vlc_error); } while (0)
+
 extern "C" MP2V_API int mp2v_recon_acquire_picture(mp2v_recon_t* ctx, mp2v_picture_t** out) {
     if (!ctx || !out) return MP2V_ERR_ARG;
     for (int attempt = 0; attempt < 4; attempt++) {
@@ -323,8 +434,11 @@ extern "C" MP2V_API int mp2v_recon_acquire_picture(mp2v_recon_t* ctx, mp2v_pictu
             }
             if (best >= 0) {
                 slot_t& s = ctx->slots[best];
+                harvest_status(ctx, s);
+                CHECK_VLC_ERROR();
                 s.state = SLOT_FILLING;
                 s.prechecked = false;
+                s.vlc = false;
                 memset(s.pub.params, 0, sizeof(mp2v_pic_params_t));
                 s.pub.params->l0_frame = s.pub.params->l1_frame = -1;
                 *out = &s.pub;
@@ -369,15 +483,8 @@ extern "C" MP2V_API int mp2v_recon_release_picture(mp2v_recon_t* ctx, mp2v_pictu
     return MP2V_OK;
 }
 
-extern "C" MP2V_API int mp2v_recon_submit(mp2v_recon_t* ctx, mp2v_picture_t* pic) {
-    if (!ctx) return MP2V_ERR_ARG;
-    slot_t* s = slot_of(ctx, pic);
-    if (!s || s->state != SLOT_FILLING) { std::lock_guard<std::mutex> lk(ctx->mu); return ctx->fail(MP2V_ERR_STATE, "submit: picture was not acquired"); }
-    // the slot belongs to the caller until it is queued: validate its records without holding the lock
-    std::string why;
-    int rc = s->prechecked ? MP2V_OK : account_and_validate(ctx, *s, (ctx->cfg.flags & MP2V_RECON_VALIDATE) != 0, &why);
-    std::lock_guard<std::mutex> lk(ctx->mu);
-    if (rc != MP2V_OK) return ctx->fail(rc, why);
+// queue a slot whose records are (or will be) complete; ctx->mu held
+static int queue_slot(mp2v_recon* ctx, slot_t* s) {
     const mp2v_pic_params_t& pp = *s->pub.params;
     // a picture cannot share a launch with a picture it reads from, nor with one touching its destination
     bool conflict = (int)ctx->pending.size() >= ctx->max_batch;
@@ -386,15 +493,109 @@ extern "C" MP2V_API int mp2v_recon_submit(mp2v_recon_t* ctx, mp2v_picture_t* pic
         if (q.dst_frame == pp.l0_frame || q.dst_frame == pp.l1_frame || q.dst_frame == pp.dst_frame ||
             q.l0_frame == pp.dst_frame || q.l1_frame == pp.dst_frame) conflict = true;
     }
-    if (conflict) { rc = flush_locked(ctx); if (rc != MP2V_OK) return rc; }
+    if (conflict) { const int rc = flush_locked(ctx); if (rc != MP2V_OK) return rc; }
     for (int d = 0; d < 2; d++) {
         const int fr = d ? pp.l1_frame : pp.l0_frame;
         if (fr >= 0 && !ctx->frame_written[fr]) return ctx->fail(MP2V_ERR_STATE, "reference frame has never been written");
     }
     s->state = SLOT_QUEUED;
     s->seq = ++ctx->seq;
-    ctx->pending.push_back(pic->slot);
+    s->picture_no = ctx->pictures_submitted++;
+    ctx->pending.push_back(s->pub.slot);
     return MP2V_OK;
+}
+
+extern "C" MP2V_API int mp2v_recon_submit(mp2v_recon_t* ctx, mp2v_picture_t* pic) {
+    if (!ctx) return MP2V_ERR_ARG;
+    slot_t* s = slot_of(ctx, pic);
+    if (!s || s->state != SLOT_FILLING) { std::lock_guard<std::mutex> lk(ctx->mu); return ctx->fail(MP2V_ERR_STATE, "submit: picture was not acquired"); }
+    if (ctx->vlc) { std::lock_guard<std::mutex> lk(ctx->mu); return ctx->fail(MP2V_ERR_STATE, "submit: this context parses on the device (MP2V_RECON_DEVICE_VLC): use mp2v_recon_submit_slices"); }
+    // the slot belongs to the caller until it is queued: validate its records without holding the lock
+    std::string why;
+    int rc = s->prechecked ? MP2V_OK : account_and_validate(ctx, *s, (ctx->cfg.flags & MP2V_RECON_VALIDATE) != 0, &why);
+    std::lock_guard<std::mutex> lk(ctx->mu);
+    if (rc != MP2V_OK) return ctx->fail(rc, why);
+    return queue_slot(ctx, s);
+}
+
+extern "C" MP2V_API int mp2v_recon_submit_slices(mp2v_recon_t* ctx, mp2v_picture_t* pic, const mp2v_pic_syntax_t* syntax,
+                                                 const mp2v_slice_ref_t* slices, int n_slices) {
+    if (!ctx) return MP2V_ERR_ARG;
+    auto fail = [&](int code, const char* what) { std::lock_guard<std::mutex> lk(ctx->mu); return ctx->fail(code, what); };
+    slot_t* s = slot_of(ctx, pic);
+    if (!s || s->state != SLOT_FILLING) return fail(MP2V_ERR_STATE, "submit_slices: picture was not acquired");
+    if (!ctx->vlc) return fail(MP2V_ERR_STATE, "submit_slices: context was created without MP2V_RECON_DEVICE_VLC");
+    if (!syntax || (n_slices > 0 && !slices) || n_slices < 0) return fail(MP2V_ERR_ARG, "submit_slices: bad arguments");
+    const mp2v_pic_params_t& pp = *s->pub.params;
+    const int nf = ctx->cfg.n_frames;
+    if (pp.dst_frame < 0 || pp.dst_frame >= nf || pp.l0_frame >= nf || pp.l1_frame >= nf) return fail(MP2V_ERR_ARG, "frame id out of range");
+    if (pp.picture_coding_type < 1 || pp.picture_coding_type > 3) return fail(MP2V_ERR_ARG, "picture_coding_type must be 1 (I), 2 (P) or 3 (B)");
+    if ((pp.picture_coding_type >= 2 && pp.l0_frame < 0) || (pp.picture_coding_type == 3 && pp.l1_frame < 0))
+        return fail(MP2V_ERR_STATE, "prediction from a missing reference frame");
+    if (syntax->intra_dc_precision < 0 || syntax->intra_dc_precision > 3) return fail(MP2V_ERR_ARG, "intra_dc_precision out of range");
+    if (n_slices > ctx->mbh) return fail(MP2V_ERR_RANGE, "the device parser takes at most one slice per macroblock row");
+    // ---- stage header + slice table + bitstream (the slot is the caller's: no lock)
+    vlc_pic_header_t& hdr = *reinterpret_cast<vlc_pic_header_t*>(s->h_staged + kVlcParamsBytes);
+    memset(&hdr, 0, sizeof(hdr));
+    hdr.sx.picture_coding_type = pp.picture_coding_type;
+    for (int a = 0; a < 2; a++) for (int b = 0; b < 2; b++) hdr.sx.f_code[a][b] = syntax->f_code[a][b];
+    hdr.sx.intra_dc_precision = syntax->intra_dc_precision;
+    hdr.sx.q_scale_type = syntax->q_scale_type != 0;
+    hdr.sx.intra_vlc_format = syntax->intra_vlc_format != 0;
+    hdr.sx.chroma_format = ctx->cfg.chroma_format;
+    hdr.sx.vertical_size = ctx->cfg.height;            // only compared with 2800 (slice_vertical_position_extension)
+    hdr.sx.mbw = ctx->mbw; hdr.sx.mbh = ctx->mbh;
+    hdr.n_slices = (uint32_t)n_slices;
+    hdr.slice_region = ctx->slice_region;
+    hdr.data_off = (uint32_t)((kVlcParamsBytes + sizeof(vlc_pic_header_t) + (size_t)ctx->mbh * sizeof(vlc_slice_t) + 15) & ~(size_t)15);
+    vlc_slice_t* table = reinterpret_cast<vlc_slice_t*>(s->h_staged + kVlcParamsBytes + sizeof(vlc_pic_header_t));
+    size_t staged_end = hdr.data_off;
+    int rows_covered = 0;
+    if (n_slices > 0) {
+        // one copy of the byte range that covers every slice (slices of a picture are contiguous in a stream)
+        const uint8_t* lo = slices[0].payload;
+        const uint8_t* hi = slices[0].payload + slices[0].bytes;
+        std::vector<uint8_t> row_seen((size_t)ctx->mbh, 0);
+        for (int i = 0; i < n_slices; i++) {
+            if (!slices[i].payload || slices[i].code < 1 || slices[i].code > 0xAF) return fail(MP2V_ERR_ARG, "submit_slices: bad slice reference");
+            lo = std::min(lo, slices[i].payload);
+            hi = std::max(hi, slices[i].payload + slices[i].bytes);
+            int row = slices[i].code - 1;
+            if (ctx->cfg.height > 2800 && slices[i].bytes > 0) row += (slices[i].payload[0] >> 5) << 7;
+            if (row < 0 || row >= ctx->mbh) return fail(MP2V_ERR_RANGE, "slice row outside the picture");
+            if (row_seen[row]) return fail(MP2V_ERR_RANGE, "the device parser takes at most one slice per macroblock row");
+            row_seen[row] = 1;
+            rows_covered++;
+        }
+        const size_t span = (size_t)(hi - lo);
+        if (hdr.data_off + span + 16 > ctx->staged_bytes) return fail(MP2V_ERR_RANGE, "coded picture larger than bitstream_capacity");
+        memcpy(s->h_staged + hdr.data_off, lo, span);
+        memset(s->h_staged + hdr.data_off + span, 0, 16);
+        for (int i = 0; i < n_slices; i++) { table[i].byte_off = (uint32_t)(slices[i].payload - lo); table[i].code = slices[i].code; }
+        staged_end = hdr.data_off + span + 16;
+    }
+    s->pub.params->n_coef = 0;
+    // ---- H2D + parse on the slot's own stream, then queue the reconstruction
+    std::lock_guard<std::mutex> lk(ctx->mu);
+    harvest_all(ctx);
+    CHECK_VLC_ERROR();
+    CK(cudaSetDevice(ctx->cfg.device), "cudaSetDevice");
+    mp2v_mb_info_t* d_mb = reinterpret_cast<mp2v_mb_info_t*>(s->d_arena + kParamsBytes);
+    CK(cudaMemcpyAsync(s->d_staged, s->h_staged, staged_end, cudaMemcpyHostToDevice, s->s_vlc), "H2D bitstream");
+    // the kernel blanks what a slice leaves uncoded in its own row; rows without any slice (never in valid streams) are blanked here
+    if (rows_covered < ctx->mbh)
+        CK(cudaMemcpyAsync(d_mb, ctx->d_blank_mb, (size_t)ctx->mb_count * sizeof(mp2v_mb_info_t), cudaMemcpyDeviceToDevice, s->s_vlc), "blank records");
+    CK(launch_vlc(s->d_staged, ctx->d_tables, d_mb, reinterpret_cast<mp2v_coef_t*>(s->d_arena + ctx->coef_off), s->d_status, n_slices,
+                  ctx->vlc_lanes, s->s_vlc), "slice parser kernel launch");
+    CK(cudaEventRecord(s->vlc_done, s->s_vlc), "event record");
+    ctx->stats.h2d_bytes += staged_end;
+    ctx->stats.d2h_bytes += (uint64_t)n_slices * sizeof(vlc_slice_status_t);
+    if (n_slices > 0) { ctx->stats.vlc_launches += 1; ctx->stats.vlc_slices += (uint64_t)n_slices; }
+    s->n_slices = n_slices;
+    s->vlc = true;
+    s->status_pending = true;
+    s->alg_bytes = 0;                                    // folded in from the parse status (harvest_status)
+    return queue_slot(ctx, s);
 }
 
 extern "C" MP2V_API int mp2v_recon_precheck(mp2v_recon_t* ctx, mp2v_picture_t* pic) {
@@ -423,6 +624,12 @@ extern "C" MP2V_API int mp2v_recon_sync(mp2v_recon_t* ctx) {
     CK(cudaStreamSynchronize(ctx->s_copy), "stream sync");
     CK(cudaStreamSynchronize(ctx->s_compute), "stream sync");
     for (auto& s : ctx->slots) if (s.state == SLOT_INFLIGHT) s.state = SLOT_FREE;
+    harvest_all(ctx);      // every parse precedes a reconstruction launch that has now finished
+    if (!ctx->vlc_error.empty()) {
+        const std::string why = ctx->vlc_error;
+        ctx->vlc_error.clear();                          // reported once; the context stays usable
+        return ctx->fail(MP2V_ERR_RANGE, why);
+    }
     return MP2V_OK;
 }
 
@@ -434,6 +641,7 @@ extern "C" MP2V_API int mp2v_recon_upload(mp2v_recon_t* ctx, mp2v_picture_t* pic
     std::lock_guard<std::mutex> lk(ctx->mu);
     slot_t* s = slot_of(ctx, pic);
     if (!s || (s->state != SLOT_FILLING && s->state != SLOT_RESIDENT)) return ctx->fail(MP2V_ERR_STATE, "upload: picture was not acquired");
+    if (ctx->vlc) return ctx->fail(MP2V_ERR_STATE, "upload: this context parses on the device (MP2V_RECON_DEVICE_VLC)");
     std::string why;
     const int rc = account_and_validate(ctx, *s, (ctx->cfg.flags & MP2V_RECON_VALIDATE) != 0, &why);
     if (rc != MP2V_OK) return ctx->fail(rc, why);
@@ -505,11 +713,13 @@ static int enqueue_frame_copy(mp2v_recon* ctx, int frame_id, uint8_t* const dst[
     return MP2V_OK;
 }
 
-static int wait_frame_copy(mp2v_recon* ctx, cudaEvent_t done) {
+static int wait_frame_copy(mp2v_recon* ctx, cudaEvent_t done, bool pooled = true) {
     const cudaError_t e = cudaEventSynchronize(done);
     std::lock_guard<std::mutex> lk(ctx->mu);
-    ctx->ev_pool.push_back(done);
+    if (pooled) ctx->ev_pool.push_back(done);
     if (e != cudaSuccess) return ctx->cuda_fail(e, "D2H frame");
+    harvest_all(ctx);      // the frame's picture has been parsed by now: a slice error surfaces with its frame
+    CHECK_VLC_ERROR();
     return MP2V_OK;
 }
 
@@ -527,6 +737,7 @@ extern "C" MP2V_API int mp2v_recon_download_frame(mp2v_recon_t* ctx, int frame_i
 extern "C" MP2V_API int mp2v_recon_map_frame(mp2v_recon_t* ctx, int frame_id, uint8_t* planes[3], int32_t strides[3]) {
     if (!ctx || !planes || !strides) return MP2V_ERR_ARG;
     cudaEvent_t done = nullptr;
+    bool pooled = true;
     {
         std::lock_guard<std::mutex> lk(ctx->mu);
         if (frame_id < 0 || frame_id >= ctx->cfg.n_frames) return ctx->fail(MP2V_ERR_ARG, "frame id out of range");
@@ -535,10 +746,16 @@ extern "C" MP2V_API int mp2v_recon_map_frame(mp2v_recon_t* ctx, int frame_id, ui
             CK(cudaHostAlloc(&ctx->h_frames[frame_id], ctx->lay.bytes, cudaHostAllocDefault), "cudaHostAlloc frame mirror");
         }
         for (int p = 0; p < 3; p++) { planes[p] = ctx->h_frames[frame_id] + ctx->lay.plane_offset[p]; strides[p] = ctx->lay.stride[p]; }
-        const int rc = enqueue_frame_copy(ctx, frame_id, planes, strides, &done);
-        if (rc != MP2V_OK) return rc;
+        if (ctx->auto_dl) { const int rc = flush_locked(ctx); if (rc != MP2V_OK) return rc; }
+        if (ctx->auto_dl && ctx->mirror_valid[frame_id]) {
+            done = ctx->mirror_ev[frame_id];           // the copy was queued with the picture's launch
+            pooled = false;
+        } else {
+            const int rc = enqueue_frame_copy(ctx, frame_id, planes, strides, &done);
+            if (rc != MP2V_OK) return rc;
+        }
     }
-    return wait_frame_copy(ctx, done);
+    return wait_frame_copy(ctx, done, pooled);
 }
 
 extern "C" MP2V_API int mp2v_recon_upload_frame(mp2v_recon_t* ctx, int frame_id, const uint8_t* const src[3], const int32_t src_stride[3]) {
@@ -553,6 +770,7 @@ extern "C" MP2V_API int mp2v_recon_upload_frame(mp2v_recon_t* ctx, int frame_id,
         CK(cudaMemcpy2D(ctx->frame_ptr(frame_id, p), (size_t)ctx->lay.stride[p], src[p], (size_t)src_stride[p],
                         (size_t)ctx->lay.width[p], (size_t)ctx->lay.height[p], cudaMemcpyHostToDevice), "H2D frame");
     ctx->frame_written[frame_id] = 1;
+    ctx->mirror_valid[frame_id] = 0;
     CK(cudaEventRecord(ctx->frame_ev[frame_id], ctx->s_compute), "event record");
     return MP2V_OK;
 }

@@ -1,0 +1,46 @@
+// Device-side slice parser: launch interface (see vlc_kernel.cu).
+#pragma once
+#include <cuda_runtime.h>
+
+#include <cstdint>
+
+#include "host/slice_core.h"
+#include "mp2v_recon.h"
+
+namespace mp2v {
+
+// One coded picture as staged for the device parser, a single H2D copy:
+//   mp2v_pic_params_t (kVlcParamsBytes) | vlc_pic_header_t | vlc_slice_t[mbh] | (16-byte aligned) bitstream bytes + 16 bytes of zero padding
+constexpr size_t kVlcParamsBytes = 512;
+struct vlc_pic_header_t {
+    slice_syntax_t sx;
+    uint32_t n_slices;
+    uint32_t slice_region;      // coefficient records reserved per slice: mbw * blocks * 64, the syntactic worst case
+    uint32_t data_off;          // byte offset of the bitstream bytes from the start of the staged block
+    uint32_t pad;
+};
+struct vlc_slice_t {
+    uint32_t byte_off;          // payload offset inside the staged bitstream bytes
+    int32_t code;               // slice_start_code value
+};
+
+// Result of parsing one slice, written by its thread with one plain 16-byte store into host memory the
+// device can address (pinned + mapped): no read-back copy, no atomics; the host sums a picture's entries.
+struct vlc_slice_status_t {
+    uint32_t error;             // slice_error_t (0 = none)
+    uint32_t n_coef;            // coefficient records written
+    uint32_t coded_blocks;      // for the byte accounting of SURVEY.md 8(d)
+    uint32_t ref_dirs;          // prediction directions summed over the slice's macroblocks
+};
+
+// the tables are copied to the device once per context
+cudaError_t vlc_upload_tables(void** d_tables);
+cudaError_t vlc_kernel_attributes(cudaFuncAttributes* out);
+
+// parse every slice of one staged picture: macroblock records to mb[], coefficient records to coef[],
+// one status entry per slice to status[]; macroblocks of a slice's row that the slice does not code
+// are written as blank intra macroblocks
+cudaError_t launch_vlc(const uint8_t* d_staged, const void* d_tables, mp2v_mb_info_t* mb, mp2v_coef_t* coef, vlc_slice_status_t* status,
+                       int n_slices, int lanes, cudaStream_t stream);
+
+}  // namespace mp2v

@@ -15,13 +15,14 @@ class DecodeParams(C.Structure):
     _fields_ = [("width", C.c_int32), ("height", C.c_int32), ("chroma_format", C.c_int32),
                 ("pictures_pool_size", C.c_int32), ("num_threads", C.c_int32), ("reordering", C.c_int32),
                 ("n_devices", C.c_int32), ("devices", C.c_int32 * 8), ("max_batch", C.c_int32), ("output_lag", C.c_int32),
-                ("download_frames", C.c_int32), ("hash_output", C.c_int32)]
+                ("download_frames", C.c_int32), ("hash_output", C.c_int32), ("host_parser", C.c_int32)]
 
 
 class DecodeStats(C.Structure):
     _fields_ = [("frames", C.c_uint64), ("pictures", C.c_uint64), ("launches", C.c_uint64), ("h2d_bytes", C.c_uint64),
                 ("d2h_bytes", C.c_uint64), ("algorithmic_bytes", C.c_uint64), ("kernel_ms", C.c_double),
-                ("parse_cpu_seconds", C.c_double), ("wall_seconds", C.c_double), ("hash", C.c_uint64)]
+                ("parse_cpu_seconds", C.c_double), ("wall_seconds", C.c_double), ("hash", C.c_uint64),
+                ("vlc_launches", C.c_uint64)]
 
 
 DECODE_EXPORTS = ["mp2v_decode_stream", "mp2v_decoder_create", "mp2v_decoder_decode", "mp2v_decoder_destroy", "mp2v_parse_stream", "mp2v_parsed_num_pictures", "mp2v_parsed_picture",
@@ -64,9 +65,11 @@ class Decoder:
     """mp2v_decoder_c(decoder_config_t{width, height, chroma_format, pictures_pool_size, num_threads, reordering})"""
 
     def __init__(self, width, height, chroma_format, pictures_pool_size=10, num_threads=8, reordering=True,
-                 devices=(0,), max_batch=0, output_lag=0):
+                 devices=(0,), max_batch=0, output_lag=0, gpu_vlc=True):
+        """gpu_vlc (mp2v_b200_options_t.gpu_vlc, default on): slices are parsed on the device and the host only finds
+        start codes; False forces the host slice parser on num_threads threads"""
         self.p = DecodeParams(width, height, chroma_format, pictures_pool_size, num_threads, 1 if reordering else 0,
-                              len(devices), (C.c_int32 * 8)(*devices), max_batch, output_lag, 1, 0)
+                              len(devices), (C.c_int32 * 8)(*devices), max_batch, output_lag, 1, 0, 0 if gpu_vlc else 1)
         self.stats = None
         self.h = None
         self._download = None

@@ -8,14 +8,14 @@ import os
 import numpy as np
 
 from . import build as _build
-from .abi import (OK, FrameLayout, MbInfo, PicParams, Picture, ReconConfig, ReconStats, mb_dtype)
+from .abi import (OK, FrameLayout, MbInfo, PicParams, PicSyntax, Picture, ReconConfig, ReconStats, SliceRef, mb_dtype)
 
 U8P = C.POINTER(C.c_uint8)
 _lib = None
 
 EXPORTS = [
     "mp2v_frame_layout", "mp2v_recon_create", "mp2v_recon_destroy", "mp2v_recon_last_error",
-    "mp2v_recon_acquire_picture", "mp2v_recon_release_picture", "mp2v_recon_submit", "mp2v_recon_precheck", "mp2v_recon_flush",
+    "mp2v_recon_acquire_picture", "mp2v_recon_release_picture", "mp2v_recon_submit", "mp2v_recon_submit_slices", "mp2v_recon_precheck", "mp2v_recon_flush",
     "mp2v_recon_sync", "mp2v_recon_upload", "mp2v_recon_run_resident", "mp2v_recon_download_frame",
     "mp2v_recon_map_frame", "mp2v_recon_upload_frame", "mp2v_recon_frame_device_ptrs",
     "mp2v_recon_set_timing", "mp2v_recon_get_stats", "mp2v_recon_timer_start", "mp2v_recon_timer_stop",
@@ -43,6 +43,7 @@ def lib():
         L.mp2v_recon_acquire_picture.argtypes = [C.c_void_p, P(P(Picture))]
         L.mp2v_recon_release_picture.argtypes = [C.c_void_p, P(Picture)]
         L.mp2v_recon_submit.argtypes = [C.c_void_p, P(Picture)]
+        L.mp2v_recon_submit_slices.argtypes = [C.c_void_p, P(Picture), P(PicSyntax), P(SliceRef), C.c_int]
         L.mp2v_recon_precheck.argtypes = [C.c_void_p, P(Picture)]
         L.mp2v_recon_flush.argtypes = [C.c_void_p]
         L.mp2v_recon_sync.argtypes = [C.c_void_p]
@@ -71,9 +72,10 @@ class Recon:
     """One reconstruction context = one device."""
 
     def __init__(self, width, height, chroma_format, n_frames=8, n_pictures=8, device=0, max_batch=0, flags=1,
-                 coef_capacity=0):
+                 coef_capacity=0, bitstream_capacity=0):
         self.L = lib()
-        cfg = ReconConfig(device, width, height, chroma_format, n_frames, n_pictures, max_batch, flags, coef_capacity, 0)
+        cfg = ReconConfig(device, width, height, chroma_format, n_frames, n_pictures, max_batch, flags, coef_capacity,
+                          bitstream_capacity)
         h = C.c_void_p()
         rc = self.L.mp2v_recon_create(C.byref(cfg), C.byref(h))
         if rc != OK:
@@ -125,6 +127,19 @@ class Recon:
 
     def submit(self, pic):
         self._ck(self.L.mp2v_recon_submit(self.h, pic))
+
+    def submit_slices(self, pic, params, data, slices, f_code, intra_dc_precision=0, q_scale_type=0, intra_vlc_format=1,
+                      dst=0, l0=-1, l1=-1):
+        """device-side parsing (contexts created with flags | RECON_DEVICE_VLC): data = uint8 array holding the
+        coded picture, slices = [(payload offset in data, payload bytes, slice_start_code value), ...]"""
+        p = pic.contents
+        C.memmove(p.params, C.byref(params), C.sizeof(PicParams))
+        p.params.contents.dst_frame, p.params.contents.l0_frame, p.params.contents.l1_frame = dst, l0, l1
+        sy = PicSyntax(((C.c_int32 * 2) * 2)((C.c_int32 * 2)(*f_code[0]), (C.c_int32 * 2)(*f_code[1])),
+                       intra_dc_precision, q_scale_type, intra_vlc_format, 0)
+        buf = np.ascontiguousarray(data, np.uint8)
+        refs = (SliceRef * max(len(slices), 1))(*[SliceRef(buf.ctypes.data + off, n, code) for off, n, code in slices])
+        self._ck(self.L.mp2v_recon_submit_slices(self.h, pic, C.byref(sy), refs, len(slices)))
 
     def upload(self, pic):
         self._ck(self.L.mp2v_recon_upload(self.h, pic))

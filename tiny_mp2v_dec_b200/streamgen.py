@@ -15,7 +15,8 @@ class GenParams(C.Structure):
                 ("alternate_scan", C.c_int32), ("q_scale_type", C.c_int32), ("intra_dc_precision", C.c_int32),
                 ("pct_skipped", C.c_int32), ("pct_intra_in_pb", C.c_int32), ("pct_coded", C.c_int32),
                 ("pct_mb_quant", C.c_int32), ("pct_big_levels", C.c_int32), ("all_blocks_coded", C.c_int32),
-                ("natural_mean_coefs", C.c_int32), ("reserved", C.c_int32 * 3)]
+                ("natural_mean_coefs", C.c_int32), ("unclamped_mv", C.c_int32),
+                ("reserved", C.c_int32 * 2)]
 
 
 class GenPicture(C.Structure):

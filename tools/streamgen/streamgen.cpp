@@ -247,6 +247,7 @@ struct mp2v_gen {
         const int f = 1 << (f_code - 1);
         int half = rng.pct(50);
         int lo = -p.mv_range, hi = p.mv_range;
+        if (p.unclamped_mv) return rng.range(lo, hi) * 2 + half;
         if (lo < -pos) lo = -pos;
         if (hi > extent - 16 - pos - half) hi = extent - 16 - pos - half;
         if (hi < lo) { half = 0; hi = extent - 16 - pos; if (hi > p.mv_range) hi = p.mv_range; if (hi < lo) hi = lo; }

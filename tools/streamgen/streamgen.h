@@ -40,7 +40,8 @@ typedef struct mp2v_gen_params {
     int32_t  pct_big_levels;       /* % of coefficients drawn from the full +-2047 escape range    */
     int32_t  all_blocks_coded;     /* cbp = all ones whenever pattern is present                   */
     int32_t  natural_mean_coefs;   /* mode 1: mean number of AC coefficients per coded block (0 = 2.6) */
-    int32_t  reserved[3];
+    int32_t  unclamped_mv;         /* 1: vectors may leave the frame (invalid streams for error-path tests) */
+    int32_t  reserved[2];
 } mp2v_gen_params_t;
 
 typedef struct mp2v_gen mp2v_gen_t;
