@@ -1,8 +1,16 @@
-// MSB-first bit reader over a padded byte buffer (64-bit window, branch-light refill).
+// MSB-first bit reader over a padded byte buffer (64-bit window).
 //
 // Contract inherited from the reference's decode API: the caller pads the stream with
 // >= 64 readable bytes; like the reference's 32-bit word reader (bitstream.h:28-34) this reader may
-// touch a few bytes past the last syntax element but never more than 8 past the position it consumed.
+// touch a few bytes past the last syntax element but never more than 12 past the position it consumed.
+//
+// Two refill strategies behind one interface (the slice syntax walk in slice_core.h is compiled for
+// both):
+//   host    one unaligned 8-byte load + bswap per refill, byte granular: refill() leaves >= 56 bits;
+//   device  aligned 32-bit words with a one-word look-ahead: the load for the NEXT word is issued when
+//           the current one is appended, so it is never on the dependent chain of the symbol loop (a
+//           GPU thread walking a slice is a pure latency chain); refill() leaves >= 33 bits.
+// kBitsAfterRefill is what callers may consume between two refills.
 #pragma once
 #include <cstdint>
 #include <cstring>
@@ -17,42 +25,60 @@ namespace mp2v {
 
 class bitreader_t {
 public:
+#ifdef __CUDA_ARCH__
+    static constexpr int kBitsAfterRefill = 33;
+#else
+    static constexpr int kBitsAfterRefill = 56;
+#endif
     bitreader_t() = default;
     MP2V_HD explicit bitreader_t(const uint8_t* p) { reset(p); }
-    MP2V_HD void reset(const uint8_t* p) { ptr_ = p; buf_ = 0; cnt_ = 0; refill(); }
 
-    // make at least 56 bits available
-    MP2V_HD inline void refill() {
-        uint64_t w;
 #ifdef __CUDA_ARCH__
-        // device: 8 bytes from an arbitrary address = three aligned words + two byte permutes
-        // (reads at most 11 bytes past ptr_; the staged bitstream carries 16 bytes of padding)
-        const uintptr_t a = (uintptr_t)ptr_;
-        const uint32_t* p32 = (const uint32_t*)(a & ~(uintptr_t)3);
-        const uint32_t sel = 0x0123u + 0x1111u * ((uint32_t)a & 3u);
-        const uint32_t w0 = __ldg(p32), w1 = __ldg(p32 + 1), w2 = __ldg(p32 + 2);
-        w = ((uint64_t)__byte_perm(w0, w1, sel) << 32) | __byte_perm(w1, w2, sel);
+    __device__ void reset(const uint8_t* p) {
+        const uintptr_t a = (uintptr_t)p;
+        wptr_ = (const uint32_t*)(a & ~(uintptr_t)3);
+        const int skip_bits = ((int)a & 3) * 8;
+        buf_ = (uint64_t)__byte_perm(__ldg(wptr_), 0u, 0x0123) << (32 + skip_bits);     // drop the bytes before p
+        cnt_ = 32 - skip_bits;
+        next_ = __ldg(++wptr_);
+        refill();
+    }
+    __device__ __forceinline__ void refill() {
+        if (cnt_ <= 32) append();
+        if (cnt_ <= 32) append();                                // only right after reset or a 32-bit gulp
+    }
 #else
+    void reset(const uint8_t* p) { ptr_ = p; buf_ = 0; cnt_ = 0; refill(); }
+    inline void refill() {
+        uint64_t w;
         memcpy(&w, ptr_, 8);
         w = __builtin_bswap64(w);
-#endif
         buf_ |= w >> cnt_;
         const int adv = (63 - cnt_) >> 3;
         ptr_ += adv;
         cnt_ += adv << 3;
     }
-    // n in 1..32; valid after refill() as long as no more than 56 bits were consumed since
+#endif
+    // n in 1..32; valid after refill() as long as no more than kBitsAfterRefill bits were consumed since
     MP2V_HD inline uint32_t peek(int n) const { return (uint32_t)(buf_ >> (64 - n)); }
-    MP2V_HD inline uint32_t peek32() const { return (uint32_t)(buf_ >> 32); }
-    MP2V_HD inline int bits_left() const { return cnt_; }
     MP2V_HD inline void skip(int n) { buf_ <<= n; cnt_ -= n; }
     MP2V_HD inline uint32_t get(int n) { refill(); const uint32_t v = peek(n); skip(n); return v; }
     MP2V_HD inline uint32_t get1() { refill(); const uint32_t v = (uint32_t)(buf_ >> 63); skip(1); return v; }
-    // position of the next unread bit, in bytes from `base` (rounded down)
-    MP2V_HD inline const uint8_t* byte_pos() const { return ptr_ - ((cnt_ + 7) >> 3); }
 
 private:
+#ifdef __CUDA_ARCH__
+    __device__ __forceinline__ void append() {
+        // the byte swap happens here, at the use: swapping right behind the load would park the
+        // (in-order) thread on the load it is supposed to run ahead of
+        buf_ |= (uint64_t)__byte_perm(next_, 0u, 0x0123) << (32 - cnt_);
+        cnt_ += 32;
+        next_ = __ldg(++wptr_);
+    }
+    const uint32_t* wptr_ = nullptr;   // the word held in next_
+    uint32_t next_ = 0;                // look-ahead word as loaded (little-endian view of big-endian data)
+#else
     const uint8_t* ptr_ = nullptr;
+#endif
     uint64_t buf_ = 0;   // unread bits, left aligned
     int cnt_ = 0;        // number of valid bits in buf_
 };

@@ -411,7 +411,13 @@ bool mp2v_decoder_c::impl_t::prepare(bool gpu_vlc) {
         d.n_slots = 2 * (opt.max_batch > 0 ? opt.max_batch : 8);
         if (d.n_slots < 6) d.n_slots = 6;
         // a slice parses at the speed of one GPU thread: throughput comes from the number of pictures in flight
-        if (gpu_vlc) { d.n_frames += 24; if (d.n_slots < 32) d.n_slots = 32; }
+        if (gpu_vlc) {
+            int slots = 48, extra_frames = 40;
+            if (const char* v = getenv("MP2V_VLC_SLOTS")) slots = atoi(v) > 0 ? atoi(v) : slots;             // dev knobs
+            if (const char* v = getenv("MP2V_VLC_FRAMES")) extra_frames = atoi(v) > 0 ? atoi(v) : extra_frames;
+            d.n_frames += extra_frames;
+            if (d.n_slots < slots || getenv("MP2V_VLC_SLOTS")) d.n_slots = slots;
+        }
         mp2v_recon_config_t rc{};
         rc.device = id; rc.width = c.width; rc.height = c.height; rc.chroma_format = c.chroma_format;
         rc.n_frames = d.n_frames; rc.n_pictures = d.n_slots; rc.max_batch = opt.max_batch; rc.flags = MP2V_RECON_VALIDATE | (gpu_vlc ? MP2V_RECON_DEVICE_VLC : 0) | (opt.download_frames ? MP2V_RECON_AUTO_DOWNLOAD : 0);

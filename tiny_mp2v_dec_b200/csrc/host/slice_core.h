@@ -111,7 +111,7 @@ MP2V_HDI bool parse_block(bitreader_t& br, mp2v_coef_t*& out, const vlc_decode_t
     if (intra) {
         const int comp = b < 4 ? 0 : 1 + (b & 1);
         int diff;
-        const dc_fast_t f = T.dc_fast[comp ? 1 : 0][br.peek(kDcFastBits)];
+        const dc_fast_t f = fetch_entry(&T.dc_fast[comp ? 1 : 0][br.peek(kDcFastBits)]);
         if (f.len != 0) { br.skip(f.len); diff = f.diff; }
         else {
             const vlc_entry_t e = T.dcsize[comp ? 1 : 0].look(br.peek(10));
@@ -134,13 +134,15 @@ MP2V_HDI bool parse_block(bitreader_t& br, mp2v_coef_t*& out, const vlc_decode_t
         *out++ = MP2V_COEF(neg ? -1 : 1, 0, b, MP2V_COEF_FIRST);
         i = 1;
     }
-    const coef_fast_t* fast = table->fast;
+    // symbols decoded per refill: an escape is 24 bits, so two of any kind fit the host reader's 56 bits
+    // (the first round reuses the refill above: at most 22 bits were consumed since); the device
+    // reader guarantees 33 and refills, off its dependent chain, before every symbol
+    constexpr int kPerRefill = bitreader_t::kBitsAfterRefill >= 48 ? 2 : 1;
+    if (kPerRefill == 1) br.refill();
     for (;;) {
-        // one refill (>= 56 bits) covers two symbols of any kind (escape = 24 bits); the first round
-        // reuses the refill above (at most 22 bits were consumed since)
         MP2V_UNROLL2
-        for (int rep = 0; rep < 2; rep++) {
-            const coef_fast_t f = fast[br.peek(kFastBits)];
+        for (int rep = 0; rep < kPerRefill; rep++) {
+            const coef_fast_t f = table->look_fast(br.peek(kFastBits));
             int run, level;
             if (f.run < kFastEob) {
                 br.skip(f.len);

@@ -21,9 +21,10 @@
 
 namespace mp2v {
 
-struct vlc_entry_t { int8_t len; int8_t pad; int16_t val; };          // len 0 = invalid code
+// (entries are aligned to their size so that one look-up is ONE load, also on the device)
+struct alignas(4) vlc_entry_t { int8_t len; int8_t pad; int16_t val; };          // len 0 = invalid code
 
-struct coef_entry_t {     // run/level tables
+struct alignas(8) coef_entry_t {     // run/level tables
     uint8_t len;          // code length WITHOUT the sign bit; 0 = invalid; root entries with sub != 0 chain to a leaf table
     uint8_t run;
     int16_t level;        // magnitude; kEob / kEscape markers below
@@ -32,6 +33,22 @@ struct coef_entry_t {     // run/level tables
 };
 constexpr int16_t kCoefEob = -1;
 constexpr int16_t kCoefEsc = -2;
+
+// One table look-up = ONE load.  The host compiler does that by itself; the device compiler splits a
+// small struct copy into one narrow load per field (and predicates some on others), which doubles the
+// latency of the look-up a slice thread spends its life waiting for -- so fetch the entry as a word.
+template <class T>
+MP2V_HD inline T fetch_entry(const T* p) {
+#ifdef __CUDA_ARCH__
+    static_assert(sizeof(T) == 4 || sizeof(T) == 8, "table entries are one or two words");
+    T r;
+    if (sizeof(T) == 4) { const uint32_t w = __ldg(reinterpret_cast<const uint32_t*>(p)); memcpy(&r, &w, 4); }
+    else { const uint2 w = __ldg(reinterpret_cast<const uint2*>(p)); memcpy(&r, &w, 8); }
+    return r;
+#else
+    return *p;
+#endif
+}
 
 template <int BITS>
 struct flat_vlc_t {
@@ -44,13 +61,13 @@ struct flat_vlc_t {
         const uint32_t lo = code << (BITS - len), n = 1u << (BITS - len);
         for (uint32_t k = 0; k < n; k++) { e[lo + k].len = (int8_t)len; e[lo + k].val = (int16_t)val; }
     }
-    MP2V_HD inline const vlc_entry_t& look(uint32_t peek_bits) const { return e[peek_bits]; }
+    MP2V_HD inline vlc_entry_t look(uint32_t peek_bits) const { return fetch_entry(&e[peek_bits]); }
 };
 
 // Fast path of the run/level decoder: one lookup on the next 11 bits resolves code AND sign for
 // every symbol whose code + sign bit fit (all the frequent ones); anything else falls back to the
 // two-level table.  4 bytes per entry, 8 KB per table.
-struct coef_fast_t {
+struct alignas(4) coef_fast_t {
     int16_t level;     // signed level (fast symbols); unused otherwise
     uint8_t run;       // 0..63 fast symbol; kFastEob / kFastSlow markers
     uint8_t len;       // bits consumed including the sign bit (fast symbols and end of block)
@@ -63,7 +80,7 @@ struct coef_vlc_t {
     coef_fast_t fast[1 << kFastBits];
     void build_fast() {
         for (uint32_t i = 0; i < (1u << kFastBits); i++) {
-            const coef_entry_t& e = look(i << (17 - kFastBits));
+            const coef_entry_t e = look(i << (17 - kFastBits));
             coef_fast_t f{0, kFastSlow, 0};
             if (e.len && e.level > 0 && e.len + 1 <= kFastBits) {
                 const int neg = (int)(i >> (kFastBits - 1 - e.len)) & 1;
@@ -101,16 +118,17 @@ struct coef_vlc_t {
         }
     }
     // peek17 = next 17 bits of the stream
-    MP2V_HD inline const coef_entry_t& look(uint32_t peek17) const {
-        const coef_entry_t& r = root[peek17 >> (17 - ROOT)];
+    MP2V_HD inline coef_entry_t look(uint32_t peek17) const {
+        const coef_entry_t r = fetch_entry(&root[peek17 >> (17 - ROOT)]);
         if (!r.sub) return r;
-        return leaves[((size_t)(r.sub - 1) << LEAF) + (peek17 & ((1u << LEAF) - 1u))];
+        return fetch_entry(&leaves[((size_t)(r.sub - 1) << LEAF) + (peek17 & ((1u << LEAF) - 1u))]);
     }
+    MP2V_HD inline coef_fast_t look_fast(uint32_t peek11) const { return fetch_entry(&fast[peek11]); }
 };
 
 // dct_dc_size + dct_dc_differential in one lookup on the next 12 bits (covers sizes whose code and
 // differential bits fit together -- every small differential); len == 0 -> take the two-step path
-struct dc_fast_t { int16_t diff; uint8_t len; uint8_t pad; };
+struct alignas(4) dc_fast_t { int16_t diff; uint8_t len; uint8_t pad; };
 constexpr int kDcFastBits = 12;
 
 struct vlc_decode_tables_t {
@@ -135,7 +153,7 @@ struct vlc_decode_tables_t {
         b14.build_fast(); b15.build_fast();
         for (int lc = 0; lc < 2; lc++)
             for (uint32_t i = 0; i < (1u << kDcFastBits); i++) {
-                const vlc_entry_t& e = dcsize[lc].look(i >> (kDcFastBits - 10));
+                const vlc_entry_t e = dcsize[lc].look(i >> (kDcFastBits - 10));
                 dc_fast_t f{0, 0, 0};
                 if (e.len && e.len + e.val <= kDcFastBits) {
                     int diff = 0;
