@@ -90,10 +90,9 @@ struct warp_smem_t {
     alignas(16) int16_t tile[kSlots][kTilePitch];
     alignas(16) uint8_t win[kWinBuf][2][fmt_t<CF>::WIN_DIR];   // [buffer][direction]
     int bound[kSlots];
-    // per-batch macroblock context for the flat dequantisation loop
-    uint32_t mb_pre[33];             // (first record index in the batch << 8) | first tile slot
-    uint32_t mb_bits[32];
-    uint32_t mb_off[32];
+    // per-batch context of the macroblocks that carry records, for the flat dequantisation loop:
+    // {first record index in the batch, coef_off, bits, first tile slot}
+    alignas(16) uint4 mb_ctx[32];
 };
 
 template <int CF>
@@ -213,9 +212,14 @@ __device__ __forceinline__ void idct_round(int16_t* slot_base, int j, bool activ
     if (p1_exact) {
         idct_lane<0>(a[0], a[1], a[2], a[3], a[4], a[5], a[6], a[7]);
         idct_lane<0>(b[0], b[1], b[2], b[3], b[4], b[5], b[6], b[7]);
-    } else {
+    } else if (p2_exact) {
         idct_lane<1>(a[0], a[1], a[2], a[3], a[4], a[5], a[6], a[7]);
         idct_lane<1>(b[0], b[1], b[2], b[3], b[4], b[5], b[6], b[7]);
+    } else {
+        // the bound that clears pass 2 also bounds every pass-1 OUTPUT: |y_c| <= bound / (16 G[c]) + E with
+        // G[c] >= 1, i.e. below 30 100 -- the 8 output additions cannot saturate either
+        idct_lane<2>(a[0], a[1], a[2], a[3], a[4], a[5], a[6], a[7]);
+        idct_lane<2>(b[0], b[1], b[2], b[3], b[4], b[5], b[6], b[7]);
     }
     if (active) {
 #pragma unroll
@@ -307,6 +311,11 @@ __device__ __forceinline__ uint32_t add_clip4(uint32_t pred, uint32_t r01, uint3
     const uint32_t lo = __vimin_s16x2_relu(__vadd2(__byte_perm(pred, 0, 0x4140), r01), 0x00ff00ffu);
     const uint32_t hi = __vimin_s16x2_relu(__vadd2(__byte_perm(pred, 0, 0x4342), r23), 0x00ff00ffu);
     return __byte_perm(lo, hi, 0x6420);
+}
+
+// intra (add=false, idct_sse2.hpp:108-109): packus of the residual alone
+__device__ __forceinline__ uint32_t clip4(uint32_t r01, uint32_t r23) {
+    return __byte_perm(__vimin_s16x2_relu(r01, 0x00ff00ffu), __vimin_s16x2_relu(r23, 0x00ff00ffu), 0x6420);
 }
 
 __device__ __forceinline__ int chroma_mv(int mv, bool halve) { return halve ? (mv >> 1) : mv; }   // floor, mb_decoder.cpp:198-206
@@ -412,15 +421,15 @@ __device__ __forceinline__ void reconstruct_mb_rows(const pic_desc_t& pd, const 
         uint32_t out[4] = {pred[0], pred[1], pred[2], pred[3]};
         if (cbp >> bl & 1) {
             const uint4 res = *reinterpret_cast<const uint4*>(&tile[base + __popc(cbp & ((1u << bl) - 1u))][rr * 8]);
-            out[0] = add_clip4(pred[0], res.x, res.y);
-            out[1] = add_clip4(pred[1], res.z, res.w);
+            if (intra) { out[0] = clip4(res.x, res.y); out[1] = clip4(res.z, res.w); }      // add=false: packus(res)
+            else { out[0] = add_clip4(pred[0], res.x, res.y); out[1] = add_clip4(pred[1], res.z, res.w); }
         }
         uint8_t* drow = pd.dst[p] + (size_t)(mby * ph + r) * batch.stride[p] + mbx * pw;
         if (wide) {
             if (cbp >> br & 1) {
                 const uint4 res = *reinterpret_cast<const uint4*>(&tile[base + __popc(cbp & ((1u << br) - 1u))][rr * 8]);
-                out[2] = add_clip4(pred[2], res.x, res.y);
-                out[3] = add_clip4(pred[3], res.z, res.w);
+                if (intra) { out[2] = clip4(res.x, res.y); out[3] = clip4(res.z, res.w); }
+                else { out[2] = add_clip4(pred[2], res.x, res.y); out[3] = add_clip4(pred[3], res.z, res.w); }
             }
             *reinterpret_cast<uint4*>(drow) = make_uint4(out[0], out[1], out[2], out[3]);
         } else {
@@ -480,8 +489,8 @@ __device__ __forceinline__ void reconstruct_mb_halfrows(const pic_desc_t& pd, co
         uint32_t out0 = pred[0], out1 = pred[1];
         if (cbp >> blk & 1) {
             const uint4 res = *reinterpret_cast<const uint4*>(&tile[base + __popc(cbp & ((1u << blk) - 1u))][(r & 7) * 8]);
-            out0 = add_clip4(pred[0], res.x, res.y);
-            out1 = add_clip4(pred[1], res.z, res.w);
+            if (intra) { out0 = clip4(res.x, res.y); out1 = clip4(res.z, res.w); }          // add=false: packus(res)
+            else { out0 = add_clip4(pred[0], res.x, res.y); out1 = add_clip4(pred[1], res.z, res.w); }
         }
         *reinterpret_cast<uint2*>(pd.dst[p] + (size_t)(mby * ph + r) * batch.stride[p] + mbx * pw + 8 * half) = make_uint2(out0, out1);
     }
@@ -526,6 +535,7 @@ __global__ void __launch_bounds__(kCtaThreads, MP2V_MINCTAS) recon_kernel(const 
     const int mb_end = min(mb_begin + run, batch.mb_count);
 
     uint4 rec_next = (mb_begin + lane < mb_end) ? __ldg(reinterpret_cast<const uint4*>(pd.mb) + mb_begin + lane) : make_uint4(0, 0, 0, 0);
+    int mby0 = mb_begin / mbw, mbx0 = mb_begin - mby0 * mbw;      // the only division of the warp; batches advance it
     for (int first = mb_begin; first < mb_end;) {
         // ---- 1. macroblock records of the batch: as many as fit the tile's coded-block slots
         // (lane i holds macroblock first+i; the records were requested during the previous batch)
@@ -533,12 +543,15 @@ __global__ void __launch_bounds__(kCtaThreads, MP2V_MINCTAS) recon_kernel(const 
         const bool have = idx < mb_end;
         uint4 rec = rec_next;
         const int cnt = have ? __popc(MP2V_MB_CBP(rec.y)) : 0;
-        int incl = cnt;
+        const int ncoef_all = have ? (int)MP2V_MB_NCOEF(rec.y) : 0;
+        // one warp scan for both prefixes: coded blocks (<= 12 each) in the low half, records (<= 768 each) in the high half
+        int scan2 = cnt | (ncoef_all << 16);
 #pragma unroll
         for (int d = 1; d < 32; d <<= 1) {
-            const int t = __shfl_up_sync(0xffffffffu, incl, d);
-            if (lane >= d) incl += t;
+            const int t = __shfl_up_sync(0xffffffffu, scan2, d);
+            if (lane >= d) scan2 += t;
         }
+        const int incl = scan2 & 0xffff;
         const int nb = max(__popc(__ballot_sync(0xffffffffu, have && incl <= kSlots)), 1);
         const int base = incl - cnt;
         const int nslots = __shfl_sync(0xffffffffu, incl, nb - 1);
@@ -546,7 +559,6 @@ __global__ void __launch_bounds__(kCtaThreads, MP2V_MINCTAS) recon_kernel(const 
         rec_next = (idx + nb < mb_end) ? __ldg(reinterpret_cast<const uint4*>(pd.mb) + idx + nb) : make_uint4(0, 0, 0, 0);
 
         // ---- 2. first macroblock's windows start loading now; they land while we dequantise and transform
-        const int mby0 = first / mbw, mbx0 = first - mby0 * mbw;      // the only division per batch
         {
             const uint4 m0 = make_uint4(__shfl_sync(0xffffffffu, rec.x, 0), __shfl_sync(0xffffffffu, rec.y, 0),
                                         __shfl_sync(0xffffffffu, rec.z, 0), __shfl_sync(0xffffffffu, rec.w, 0));
@@ -555,48 +567,44 @@ __global__ void __launch_bounds__(kCtaThreads, MP2V_MINCTAS) recon_kernel(const 
         }
 
         // ---- 3. zero the used slots (QFS[64] = {0}, mb_decoder.cpp:159), then dequantise + saturate + mismatch.
-        // All records of the batch are walked as ONE flat index space (lane = record): a lane finds its
-        // macroblock by binary search over the per-batch record prefix, so sparse P/B macroblocks do not
-        // cost a loop trip each.
+        // All records of the batch are walked as ONE flat index space (lane = record), so sparse P/B
+        // macroblocks do not cost a loop trip each.
         for (int i = lane; i < nslots * 8; i += 32)
             reinterpret_cast<uint4*>(&ws.tile[i >> 3][0])[i & 7] = make_uint4(0, 0, 0, 0);
         if (lane < kSlots) ws.bound[lane] = 0;
-        const int ncoef = lane < nb ? (int)MP2V_MB_NCOEF(rec.y) : 0;
-        int cincl = ncoef;
-#pragma unroll
-        for (int d = 1; d < 32; d <<= 1) {
-            const int t = __shfl_up_sync(0xffffffffu, cincl, d);
-            if (lane >= d) cincl += t;
+        const int ncoef = lane < nb ? ncoef_all : 0;
+        const int total = __shfl_sync(0xffffffffu, scan2, nb - 1) >> 16;     // records of the nb macroblocks taken
+        const int start = (scan2 >> 16) - ncoef_all;                         // this lane's macroblock: first record index in the batch
+        const bool ne = ncoef > 0;
+        {   // compact list of the macroblocks that have records
+            const uint32_t ne_mask = __ballot_sync(0xffffffffu, ne);
+            if (ne) ws.mb_ctx[__popc(ne_mask & ((1u << lane) - 1u))] = make_uint4((uint32_t)start, rec.x, rec.y, (uint32_t)base);
         }
-        const int total = __shfl_sync(0xffffffffu, cincl, 31);
-        ws.mb_pre[lane] = ((uint32_t)(cincl - ncoef) << 8) | (uint32_t)(lane < nb ? base : nslots);
-        ws.mb_bits[lane] = rec.y;
-        ws.mb_off[lane] = rec.x;
-        if (lane == 0) ws.mb_pre[32] = (uint32_t)total << 8;
         __syncwarp();
         uint32_t parity = 0;                 // bit s = parity of the coefficient sum of tile slot s
-        // software pipelined: the record of the NEXT trip is located (binary search) and requested
-        // before the current one is processed, so its global-memory latency is off the critical path
-        auto fetch = [&](int f, uint32_t& c, uint32_t& pre, uint32_t& m_bits) {
-            c = 0; pre = 0; m_bits = 0;
-            if (f < total) {
-                int lo = 0, hi = nb;         // last macroblock whose first record index is <= f
-#pragma unroll
-                for (int st = 0; st < 5; st++) {
-                    const int mid = (lo + hi) >> 1;
-                    const bool ge = (int)(ws.mb_pre[mid] >> 8) <= f;
-                    lo = ge ? mid : lo; hi = ge ? hi : mid;
-                }
-                pre = ws.mb_pre[lo]; m_bits = ws.mb_bits[lo];
-                c = __ldg(pd.coef + ws.mb_off[lo] + (f - (int)(pre >> 8)));
+        // Record f of the flat space belongs to the last macroblock whose first record index is <= f.  Per
+        // trip of 32 records the owners are found with two warp votes instead of a search per lane: the
+        // lanes that HOLD macroblocks mark where theirs starts inside the trip (REDUX.OR) and count the
+        // ones that started before it (ballot); a record lane then counts the marks up to itself.
+        // Software pipelined: the record of the NEXT trip is requested before the current one is
+        // processed, so its global-memory latency is off the critical path.
+        auto fetch = [&](int f0, uint32_t& c, uint4& ctx) {
+            const int rel = start - f0;
+            const uint32_t starts = __reduce_or_sync(0xffffffffu, (ne && (unsigned)rel < 32u) ? 1u << rel : 0u);
+            const int before = __popc(__ballot_sync(0xffffffffu, ne && rel < 0));
+            c = 0; ctx = make_uint4(0, 0, 0, 0);
+            if (f0 + lane < total) {
+                ctx = ws.mb_ctx[before + __popc(starts & (0xffffffffu >> (31 - lane))) - 1];
+                c = __ldg(pd.coef + ctx.y + (uint32_t)(f0 + lane - (int)ctx.x));
             }
         };
-        uint32_t c_nx, pre_nx, bits_nx;
-        fetch(lane, c_nx, pre_nx, bits_nx);
+        uint32_t c_nx;
+        uint4 ctx_nx;
+        fetch(0, c_nx, ctx_nx);
         for (int f0 = 0; f0 < total; f0 += 32) {
             const int f = f0 + lane;
-            const uint32_t c = c_nx, pre = pre_nx, m_bits = bits_nx;
-            fetch(f + 32, c_nx, pre_nx, bits_nx);
+            const uint32_t c = c_nx, m_bits = ctx_nx.z, slot0 = ctx_nx.w;
+            fetch(f0 + 32, c_nx, ctx_nx);
             uint32_t pbit = 0;
             if (f < total) {
                 const uint32_t cbp = MP2V_MB_CBP(m_bits);
@@ -606,7 +614,7 @@ __global__ void __launch_bounds__(kCtaThreads, MP2V_MINCTAS) recon_kernel(const 
                     const int qs = MP2V_MB_QSCALE(m_bits);
                     const int level = (int)(short)(c & 0xffffu);
                     const int pos = (c >> 16) & 63;
-                    const int slot = (int)(pre & 0xffu) + __popc(cbp & ((1u << blk) - 1u));
+                    const int slot = (int)slot0 + __popc(cbp & ((1u << blk) - 1u));
                     const bool raw = (c & MP2V_COEF_RAW) != 0, first = (c & MP2V_COEF_FIRST) != 0;
                     const int w = s.W[(blk < 6 ? 0 : 2) + (intra ? 0 : 1)][pos];            // luma matrices for blocks 4,5 (:184-185)
                     const int mag = abs(level);
@@ -669,6 +677,7 @@ __global__ void __launch_bounds__(kCtaThreads, MP2V_MINCTAS) recon_kernel(const 
         }
         cp_async_wait<0>();
         first += nb;
+        mbx0 = mbx; mby0 = mby;
     }
 }
 
