@@ -7,7 +7,8 @@ One step = one pass of the hot path over the whole workload stream (all its pict
   value     frames/s with every picture's records already resident in HBM: device time of K steps of
             batched reconstruction launches (CUDA events on the launching stream), max over ranks
   e2e       frames/s through the reference-facing decode API (mp2v_decoder_c via the C ABI) from a host
-            buffer: host slice parsing + H2D of the records + kernels + D2H of every frame, wall clock
+            buffer: start-code index + H2D of the coded slices + device slice parsing + reconstruction +
+            D2H of every frame, wall clock (the host-parser mode of the same API is timed beside it)
   roofline  algorithmic bytes (OUT + REF + 128 B/coded block + 16 B/MB) / per-launch
             CUDA-event time of the reconstruction kernel, against the measured HBM peak
   cpu_baseline  the unmodified reference (oracle/_ref, its own multi-threaded decoder) on this box's
@@ -25,6 +26,10 @@ import sys
 import tempfile
 import threading
 import time
+
+# the decoder parses every picture in flight on its own CUDA stream: give the streams their own hardware
+# work queues (must be set before the process's first CUDA call; the library does the same when it is first)
+os.environ.setdefault("CUDA_DEVICE_MAX_CONNECTIONS", "32")
 
 ROOT = os.path.dirname(os.path.abspath(__file__))
 sys.path.insert(0, ROOT)

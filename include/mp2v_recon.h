@@ -209,6 +209,13 @@ typedef struct mp2v_slice_ref {
 } mp2v_slice_ref_t;
 MP2V_API int  mp2v_recon_submit_slices(mp2v_recon_t* ctx, mp2v_picture_t* pic, const mp2v_pic_syntax_t* syntax,
                                        const mp2v_slice_ref_t* slices, int n_slices);
+/* The same in two steps, for callers that prepare pictures on several threads: stage_slices
+ * validates the arguments and copies the coded bytes into the picture's pinned staging buffer (no
+ * device work, no context lock: any thread, any order, disjoint pictures); submit_staged issues
+ * the copy + parse + reconstruction and, like submit, must be called in coded order.             */
+MP2V_API int  mp2v_recon_stage_slices(mp2v_recon_t* ctx, mp2v_picture_t* pic, const mp2v_pic_syntax_t* syntax,
+                                      const mp2v_slice_ref_t* slices, int n_slices);
+MP2V_API int  mp2v_recon_submit_staged(mp2v_recon_t* ctx, mp2v_picture_t* pic);
 
 MP2V_API int  mp2v_recon_flush(mp2v_recon_t* ctx);               /* launch whatever is queued       */
 MP2V_API int  mp2v_recon_sync(mp2v_recon_t* ctx);                /* flush + wait for the device     */

@@ -66,10 +66,13 @@ struct pic_task_t {
     int dst = -1, l0 = -1, l1 = -1;    // device frame ids
     mp2v_picture_t* rp = nullptr;
     coef_arena_t arena;
-    std::atomic<int> next_slice{0};    // next slice index a worker may claim
+    int n_jobs = 0;                    // worker jobs of this picture: its slices (host parser) or 1 (stage for the device parser)
+    std::atomic<int> next_slice{0};    // next job index a worker may claim
     std::atomic<int> remaining{0};
     std::atomic<bool> ok{true};
     const char* error = nullptr;
+    std::string error_text;            // storage for messages that are not literals
+    double ts_queued = 0, ts_staged = 0, ts_submitted = 0, ts_mapped = 0;   // MP2V_PROFILE=2: milliseconds since decode() began
     bool parsed = false, submitted = false;
 };
 
@@ -97,6 +100,8 @@ struct shared_t {
     std::atomic<int64_t> parse_ns{0};
     std::atomic<int64_t> feeder_wait_ns{0}, feeder_work_ns{0}, submit_ns{0}, precheck_ns{0}, out_wait_ns{0}, out_map_ns{0}, worker_idle_ns{0};
     std::vector<pipeline_t*> pipes;
+    clock_t_::time_point t_origin;
+    double now_ms() const { return std::chrono::duration<double, std::milli>(clock_t_::now() - t_origin).count(); }
 
     void fail(const std::string& why);
 };
@@ -137,7 +142,6 @@ void shared_t::fail(const std::string& why) {
 
 void pipeline_t::feeder() {
     int refs[2] = {-1, -1};   // local task indices of the two live references
-    std::vector<mp2v_slice_ref_t> slice_refs;
     auto unref = [&](int k) { if (k >= 0) release_frame_use(tasks[k].dst); };
     for (size_t k = 0; k < tasks.size() && !sh->failed.load(); k++) {
         pic_task_t& t = tasks[k];
@@ -178,26 +182,17 @@ void pipeline_t::feeder() {
         pp.alternate_scan = info.alternate_scan;
         pp.dst_frame = t.dst; pp.l0_frame = t.l0; pp.l1_frame = t.l1;
         if (sh->opt.gpu_vlc) {
-            // device-side parsing: hand the coded slices over; submission is in coded order by construction
+            // device-side parsing: a worker stages the coded slices (one job per picture), submission stays in coded order
             if (!picture_in_envelope(info)) { sh->fail("only progressive frame pictures with frame prediction are supported (the reference's envelope)"); break; }
-            mp2v_pic_syntax_t sy{};
-            for (int a = 0; a < 2; a++) for (int b = 0; b < 2; b++) sy.f_code[a][b] = info.f_code[a][b];
-            sy.intra_dc_precision = info.intra_dc_precision;
-            sy.q_scale_type = info.q_scale_type;
-            sy.intra_vlc_format = info.intra_vlc_format;
-            slice_refs.clear();
-            for (const slice_ref_t& sr : t.src->slices) slice_refs.push_back({sr.payload, sr.bytes, sr.code});
-            if (mp2v_recon_submit_slices(recon, t.rp, &sy, slice_refs.data(), (int)slice_refs.size()) != MP2V_OK) {
-                sh->fail(std::string("picture ") + std::to_string(k) + ": " + mp2v_recon_last_error(recon));
-                break;
-            }
+            t.n_jobs = 1;
+            t.ts_queued = sh->now_ms();
+            t.remaining.store(1);
+            t.next_slice.store(0);
             {
-                std::lock_guard<std::mutex> lk(mu);
-                t.parsed = t.submitted = true;
-                next_submit++;
-                in_parse--;
+                std::lock_guard<std::mutex> lk(sh->qmu);
+                sh->queue.push_back(&t);
             }
-            cv.notify_all();
+            sh->qcv.notify_one();
             sh->feeder_work_ns.fetch_add(std::chrono::duration_cast<std::chrono::nanoseconds>(clock_t_::now() - tf1).count(), std::memory_order_relaxed);
             continue;
         }
@@ -210,6 +205,7 @@ void pipeline_t::feeder() {
         t.arena.overflow.store(false);
         const int ns = (int)t.src->slices.size();
         if (ns == 0) { on_parsed(&t); continue; }
+        t.n_jobs = ns;
         t.remaining.store(ns);
         t.next_slice.store(0);
         {
@@ -227,7 +223,7 @@ void pipeline_t::feeder() {
 void pipeline_t::on_parsed(pic_task_t* t) {
     // record validation / byte accounting is per picture: do it before taking the submission lock
     const auto ts0 = clock_t_::now();
-    if (t->ok.load() && !t->arena.overflow.load() && t->rp) {
+    if (!sh->opt.gpu_vlc && t->ok.load() && !t->arena.overflow.load() && t->rp) {
         t->rp->params->n_coef = t->arena.next.load();
         if (mp2v_recon_precheck(recon, t->rp) != MP2V_OK) { t->error = "records failed validation (motion vector outside the frame or bad offsets)"; t->ok.store(false); }
     }
@@ -242,9 +238,14 @@ void pipeline_t::on_parsed(pic_task_t* t) {
             sh->fail(std::string("picture ") + std::to_string(next_submit) + ": " + (s.error ? s.error : "coefficient arena exhausted"));
             break;
         }
-        s.rp->params->n_coef = s.arena.next.load();
-        if (mp2v_recon_submit(recon, s.rp) != MP2V_OK) { sh->fail(std::string("submit: ") + mp2v_recon_last_error(recon)); break; }
+        if (sh->opt.gpu_vlc) {
+            if (mp2v_recon_submit_staged(recon, s.rp) != MP2V_OK) { sh->fail(std::string("picture ") + std::to_string(next_submit) + ": " + mp2v_recon_last_error(recon)); break; }
+        } else {
+            s.rp->params->n_coef = s.arena.next.load();
+            if (mp2v_recon_submit(recon, s.rp) != MP2V_OK) { sh->fail(std::string("submit: ") + mp2v_recon_last_error(recon)); break; }
+        }
         s.submitted = true;
+        s.ts_submitted = sh->now_ms();
         next_submit++;
         in_parse--;
     }
@@ -271,6 +272,7 @@ void pipeline_t::output() {
             if (mp2v_recon_map_frame(recon, t.dst, planes, strides) != MP2V_OK) { sh->fail(std::string("map_frame: ") + mp2v_recon_last_error(recon)); return false; }
         }
         sh->out_map_ns.fetch_add(std::chrono::duration_cast<std::chrono::nanoseconds>(clock_t_::now() - to1).count(), std::memory_order_relaxed);
+        t.ts_mapped = sh->now_ms();
         {   // display order across GOP chains: chain g is shown after chain g-1
             std::unique_lock<std::mutex> lk(sh->gmu);
             sh->gcv.wait(lk, [&] { return sh->failed.load() || sh->emit_gop == t.src->gop; });
@@ -304,6 +306,7 @@ void pipeline_t::output() {
 }
 
 void worker_main(shared_t* sh) {
+    std::vector<mp2v_slice_ref_t> slice_refs;
     for (;;) {
         pic_task_t* t = nullptr;
         int slice = -1;
@@ -311,7 +314,7 @@ void worker_main(shared_t* sh) {
             std::unique_lock<std::mutex> lk(sh->qmu);
             for (;;) {
                 // drop pictures whose slices have all been claimed, claim one from the first that has any
-                while (!sh->queue.empty() && sh->queue.front()->next_slice.load(std::memory_order_relaxed) >= (int)sh->queue.front()->src->slices.size())
+                while (!sh->queue.empty() && sh->queue.front()->next_slice.load(std::memory_order_relaxed) >= sh->queue.front()->n_jobs)
                     sh->queue.pop_front();
                 if (!sh->queue.empty()) { t = sh->queue.front(); break; }
                 if (sh->stop) return;
@@ -321,9 +324,29 @@ void worker_main(shared_t* sh) {
             }
         }
         // claim slices of this picture without the lock until it runs dry
-        const int ns = (int)t->src->slices.size();
+        const int ns = t->n_jobs;
         while ((slice = t->next_slice.fetch_add(1, std::memory_order_relaxed)) < ns) {
-            if (!sh->failed.load(std::memory_order_relaxed)) {
+            if (sh->opt.gpu_vlc) {
+                if (!sh->failed.load(std::memory_order_relaxed)) {
+                    // stage the coded picture for the device parser: bytes into the slot's pinned buffer, no device work
+                    const picture_info_t& info = t->src->info;
+                    mp2v_pic_syntax_t sy{};
+                    for (int a = 0; a < 2; a++) for (int b = 0; b < 2; b++) sy.f_code[a][b] = info.f_code[a][b];
+                    sy.intra_dc_precision = info.intra_dc_precision;
+                    sy.q_scale_type = info.q_scale_type;
+                    sy.intra_vlc_format = info.intra_vlc_format;
+                    std::vector<mp2v_slice_ref_t>& refs = slice_refs;
+                    refs.clear();
+                    for (const slice_ref_t& sr : t->src->slices) refs.push_back({sr.payload, sr.bytes, sr.code});
+                    const int stage_rc = mp2v_recon_stage_slices(t->pipe->recon, t->rp, &sy, refs.data(), (int)refs.size());
+                    t->ts_staged = sh->now_ms();
+                    if (stage_rc != MP2V_OK) {
+                        t->error_text = mp2v_recon_last_error(t->pipe->recon);
+                        t->error = t->error_text.c_str();
+                        t->ok.store(false);
+                    }
+                }
+            } else if (!sh->failed.load(std::memory_order_relaxed)) {
                 const auto t0 = clock_t_::now();
                 const slice_ref_t& sr = t->src->slices[slice];
                 const slice_result_t r = parse_slice(sr.payload, sr.code, t->src->seq, t->src->info, sh->mbw, sh->mbh, t->rp->mb, t->arena);
@@ -466,6 +489,7 @@ bool mp2v_decoder_c::decode(uint8_t* buffer, int len) {
     if (!index_stream(buffer, (size_t)len, index, m->cfg.num_threads)) { m->error = index.error; return false; }
     const auto t_indexed = clock_t_::now();
     shared_t sh;
+    sh.t_origin = t_begin;
     sh.cfg = m->cfg; sh.opt = m->opt; sh.renderer = m->renderer;
     sh.mbw = m->cfg.width / 16; sh.mbh = m->cfg.height / 16;
     for (const auto& pic : index.pictures)
@@ -497,7 +521,7 @@ bool mp2v_decoder_c::decode(uint8_t* buffer, int len) {
     std::vector<std::thread> workers;
     {
         int nthreads = m->cfg.num_threads > MAX_NUM_THREADS ? MAX_NUM_THREADS : m->cfg.num_threads;
-        if (sh.opt.gpu_vlc) nthreads = 0;        // no host slice parsing
+        if (sh.opt.gpu_vlc && nthreads > 4) nthreads = 4;        // no host slice parsing: workers only stage the coded bytes
         for (int i = 0; i < nthreads; i++) workers.emplace_back(worker_main, &sh);
         for (auto& p : pipes) if (!p.tasks.empty()) {
             p.feeder_thread = std::thread(&pipeline_t::feeder, &p);
@@ -532,6 +556,13 @@ bool mp2v_decoder_c::decode(uint8_t* buffer, int len) {
         fprintf(stderr, "[mp2v profile] pictures %zu  parse %.1f ms(cpu)  worker idle %.1f ms(sum)  feeder wait %.1f work %.1f ms  precheck %.1f ms  submit(+lock) %.1f ms  output wait %.1f map %.1f ms\n",
                 index.pictures.size(), sh.parse_ns.load() * 1e-6, sh.worker_idle_ns.load() * 1e-6, sh.feeder_wait_ns.load() * 1e-6, sh.feeder_work_ns.load() * 1e-6,
                 sh.precheck_ns.load() * 1e-6, sh.submit_ns.load() * 1e-6, sh.out_wait_ns.load() * 1e-6, sh.out_map_ns.load() * 1e-6);
+    if (const char* pv = getenv("MP2V_PROFILE")) if (atoi(pv) >= 2)
+        for (auto& p : pipes)
+            for (size_t k = 0; k < p.tasks.size(); k++) {
+                const pic_task_t& t = p.tasks[k];
+                fprintf(stderr, "[mp2v timeline] pic %3zu type %d  queued %7.3f  staged %7.3f  submitted %7.3f  mapped %7.3f ms\n", k, t.src->info.picture_coding_type,
+                        t.ts_queued, t.ts_staged, t.ts_submitted, t.ts_mapped);
+            }
     m->stats.wall_seconds = std::chrono::duration<double>(clock_t_::now() - t_begin).count();
     if (sh.failed.load()) {
         // pictures may be left acquired / queued inside the contexts: rebuild them on the next call

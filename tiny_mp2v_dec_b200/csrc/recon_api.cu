@@ -7,7 +7,9 @@
 #include <algorithm>
 #include <condition_variable>
 #include <cstdio>
+#include <cstdlib>
 #include <cstring>
+#include <deque>
 #include <mutex>
 #include <string>
 #include <vector>
@@ -38,7 +40,10 @@ struct slot_t {
     uint8_t* d_staged = nullptr;
     vlc_slice_status_t* h_status = nullptr;   // pinned + mapped: one entry per slice, written by the kernel
     vlc_slice_status_t* d_status = nullptr;   // the device's address of h_status
-    int n_slices = 0;
+    int n_slices = 0, rows_covered = 0;
+    size_t staged_end = 0;
+    bool staged = false;               // stage_slices done, submit_staged pending
+    int trace_idx = -1;
     cudaStream_t s_vlc = nullptr;
     cudaEvent_t vlc_done = nullptr;    // H2D + parse + status read-back of the picture now in the slot
     bool vlc = false;                  // the slot's records come from the device parser
@@ -82,8 +87,15 @@ struct mp2v_recon {
     uint32_t slice_region = 0;
     void* d_tables = nullptr;
     uint8_t* d_blank_mb = nullptr;             // mb_count blank records, copied over a slot's records before each parse
+    // MP2V_TRACE=1 (development): device timestamps per picture, dumped to stderr by mp2v_recon_sync
+    struct trace_rec_t { uint64_t picture_no; cudaEvent_t h2d, vlc, recon, d2h; };
+    bool trace = false;
+    cudaEvent_t trace_base = nullptr;
+    std::vector<trace_rec_t> trace_log;
+    std::deque<int> status_fifo;               // slots whose parse status has not been folded in yet, submission order
     std::string vlc_error;                     // sticky: first slice error reported by the device parser
     uint64_t pictures_submitted = 0;
+    int batch_ramp = 1;                        // launch batch limit right after a sync: 1, 2, 4, ... max_batch (first frames out early)
 
     int fail(int code, const std::string& what) { err = what; return code; }
     int cuda_fail(cudaError_t e, const char* what) {
@@ -160,6 +172,10 @@ static int create_impl(mp2v_recon* ctx) {
     ctx->nblk = c.chroma_format == 1 ? 6 : c.chroma_format == 2 ? 8 : 12;
     ctx->mbw = c.width / 16; ctx->mbh = c.height / 16; ctx->mb_count = ctx->mbw * ctx->mbh;
     ctx->max_batch = c.max_batch ? c.max_batch : 8;
+    // One stream per picture slot parses concurrently: with the default 8 hardware work queues the
+    // streams alias and independent parses queue up behind one another (measured: 8 at a time).  Only
+    // effective when this is the process's first CUDA call; otherwise the embedding application sets it.
+    setenv("CUDA_DEVICE_MAX_CONNECTIONS", "32", 0);
     int ndev = 0;
     cudaError_t e = cudaGetDeviceCount(&ndev);
     if (e != cudaSuccess || ndev == 0) return ctx->fail(MP2V_ERR_CUDA, std::string("no CUDA device: ") + cudaGetErrorString(e));
@@ -183,6 +199,7 @@ static int create_impl(mp2v_recon* ctx) {
     ctx->frame_ev.assign(c.n_frames, nullptr);
     ctx->frame_written.assign(c.n_frames, 0);
     for (auto& ev : ctx->frame_ev) CK(cudaEventCreateWithFlags(&ev, cudaEventDisableTiming), "event");
+    if (const char* v = getenv("MP2V_TRACE")) ctx->trace = atoi(v) != 0;
     ctx->auto_dl = (c.flags & MP2V_RECON_AUTO_DOWNLOAD) != 0;
     ctx->mirror_valid.assign(c.n_frames, 0);
     if (ctx->auto_dl) {
@@ -307,6 +324,7 @@ static int launch_slots(mp2v_recon* ctx, const int* ids, int n, bool download = 
         ctx->frame_written[f] = 1;
         ctx->mirror_valid[f] = 0;
         ctx->stats.algorithmic_bytes += s.alg_bytes;
+        if (ctx->trace && s.vlc && s.trace_idx >= 0) CK(cudaEventRecord(ctx->trace_log[s.trace_idx].recon, ctx->s_compute), "event record");
     }
     if (download) {
         // the copies queue up on the D2H stream behind this launch and overlap the launches that follow
@@ -315,6 +333,7 @@ static int launch_slots(mp2v_recon* ctx, const int* ids, int n, bool download = 
             const int f = ctx->slots[ids[i]].pub.params->dst_frame;
             CK(cudaMemcpyAsync(ctx->h_frames[f], ctx->frame_ptr(f, 0), ctx->lay.bytes, cudaMemcpyDeviceToHost, ctx->s_d2h), "D2H frame");
             CK(cudaEventRecord(ctx->mirror_ev[f], ctx->s_d2h), "event record");
+            if (ctx->trace && ctx->slots[ids[i]].vlc && ctx->slots[ids[i]].trace_idx >= 0) CK(cudaEventRecord(ctx->trace_log[ctx->slots[ids[i]].trace_idx].d2h, ctx->s_d2h), "event record");
             ctx->mirror_valid[f] = 1;
             ctx->stats.d2h_bytes += ctx->lay.bytes;
         }
@@ -344,6 +363,7 @@ static int flush_locked(mp2v_recon* ctx) {
     }
     const int rc = launch_slots(ctx, ctx->pending.data(), (int)ctx->pending.size(), ctx->auto_dl);
     if (rc != MP2V_OK) return rc;
+    if (ctx->batch_ramp < ctx->max_batch) ctx->batch_ramp *= 2;
     for (int id : ctx->pending) {
         slot_t& s = ctx->slots[id];
         CK(cudaEventRecord(s.done, ctx->s_compute), "event record");
@@ -398,8 +418,7 @@ static int account_and_validate(mp2v_recon* ctx, slot_t& s, bool validate, std::
 // device-side slice parsing
 
 // Fold the parse results that have arrived into the statistics and the sticky error (ctx->mu held).
-static void harvest_status(mp2v_recon* ctx, slot_t& s) {
-    if (!s.status_pending || cudaEventQuery(s.vlc_done) != cudaSuccess) return;
+static void fold_status(mp2v_recon* ctx, slot_t& s) {
     s.status_pending = false;
     uint64_t n_coef = 0, coded = 0, dirs = 0;
     for (int i = 0; i < s.n_slices; i++) {
@@ -414,7 +433,16 @@ static void harvest_status(mp2v_recon* ctx, slot_t& s) {
     ctx->stats.algorithmic_bytes += out_bytes + dirs * mb_bytes + 128u * coded + 16u * (uint64_t)ctx->mb_count;
     ctx->stats.vlc_coefs += n_coef;
 }
-static void harvest_all(mp2v_recon* ctx) { if (ctx->vlc) for (auto& s : ctx->slots) harvest_status(ctx, s); }
+// Parses finish (almost) in submission order: fold from the front of the queue and stop at the first
+// one still running, so a call costs one event query, not one per slot.
+static void harvest_all(mp2v_recon* ctx) {
+    while (!ctx->status_fifo.empty()) {
+        slot_t& s = ctx->slots[ctx->status_fifo.front()];
+        if (cudaEventQuery(s.vlc_done) != cudaSuccess) break;
+        fold_status(ctx, s);
+        ctx->status_fifo.pop_front();
+    }
+}
 #define CHECK_VLC_ERROR() do { if (!ctx->vlc_error.empty()) return ctx->fail(MP2V_ERR_RANGE, ctx->vlc_error); } while (0)
 
 extern "C" MP2V_API int mp2v_recon_acquire_picture(mp2v_recon_t* ctx, mp2v_picture_t** out) {
@@ -427,28 +455,26 @@ extern "C" MP2V_API int mp2v_recon_acquire_picture(mp2v_recon_t* ctx, mp2v_pictu
             int best = -1;
             for (size_t i = 0; i < ctx->slots.size(); i++)
                 if (ctx->slots[i].state == SLOT_FREE) { best = (int)i; break; }
-            if (best < 0) {
-                // an in-flight slot whose launch already finished is as good as a free one
-                for (size_t i = 0; i < ctx->slots.size() && best < 0; i++)
-                    if (ctx->slots[i].state == SLOT_INFLIGHT && cudaEventQuery(ctx->slots[i].done) == cudaSuccess) best = (int)i;
+            // the oldest in-flight slot: as good as a free one if its launch already finished (one event query, not one per slot)
+            for (size_t i = 0; i < ctx->slots.size() && best < 0; i++) {
+                slot_t& s = ctx->slots[i];
+                if (s.state == SLOT_INFLIGHT && (candidate < 0 || s.seq < ctx->slots[candidate].seq)) candidate = (int)i;
             }
+            if (best < 0 && candidate >= 0 && cudaEventQuery(ctx->slots[candidate].done) == cudaSuccess) best = candidate;
             if (best >= 0) {
                 slot_t& s = ctx->slots[best];
-                harvest_status(ctx, s);
+                harvest_all(ctx);        // a finished launch implies every parse queued before it has finished
                 CHECK_VLC_ERROR();
                 s.state = SLOT_FILLING;
                 s.prechecked = false;
                 s.vlc = false;
+                s.staged = false;
                 memset(s.pub.params, 0, sizeof(mp2v_pic_params_t));
                 s.pub.params->l0_frame = s.pub.params->l1_frame = -1;
                 *out = &s.pub;
                 return MP2V_OK;
             }
-            // otherwise wait (outside the lock) for the oldest in-flight slot; launch queued work first
-            for (size_t i = 0; i < ctx->slots.size(); i++) {
-                slot_t& s = ctx->slots[i];
-                if (s.state == SLOT_INFLIGHT && (candidate < 0 || s.seq < ctx->slots[candidate].seq)) candidate = (int)i;
-            }
+            // otherwise wait (outside the lock) for that oldest in-flight slot; launch queued work first
             if (candidate < 0) {
                 if (ctx->pending.empty()) return ctx->fail(MP2V_ERR_STATE, "no picture slot available (all slots are being filled or resident)");
                 const int rc = flush_locked(ctx);
@@ -487,7 +513,7 @@ extern "C" MP2V_API int mp2v_recon_release_picture(mp2v_recon_t* ctx, mp2v_pictu
 static int queue_slot(mp2v_recon* ctx, slot_t* s) {
     const mp2v_pic_params_t& pp = *s->pub.params;
     // a picture cannot share a launch with a picture it reads from, nor with one touching its destination
-    bool conflict = (int)ctx->pending.size() >= ctx->max_batch;
+    bool conflict = (int)ctx->pending.size() >= std::min(ctx->max_batch, ctx->batch_ramp);
     for (int id : ctx->pending) {
         const mp2v_pic_params_t& q = *ctx->slots[id].pub.params;
         if (q.dst_frame == pp.l0_frame || q.dst_frame == pp.l1_frame || q.dst_frame == pp.dst_frame ||
@@ -518,14 +544,14 @@ extern "C" MP2V_API int mp2v_recon_submit(mp2v_recon_t* ctx, mp2v_picture_t* pic
     return queue_slot(ctx, s);
 }
 
-extern "C" MP2V_API int mp2v_recon_submit_slices(mp2v_recon_t* ctx, mp2v_picture_t* pic, const mp2v_pic_syntax_t* syntax,
-                                                 const mp2v_slice_ref_t* slices, int n_slices) {
+extern "C" MP2V_API int mp2v_recon_stage_slices(mp2v_recon_t* ctx, mp2v_picture_t* pic, const mp2v_pic_syntax_t* syntax,
+                                                const mp2v_slice_ref_t* slices, int n_slices) {
     if (!ctx) return MP2V_ERR_ARG;
     auto fail = [&](int code, const char* what) { std::lock_guard<std::mutex> lk(ctx->mu); return ctx->fail(code, what); };
     slot_t* s = slot_of(ctx, pic);
-    if (!s || s->state != SLOT_FILLING) return fail(MP2V_ERR_STATE, "submit_slices: picture was not acquired");
-    if (!ctx->vlc) return fail(MP2V_ERR_STATE, "submit_slices: context was created without MP2V_RECON_DEVICE_VLC");
-    if (!syntax || (n_slices > 0 && !slices) || n_slices < 0) return fail(MP2V_ERR_ARG, "submit_slices: bad arguments");
+    if (!s || s->state != SLOT_FILLING) return fail(MP2V_ERR_STATE, "stage_slices: picture was not acquired");
+    if (!ctx->vlc) return fail(MP2V_ERR_STATE, "stage_slices: context was created without MP2V_RECON_DEVICE_VLC");
+    if (!syntax || (n_slices > 0 && !slices) || n_slices < 0) return fail(MP2V_ERR_ARG, "stage_slices: bad arguments");
     const mp2v_pic_params_t& pp = *s->pub.params;
     const int nf = ctx->cfg.n_frames;
     if (pp.dst_frame < 0 || pp.dst_frame >= nf || pp.l0_frame >= nf || pp.l1_frame >= nf) return fail(MP2V_ERR_ARG, "frame id out of range");
@@ -557,7 +583,7 @@ extern "C" MP2V_API int mp2v_recon_submit_slices(mp2v_recon_t* ctx, mp2v_picture
         const uint8_t* hi = slices[0].payload + slices[0].bytes;
         std::vector<uint8_t> row_seen((size_t)ctx->mbh, 0);
         for (int i = 0; i < n_slices; i++) {
-            if (!slices[i].payload || slices[i].code < 1 || slices[i].code > 0xAF) return fail(MP2V_ERR_ARG, "submit_slices: bad slice reference");
+            if (!slices[i].payload || slices[i].code < 1 || slices[i].code > 0xAF) return fail(MP2V_ERR_ARG, "stage_slices: bad slice reference");
             lo = std::min(lo, slices[i].payload);
             hi = std::max(hi, slices[i].payload + slices[i].bytes);
             int row = slices[i].code - 1;
@@ -575,27 +601,57 @@ extern "C" MP2V_API int mp2v_recon_submit_slices(mp2v_recon_t* ctx, mp2v_picture
         staged_end = hdr.data_off + span + 16;
     }
     s->pub.params->n_coef = 0;
+    s->n_slices = n_slices;
+    s->staged_end = staged_end;
+    s->rows_covered = rows_covered;
+    s->staged = true;
+    return MP2V_OK;
+}
+
+extern "C" MP2V_API int mp2v_recon_submit_staged(mp2v_recon_t* ctx, mp2v_picture_t* pic) {
+    if (!ctx) return MP2V_ERR_ARG;
+    slot_t* s = slot_of(ctx, pic);
     // ---- H2D + parse on the slot's own stream, then queue the reconstruction
     std::lock_guard<std::mutex> lk(ctx->mu);
-    harvest_all(ctx);
+    if (!s || s->state != SLOT_FILLING || !s->staged) return ctx->fail(MP2V_ERR_STATE, "submit_staged: picture was not staged with mp2v_recon_stage_slices");
+    s->staged = false;
+    const int n_slices = s->n_slices;
+    const size_t staged_end = s->staged_end;
+    const int rows_covered = s->rows_covered;
     CHECK_VLC_ERROR();
     CK(cudaSetDevice(ctx->cfg.device), "cudaSetDevice");
     mp2v_mb_info_t* d_mb = reinterpret_cast<mp2v_mb_info_t*>(s->d_arena + kParamsBytes);
+    s->trace_idx = -1;
+    if (ctx->trace) {
+        if (!ctx->trace_base) { CK(cudaEventCreate(&ctx->trace_base), "event"); CK(cudaEventRecord(ctx->trace_base, s->s_vlc), "event record"); }
+        mp2v_recon::trace_rec_t tr{ctx->pictures_submitted, nullptr, nullptr, nullptr, nullptr};
+        CK(cudaEventCreate(&tr.h2d), "event"); CK(cudaEventCreate(&tr.vlc), "event"); CK(cudaEventCreate(&tr.recon), "event"); CK(cudaEventCreate(&tr.d2h), "event");
+        s->trace_idx = (int)ctx->trace_log.size();
+        ctx->trace_log.push_back(tr);
+    }
     CK(cudaMemcpyAsync(s->d_staged, s->h_staged, staged_end, cudaMemcpyHostToDevice, s->s_vlc), "H2D bitstream");
+    if (s->trace_idx >= 0) CK(cudaEventRecord(ctx->trace_log[s->trace_idx].h2d, s->s_vlc), "event record");
     // the kernel blanks what a slice leaves uncoded in its own row; rows without any slice (never in valid streams) are blanked here
     if (rows_covered < ctx->mbh)
         CK(cudaMemcpyAsync(d_mb, ctx->d_blank_mb, (size_t)ctx->mb_count * sizeof(mp2v_mb_info_t), cudaMemcpyDeviceToDevice, s->s_vlc), "blank records");
     CK(launch_vlc(s->d_staged, ctx->d_tables, d_mb, reinterpret_cast<mp2v_coef_t*>(s->d_arena + ctx->coef_off), s->d_status, n_slices,
                   ctx->vlc_lanes, s->s_vlc), "slice parser kernel launch");
+    if (s->trace_idx >= 0) CK(cudaEventRecord(ctx->trace_log[s->trace_idx].vlc, s->s_vlc), "event record");
     CK(cudaEventRecord(s->vlc_done, s->s_vlc), "event record");
     ctx->stats.h2d_bytes += staged_end;
     ctx->stats.d2h_bytes += (uint64_t)n_slices * sizeof(vlc_slice_status_t);
     if (n_slices > 0) { ctx->stats.vlc_launches += 1; ctx->stats.vlc_slices += (uint64_t)n_slices; }
-    s->n_slices = n_slices;
     s->vlc = true;
     s->status_pending = true;
+    ctx->status_fifo.push_back(s->pub.slot);
     s->alg_bytes = 0;                                    // folded in from the parse status (harvest_status)
     return queue_slot(ctx, s);
+}
+
+extern "C" MP2V_API int mp2v_recon_submit_slices(mp2v_recon_t* ctx, mp2v_picture_t* pic, const mp2v_pic_syntax_t* syntax,
+                                                 const mp2v_slice_ref_t* slices, int n_slices) {
+    const int rc = mp2v_recon_stage_slices(ctx, pic, syntax, slices, n_slices);
+    return rc != MP2V_OK ? rc : mp2v_recon_submit_staged(ctx, pic);
 }
 
 extern "C" MP2V_API int mp2v_recon_precheck(mp2v_recon_t* ctx, mp2v_picture_t* pic) {
@@ -624,6 +680,22 @@ extern "C" MP2V_API int mp2v_recon_sync(mp2v_recon_t* ctx) {
     CK(cudaStreamSynchronize(ctx->s_copy), "stream sync");
     CK(cudaStreamSynchronize(ctx->s_compute), "stream sync");
     for (auto& s : ctx->slots) if (s.state == SLOT_INFLIGHT) s.state = SLOT_FREE;
+    ctx->batch_ramp = 1;
+    if (ctx->trace && !ctx->trace_log.empty()) {
+        cudaStreamSynchronize(ctx->s_d2h);
+        for (auto& tr : ctx->trace_log) {
+            float a = -1, b = -1, c = -1, d = -1;
+            cudaEventElapsedTime(&a, ctx->trace_base, tr.h2d); cudaEventElapsedTime(&b, ctx->trace_base, tr.vlc);
+            cudaEventElapsedTime(&c, ctx->trace_base, tr.recon);
+            if (cudaEventQuery(tr.d2h) == cudaSuccess) cudaEventElapsedTime(&d, ctx->trace_base, tr.d2h);
+            fprintf(stderr, "[mp2v trace] pic %3llu  h2d %7.3f  vlc %7.3f  recon %7.3f  d2h %7.3f ms\n", (unsigned long long)tr.picture_no, a, b, c, d);
+            cudaEventDestroy(tr.h2d); cudaEventDestroy(tr.vlc); cudaEventDestroy(tr.recon); cudaEventDestroy(tr.d2h);
+        }
+        cudaGetLastError();   // an event never recorded (no download) reports an error that is not ours
+        ctx->trace_log.clear();
+        cudaEventDestroy(ctx->trace_base);
+        ctx->trace_base = nullptr;
+    }
     harvest_all(ctx);      // every parse precedes a reconstruction launch that has now finished
     if (!ctx->vlc_error.empty()) {
         const std::string why = ctx->vlc_error;

@@ -15,7 +15,7 @@ _lib = None
 
 EXPORTS = [
     "mp2v_frame_layout", "mp2v_recon_create", "mp2v_recon_destroy", "mp2v_recon_last_error",
-    "mp2v_recon_acquire_picture", "mp2v_recon_release_picture", "mp2v_recon_submit", "mp2v_recon_submit_slices", "mp2v_recon_precheck", "mp2v_recon_flush",
+    "mp2v_recon_acquire_picture", "mp2v_recon_release_picture", "mp2v_recon_submit", "mp2v_recon_submit_slices", "mp2v_recon_stage_slices", "mp2v_recon_submit_staged", "mp2v_recon_precheck", "mp2v_recon_flush",
     "mp2v_recon_sync", "mp2v_recon_upload", "mp2v_recon_run_resident", "mp2v_recon_download_frame",
     "mp2v_recon_map_frame", "mp2v_recon_upload_frame", "mp2v_recon_frame_device_ptrs",
     "mp2v_recon_set_timing", "mp2v_recon_get_stats", "mp2v_recon_timer_start", "mp2v_recon_timer_stop",
@@ -44,6 +44,8 @@ def lib():
         L.mp2v_recon_release_picture.argtypes = [C.c_void_p, P(Picture)]
         L.mp2v_recon_submit.argtypes = [C.c_void_p, P(Picture)]
         L.mp2v_recon_submit_slices.argtypes = [C.c_void_p, P(Picture), P(PicSyntax), P(SliceRef), C.c_int]
+        L.mp2v_recon_stage_slices.argtypes = [C.c_void_p, P(Picture), P(PicSyntax), P(SliceRef), C.c_int]
+        L.mp2v_recon_submit_staged.argtypes = [C.c_void_p, P(Picture)]
         L.mp2v_recon_precheck.argtypes = [C.c_void_p, P(Picture)]
         L.mp2v_recon_flush.argtypes = [C.c_void_p]
         L.mp2v_recon_sync.argtypes = [C.c_void_p]

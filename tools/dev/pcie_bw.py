@@ -17,3 +17,26 @@ for name, src, dst in (("H2D", h, d), ("D2H", d, h)):
         dt = time.perf_counter() - t0
         moved = reps * (n // chunk) * chunk
         print("%s chunk %9d B: %.1f GB/s" % (name, chunk, moved / dt / 1e9))
+
+# D2H of frame-sized chunks while small H2D copies run on another stream (the decoder's traffic pattern)
+s1, s2 = torch.cuda.Stream(), torch.cuda.Stream()
+hh = torch.empty(64 << 20, dtype=torch.uint8).pin_memory()
+dd = torch.empty(64 << 20, dtype=torch.uint8, device="cuda")
+chunk, small = 3133440, 225 * 1024
+for with_h2d in (False, True):
+    torch.cuda.synchronize()
+    t0 = time.perf_counter()
+    reps = 5
+    for _ in range(reps):
+        k = 0
+        for o in range(0, n - chunk + 1, chunk):
+            with torch.cuda.stream(s1):
+                h[o:o + chunk].copy_(d[o:o + chunk], non_blocking=True)
+            if with_h2d:
+                with torch.cuda.stream(s2):
+                    so = (k * small) % ((64 << 20) - small)
+                    dd[so:so + small].copy_(hh[so:so + small], non_blocking=True)
+                k += 1
+    torch.cuda.synchronize()
+    dt = time.perf_counter() - t0
+    print("D2H 3.1 MB chunks%s: %.1f GB/s" % (" + concurrent 225 KB H2D per chunk" if with_h2d else "", reps * (n // chunk) * chunk / dt / 1e9))
