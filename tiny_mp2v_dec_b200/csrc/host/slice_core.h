@@ -134,14 +134,60 @@ MP2V_HDI bool parse_block(bitreader_t& br, mp2v_coef_t*& out, const vlc_decode_t
         *out++ = MP2V_COEF(neg ? -1 : 1, 0, b, MP2V_COEF_FIRST);
         i = 1;
     }
-    // symbols decoded per refill: an escape is 24 bits, so two of any kind fit the host reader's 56 bits
-    // (the first round reuses the refill above: at most 22 bits were consumed since); the device
-    // reader guarantees 33 and refills, off its dependent chain, before every symbol
-    constexpr int kPerRefill = bitreader_t::kBitsAfterRefill >= 48 ? 2 : 1;
-    if (kPerRefill == 1) br.refill();
+#ifdef __CUDA_ARCH__
+    // Device loop.  A slice thread's time is its instruction count (one warp, no ILP to speak of), so a
+    // fast symbol is: look up one pre-assembled word, add it to the running {position, block} word q --
+    // that IS the record -- store, keep its upper half as the next q.  q = ((i - 1) << 16 | block << 22)
+    // modulo 2^32; a position past 63 carries into the block field, which is the range check.
+    {
+        const uint32_t* gfast = table->gpu_fast;
+        uint32_t q = (((uint32_t)i << 16) | blk_bits) - 0x10000u;
+        mp2v_coef_t* o = out;
+        for (;;) {
+            br.refill();                                       // >= 33 bits: any one symbol (escape = 24)
+            const uint32_t e = __ldg(gfast + br.peek(kFastBits));
+            uint32_t rec;
+            if ((int32_t)e >= 0) {
+                br.skip((int)(e >> 24));
+                rec = q + (e & 0x007fffffu);
+            } else if (e & 0x40000000u) {                      // end of block
+                br.skip((int)((e >> 24) & 15u));
+                out = o;
+                return true;
+            } else {
+                const coef_entry_t s = table->look(br.peek(17));
+                int run, level;
+                if (s.level > 0) {
+                    br.skip(s.len);
+                    const int neg = (int)br.peek(1);
+                    br.skip(1);
+                    run = s.run;
+                    level = (s.level ^ -neg) + neg;
+                } else if (s.level == kCoefEob && s.len) {
+                    br.skip(s.len);
+                    out = o;
+                    return true;
+                } else if (s.level == kCoefEsc && s.len) {     // 6-bit run, 12-bit two's complement level
+                    br.skip(6);
+                    run = (int)br.peek(6); br.skip(6);
+                    level = ((int)br.peek(12) ^ 0x800) - 0x800; br.skip(12);
+                } else {
+                    out = o;
+                    return false;
+                }
+                rec = q + ((uint32_t)(run + 1) << 16) + (uint32_t)(uint16_t)level;
+            }
+            if ((rec >> 22) != (uint32_t)b) { out = o; return false; }      // i + run > 63
+            *o++ = rec;
+            q = rec & 0xffff0000u;
+        }
+    }
+#else
+    // Host loop.  Symbols decoded per refill: an escape is 24 bits, so two of any kind fit the 56 bits a
+    // refill guarantees (the first round reuses the refill above: at most 22 bits were consumed since).
     for (;;) {
         MP2V_UNROLL2
-        for (int rep = 0; rep < kPerRefill; rep++) {
+        for (int rep = 0; rep < 2; rep++) {
             const coef_fast_t f = table->look_fast(br.peek(kFastBits));
             int run, level;
             if (f.run < kFastEob) {
@@ -176,6 +222,7 @@ MP2V_HDI bool parse_block(bitreader_t& br, mp2v_coef_t*& out, const vlc_decode_t
         }
         br.refill();
     }
+#endif
 }
 
 // the reference does not clamp vectors: one that leaves the frame is an error here

@@ -78,6 +78,11 @@ constexpr int kFastBits = 11;
 struct coef_vlc_t {
     static constexpr int ROOT = 8, LEAF = 9;                      // longest code is 16 bits (+ sign)
     coef_fast_t fast[1 << kFastBits];
+    // The same table pre-assembled for the device parser, whose cost is instructions per symbol: a fast
+    // symbol's coefficient record is `q + (entry & 0x7fffff)` where q carries block and position:
+    //   [15:0] level (two's complement)  [22:16] run + 1  [27:24] bits consumed (incl. sign)
+    //   [31] not a fast symbol -> [30] end of block (then [27:24] = its length), else take the two-level table
+    uint32_t gpu_fast[1 << kFastBits];
     void build_fast() {
         for (uint32_t i = 0; i < (1u << kFastBits); i++) {
             const coef_entry_t e = look(i << (17 - kFastBits));
@@ -89,6 +94,8 @@ struct coef_vlc_t {
                 f.run = kFastEob; f.len = e.len;
             }
             fast[i] = f;
+            gpu_fast[i] = f.run < kFastEob ? ((uint32_t)(uint16_t)f.level | ((uint32_t)(f.run + 1) << 16) | ((uint32_t)f.len << 24))
+                        : f.run == kFastEob ? (0xc0000000u | ((uint32_t)f.len << 24)) : 0x80000000u;
         }
     }
     static constexpr int MAX_LEAVES = 8;                          // distinct 8-bit prefixes with longer codes (B.14/B.15 need 6)
