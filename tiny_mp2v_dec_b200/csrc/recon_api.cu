@@ -186,9 +186,15 @@ static int create_impl(mp2v_recon* ctx) {
     cudaFuncAttributes fa;
     e = recon_kernel_attributes(c.chroma_format, &fa);   // fails loudly when the sm_100a image cannot load on this device
     if (e != cudaSuccess) return ctx->cuda_fail(e, "reconstruction kernel image not usable on this device (built for sm_100a only)");
+    // Priorities: frames leaving the device first, then reconstruction, then (default priority) the slice
+    // parses -- of which dozens are resident at any time and which otherwise crowd out the stages that
+    // free their slots and frames.
+    int prio_least = 0, prio_greatest = 0;
+    CK(cudaDeviceGetStreamPriorityRange(&prio_least, &prio_greatest), "stream priority range");
+    const int prio_mid = prio_greatest < prio_least - 1 ? prio_greatest + 1 : prio_greatest;
     CK(cudaStreamCreateWithFlags(&ctx->s_copy, cudaStreamNonBlocking), "stream");
-    CK(cudaStreamCreateWithFlags(&ctx->s_compute, cudaStreamNonBlocking), "stream");
-    CK(cudaStreamCreateWithFlags(&ctx->s_d2h, cudaStreamNonBlocking), "stream");
+    CK(cudaStreamCreateWithPriority(&ctx->s_compute, cudaStreamNonBlocking, prio_mid), "stream");
+    CK(cudaStreamCreateWithPriority(&ctx->s_d2h, cudaStreamNonBlocking, prio_greatest), "stream");
     CK(cudaEventCreateWithFlags(&ctx->ev_h2d, cudaEventDisableTiming), "event");
     CK(cudaEventCreate(&ctx->ev_t0), "event");
     CK(cudaEventCreate(&ctx->ev_t1), "event");

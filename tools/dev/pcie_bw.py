@@ -40,3 +40,24 @@ for with_h2d in (False, True):
     torch.cuda.synchronize()
     dt = time.perf_counter() - t0
     print("D2H 3.1 MB chunks%s: %.1f GB/s" % (" + concurrent 225 KB H2D per chunk" if with_h2d else "", reps * (n // chunk) * chunk / dt / 1e9))
+
+# the decoder's pattern: frame-sized D2H into many separate pinned buffers, with and without kernels running
+bufs = [torch.empty(chunk, dtype=torch.uint8).pin_memory() for _ in range(58)]
+srcs = d[:58 * chunk].view(58, chunk)
+x = torch.randn(8192, 8192, device="cuda", dtype=torch.bfloat16)
+for busy in (False, True):
+    torch.cuda.synchronize()
+    t0 = time.perf_counter()
+    reps = 8
+    for _ in range(reps):
+        if busy:
+            with torch.cuda.stream(s2):
+                for _ in range(6):
+                    x = (x @ x).clamp_(-1, 1)
+        with torch.cuda.stream(s1):
+            for k in range(58):
+                bufs[k].copy_(srcs[k], non_blocking=True)
+    s1.synchronize()
+    dt = time.perf_counter() - t0
+    torch.cuda.synchronize()
+    print("D2H 58 separate pinned frame buffers%s: %.1f GB/s" % (", GEMMs running" if busy else "", reps * 58 * chunk / dt / 1e9))
