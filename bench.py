@@ -392,16 +392,16 @@ def main():
     from tiny_mp2v_dec_b200.decoder import Decoder
     threads = max(1, host_threads(world) - 2)      # two cores stay free for the decoder's feeder and output threads
 
-    def time_decoder(gpu_vlc, steps):
+    def time_decoder(gpu_vlc, steps, download=True):
         dec = Decoder(wl["width"], wl["height"], wl["chroma_format"], pictures_pool_size=10, num_threads=threads,
-                      devices=(local,), max_batch=8, output_lag=6, gpu_vlc=gpu_vlc).prepare(download=True)
+                      devices=(local,), max_batch=8, output_lag=6, gpu_vlc=gpu_vlc).prepare(download=download)
         for _ in range(2):
-            dec.decode(stream.padded, stream.size, want_output=False, download=True)
+            dec.decode(stream.padded, stream.size, want_output=False, download=download)
         barrier()
         t0 = time.perf_counter()
         stats = []
         for _ in range(steps):
-            dec.decode(stream.padded, stream.size, want_output=False, download=True)
+            dec.decode(stream.padded, stream.size, want_output=False, download=download)
             stats.append((dec.stats.h2d_bytes, dec.stats.d2h_bytes, dec.stats.parse_cpu_seconds, dec.stats.kernel_ms,
                           dec.stats.launches + dec.stats.vlc_launches))
         torch.cuda.synchronize()
@@ -412,6 +412,7 @@ def main():
 
     e2e_s, (h2d, d2h, _, _, e2e_launches) = time_decoder(True, args.steps)
     host_s, (host_h2d, _, parse_cpu, _, _) = time_decoder(False, args.steps)
+    nodl_s, _ = time_decoder(True, args.steps, download=False)      # frames stay on the device (zero-copy consumer)
     clocks = sampler.stop()          # sampled across the timed regions (the resident steps alone last a few ms)
     e2e_value = total_frames / e2e_s
     host_e2e_value = total_frames / host_s
@@ -461,6 +462,8 @@ def main():
             "e2e": {"value": round(e2e_value, 1), "unit": "frames/s", "h2d_bytes_per_step": int(h2d), "d2h_bytes_per_step": int(d2h),
                     "slice_parser": "device (mp2v_b200_options_t.gpu_vlc, the API default)", "gpu_launches_per_step": int(e2e_launches),
                     "d2h_gbs": round(d2h * args.steps / e2e_s / 1e9, 1),
+                    "without_frame_download": {"value": round(total_frames / nodl_s, 1), "unit": "frames/s",
+                                               "note": "same call, download_frames=false: what the D2H of every frame costs"},
                     "host_parser_mode": {"value": round(host_e2e_value, 1), "unit": "frames/s", "host_threads": threads,
                                          "h2d_bytes_per_step": int(host_h2d), "host_parse_cpu_s_per_step": round(parse_cpu, 4),
                                          "host_parse_fps_per_core": round(n_frames / parse_cpu, 1) if parse_cpu > 0 else None,

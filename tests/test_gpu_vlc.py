@@ -107,3 +107,39 @@ def test_stream_outside_the_device_envelope_takes_the_host_parser():
     # the same decoder object goes back to the device parser for a stream inside the envelope
     assert d.decode(s.padded, s.size) == want
     assert d.stats.vlc_launches == len(s.pictures)
+
+
+@pytest.mark.parametrize("cf", [1, 3])
+def test_corrupted_streams_never_hang_or_fault(cf):
+    """compute-sanitizer is not available on this pool, so memory safety of the device parser is exercised the
+    blunt way: 60 seeded corruptions of slice data (byte flips, zero runs, 0xFF runs) through BOTH parsers.
+    Every decode must return -- success or ReconError -- and afterwards the same process must still decode the
+    clean stream bit-exactly (a faulted kernel would poison the CUDA context for everything after it)."""
+    s = Stream(352, 288, cf, seed=310 + cf, n_gops=2, gop_n=9, gop_m=3, qscale_code_max=31, pct_big_levels=5)
+    want = O.oracle_decode_stream(s)
+    rng = np.random.default_rng(1234 + cf)
+    sc = _start_codes(s.padded, s.size)
+    slices = [int(o) for o in sc if 1 <= s.padded[o + 3] <= 0xAF]
+    outcomes = {True: [0, 0], False: [0, 0]}
+    for trial in range(60):
+        buf = s.padded.copy()
+        for _ in range(int(rng.integers(1, 4))):
+            at = slices[int(rng.integers(0, len(slices)))] + 4 + int(rng.integers(0, 200))
+            at = min(at, s.size - 8)
+            kind = int(rng.integers(0, 3))
+            if kind == 0:
+                buf[at] ^= 1 << int(rng.integers(0, 8))
+            elif kind == 1:
+                buf[at:at + int(rng.integers(1, 12))] = 0xFF
+            else:
+                buf[at:at + int(rng.integers(1, 6))] = rng.integers(1, 255, dtype=np.uint8)   # no new start codes
+        for gpu_vlc in (True, False):
+            try:
+                Decoder(352, 288, cf, num_threads=2, gpu_vlc=gpu_vlc).decode(buf, s.size)
+                outcomes[gpu_vlc][0] += 1
+            except ReconError:
+                outcomes[gpu_vlc][1] += 1
+    assert sum(outcomes[True]) == sum(outcomes[False]) == 60
+    assert outcomes[True][1] > 0 and outcomes[False][1] > 0          # some corruptions are detected as syntax errors
+    for gpu_vlc in (True, False):
+        assert Decoder(352, 288, cf, num_threads=2, gpu_vlc=gpu_vlc).decode(s.padded, s.size) == want

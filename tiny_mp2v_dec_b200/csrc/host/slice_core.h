@@ -142,45 +142,54 @@ MP2V_HDI bool parse_block(bitreader_t& br, mp2v_coef_t*& out, const vlc_decode_t
     {
         const uint32_t* gfast = table->gpu_fast;
         uint32_t q = (((uint32_t)i << 16) | blk_bits) - 0x10000u;
-        mp2v_coef_t* o = out;
+        mp2v_coef_t* const o0 = out;
+        uint32_t n = 0;                                        // 32-bit record index: one add per record, not a 64-bit pointer bump
+        bool ok = false;
         for (;;) {
-            br.refill();                                       // >= 33 bits: any one symbol (escape = 24)
-            const uint32_t e = __ldg(gfast + br.peek(kFastBits));
-            uint32_t rec;
-            if ((int32_t)e >= 0) {
+            // tight loop over fast symbols only (its own loop so that the rare paths below do not shape its code)
+            uint32_t e, rec;
+            for (;;) {
+                br.refill();                                   // >= 33 bits: any one symbol (escape = 24)
+                e = __ldg(gfast + br.peek(kFastBits));
+                if ((int32_t)e < 0) break;
                 br.skip((int)(e >> 24));
                 rec = q + (e & 0x007fffffu);
-            } else if (e & 0x40000000u) {                      // end of block
-                br.skip((int)((e >> 24) & 15u));
-                out = o;
-                return true;
-            } else {
-                const coef_entry_t s = table->look(br.peek(17));
-                int run, level;
-                if (s.level > 0) {
-                    br.skip(s.len);
-                    const int neg = (int)br.peek(1);
-                    br.skip(1);
-                    run = s.run;
-                    level = (s.level ^ -neg) + neg;
-                } else if (s.level == kCoefEob && s.len) {
-                    br.skip(s.len);
-                    out = o;
-                    return true;
-                } else if (s.level == kCoefEsc && s.len) {     // 6-bit run, 12-bit two's complement level
-                    br.skip(6);
-                    run = (int)br.peek(6); br.skip(6);
-                    level = ((int)br.peek(12) ^ 0x800) - 0x800; br.skip(12);
-                } else {
-                    out = o;
-                    return false;
-                }
-                rec = q + ((uint32_t)(run + 1) << 16) + (uint32_t)(uint16_t)level;
+                if ((rec >> 22) != (uint32_t)b) break;         // i + run > 63
+                o0[n++] = rec;
+                q = rec & 0xffff0000u;
             }
-            if ((rec >> 22) != (uint32_t)b) { out = o; return false; }      // i + run > 63
-            *o++ = rec;
+            if ((int32_t)e >= 0) break;                        // range error inside the tight loop
+            if (e & 0x40000000u) {                             // end of block
+                br.skip((int)((e >> 24) & 15u));
+                ok = true;
+                break;
+            }
+            const coef_entry_t s = table->look(br.peek(17));
+            int run, level;
+            if (s.level > 0) {
+                br.skip(s.len);
+                const int neg = (int)br.peek(1);
+                br.skip(1);
+                run = s.run;
+                level = (s.level ^ -neg) + neg;
+            } else if (s.level == kCoefEob && s.len) {
+                br.skip(s.len);
+                ok = true;
+                break;
+            } else if (s.level == kCoefEsc && s.len) {         // 6-bit run, 12-bit two's complement level
+                br.skip(6);
+                run = (int)br.peek(6); br.skip(6);
+                level = ((int)br.peek(12) ^ 0x800) - 0x800; br.skip(12);
+            } else {
+                break;
+            }
+            rec = q + ((uint32_t)(run + 1) << 16) + (uint32_t)(uint16_t)level;
+            if ((rec >> 22) != (uint32_t)b) break;             // i + run > 63
+            o0[n++] = rec;
             q = rec & 0xffff0000u;
         }
+        out = o0 + n;
+        return ok;
     }
 #else
     // Host loop.  Symbols decoded per refill: an escape is 24 bits, so two of any kind fit the 56 bits a
