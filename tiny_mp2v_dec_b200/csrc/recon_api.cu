@@ -657,7 +657,7 @@ extern "C" MP2V_API int mp2v_recon_submit_staged(mp2v_recon_t* ctx, mp2v_picture
     s->vlc = true;
     s->status_pending = true;
     ctx->status_fifo.push_back(s->pub.slot);
-    s->alg_bytes = 0;                                    // folded in from the parse status (harvest_status)
+    s->alg_bytes = 0;                                    // folded in from the parse status (fold_status)
     return queue_slot(ctx, s);
 }
 
