@@ -432,6 +432,25 @@ def main():
                  "launches_per_step": int(st2.launches) // args.steps,
                  "roofline_achieved_gbs": round(st2.algorithmic_bytes / (st2.kernel_ms * 1e-3) / 1e9, 1),
                  "roofline_frac": round(st2.algorithmic_bytes / (st2.kernel_ms * 1e-3) / 1e9 / peak, 4)}
+        # the output-path kernel (planar 4:2:0 -> NV12 for GPU consumers) on the frames that run left in the pool
+        try:
+            import ctypes as C
+            fw, fh = wl2["width"], wl2["height"]
+            nv = torch.empty((n2, fh * 3 // 2, fw), dtype=torch.uint8, device="cuda:%d" % local)
+            ids = (C.c_int32 * n2)(*range(n2))
+            ptrs = (C.c_void_p * n2)(*[nv[f].data_ptr() for f in range(n2)])
+            reps = 20
+            for timed in (False, True):
+                r2.timer_start()
+                for _ in range(reps):
+                    r2._ck(r2.L.mp2v_recon_convert_frames_nv12(r2.h, ids, ptrs, n2, fw))
+                ms_nv = r2.timer_stop()
+            gbs_nv = 2 * (fw * fh * 3 // 2) * n2 * reps / (ms_nv * 1e-3) / 1e9
+            extra["nv12_output_kernel"] = {"frames_per_s": round(n2 * reps / (ms_nv * 1e-3), 1), "achieved_gbs": round(gbs_nv, 1),
+                                           "frac_of_hbm_peak": round(gbs_nv / peak, 4), "bytes": "read + write = 2 x frame bytes"}
+            del nv
+        except Exception as e:      # an extra, never the bench line's reason to fail
+            extra["nv12_output_kernel"] = {"error": repr(e)}
         r2.close()
 
     # ---- CPU baseline beside it (rank 0, N = 1 only): the unmodified reference on this box's cores

@@ -23,7 +23,7 @@ STREAMGEN_LIB = os.path.join(LIB, "libmp2v_streamgen.so")
 ORACLE_LIB = os.path.join(ROOT, "oracle", "libmp2v_oracle.so")
 REF_LIB = os.path.join(ROOT, "oracle", "_ref", "libmp2v_ref.so")
 
-CUDA_SOURCES = ["recon_kernels.cu", "vlc_kernel.cu", "recon_api.cu"]
+CUDA_SOURCES = ["recon_kernels.cu", "vlc_kernel.cu", "convert_kernel.cu", "recon_api.cu"]
 HOST_SOURCES = ["host/mp2v_parser.cpp", "host/stream_index.cpp", "host/decoder.cpp", "host/decoder_capi.cpp"]
 
 

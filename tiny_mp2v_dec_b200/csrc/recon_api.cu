@@ -867,6 +867,40 @@ extern "C" MP2V_API int mp2v_recon_frame_device_ptrs(mp2v_recon_t* ctx, int fram
     return MP2V_OK;
 }
 
+extern "C" MP2V_API int mp2v_recon_convert_frames_nv12(mp2v_recon_t* ctx, const int32_t* frame_ids, void* const* dst_device, int n, int32_t dst_pitch) {
+    if (!ctx || !frame_ids || !dst_device || n < 0) return MP2V_ERR_ARG;
+    std::lock_guard<std::mutex> lk(ctx->mu);
+    if (ctx->cfg.chroma_format != 1) return ctx->fail(MP2V_ERR_ARG, "NV12 is a 4:2:0 format");
+    if (dst_pitch < ctx->cfg.width || (dst_pitch & 15)) return ctx->fail(MP2V_ERR_ARG, "NV12 destination must be 16-byte aligned with a pitch that is a multiple of 16 and >= width");
+    const int rc = flush_locked(ctx);
+    if (rc != MP2V_OK) return rc;
+    for (int i = 0; i < n; i++) {
+        if (frame_ids[i] < 0 || frame_ids[i] >= ctx->cfg.n_frames) return ctx->fail(MP2V_ERR_ARG, "frame id out of range");
+        if (!dst_device[i] || ((uintptr_t)dst_device[i] & 15)) return ctx->fail(MP2V_ERR_ARG, "NV12 destination must be 16-byte aligned with a pitch that is a multiple of 16 and >= width");
+        if (!ctx->frame_written[frame_ids[i]]) return ctx->fail(MP2V_ERR_STATE, "frame has never been written");
+    }
+    CK(cudaSetDevice(ctx->cfg.device), "cudaSetDevice");
+    // on the compute stream: ordered behind the launches that write the frames and ahead of any that overwrites them
+    for (int first = 0; first < n; first += kMaxBatch) {
+        nv12_batch_t b{};
+        b.n_frames = std::min(n - first, (int)kMaxBatch);
+        b.width = ctx->cfg.width; b.height = ctx->cfg.height;
+        b.stride_y = ctx->lay.stride[0]; b.stride_c = ctx->lay.stride[1]; b.dst_pitch = dst_pitch;
+        for (int i = 0; i < b.n_frames; i++)
+            b.frame[i] = {ctx->frame_ptr(frame_ids[first + i], 0), ctx->frame_ptr(frame_ids[first + i], 1), ctx->frame_ptr(frame_ids[first + i], 2),
+                          static_cast<uint8_t*>(dst_device[first + i])};
+        CK(launch_nv12(b, ctx->s_compute), "NV12 conversion launch");
+        ctx->stats.launches += 1;
+    }
+    return MP2V_OK;
+}
+
+extern "C" MP2V_API int mp2v_recon_convert_frame_nv12(mp2v_recon_t* ctx, int frame_id, void* dst_device, int32_t dst_pitch) {
+    const int32_t id = frame_id;
+    void* const dst = dst_device;
+    return mp2v_recon_convert_frames_nv12(ctx, &id, &dst, 1, dst_pitch);
+}
+
 // ---------------------------------------------------------------------------------------------
 // statistics
 

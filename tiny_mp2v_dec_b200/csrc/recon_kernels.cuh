@@ -50,6 +50,14 @@ struct batch_desc_t {
 // grid = n_pics * ctas_per_pic; returns the CUDA error of the launch
 cudaError_t launch_recon(int chroma_format, const batch_desc_t& batch, cudaStream_t stream);
 
+// planar 4:2:0 frames -> NV12 (Y plane, then interleaved Cb/Cr rows) in the caller's device buffers (convert_kernel.cu)
+struct nv12_frame_t { const uint8_t* y; const uint8_t* cb; const uint8_t* cr; uint8_t* dst; };
+struct nv12_batch_t {
+    nv12_frame_t frame[kMaxBatch];
+    int32_t n_frames, width, height, stride_y, stride_c, dst_pitch;
+};
+cudaError_t launch_nv12(const nv12_batch_t& batch, cudaStream_t stream);
+
 // registers / shared memory of the kernels as compiled, for DESIGN.md and the occupancy report
 cudaError_t recon_kernel_attributes(int chroma_format, cudaFuncAttributes* out);
 

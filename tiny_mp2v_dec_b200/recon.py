@@ -17,7 +17,7 @@ EXPORTS = [
     "mp2v_frame_layout", "mp2v_recon_create", "mp2v_recon_destroy", "mp2v_recon_last_error",
     "mp2v_recon_acquire_picture", "mp2v_recon_release_picture", "mp2v_recon_submit", "mp2v_recon_submit_slices", "mp2v_recon_stage_slices", "mp2v_recon_submit_staged", "mp2v_recon_precheck", "mp2v_recon_flush",
     "mp2v_recon_sync", "mp2v_recon_upload", "mp2v_recon_run_resident", "mp2v_recon_download_frame",
-    "mp2v_recon_map_frame", "mp2v_recon_upload_frame", "mp2v_recon_frame_device_ptrs",
+    "mp2v_recon_map_frame", "mp2v_recon_upload_frame", "mp2v_recon_frame_device_ptrs", "mp2v_recon_convert_frame_nv12", "mp2v_recon_convert_frames_nv12",
     "mp2v_recon_set_timing", "mp2v_recon_get_stats", "mp2v_recon_timer_start", "mp2v_recon_timer_stop",
 ]
 
@@ -55,6 +55,8 @@ def lib():
         L.mp2v_recon_map_frame.argtypes = [C.c_void_p, C.c_int, U8P * 3, C.c_int32 * 3]
         L.mp2v_recon_upload_frame.argtypes = [C.c_void_p, C.c_int, U8P * 3, C.c_int32 * 3]
         L.mp2v_recon_frame_device_ptrs.argtypes = [C.c_void_p, C.c_int, C.c_void_p * 3, C.c_int32 * 3]
+        L.mp2v_recon_convert_frame_nv12.argtypes = [C.c_void_p, C.c_int, C.c_void_p, C.c_int32]
+        L.mp2v_recon_convert_frames_nv12.argtypes = [C.c_void_p, P(C.c_int32), P(C.c_void_p), C.c_int, C.c_int32]
         L.mp2v_recon_set_timing.argtypes = [C.c_void_p, C.c_int]
         L.mp2v_recon_get_stats.argtypes = [C.c_void_p, P(ReconStats), C.c_int]
         L.mp2v_recon_timer_start.argtypes = [C.c_void_p]
@@ -175,6 +177,17 @@ class Recon:
         ptrs = (U8P * 3)(*[a.ctypes.data_as(U8P) for a in planes])
         strides = (C.c_int32 * 3)(*[a.shape[1] for a in planes])
         self._ck(self.L.mp2v_recon_upload_frame(self.h, frame_id, ptrs, strides))
+
+    def convert_nv12(self, frame_id, dst_device_ptr, dst_pitch):
+        """frame -> NV12 in a device buffer of the caller (e.g. a torch CUDA tensor's data_ptr()); asynchronous"""
+        self._ck(self.L.mp2v_recon_convert_frame_nv12(self.h, frame_id, C.c_void_p(dst_device_ptr), dst_pitch))
+
+    def convert_nv12_batch(self, frame_ids, dst_device_ptrs, dst_pitch):
+        """several frames, 32 per launch"""
+        n = len(frame_ids)
+        ids = (C.c_int32 * n)(*frame_ids)
+        ptrs = (C.c_void_p * n)(*dst_device_ptrs)
+        self._ck(self.L.mp2v_recon_convert_frames_nv12(self.h, ids, ptrs, n, dst_pitch))
 
     # ---- statistics
     def set_timing(self, on=True):
