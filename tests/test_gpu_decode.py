@@ -174,3 +174,25 @@ def test_bench_workload_full_size_consistency(gpu_vlc):
         first = Stream(wl["width"], wl["height"], wl["chroma_format"], seed=wl["config_id"], **dict(g, n_gops=1))
         want = O.oracle_decode_stream(first)
         assert a[:len(want)] == want
+
+
+def test_concurrent_decoders_share_one_gpu(gpu_vlc):
+    """BASELINE.json config 5 in miniature: several independent streams decoded at the same time by separate
+    decoder objects on one device (one thread each), every output bit-exact"""
+    import threading
+    streams = [Stream(352, 288, 1 + (k % 3), seed=400 + k, n_gops=2, gop_n=9, gop_m=3, mode=k % 2) for k in range(6)]
+    want = [O.oracle_decode_stream(s) for s in streams]
+    got = [None] * len(streams)
+
+    def work(k):
+        s = streams[k]
+        d = Decoder(352, 288, s.chroma_format, num_threads=2, gpu_vlc=gpu_vlc)
+        for _ in range(3):
+            got[k] = d.decode(s.padded, s.size)
+
+    threads = [threading.Thread(target=work, args=(k,)) for k in range(len(streams))]
+    for t in threads:
+        t.start()
+    for t in threads:
+        t.join()
+    assert got == want
