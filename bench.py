@@ -271,7 +271,7 @@ def measure_resident(wl, stream, steps, warmup, device, world=1):
     from tiny_mp2v_dec_b200.recon import Recon
     w, h, cf = wl["width"], wl["height"], wl["chroma_format"]
     pics, parse_wall, parse_cpu, n = parse_stream(stream.padded, stream.size, w, h, cf, threads=host_threads(world))
-    r = Recon(w, h, cf, n_frames=n, n_pictures=n, device=device, max_batch=32, flags=1)
+    r = Recon(w, h, cf, n_frames=n, n_pictures=n, device=device, max_batch=128, flags=1)
     hnds = []
     for i, p in enumerate(pics):
         hnd = r.acquire()

@@ -137,7 +137,7 @@ typedef struct mp2v_recon_config {
     int32_t chroma_format;         /* 1 = 4:2:0, 2 = 4:2:2, 3 = 4:4:4 (mp2v_hdr.h:56-58)          */
     int32_t n_frames;              /* device frame pool size (>= 3)                              */
     int32_t n_pictures;            /* picture slots in flight (pinned + device arenas)           */
-    int32_t max_batch;             /* max pictures fused into one launch (0 = default, <= 32)    */
+    int32_t max_batch;             /* max pictures fused into one launch (0 = default, <= 128)    */
     int32_t flags;                 /* MP2V_RECON_* below                                         */
     uint32_t coef_capacity;        /* coefficient records per picture slot; 0 = worst case
                                       (mb_count * blocks * 64).  submit fails with MP2V_ERR_RANGE

@@ -46,7 +46,7 @@ __global__ void __launch_bounds__(kNv12Threads) planar420_to_nv12_kernel(const _
 }  // namespace
 
 cudaError_t launch_nv12(const nv12_batch_t& batch, cudaStream_t stream) {
-    if (batch.n_frames < 1 || batch.n_frames > kMaxBatch) return cudaErrorInvalidValue;
+    if (batch.n_frames < 1 || batch.n_frames > kMaxNv12Batch) return cudaErrorInvalidValue;
     const int groups = (batch.height + (batch.height >> 1) + kNv12Rows - 1) / kNv12Rows;
     int ctas = groups;
     const int cap = (148 * 16 + batch.n_frames - 1) / batch.n_frames;     // 16 resident CTAs of 128 threads per SM over the whole launch

@@ -881,9 +881,9 @@ extern "C" MP2V_API int mp2v_recon_convert_frames_nv12(mp2v_recon_t* ctx, const 
     }
     CK(cudaSetDevice(ctx->cfg.device), "cudaSetDevice");
     // on the compute stream: ordered behind the launches that write the frames and ahead of any that overwrites them
-    for (int first = 0; first < n; first += kMaxBatch) {
+    for (int first = 0; first < n; first += kMaxNv12Batch) {
         nv12_batch_t b{};
-        b.n_frames = std::min(n - first, (int)kMaxBatch);
+        b.n_frames = std::min(n - first, (int)kMaxNv12Batch);
         b.width = ctx->cfg.width; b.height = ctx->cfg.height;
         b.stride_y = ctx->lay.stride[0]; b.stride_c = ctx->lay.stride[1]; b.dst_pitch = dst_pitch;
         for (int i = 0; i < b.n_frames; i++)

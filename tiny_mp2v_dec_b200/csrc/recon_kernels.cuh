@@ -6,7 +6,8 @@
 
 namespace mp2v {
 
-constexpr int kMaxBatch = 32;        // pictures fused into one launch (descriptors travel as kernel arguments)
+constexpr int kMaxBatch = 128;       // pictures fused into one launch (descriptors travel as kernel arguments: 104 B each, 13 KB of the 32 KB limit)
+constexpr int kMaxNv12Batch = 32;    // frames per NV12 conversion launch
 constexpr int kCtaThreads = 128;
 
 // A warp owns `mbs_per_warp` consecutive macroblocks and walks them in batches of <= MP2V_SLOTS coded
@@ -53,7 +54,7 @@ cudaError_t launch_recon(int chroma_format, const batch_desc_t& batch, cudaStrea
 // planar 4:2:0 frames -> NV12 (Y plane, then interleaved Cb/Cr rows) in the caller's device buffers (convert_kernel.cu)
 struct nv12_frame_t { const uint8_t* y; const uint8_t* cb; const uint8_t* cr; uint8_t* dst; };
 struct nv12_batch_t {
-    nv12_frame_t frame[kMaxBatch];
+    nv12_frame_t frame[kMaxNv12Batch];
     int32_t n_frames, width, height, stride_y, stride_c, dst_pitch;
 };
 cudaError_t launch_nv12(const nv12_batch_t& batch, cudaStream_t stream);

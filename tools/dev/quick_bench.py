@@ -8,7 +8,7 @@ from tiny_mp2v_dec_b200.recon import Recon
 from tiny_mp2v_dec_b200.streamgen import Stream
 
 
-def run(name, w, h, cf, reps=20, max_batch=32, **kw):
+def run(name, w, h, cf, reps=20, max_batch=128, **kw):
     t0 = time.time()
     s = Stream(w, h, cf, **kw)
     n = len(s.pictures)
