@@ -219,6 +219,9 @@ MP2V_API int  mp2v_recon_submit_staged(mp2v_recon_t* ctx, mp2v_picture_t* pic);
 
 MP2V_API int  mp2v_recon_flush(mp2v_recon_t* ctx);               /* launch whatever is queued       */
 MP2V_API int  mp2v_recon_sync(mp2v_recon_t* ctx);                /* flush + wait for the device     */
+/* After an error: wait for whatever was issued, give every picture slot back, forget queued pictures,
+ * frame contents and the pending error -- the context is as after creation, without re-allocating. */
+MP2V_API int  mp2v_recon_reset(mp2v_recon_t* ctx);
 
 /* Device-resident mode (benchmarks, re-decode): copy a filled picture to its device arena once,
  * keep the slot, then reconstruct any list of resident pictures without host traffic.

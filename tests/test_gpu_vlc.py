@@ -121,6 +121,7 @@ def test_corrupted_streams_never_hang_or_fault(cf):
     sc = _start_codes(s.padded, s.size)
     slices = [int(o) for o in sc if 1 <= s.padded[o + 3] <= 0xAF]
     outcomes = {True: [0, 0], False: [0, 0]}
+    decoders = {v: Decoder(352, 288, cf, num_threads=2, gpu_vlc=v) for v in (True, False)}   # reused across failures
     for trial in range(60):
         buf = s.padded.copy()
         for _ in range(int(rng.integers(1, 4))):
@@ -135,11 +136,11 @@ def test_corrupted_streams_never_hang_or_fault(cf):
                 buf[at:at + int(rng.integers(1, 6))] = rng.integers(1, 255, dtype=np.uint8)   # no new start codes
         for gpu_vlc in (True, False):
             try:
-                Decoder(352, 288, cf, num_threads=2, gpu_vlc=gpu_vlc).decode(buf, s.size)
+                decoders[gpu_vlc].decode(buf, s.size)
                 outcomes[gpu_vlc][0] += 1
             except ReconError:
                 outcomes[gpu_vlc][1] += 1
     assert sum(outcomes[True]) == sum(outcomes[False]) == 60
     assert outcomes[True][1] > 0 and outcomes[False][1] > 0          # some corruptions are detected as syntax errors
     for gpu_vlc in (True, False):
-        assert Decoder(352, 288, cf, num_threads=2, gpu_vlc=gpu_vlc).decode(s.padded, s.size) == want
+        assert decoders[gpu_vlc].decode(s.padded, s.size) == want

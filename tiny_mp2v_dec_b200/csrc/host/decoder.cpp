@@ -565,8 +565,11 @@ bool mp2v_decoder_c::decode(uint8_t* buffer, int len) {
             }
     m->stats.wall_seconds = std::chrono::duration<double>(clock_t_::now() - t_begin).count();
     if (sh.failed.load()) {
-        // pictures may be left acquired / queued inside the contexts: rebuild them on the next call
-        m->release();
+        // pictures may be left acquired / queued inside the contexts: give every slot back (no re-allocation);
+        // a context that cannot even do that (a CUDA error) is rebuilt by the next call
+        bool reset_ok = true;
+        for (auto& p : pipes) reset_ok = reset_ok && mp2v_recon_reset(p.recon) == MP2V_OK;
+        if (!reset_ok) m->release();
         m->error = sh.error;
         return false;
     }

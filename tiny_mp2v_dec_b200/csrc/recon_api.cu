@@ -694,6 +694,7 @@ extern "C" MP2V_API int mp2v_recon_sync(mp2v_recon_t* ctx) {
     CK(cudaStreamSynchronize(ctx->s_compute), "stream sync");
     for (auto& s : ctx->slots) if (s.state == SLOT_INFLIGHT) s.state = SLOT_FREE;
     ctx->batch_ramp = 1;
+    ctx->pictures_submitted = 0;                         // slice errors name pictures by their number since the last sync
     if (ctx->trace && !ctx->trace_log.empty()) {
         cudaStreamSynchronize(ctx->s_d2h);
         for (auto& tr : ctx->trace_log) {
@@ -715,6 +716,27 @@ extern "C" MP2V_API int mp2v_recon_sync(mp2v_recon_t* ctx) {
         ctx->vlc_error.clear();                          // reported once; the context stays usable
         return ctx->fail(MP2V_ERR_RANGE, why);
     }
+    return MP2V_OK;
+}
+
+extern "C" MP2V_API int mp2v_recon_reset(mp2v_recon_t* ctx) {
+    if (!ctx) return MP2V_ERR_ARG;
+    std::lock_guard<std::mutex> lk(ctx->mu);
+    CK(cudaSetDevice(ctx->cfg.device), "cudaSetDevice");
+    // whatever was issued runs to completion (records of a failed picture are garbage-safe by construction)
+    for (auto& s : ctx->slots) if (s.s_vlc) CK(cudaStreamSynchronize(s.s_vlc), "stream sync");
+    CK(cudaStreamSynchronize(ctx->s_copy), "stream sync");
+    CK(cudaStreamSynchronize(ctx->s_compute), "stream sync");
+    CK(cudaStreamSynchronize(ctx->s_d2h), "stream sync");
+    ctx->pending.clear();
+    ctx->status_fifo.clear();
+    for (auto& s : ctx->slots) { s.state = SLOT_FREE; s.staged = false; s.status_pending = false; s.prechecked = false; s.vlc = false; }
+    std::fill(ctx->frame_written.begin(), ctx->frame_written.end(), 0);
+    std::fill(ctx->mirror_valid.begin(), ctx->mirror_valid.end(), 0);
+    ctx->vlc_error.clear();
+    ctx->err.clear();
+    ctx->batch_ramp = 1;
+    ctx->pictures_submitted = 0;
     return MP2V_OK;
 }
 

@@ -16,7 +16,7 @@ _lib = None
 EXPORTS = [
     "mp2v_frame_layout", "mp2v_recon_create", "mp2v_recon_destroy", "mp2v_recon_last_error",
     "mp2v_recon_acquire_picture", "mp2v_recon_release_picture", "mp2v_recon_submit", "mp2v_recon_submit_slices", "mp2v_recon_stage_slices", "mp2v_recon_submit_staged", "mp2v_recon_precheck", "mp2v_recon_flush",
-    "mp2v_recon_sync", "mp2v_recon_upload", "mp2v_recon_run_resident", "mp2v_recon_download_frame",
+    "mp2v_recon_sync", "mp2v_recon_reset", "mp2v_recon_upload", "mp2v_recon_run_resident", "mp2v_recon_download_frame",
     "mp2v_recon_map_frame", "mp2v_recon_upload_frame", "mp2v_recon_frame_device_ptrs", "mp2v_recon_convert_frame_nv12", "mp2v_recon_convert_frames_nv12",
     "mp2v_recon_set_timing", "mp2v_recon_get_stats", "mp2v_recon_timer_start", "mp2v_recon_timer_stop",
 ]
@@ -49,6 +49,7 @@ def lib():
         L.mp2v_recon_precheck.argtypes = [C.c_void_p, P(Picture)]
         L.mp2v_recon_flush.argtypes = [C.c_void_p]
         L.mp2v_recon_sync.argtypes = [C.c_void_p]
+        L.mp2v_recon_reset.argtypes = [C.c_void_p]
         L.mp2v_recon_upload.argtypes = [C.c_void_p, P(Picture)]
         L.mp2v_recon_run_resident.argtypes = [C.c_void_p, P(P(Picture)), P(C.c_int32), C.c_int]
         L.mp2v_recon_download_frame.argtypes = [C.c_void_p, C.c_int, U8P * 3, C.c_int32 * 3]
@@ -162,6 +163,9 @@ class Recon:
 
     def sync(self):
         self._ck(self.L.mp2v_recon_sync(self.h))
+
+    def reset(self):
+        self._ck(self.L.mp2v_recon_reset(self.h))
 
     # ---- frames
     def download(self, frame_id):
