@@ -13,11 +13,16 @@
  *   mp2v_picture_c::init() quantiser_matrices     decoder.cpp:154-192     mp2v_pic_params_t.W
  *   frame_c planes / strides / pool               decoder.cpp:44-105      device frame pool (frame ids)
  *   picture dependencies + display hand-off       threads.cpp, decoder.cpp:346-379   submit order + map_frame
+ *   decode_slice -> parse_macroblock / parse_block decoder.cpp:107-152,              mp2v_recon_submit_slices:
+ *     (VLC, DC / PMV prediction, skipped MBs)      mb_decoder.cpp:74-155, 521-641     slice-parallel parser kernel
+ *   sample's planar YUV write from host memory    tiny_mp2v_dec.cpp:11-17            frame_device_ptrs / convert_frames_nv12
  *
- * The host slice parser (VLC, DC prediction, motion-vector prediction, skipped-macroblock
- * resolution) fills one mp2v_picture_t per coded picture in pinned memory; mp2v_recon_submit()
- * copies it to the device and reconstructs the whole picture (batched with any other submitted
- * pictures that do not depend on each other) with hand-written sm_100a kernels.  There is no CPU
+ * Two ways in.  (1) A host slice parser (VLC, DC prediction, motion-vector prediction, skipped-
+ * macroblock resolution) fills one mp2v_picture_t per coded picture in pinned memory and
+ * mp2v_recon_submit() copies it to the device.  (2) With MP2V_RECON_DEVICE_VLC the caller hands over
+ * the picture's coded slices (mp2v_recon_submit_slices) and a kernel produces the same records on
+ * the device.  Either way the whole picture is reconstructed (batched with any other submitted
+ * pictures that do not depend on each other) by hand-written sm_100a kernels.  There is no CPU
  * fallback: every entry point fails with MP2V_ERR_CUDA when no device / kernel image is usable.
  *
  * Plain C: pointers and sizes only, no C++ or torch types.  Thread-safety: one context may be used
