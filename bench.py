@@ -64,6 +64,26 @@ WORKLOADS = {
 DEFAULT_WORKLOAD = "1080p420_intra"
 
 
+# The contract is ONE JSON line on stdout.  Libraries write there too (NCCL prints its version banner to fd 1 on
+# the GPU boxes), so the real stdout is kept aside for that line and fd 1 is pointed at stderr for everything else.
+_RESULT_OUT = None
+
+
+def _claim_stdout():
+    global _RESULT_OUT
+    if _RESULT_OUT is None:
+        sys.stdout.flush()
+        _RESULT_OUT = os.fdopen(os.dup(1), "w")
+        os.dup2(2, 1)
+    return _RESULT_OUT
+
+
+def emit(line):
+    out = _claim_stdout()
+    out.write(json.dumps(line) + "\n")
+    out.flush()
+
+
 def log(*a):
     print(*a, file=sys.stderr, flush=True)
 
@@ -239,7 +259,7 @@ def reference_arm(args, wl_name, wl):
             "mpixel_per_s": round(mpix, 1),
             "cpu_baseline": {"value": round(fps, 2), "unit": "frames/s", "cores": cores, "kind": kind, "sample": sample},
             "e2e": {"value": round(fps, 2), "unit": "frames/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
-    print(json.dumps(line), flush=True)
+    emit(line)
     return 0
 
 
@@ -300,6 +320,7 @@ def main():
     ap.add_argument("--cpu-dryrun", action="store_true",
                     help="host-only: shard generation + slice parsing per rank over gloo (exercises the N>1 plumbing without a GPU)")
     args = ap.parse_args()
+    _claim_stdout()
     args.warmup = max(args.warmup, 3) if args.impl == "ours" else args.warmup
     wl = WORKLOADS[args.workload]
     if args.impl == "reference":
@@ -354,10 +375,10 @@ def main():
         total = sum_over_ranks(float(n)) * args.steps
         ncoef = sum_over_ranks(float(sum(len(p.coef) for p in pics)))
         if rank == 0:
-            print(json.dumps({"dryrun": True, "metric": "host_parse_frames_per_second", "value": round(total / secs, 1),
+            emit({"dryrun": True, "metric": "host_parse_frames_per_second", "value": round(total / secs, 1),
                               "unit": "frames/s", "n_ranks": world, "steps": args.steps, "frames_per_step": int(total / args.steps),
                               "coef_records_all_ranks": int(ncoef), "scaling": "weak",
-                              "config": {"workload": args.workload}}), flush=True)
+                              "config": {"workload": args.workload}})
         if world > 1:
             dist.destroy_process_group()
         return 0
@@ -493,7 +514,7 @@ def main():
         }
         if extra:
             line["also_measured"] = extra
-        print(json.dumps(line), flush=True)
+        emit(line)
     if world > 1:
         dist.destroy_process_group()
     return 0
