@@ -13,10 +13,10 @@ namespace mp2v {
 
 namespace {
 
-constexpr int kNv12Threads = 128, kNv12Rows = 4;
+constexpr int kNv12Threads = 128, kNv12Rows = 8;
 
-// A CTA walks groups of 4 output rows; a thread owns 16-byte column units of those rows: all 4 (or 8) loads are
-// issued before the first store, no divisions, streaming stores (the consumer, not this kernel, re-reads the data).
+// A CTA walks groups of 8 output rows; a thread owns 16-byte column units of those rows: all 8 (chroma: 16) loads
+// are issued before the first store, no divisions, streaming stores (the consumer, not this kernel, re-reads the data).
 __global__ void __launch_bounds__(kNv12Threads) planar420_to_nv12_kernel(const __grid_constant__ nv12_batch_t b) {
     const nv12_frame_t& f = b.frame[blockIdx.y];
     const int units_per_row = b.width >> 4;                   // width is a multiple of 16
