@@ -289,7 +289,16 @@ extern "C" MP2V_API int mp2v_recon_create(const mp2v_recon_config_t* cfg, mp2v_r
 
 extern "C" MP2V_API void mp2v_recon_destroy(mp2v_recon_t* ctx) { destroy_ctx(ctx); }
 
-extern "C" MP2V_API const char* mp2v_recon_last_error(mp2v_recon_t* ctx) { return ctx ? ctx->err.c_str() : g_create_error.c_str(); }
+extern "C" MP2V_API const char* mp2v_recon_last_error(mp2v_recon_t* ctx) {
+    if (!ctx) return g_create_error.c_str();
+    // several threads use one context: hand out a per-thread copy taken under the lock, not the shared string
+    thread_local std::string copy;
+    {
+        std::lock_guard<std::mutex> lk(ctx->mu);
+        copy = ctx->err;
+    }
+    return copy.c_str();
+}
 
 // ---------------------------------------------------------------------------------------------
 // launching
