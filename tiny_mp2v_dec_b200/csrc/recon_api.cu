@@ -82,6 +82,7 @@ struct mp2v_recon {
     bool timing = false;
     std::vector<std::pair<cudaEvent_t, cudaEvent_t>> timed;   // (start, stop) of launches not yet summed
     std::vector<cudaEvent_t> ev_pool;
+    std::vector<cudaEvent_t> timing_pool;      // timing-enabled events for the per-launch stopwatch
     // device-side slice parsing
     bool vlc = false;
     int vlc_lanes = 1;
@@ -156,6 +157,7 @@ static void destroy_ctx(mp2v_recon* ctx) {
     for (auto e : ctx->frame_ev) if (e) cudaEventDestroy(e);
     for (auto e : ctx->mirror_ev) if (e) cudaEventDestroy(e);
     for (auto e : ctx->ev_pool) cudaEventDestroy(e);
+    for (auto e : ctx->timing_pool) cudaEventDestroy(e);
     for (auto& pr : ctx->timed) { cudaEventDestroy(pr.first); cudaEventDestroy(pr.second); }
     if (ctx->ev_h2d) cudaEventDestroy(ctx->ev_h2d);
     if (ctx->ev_t0) cudaEventDestroy(ctx->ev_t0);
@@ -328,8 +330,11 @@ static int launch_slots(mp2v_recon* ctx, const int* ids, int n, bool download = 
     for (int i = 0; i < n; i++) fill_desc(ctx, ctx->slots[ids[i]], b.pic[i]);
     cudaEvent_t t0 = nullptr, t1 = nullptr;
     if (ctx->timing) {
-        t0 = cudaEvent_t(); t1 = cudaEvent_t();
-        CK(cudaEventCreate(&t0), "event"); CK(cudaEventCreate(&t1), "event");
+        // timing events are recycled (get_stats hands them back): creating a pair per launch cost ~10 us under the lock
+        for (cudaEvent_t* e : {&t0, &t1}) {
+            if (!ctx->timing_pool.empty()) { *e = ctx->timing_pool.back(); ctx->timing_pool.pop_back(); }
+            else CK(cudaEventCreate(e), "event");
+        }
         CK(cudaEventRecord(t0, ctx->s_compute), "event record");
     }
     CK(launch_recon(ctx->cfg.chroma_format, b, ctx->s_compute), "reconstruction kernel launch");
@@ -952,7 +957,7 @@ extern "C" MP2V_API int mp2v_recon_get_stats(mp2v_recon_t* ctx, mp2v_recon_stats
             float ms = 0.f;
             CK(cudaEventElapsedTime(&ms, pr.first, pr.second), "event elapsed");
             ctx->stats.kernel_ms += ms;
-            cudaEventDestroy(pr.first); cudaEventDestroy(pr.second);
+            ctx->timing_pool.push_back(pr.first); ctx->timing_pool.push_back(pr.second);
         }
         ctx->timed.clear();
     }
