@@ -14,7 +14,7 @@
 // -> look-up) and the warps of all slices hide one another's latency.  The parser's issue-slot cost
 // is a few percent of the machine; the reconstruction kernel keeps the rest.
 //
-// Memory: tables (~150 KB, pointer-free, copied once) are read through the read-only path and stay
+// Memory: tables (~155 KB, pointer-free, copied once) are read through the read-only path and stay
 // L1/L2 resident; the bitstream is read 12 aligned bytes at a time (bitreader_t::refill); records are
 // written sequentially by the owning thread and merge into full sectors in L2.
 #include "vlc_kernel.cuh"
