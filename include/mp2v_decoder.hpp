@@ -21,6 +21,8 @@
 #include <string>
 #include <vector>
 
+#include "mp2v_stream_headers.h"
+
 #if defined(__GNUC__)
 #define MP2V_CXX_API __attribute__((visibility("default")))
 #else
@@ -72,6 +74,8 @@ struct mp2v_b200_options_t {
                                       // take the host slice parser on num_threads worker threads instead.
 };
 
+class mp2v_picture_c;   // the reference's per-picture task object (decoder.h:56-80); only ever named by flush()
+
 class MP2V_CXX_API mp2v_decoder_c {
 public:
     mp2v_decoder_c();
@@ -79,7 +83,18 @@ public:
     ~mp2v_decoder_c();
     bool decoder_init(const decoder_config_t& config, std::function<void(frame_c*)> renderer);
     bool decode(uint8_t* buffer, int len);
-    void flush();
+    // decoder.h:101.  decode() is one-shot and drains everything itself (the reference's decode() ends with
+    // flush(cur_pic), decoder.cpp:326-327), so there is never anything left to flush; the argument is ignored.
+    void flush(mp2v_picture_c* cur_pic = nullptr);
+
+    // headers & user data of the stream last given to decode() (decoder.h:120-131): the last occurrence of
+    // each header, all user_data() bytes in stream order; the optional ones stay nullptr when the stream has none
+    std::vector<uint8_t> user_data;
+    sequence_header_t m_sequence_header = {};
+    sequence_extension_t m_sequence_extension = {};
+    sequence_display_extension_t* m_sequence_display_extension = nullptr;
+    sequence_scalable_extension_t* m_sequence_scalable_extension = nullptr;
+    group_of_pictures_header_t* m_group_of_pictures_header = nullptr;
 
     // extensions
     void set_options(const mp2v_b200_options_t& opt);

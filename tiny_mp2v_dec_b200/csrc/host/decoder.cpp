@@ -464,7 +464,27 @@ mp2v_decoder_c::mp2v_decoder_c() : m(new impl_t) {
 mp2v_decoder_c::mp2v_decoder_c(const decoder_config_t& config, std::function<void(frame_c*)> renderer) : mp2v_decoder_c() {
     decoder_init(config, renderer);
 }
-mp2v_decoder_c::~mp2v_decoder_c() { m->release(); }
+mp2v_decoder_c::~mp2v_decoder_c() {
+    m->release();
+    delete m_sequence_display_extension;
+    delete m_sequence_scalable_extension;
+    delete m_group_of_pictures_header;
+}
+
+// the public header members (decoder.h:120-131) of the stream just indexed
+static void publish_headers(mp2v_decoder_c& d, const stream_headers_t& h) {
+    d.user_data = h.user_data;
+    d.m_sequence_header = h.sequence_header;
+    d.m_sequence_extension = h.sequence_extension;
+    auto set = [](auto*& dst, bool have, const auto& src) {
+        if (!have) { delete dst; dst = nullptr; return; }
+        if (!dst) dst = new typename std::remove_reference<decltype(*dst)>::type;
+        *dst = src;
+    };
+    set(d.m_sequence_display_extension, h.have_display_extension, h.sequence_display_extension);
+    set(d.m_sequence_scalable_extension, h.have_scalable_extension, h.sequence_scalable_extension);
+    set(d.m_group_of_pictures_header, h.have_gop_header, h.group_of_pictures_header);
+}
 
 bool mp2v_decoder_c::decoder_init(const decoder_config_t& config, std::function<void(frame_c*)> renderer) {
     m->cfg = config;
@@ -479,7 +499,7 @@ void mp2v_decoder_c::set_options(const mp2v_b200_options_t& opt) { m->release();
 bool mp2v_decoder_c::prepare() { return m->initialised && m->prepare(m->opt.gpu_vlc); }
 const char* mp2v_decoder_c::last_error() const { return m->error.c_str(); }
 mp2v_decoder_c::stats_t mp2v_decoder_c::stats() const { return m->stats; }
-void mp2v_decoder_c::flush() {}   // decode() is one-shot and drains everything itself (as the reference's always does)
+void mp2v_decoder_c::flush(mp2v_picture_c*) {}   // decode() is one-shot and drains everything itself (as the reference's always does)
 
 bool mp2v_decoder_c::decode(uint8_t* buffer, int len) {
     if (!m->initialised) return false;
@@ -487,13 +507,22 @@ bool mp2v_decoder_c::decode(uint8_t* buffer, int len) {
     m->error.clear();
     stream_index_t index;
     if (!index_stream(buffer, (size_t)len, index, m->cfg.num_threads)) { m->error = index.error; return false; }
+    publish_headers(*this, index.headers);
     const auto t_indexed = clock_t_::now();
     shared_t sh;
     sh.t_origin = t_begin;
     sh.cfg = m->cfg; sh.opt = m->opt; sh.renderer = m->renderer;
     sh.mbw = m->cfg.width / 16; sh.mbh = m->cfg.height / 16;
-    for (const auto& pic : index.pictures)
+    for (const auto& pic : index.pictures) {
         if (pic.seq.chroma_format != m->cfg.chroma_format) { m->error = "stream chroma_format differs from decoder_config_t.chroma_format"; return false; }
+        // the reference trusts decoder_config_t blindly (decoder.cpp:44-66); a stream of another coded size would be
+        // reconstructed into the wrong geometry, so it is refused here
+        if (pic.seq.have_sequence_header && (((pic.seq.horizontal_size + 15) & ~15) != m->cfg.width || ((pic.seq.vertical_size + 15) & ~15) != m->cfg.height)) {
+            m->error = "stream coded size " + std::to_string(pic.seq.horizontal_size) + "x" + std::to_string(pic.seq.vertical_size) +
+                       " (rounded up to macroblocks) differs from decoder_config_t " + std::to_string(m->cfg.width) + "x" + std::to_string(m->cfg.height);
+            return false;
+        }
+    }
     sh.gop_size.assign(index.n_gops > 0 ? index.n_gops : 1, 0);
     sh.gop_emitted.assign(sh.gop_size.size(), 0);
     for (const auto& pic : index.pictures) sh.gop_size[pic.gop]++;

@@ -29,7 +29,10 @@ void read_matrix(bitreader_t& br, uint8_t m[64]) {
 
 sequence_info_t::sequence_info_t() {
     const scan_tables_t& t = scan_tables();
-    for (int i = 0; i < 64; i++) { intra_matrix[i] = kDefaultIntraRaster[t.shuffle[0][i]]; non_intra_matrix[i] = 16; }
+    for (int i = 0; i < 64; i++) {
+        intra_matrix[i] = chroma_intra_matrix[i] = kDefaultIntraRaster[t.shuffle[0][i]];
+        non_intra_matrix[i] = chroma_non_intra_matrix[i] = 16;
+    }
 }
 
 const uint8_t* find_start_code(const uint8_t* p, const uint8_t* end) {
@@ -55,6 +58,9 @@ bool parse_sequence_header(const uint8_t* payload, sequence_info_t& seq) {
     memcpy(seq.non_intra_matrix, defaults.non_intra_matrix, 64);
     if (br.get1()) read_matrix(br, seq.intra_matrix);
     if (br.get1()) read_matrix(br, seq.non_intra_matrix);
+    // a sequence header resets all four: the chroma matrices take the luminance ones (6.3.11)
+    memcpy(seq.chroma_intra_matrix, seq.intra_matrix, 64);
+    memcpy(seq.chroma_non_intra_matrix, seq.non_intra_matrix, 64);
     seq.have_sequence_header = true;
     return seq.horizontal_size > 0 && seq.vertical_size > 0;
 }
@@ -68,8 +74,8 @@ bool parse_picture_header(const uint8_t* payload, const sequence_info_t& seq, pi
     if (pic.picture_coding_type == 2 || pic.picture_coding_type == 3) br.get(4);   // full_pel_forward_vector, forward_f_code (MPEG-1 fields)
     if (pic.picture_coding_type == 3) br.get(4);
     // matrices in force: sequence-level ones until a quant_matrix_extension replaces them (6.3.11)
-    memcpy(pic.tx[0], seq.intra_matrix, 64); memcpy(pic.tx[2], seq.intra_matrix, 64);
-    memcpy(pic.tx[1], seq.non_intra_matrix, 64); memcpy(pic.tx[3], seq.non_intra_matrix, 64);
+    memcpy(pic.tx[0], seq.intra_matrix, 64); memcpy(pic.tx[2], seq.chroma_intra_matrix, 64);
+    memcpy(pic.tx[1], seq.non_intra_matrix, 64); memcpy(pic.tx[3], seq.chroma_non_intra_matrix, 64);
     return pic.picture_coding_type >= 1 && pic.picture_coding_type <= 3;
 }
 
@@ -109,6 +115,8 @@ bool parse_extension(const uint8_t* payload, sequence_info_t& seq, picture_info_
         // keep them in force for later pictures of the sequence as well
         memcpy(seq.intra_matrix, pic->tx[0], 64);
         memcpy(seq.non_intra_matrix, pic->tx[1], 64);
+        memcpy(seq.chroma_intra_matrix, pic->tx[2], 64);
+        memcpy(seq.chroma_non_intra_matrix, pic->tx[3], 64);
         return true;
     }
     default:

@@ -19,7 +19,9 @@ struct sequence_info_t {
     int chroma_format = 1;
     int progressive_sequence = 1;
     bool have_sequence_header = false, have_sequence_extension = false;
-    uint8_t intra_matrix[64], non_intra_matrix[64];   // sequence-level matrices in zig-zag order (defaults until loaded)
+    // matrices in force (zig-zag order): defaults until a sequence header or a quant_matrix_extension loads them;
+    // they persist until the next sequence header (ISO/IEC 13818-2 6.3.11), the chroma pair included
+    uint8_t intra_matrix[64], non_intra_matrix[64], chroma_intra_matrix[64], chroma_non_intra_matrix[64];
     sequence_info_t();
 };
 

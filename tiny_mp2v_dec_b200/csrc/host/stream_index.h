@@ -8,6 +8,7 @@
 #include <vector>
 
 #include "mp2v_parser.h"
+#include "mp2v_stream_headers.h"
 
 namespace mp2v {
 
@@ -24,8 +25,20 @@ struct coded_picture_t {
     int gop = 0;              // index of the closed GOP chain this picture belongs to (sharding unit)
 };
 
+// the sequence-level headers as the decode API publishes them (mp2v_decoder_c's public members): last occurrence of each
+struct stream_headers_t {
+    sequence_header_t sequence_header = {};
+    sequence_extension_t sequence_extension = {};
+    sequence_display_extension_t sequence_display_extension = {};
+    sequence_scalable_extension_t sequence_scalable_extension = {};
+    group_of_pictures_header_t group_of_pictures_header = {};
+    bool have_display_extension = false, have_scalable_extension = false, have_gop_header = false;
+    std::vector<uint8_t> user_data;          // every user_data() payload, stream order
+};
+
 struct stream_index_t {
     std::vector<coded_picture_t> pictures;   // coded order
+    stream_headers_t headers;
     int n_gops = 0;
     std::string error;
 };

@@ -61,6 +61,7 @@ struct mp2v_recon {
     int nblk = 0, mbw = 0, mbh = 0, mb_count = 0, max_batch = 0;
     size_t frame_alloc = 0, arena_bytes = 0, coef_off = 0;
     uint8_t* d_frames = nullptr;
+    recon_tmaps_t tmaps{};                     // TMA descriptors of the frame pool (reference windows)
     std::vector<uint8_t*> h_frames;            // pinned mirrors, allocated on first map
     std::vector<cudaEvent_t> frame_ev;         // last writer of each frame
     std::vector<uint8_t> frame_written;
@@ -70,6 +71,9 @@ struct mp2v_recon {
     std::vector<int> mirror_ev_of;             // frame id -> index into mirror_ev
     uint64_t mirror_batches = 0;
     std::vector<uint8_t> mirror_valid;         // mirror_ev covers the frame's current content
+    // a copy of a frame to the host (D2H stream) must finish before a later picture overwrites the frame (compute stream)
+    std::vector<cudaEvent_t> read_ev;          // per frame: behind its last queued copy
+    std::vector<uint8_t> read_pending;         // since the frame's last writer was launched: 1 = read_ev[f] recorded, 2 = a launch's mirror event covers a copy
     cudaStream_t s_copy = nullptr, s_compute = nullptr, s_d2h = nullptr;
     cudaEvent_t ev_h2d = nullptr, ev_t0 = nullptr, ev_t1 = nullptr;
     std::vector<slot_t> slots;
@@ -156,6 +160,7 @@ static void destroy_ctx(mp2v_recon* ctx) {
     for (auto* h : ctx->h_frames) if (h) cudaFreeHost(h);
     for (auto e : ctx->frame_ev) if (e) cudaEventDestroy(e);
     for (auto e : ctx->mirror_ev) if (e) cudaEventDestroy(e);
+    for (auto e : ctx->read_ev) if (e) cudaEventDestroy(e);
     for (auto e : ctx->ev_pool) cudaEventDestroy(e);
     for (auto e : ctx->timing_pool) cudaEventDestroy(e);
     for (auto& pr : ctx->timed) { cudaEventDestroy(pr.first); cudaEventDestroy(pr.second); }
@@ -205,6 +210,7 @@ static int create_impl(mp2v_recon* ctx) {
     ctx->frame_alloc = (ctx->lay.bytes + 2 * (size_t)ctx->lay.stride[0] + 256 + 255) & ~(size_t)255;
     CK(cudaMalloc(&ctx->d_frames, ctx->frame_alloc * c.n_frames), "cudaMalloc frames");
     CK(cudaMemset(ctx->d_frames, 0, ctx->frame_alloc * c.n_frames), "cudaMemset frames");
+    CK(make_frame_tmaps(c.chroma_format, ctx->d_frames, ctx->lay, ctx->frame_alloc, c.n_frames, &ctx->tmaps), "TMA descriptors of the frame pool");
     ctx->h_frames.assign(c.n_frames, nullptr);
     ctx->frame_ev.assign(c.n_frames, nullptr);
     ctx->frame_written.assign(c.n_frames, 0);
@@ -212,6 +218,9 @@ static int create_impl(mp2v_recon* ctx) {
     if (const char* v = getenv("MP2V_TRACE")) ctx->trace = atoi(v) != 0;
     ctx->auto_dl = (c.flags & MP2V_RECON_AUTO_DOWNLOAD) != 0;
     ctx->mirror_valid.assign(c.n_frames, 0);
+    ctx->read_ev.assign(c.n_frames, nullptr);
+    ctx->read_pending.assign(c.n_frames, 0);
+    for (auto& ev : ctx->read_ev) CK(cudaEventCreateWithFlags(&ev, cudaEventDisableTiming), "event");
     if (ctx->auto_dl) {
         // one event per launch, not per frame: an event between two copies costs the copy engine a bubble of
         // several microseconds (measured 67 vs 60 us per 3 MB frame).  At most n_frames launches are outstanding.
@@ -230,7 +239,8 @@ static int create_impl(mp2v_recon* ctx) {
     const uint32_t cap = ctx->vlc ? (uint32_t)worst : (c.coef_capacity ? c.coef_capacity : (uint32_t)worst);
     const uint32_t host_cap = ctx->vlc ? 0u : cap;
     ctx->coef_off = kParamsBytes + (((size_t)ctx->mb_count * sizeof(mp2v_mb_info_t) + 255) & ~(size_t)255);
-    ctx->arena_bytes = ctx->coef_off + (size_t)cap * sizeof(mp2v_coef_t);
+    // + 256: the kernel requests up to 32 records past a macroblock's last one (prefetch of the next batch)
+    ctx->arena_bytes = ctx->coef_off + (size_t)cap * sizeof(mp2v_coef_t) + 256;
     const size_t host_arena_bytes = ctx->coef_off + (size_t)host_cap * sizeof(mp2v_coef_t);
     if (ctx->vlc) {
         cudaFuncAttributes va;
@@ -315,7 +325,7 @@ static void fill_desc(mp2v_recon* ctx, const slot_t& s, pic_desc_t& d) {
         d.l0[p] = pp.l0_frame >= 0 ? ctx->frame_ptr(pp.l0_frame, p) : nullptr;
         d.l1[p] = pp.l1_frame >= 0 ? ctx->frame_ptr(pp.l1_frame, p) : nullptr;
     }
-    d.cta_begin = 0; d.pad = 0;
+    d.l0_id = pp.l0_frame; d.l1_id = pp.l1_frame;
 }
 
 // one launch over `ids` (<= max_batch slots whose records are already on, or on their way to, the device)
@@ -328,6 +338,13 @@ static int launch_slots(mp2v_recon* ctx, const int* ids, int n, bool download = 
     const int g = b.mbs_per_warp * (kCtaThreads / 32);
     b.ctas_per_pic = (ctx->mb_count + g - 1) / g;
     for (int i = 0; i < n; i++) fill_desc(ctx, ctx->slots[ids[i]], b.pic[i]);
+    // a frame whose copy to the host is still queued must not be overwritten under it
+    for (int i = 0; i < n; i++) {
+        const int f = ctx->slots[ids[i]].pub.params->dst_frame;
+        if (ctx->read_pending[f] & 1) CK(cudaStreamWaitEvent(ctx->s_compute, ctx->read_ev[f], 0), "stream wait");
+        if (ctx->read_pending[f] & 2) CK(cudaStreamWaitEvent(ctx->s_compute, ctx->mirror_ev[ctx->mirror_ev_of[f]], 0), "stream wait");
+        ctx->read_pending[f] = 0;
+    }
     cudaEvent_t t0 = nullptr, t1 = nullptr;
     if (ctx->timing) {
         // timing events are recycled (get_stats hands them back): creating a pair per launch cost ~10 us under the lock
@@ -337,7 +354,7 @@ static int launch_slots(mp2v_recon* ctx, const int* ids, int n, bool download = 
         }
         CK(cudaEventRecord(t0, ctx->s_compute), "event record");
     }
-    CK(launch_recon(ctx->cfg.chroma_format, b, ctx->s_compute), "reconstruction kernel launch");
+    CK(launch_recon(ctx->cfg.chroma_format, b, ctx->tmaps, ctx->s_compute), "reconstruction kernel launch");
     if (ctx->timing) {
         CK(cudaEventRecord(t1, ctx->s_compute), "event record");
         ctx->timed.emplace_back(t0, t1);
@@ -361,6 +378,7 @@ static int launch_slots(mp2v_recon* ctx, const int* ids, int n, bool download = 
             ctx->mirror_ev_of[f] = ev;
             if (ctx->trace && ctx->slots[ids[i]].vlc && ctx->slots[ids[i]].trace_idx >= 0) CK(cudaEventRecord(ctx->trace_log[ctx->slots[ids[i]].trace_idx].d2h, ctx->s_d2h), "event record");
             ctx->mirror_valid[f] = 1;
+            ctx->read_pending[f] |= 2;                     // covered by this launch's mirror event
             ctx->stats.d2h_bytes += ctx->lay.bytes;
         }
         CK(cudaEventRecord(ctx->mirror_ev[ev], ctx->s_d2h), "event record");
@@ -536,6 +554,18 @@ extern "C" MP2V_API int mp2v_recon_release_picture(mp2v_recon_t* ctx, mp2v_pictu
     return MP2V_OK;
 }
 
+// a reference must have been written by a launched picture or be the destination of a queued one; ctx->mu held
+static bool references_available(const mp2v_recon* ctx, const mp2v_pic_params_t& pp) {
+    for (int d = 0; d < 2; d++) {
+        const int fr = d ? pp.l1_frame : pp.l0_frame;
+        if (fr < 0 || ctx->frame_written[fr]) continue;
+        bool queued = false;
+        for (int id : ctx->pending) queued = queued || ctx->slots[id].pub.params->dst_frame == fr;
+        if (!queued) return false;
+    }
+    return true;
+}
+
 // queue a slot whose records are (or will be) complete; ctx->mu held
 static int queue_slot(mp2v_recon* ctx, slot_t* s) {
     const mp2v_pic_params_t& pp = *s->pub.params;
@@ -646,6 +676,8 @@ extern "C" MP2V_API int mp2v_recon_submit_staged(mp2v_recon_t* ctx, mp2v_picture
     const size_t staged_end = s->staged_end;
     const int rows_covered = s->rows_covered;
     CHECK_VLC_ERROR();
+    // everything queue_slot can refuse is checked before any device work is issued for the picture
+    if (!references_available(ctx, *s->pub.params)) { s->staged = true; return ctx->fail(MP2V_ERR_STATE, "reference frame has never been written"); }
     CK(cudaSetDevice(ctx->cfg.device), "cudaSetDevice");
     mp2v_mb_info_t* d_mb = reinterpret_cast<mp2v_mb_info_t*>(s->d_arena + kParamsBytes);
     s->trace_idx = -1;
@@ -706,6 +738,8 @@ extern "C" MP2V_API int mp2v_recon_sync(mp2v_recon_t* ctx) {
     CK(cudaSetDevice(ctx->cfg.device), "cudaSetDevice");
     CK(cudaStreamSynchronize(ctx->s_copy), "stream sync");
     CK(cudaStreamSynchronize(ctx->s_compute), "stream sync");
+    CK(cudaStreamSynchronize(ctx->s_d2h), "stream sync");      // queued frame copies (auto download, downloads of other threads)
+    std::fill(ctx->read_pending.begin(), ctx->read_pending.end(), 0);
     for (auto& s : ctx->slots) if (s.state == SLOT_INFLIGHT) s.state = SLOT_FREE;
     ctx->batch_ramp = 1;
     ctx->pictures_submitted = 0;                         // slice errors name pictures by their number since the last sync
@@ -747,6 +781,7 @@ extern "C" MP2V_API int mp2v_recon_reset(mp2v_recon_t* ctx) {
     for (auto& s : ctx->slots) { s.state = SLOT_FREE; s.staged = false; s.status_pending = false; s.prechecked = false; s.vlc = false; }
     std::fill(ctx->frame_written.begin(), ctx->frame_written.end(), 0);
     std::fill(ctx->mirror_valid.begin(), ctx->mirror_valid.end(), 0);
+    std::fill(ctx->read_pending.begin(), ctx->read_pending.end(), 0);
     ctx->vlc_error.clear();
     ctx->err.clear();
     ctx->batch_ramp = 1;
@@ -831,6 +866,8 @@ static int enqueue_frame_copy(mp2v_recon* ctx, int frame_id, uint8_t* const dst[
     }
     *done = ctx->get_event();
     CK(cudaEventRecord(*done, ctx->s_d2h), "event record");
+    CK(cudaEventRecord(ctx->read_ev[frame_id], ctx->s_d2h), "event record");
+    ctx->read_pending[frame_id] |= 1;
     return MP2V_OK;
 }
 
@@ -898,7 +935,7 @@ extern "C" MP2V_API int mp2v_recon_upload_frame(mp2v_recon_t* ctx, int frame_id,
 
 extern "C" MP2V_API int mp2v_recon_frame_device_ptrs(mp2v_recon_t* ctx, int frame_id, void* planes[3], int32_t strides[3]) {
     if (!ctx || !planes || !strides) return MP2V_ERR_ARG;
-    if (frame_id < 0 || frame_id >= ctx->cfg.n_frames) return ctx->fail(MP2V_ERR_ARG, "frame id out of range");
+    if (frame_id < 0 || frame_id >= ctx->cfg.n_frames) { std::lock_guard<std::mutex> lk(ctx->mu); return ctx->fail(MP2V_ERR_ARG, "frame id out of range"); }
     for (int p = 0; p < 3; p++) { planes[p] = ctx->frame_ptr(frame_id, p); strides[p] = ctx->lay.stride[p]; }
     return MP2V_OK;
 }

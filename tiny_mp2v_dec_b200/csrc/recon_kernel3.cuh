@@ -1,0 +1,463 @@
+// Reconstruction kernel, third cut (included by recon_kernels.cu inside namespace mp2v; it shares the
+// 16-bit lane arithmetic, the packed-byte averages and the bound tables defined there).
+//
+// Same contract and the same warp-autonomous decomposition as recon_kernel<CF> (a warp owns a run of
+// consecutive macroblocks and walks it in batches of <= 24 coded blocks); what changed is where the
+// instructions go (ncu of the second cut: 588 warp instructions per macroblock, issue bound):
+//
+//   reference windows   one TMA box load per plane and direction (cp.async.bulk.tensor.3d over the
+//                       frame pool viewed as [frame][row][pixel], completion on a per-warp mbarrier)
+//                       instead of 3-4 per-lane cp.async trips with their per-lane address math.  A
+//                       box must start on a 16-byte boundary of the innermost dimension (measured:
+//                       any other x coordinate raises an illegal-instruction fault), so a box is
+//                       32 bytes wide from (x & ~15) and the rows are read at the byte offset x & 15.
+//                       Boxes that leave the plane are zero-filled by the TMA unit: a bad vector
+//                       cannot fault.
+//   inverse transform   one lane per column in pass 1 and one lane per row in pass 2 (8 lanes per
+//                       block, 4 blocks per trip): 16-bit shared-memory loads sign-extend and 16-bit
+//                       stores pack, pass 2 reads its row with one conflict-free 128-bit load.
+//   mismatch control    a toggle that only turns F[63] from 0 into 1 is dropped: column 7 of pass 1
+//                       maps x7 = 1 to (1 * 25570) >> 16 = 0, i.e. to an all-zero column
+//                       (idct_sse2.hpp:32,41) -- the block is bit-identical without it.
+//   coefficient records the first 32 records of the NEXT batch are requested while this batch is
+//                       transformed (the one exposed global-memory latency of the second cut: 14 %
+//                       of all stall samples sat on that load).
+//   output              every lane owns the same (plane, row) of every macroblock: block indices,
+//                       window offsets and the destination pointer are per-lane constants / running
+//                       pointers instead of being recomputed per macroblock.
+#pragma once
+
+namespace v3 {
+
+#ifndef MP2V_V3_WINBUF
+#define MP2V_V3_WINBUF 1
+#endif
+#ifndef MP2V_V3_MINCTAS
+#define MP2V_V3_MINCTAS 8
+#endif
+constexpr int kSlots = 24;                 // coded blocks per batch
+constexpr int kTileRows = kSlots + 1;      // + one spare row: a record naming an uncoded block lands there at worst
+constexpr int kWinBuf = MP2V_V3_WINBUF;    // window buffers per warp (2: the next macroblock's boxes load during this one)
+constexpr int kWarps = kCtaThreads / 32;
+constexpr int kBoxW = 32;                  // bytes per box row: 16-byte aligned start + up to 15 bytes of offset + 17 pixels
+
+constexpr int align128(int x) { return (x + 127) & ~127; }
+
+template <int CF>
+struct geo_t {
+    static constexpr int NBLK = CF == 1 ? 6 : CF == 2 ? 8 : 12;
+    static constexpr int CW = CF == 3 ? 16 : 8;      // chroma macroblock width
+    static constexpr int CH = CF == 1 ? 8 : 16;      // chroma macroblock height
+    static constexpr int Y_BYTES = kBoxW * 17, C_BYTES = kBoxW * (CH + 1);
+    static constexpr int CB_OFF = align128(Y_BYTES), CR_OFF = CB_OFF + align128(C_BYTES);
+    static constexpr int DIR_BYTES = CR_OFF + align128(C_BYTES);      // every box 128-byte aligned
+    static constexpr uint32_t TX_BYTES = Y_BYTES + 2 * C_BYTES;      // bytes one direction's three boxes deliver
+};
+
+template <int CF>
+struct alignas(128) warp_smem_t {
+    alignas(128) uint8_t win[kWinBuf][2][geo_t<CF>::DIR_BYTES];   // [buffer][direction]
+    alignas(16) int16_t tile[kTileRows][kTilePitch];
+    // macroblocks of the batch that carry records: {first record index in the batch, coef_off - that index,
+    // cbp | W row offset << 16, first slot | qscale << 8 | shift << 16}
+    alignas(16) uint4 mb_ctx[32];
+    alignas(16) int bound[kTileRows + 3];  // saturation bound per slot
+    alignas(8) uint64_t mbar[kWinBuf];
+};
+
+template <int CF>
+struct cta_smem_t {
+    warp_smem_t<CF> w[kWarps];
+    alignas(16) uint8_t W[4][64];          // quantiser matrices by scan position
+    alignas(16) uint8_t scan[64];          // scan position -> tile index (g_scan_trans)
+    alignas(16) uint16_t bwp[64];          // bound weight by scan position
+};
+
+// ---- mbarrier / TMA wrappers (PTX ISA 8.6, sm_100a)
+__device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+__device__ __forceinline__ void mbar_init(uint64_t* bar, uint32_t count) {
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count) : "memory");
+}
+__device__ __forceinline__ void mbar_fence_init() { asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory"); }
+__device__ __forceinline__ void mbar_expect_tx(uint64_t* bar, uint32_t bytes) {
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
+}
+// Bounded: a box that never arrives traps instead of hanging the device.
+__device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
+    uint32_t done = 0;
+    for (int spins = 0; spins < (1 << 22); spins++) {
+        asm volatile(
+            "{\n\t.reg .pred p;\n\t"
+            "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
+            "selp.u32 %0, 1, 0, p;\n\t}"
+            : "=r"(done) : "r"(smem_u32(bar)), "r"(parity) : "memory");
+        if (done) return;
+    }
+    __trap();
+}
+// one box of a [frame][row][pixel] plane tensor; coordinates in elements, innermost first; x must be a multiple of 16
+__device__ __forceinline__ void tma_box_3d(void* dst, const CUtensorMap* tm, int x, int y, int z, uint64_t* bar) {
+    asm volatile("cp.async.bulk.tensor.3d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%2, %3, %4}], [%5];"
+                 ::"r"(smem_u32(dst)), "l"(reinterpret_cast<uint64_t>(tm)), "r"(x), "r"(y), "r"(z), "r"(smem_u32(bar)) : "memory");
+}
+
+// prediction of one unit (NW words = 4 * NW pixels) from a staged box row at byte offset o; half-pel
+// averaging in the reference's order (mc_c.hpp:3-17): H = avg(p[x], p[x+1]), V = avg(p[x], p[x+stride]),
+// HV = avg(H(row), H(row + 1)).  32-bit loads at the dynamic word offset, funnel shifts for the byte part.
+template <int NW>
+__device__ __forceinline__ void pred_unit(const uint8_t* row, int o, int hx, int hy, uint32_t (&out)[NW]) {
+    const int sh = (o & 3) * 8;
+    const uint32_t* p = reinterpret_cast<const uint32_t*>(row + (o & ~3));
+    uint32_t w[NW + 1];
+#pragma unroll
+    for (int i = 0; i <= NW; i++) w[i] = p[i];
+#pragma unroll
+    for (int j = 0; j < NW; j++) out[j] = __funnelshift_rc(w[j], w[j + 1], sh);
+    if (hx) {
+#pragma unroll
+        for (int j = 0; j < NW; j++) out[j] = avg4(out[j], __funnelshift_rc(w[j], w[j + 1], sh + 8));
+    }
+    if (hy) {
+        uint32_t b[NW];
+#pragma unroll
+        for (int i = 0; i <= NW; i++) w[i] = p[i + kBoxW / 4];      // next box row
+#pragma unroll
+        for (int j = 0; j < NW; j++) b[j] = __funnelshift_rc(w[j], w[j + 1], sh);
+        if (hx) {
+#pragma unroll
+            for (int j = 0; j < NW; j++) b[j] = avg4(b[j], __funnelshift_rc(w[j], w[j + 1], sh + 8));
+        }
+#pragma unroll
+        for (int j = 0; j < NW; j++) out[j] = avg4(out[j], b[j]);
+    }
+}
+
+// residual of block `blk` (row rr) on top of two words of prediction, or alone for intra macroblocks
+__device__ __forceinline__ void add_residual(const int16_t (*tile)[kTilePitch], int base, uint32_t cbp, uint32_t below, int blk, int rr8, bool intra,
+                                             uint32_t& o0, uint32_t& o1) {
+    if (cbp >> blk & 1) {
+        const uint4 res = *reinterpret_cast<const uint4*>(&tile[base + __popc(cbp & below)][rr8]);
+        if (intra) { o0 = clip4(res.x, res.y); o1 = clip4(res.z, res.w); }      // add=false: packus(res), idct_sse2.hpp:108-109
+        else { o0 = add_clip4(o0, res.x, res.y); o1 = add_clip4(o1, res.z, res.w); }
+    }
+}
+
+template <int CF>
+__global__ void __launch_bounds__(kCtaThreads, MP2V_V3_MINCTAS)
+recon_kernel3(const __grid_constant__ batch_desc_t batch, const __grid_constant__ recon_tmaps_t tm) {
+    using G = geo_t<CF>;
+    extern __shared__ uint8_t smem_raw[];
+    cta_smem_t<CF>& s = *reinterpret_cast<cta_smem_t<CF>*>(smem_raw + ((128u - (smem_u32(smem_raw) & 127u)) & 127u));
+
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const int pi = blockIdx.x / batch.ctas_per_pic;
+    const int grp = blockIdx.x - pi * batch.ctas_per_pic;
+    const pic_desc_t& pd = batch.pic[pi];
+    warp_smem_t<CF>& ws = s.w[warp];
+
+    // ---- picture tables + this warp's barriers (the only CTA-wide barrier)
+    if (tid < 64) {
+        reinterpret_cast<uint32_t*>(&s.W[0][0])[tid] = reinterpret_cast<const uint32_t*>(&pd.params->W[0][0])[tid];
+        const int alt = pd.params->alternate_scan ? 1 : 0;
+        const int t = c_scan_trans[alt][tid];
+        s.scan[tid] = (uint8_t)t;
+        s.bwp[tid] = c_bound_w[t];
+    }
+    if (lane == 0) {
+#pragma unroll
+        for (int b = 0; b < kWinBuf; b++) mbar_init(&ws.mbar[b], 1);
+        mbar_fence_init();
+    }
+    __syncthreads();
+
+    const int mbw = batch.mbw;
+    const int run = batch.mbs_per_warp;
+    const int mb_begin = (grp * kWarps + warp) * run;
+    const int mb_end = min(mb_begin + run, batch.mb_count);
+    if (mb_begin >= mb_end) return;
+    const uint32_t lt_mask = (1u << lane) - 1u, le_mask = 0xffffffffu >> (31 - lane);
+
+    // ---- per-lane constants of the output stage.  4:2:0: lane = one whole row (16 luma rows, 8 Cb, 8 Cr: one
+    // trip of four-word units, the chroma lanes drop two words).  4:2:2 / 4:4:4: trips of 8-pixel half rows.
+    constexpr int NT = CF == 1 ? 1 : CF == 2 ? 2 : 3;      // trips per macroblock
+    constexpr int NW = CF == 1 ? 4 : 2;                    // words per unit
+    int u_woff[NT], u_xoff[NT], u_blk[NT], u_rr8[NT], u_adv[NT], u_wrap[NT];
+    uint32_t u_below[NT];
+    uint8_t* u_dst[NT];
+    bool u_chroma[NT];
+    int mby0 = mb_begin / mbw, mbx0 = mb_begin - mby0 * mbw;      // the only division of the warp
+#pragma unroll
+    for (int t = 0; t < NT; t++) {
+        int p, r, half;
+        if (CF == 1) { p = lane < 16 ? 0 : lane < 24 ? 1 : 2; r = lane < 16 ? lane : (lane & 7); half = 0; }
+        else if (CF == 2) { p = t == 0 ? 0 : 1 + (lane >> 4); r = t == 0 ? lane >> 1 : lane & 15; half = t == 0 ? lane & 1 : 0; }
+        else { p = t; r = lane >> 1; half = lane & 1; }
+        u_chroma[t] = p != 0;
+        u_woff[t] = (p == 0 ? 0 : p == 1 ? G::CB_OFF : G::CR_OFF) + r * kBoxW;
+        u_xoff[t] = 8 * half;
+        // the 8x8 block this unit's (left) half belongs to (block geometry: mb_decoder.cpp:177-195)
+        int blk;
+        if (p == 0) blk = (r >> 3) * 2 + half;
+        else if (CF == 1) blk = 3 + p;
+        else if (CF == 2) blk = 3 + p + ((r >> 3) << 1);
+        else blk = 3 + p + ((r >> 3) << 1) + 4 * half;
+        u_blk[t] = blk;
+        u_below[t] = (1u << blk) - 1u;
+        u_rr8[t] = (r & 7) * 8;
+        const int pw = p ? G::CW : 16, ph = p ? G::CH : 16;
+        u_dst[t] = pd.dst[p] + (size_t)(mby0 * ph + r) * batch.stride[p] + mbx0 * pw + 8 * half;
+        u_adv[t] = pw;                                                     // destination step to the next macroblock of the row ...
+        u_wrap[t] = ph * batch.stride[p] - (mbw - 1) * pw;                 // ... and from the last one to the first of the next row
+    }
+
+    uint32_t wphase = 0;                                   // bit b: parity the next wait on buffer b expects
+    uint4 rec_next = (mb_begin + lane < mb_end) ? __ldg(reinterpret_cast<const uint4*>(pd.mb) + mb_begin + lane) : make_uint4(0, 0, 0, 0);
+    // guess of the next batch's first 32 coefficient records (right when its records are contiguous, which they are inside a slice)
+    uint32_t pref_idx = 0xffffffffu, pref_c = 0;
+
+    // boxes of one macroblock (its record broadcast in m_*), issued by one lane into window buffer `buf`
+    auto issue_windows = [&](uint32_t m_y, uint32_t m_z, uint32_t m_w, int ix, int iy, int buf) {
+        if ((m_y & MP2V_MB_INTRA) || lane != 0) return;
+        const uint32_t ndir = ((m_y & MP2V_MB_FWD) ? 1u : 0u) + ((m_y & MP2V_MB_BWD) ? 1u : 0u);
+        mbar_expect_tx(&ws.mbar[buf], ndir * G::TX_BYTES);
+#pragma unroll
+        for (int d = 0; d < 2; d++) {
+            if (!(m_y & (d ? MP2V_MB_BWD : MP2V_MB_FWD))) continue;
+            const uint32_t mvw = d ? m_w : m_z;
+            const int mvx = (int)(short)(mvw & 0xffffu), mvy = (int)mvw >> 16;
+            const int cx = CF < 3 ? mvx >> 1 : mvx, cy = CF < 2 ? mvy >> 1 : mvy;     // chroma vector: floor (mb_decoder.cpp:198-206)
+            const int z = d ? pd.l1_id : pd.l0_id;
+            const int cxa = (ix * G::CW + (cx >> 1)) & ~15, cya = iy * G::CH + (cy >> 1);
+            uint8_t* w = &ws.win[buf][d][0];
+            tma_box_3d(w, &tm.plane[0], (ix * 16 + (mvx >> 1)) & ~15, iy * 16 + (mvy >> 1), z, &ws.mbar[buf]);
+            tma_box_3d(w + G::CB_OFF, &tm.plane[1], cxa, cya, z, &ws.mbar[buf]);
+            tma_box_3d(w + G::CR_OFF, &tm.plane[2], cxa, cya, z, &ws.mbar[buf]);
+        }
+    };
+
+    int16_t* const tile0 = &ws.tile[0][0];
+    for (int first = mb_begin; first < mb_end;) {
+        // ---- 1. macroblock records of the batch: as many as fit the tile's coded-block slots
+        const int idx = first + lane;
+        const bool have = idx < mb_end;
+        const uint4 rec = rec_next;
+        const int cnt = have ? __popc(MP2V_MB_CBP(rec.y)) : 0;
+        const int ncoef_all = have ? (int)MP2V_MB_NCOEF(rec.y) : 0;
+        int scan2 = cnt | (ncoef_all << 16);       // both prefixes in one scan: coded blocks (low half), records (high half)
+#pragma unroll
+        for (int d = 1; d < 32; d <<= 1) {
+            const int t = __shfl_up_sync(0xffffffffu, scan2, d);
+            if (lane >= d) scan2 += t;
+        }
+        const int incl = scan2 & 0xffff;
+        const int nb = max(__popc(__ballot_sync(0xffffffffu, have && incl <= kSlots)), 1);
+        const int base = incl - cnt;
+        const int nslots = __shfl_sync(0xffffffffu, incl, nb - 1);
+        rec_next = (idx + nb < mb_end) ? __ldg(reinterpret_cast<const uint4*>(pd.mb) + idx + nb) : make_uint4(0, 0, 0, 0);
+
+        // ---- 2. per-macroblock context of the flat dequantisation loop, and the first trip's records on their way
+        const int ncoef = lane < nb ? ncoef_all : 0;
+        const int total = __shfl_sync(0xffffffffu, scan2, nb - 1) >> 16;
+        const int start = (scan2 >> 16) - ncoef_all;
+        const bool ne = ncoef > 0;
+        {
+            const uint32_t ne_mask = __ballot_sync(0xffffffffu, ne);
+            const uint32_t ni = (rec.y & MP2V_MB_INTRA) ? 0u : 1u;
+            if (ne) ws.mb_ctx[__popc(ne_mask & lt_mask)] = make_uint4((uint32_t)start, rec.x - (uint32_t)start, MP2V_MB_CBP(rec.y) | (ni << 22),
+                                                                      (uint32_t)base | (MP2V_MB_QSCALE(rec.y) << 8) | ((4u + ni) << 16));
+        }
+        __syncwarp();
+        // All records of the batch are ONE flat index space (lane = record).  The owner of record f is the last
+        // macroblock whose first record index is <= f: per trip of 32 records the lanes that HOLD macroblocks mark
+        // where theirs starts inside the trip (REDUX.OR) and count those that started before it (ballot).
+        auto fetch = [&](int f0, uint32_t& c, uint4& ctx, bool use_pref) {
+            const int rel = start - f0;
+            const uint32_t starts = __reduce_or_sync(0xffffffffu, (ne && (unsigned)rel < 32u) ? 1u << rel : 0u);
+            const int before = __popc(__ballot_sync(0xffffffffu, ne && rel < 0));
+            c = 0; ctx = make_uint4(0, 0, 0, 0);
+            if (f0 + lane < total) {
+                ctx = ws.mb_ctx[before + __popc(starts & le_mask) - 1];
+                const uint32_t ci = ctx.y + (uint32_t)(f0 + lane);
+                c = (use_pref && ci == pref_idx) ? pref_c : __ldg(pd.coef + ci);
+            }
+        };
+        uint32_t c_nx;
+        uint4 ctx_nx;
+        fetch(0, c_nx, ctx_nx, true);
+
+        // ---- 3. the first macroblocks' boxes start loading now; they land while we dequantise and transform
+        {
+            int ix = mbx0, iy = mby0;
+#pragma unroll
+            for (int b = 0; b < kWinBuf; b++) {
+                if (b < nb) issue_windows(__shfl_sync(0xffffffffu, rec.y, b), __shfl_sync(0xffffffffu, rec.z, b), __shfl_sync(0xffffffffu, rec.w, b), ix, iy, b);
+                if (++ix == mbw) { ix = 0; iy++; }
+            }
+        }
+
+        // ---- 4. clear the used slots (QFS[64] = {0}, mb_decoder.cpp:159) and bounds; dequantise
+        for (int i = lane; i < nslots * 8; i += 32) reinterpret_cast<uint4*>(tile0)[(i >> 3) * (kTilePitch / 8) + (i & 7)] = make_uint4(0, 0, 0, 0);
+        if (lane < 7) reinterpret_cast<uint4*>(ws.bound)[lane] = make_uint4(0, 0, 0, 0);
+        __syncwarp();
+        uint32_t parity = 0;                 // bit s = parity of the coefficient sum of tile slot s
+        uint32_t col7 = 0;                   // bit s = column 7 of slot s holds a coefficient
+        for (int f0 = 0; f0 < total; f0 += 32) {
+            const uint32_t c = c_nx, cz = ctx_nx.z, pk = ctx_nx.w;
+            const bool live = f0 + lane < total;
+            fetch(f0 + 32, c_nx, ctx_nx, false);
+            uint32_t pbit = 0, c7bit = 0;
+            if (live) {
+                const int blk = (c >> 22) & 15;
+                const int slot = (int)(pk & 0xffu) + __popc(cz & 0xfffu & ((1u << blk) - 1u));      // <= kSlots even for a record naming an uncoded block
+                const int qs = (pk >> 8) & 0xff, sh = pk >> 16;
+                const int level = (int)(short)(c & 0xffffu);
+                const int pos = (c >> 16) & 63;
+                const bool raw = (c & MP2V_COEF_RAW) != 0, first_coef = (c & MP2V_COEF_FIRST) != 0;
+                const int w = (&s.W[0][0])[((CF > 1 && blk >= 6) ? 128 : 0) + ((cz >> 16) & 0x40) + pos];     // luma matrices for blocks 4,5 (:184-185)
+                const int mag = abs(level);
+                // intra (level*W*qs)>>4, non-intra ((2*level+1)*W*qs)>>5 (:142-143); "1s" is the latter with level 1 (:84)
+                int val = (((sh == 5 ? 2 * mag + 1 : mag) * w) * qs) >> sh;
+                val = level < 0 ? -val : val;                                              // :144
+                const int clamped = max(min((int)(short)val, 2047), -2048);                // int16 wrap, then clamp (:146)
+                val = raw ? level : first_coef ? val : clamped;                            // DC as is (:160); "1s" unclamped (:84)
+                const int idx2 = s.scan[pos];
+                const int av = abs(val), bwv = s.bwp[pos];
+                // weighted L1 norm for the saturation bound; +1: the mismatch toggle may change |F[63]| by one
+                const int wsum = raw ? (av <= kMaxFirstCoef ? av * bwv : kBoundWild) : (av + 1) * bwv;
+                pbit = raw ? 0u : (uint32_t)(val & 1) << slot;                             // DC is not part of the sum (:160)
+                c7bit = (idx2 & 7) == 7 ? 1u << slot : 0u;
+                tile0[slot * kTilePitch + idx2] = (int16_t)val;
+                atomicAdd(&ws.bound[slot], wsum);
+            }
+            parity ^= __reduce_xor_sync(0xffffffffu, pbit);
+            col7 |= __reduce_or_sync(0xffffffffu, c7bit);
+        }
+        // the next batch's first records: requested now, used after this batch's transform and output
+        {
+            const uint32_t nxt = __ballot_sync(0xffffffffu, MP2V_MB_NCOEF(rec_next.y) != 0);
+            const uint32_t off = __shfl_sync(0xffffffffu, rec_next.x, nxt ? __ffs(nxt) - 1 : 0);
+            pref_idx = nxt ? off + (uint32_t)lane : 0xffffffffu;
+            if (nxt) pref_c = __ldg(pd.coef + pref_idx);      // (arenas are padded: 32 records past the last one stay inside the allocation)
+        }
+        __syncwarp();
+        // qfs[63] ^= (sum & 1) ^ 1 (:150-152) -- only where column 7 already holds something (see the header)
+        if (lane < nslots && (col7 >> lane & 1u)) tile0[lane * kTilePitch + 63] ^= (int16_t)(((parity >> lane) & 1u) ^ 1u);
+
+        // ---- 5. inverse transform; arithmetic variant for the whole batch from the per-block bounds (a toggled-in F[63] = 1 counts too)
+        const int bnd = lane < nslots ? ws.bound[lane] + (int)s.bwp[63] : 0;      // scan position 63 is tile index 63 in both scans
+        const bool p1_exact = __any_sync(0xffffffffu, bnd >= kBoundWild);
+        const bool p2_exact = __any_sync(0xffffffffu, bnd > kBoundLimit);
+        __syncwarp();
+        // pass 1: one lane per column, in place; the transform runs across the vector index k (idct_sse2.hpp:98)
+        for (int i0 = 0; i0 < nslots * 8; i0 += 32) {
+            const int i = i0 + lane;
+            const bool act = i < nslots * 8;
+            int16_t* p = tile0 + (act ? i >> 3 : 0) * kTilePitch + (i & 7);
+            int x[8];
+#pragma unroll
+            for (int k = 0; k < 8; k++) x[k] = act ? (int)p[k * 8] : 0;
+            if (p1_exact) idct_lane<0>(x[0], x[1], x[2], x[3], x[4], x[5], x[6], x[7]);
+            else if (p2_exact) idct_lane<1>(x[0], x[1], x[2], x[3], x[4], x[5], x[6], x[7]);
+            else idct_lane<2>(x[0], x[1], x[2], x[3], x[4], x[5], x[6], x[7]);     // the bound that clears pass 2 also bounds every pass-1 output
+            if (act) {
+#pragma unroll
+                for (int k = 0; k < 8; k++) p[k * 8] = (int16_t)x[k];
+            }
+        }
+        __syncwarp();
+        // pass 2: one lane per row of the transposed block (transpose_8x8_sse2 is the addressing); output r of
+        // row k is res[r][k], shifted down by 6 (idct_sse2.hpp:100-107)
+        for (int i0 = 0; i0 < nslots * 8; i0 += 32) {
+            const int i = i0 + lane;
+            const bool act = i < nslots * 8;
+            int16_t* t = tile0 + (act ? i >> 3 : 0) * kTilePitch;
+            const int k = i & 7;
+            const uint4 q = *reinterpret_cast<const uint4*>(t + k * 8);      // a quarter warp reads the 128 contiguous bytes of one block
+            int x[8] = {(int)(short)(q.x & 0xffffu), (int)q.x >> 16, (int)(short)(q.y & 0xffffu), (int)q.y >> 16,
+                        (int)(short)(q.z & 0xffffu), (int)q.z >> 16, (int)(short)(q.w & 0xffffu), (int)q.w >> 16};
+            __syncwarp();      // the eight rows of a block sit in one trip: all are in registers before any is overwritten
+            if (p2_exact) idct_lane<0>(x[0], x[1], x[2], x[3], x[4], x[5], x[6], x[7]);
+            else idct_lane<2>(x[0], x[1], x[2], x[3], x[4], x[5], x[6], x[7]);
+            if (act) {
+#pragma unroll
+                for (int r = 0; r < 8; r++) t[r * 8 + k] = (int16_t)(x[r] >> 6);      // _mm_srai_epi16(., 6)
+            }
+        }
+        __syncwarp();
+
+        // ---- 6. prediction + residual + clip + store, macroblock by macroblock
+        int mbx = mbx0, mby = mby0;
+        for (int mi = 0; mi < nb; mi++) {
+            const uint32_t m_y = __shfl_sync(0xffffffffu, rec.y, mi), m_z = __shfl_sync(0xffffffffu, rec.z, mi), m_w = __shfl_sync(0xffffffffu, rec.w, mi);
+            const int mbase = __shfl_sync(0xffffffffu, base, mi);
+            const uint32_t cbp = MP2V_MB_CBP(m_y);
+            const bool intra = (m_y & MP2V_MB_INTRA) != 0;
+            const int buf = mi & (kWinBuf - 1);
+            uint32_t pred[NT][NW];
+#pragma unroll
+            for (int t = 0; t < NT; t++) {
+#pragma unroll
+                for (int j = 0; j < NW; j++) pred[t][j] = 0;
+            }
+            if (!intra) {
+                mbar_wait(&ws.mbar[buf], (wphase >> buf) & 1u);
+                wphase ^= 1u << buf;
+                const int odd8 = (mbx & 1) << 3;      // (mbx * 8) & 15 for the 8-pixel-wide chroma of 4:2:0 / 4:2:2
+                bool have_pred = false;
+#pragma unroll
+                for (int d = 0; d < 2; d++) {
+                    if (!(m_y & (d ? MP2V_MB_BWD : MP2V_MB_FWD))) continue;      // warp-uniform
+                    const uint32_t mvw = d ? m_w : m_z;
+                    const int mvx = (int)(short)(mvw & 0xffffu), mvy = (int)mvw >> 16;
+#pragma unroll
+                    for (int t = 0; t < NT; t++) {
+                        // this unit's vector: luma as coded, chroma floor-halved where the format subsamples (mb_decoder.cpp:198-206)
+                        const int cx = (u_chroma[t] && CF < 3) ? mvx >> 1 : mvx, cy = (u_chroma[t] && CF < 2) ? mvy >> 1 : mvy;
+                        const int o = ((((u_chroma[t] && CF < 3) ? odd8 : 0) + (cx >> 1)) & 15) + u_xoff[t];
+                        uint32_t q[NW];
+                        pred_unit<NW>(&ws.win[buf][d][0] + u_woff[t], o, cx & 1, cy & 1, q);
+                        if (have_pred) {
+#pragma unroll
+                            for (int j = 0; j < NW; j++) pred[t][j] = avg4(q[j], pred[t][j]);      // avg(backward, forward) (mb_decoder.cpp:240-249)
+                        } else {
+#pragma unroll
+                            for (int j = 0; j < NW; j++) pred[t][j] = q[j];
+                        }
+                    }
+                    have_pred = true;
+                }
+            }
+            __syncwarp();      // every lane has read this buffer: the boxes of a later macroblock may overwrite it
+            if (mi + kWinBuf < nb) {
+                int ix = mbx, iy = mby;
+#pragma unroll
+                for (int a = 0; a < kWinBuf; a++) { if (++ix == mbw) { ix = 0; iy++; } }
+                const int nx = mi + kWinBuf;
+                issue_windows(__shfl_sync(0xffffffffu, rec.y, nx), __shfl_sync(0xffffffffu, rec.z, nx), __shfl_sync(0xffffffffu, rec.w, nx), ix, iy, buf);
+            }
+            const bool row_end = mbx + 1 == mbw;
+#pragma unroll
+            for (int t = 0; t < NT; t++) {
+                add_residual(ws.tile, mbase, cbp, u_below[t], u_blk[t], u_rr8[t], intra, pred[t][0], pred[t][1]);
+                if (CF == 1) {
+                    // whole rows: the right-hand block too for luma rows (the chroma lanes drop their upper two words)
+                    if (lane < 16) {
+                        add_residual(ws.tile, mbase, cbp, u_below[t] * 2u + 1u, u_blk[t] + 1, u_rr8[t], intra, pred[t][2], pred[t][3]);
+                        *reinterpret_cast<uint4*>(u_dst[t]) = make_uint4(pred[t][0], pred[t][1], pred[t][2], pred[t][3]);
+                    } else {
+                        *reinterpret_cast<uint2*>(u_dst[t]) = make_uint2(pred[t][0], pred[t][1]);
+                    }
+                } else {
+                    *reinterpret_cast<uint2*>(u_dst[t]) = make_uint2(pred[t][0], pred[t][1]);
+                }
+                u_dst[t] += row_end ? u_wrap[t] : u_adv[t];      // next macroblock: one to the right, or the first of the next macroblock row
+            }
+            if (row_end) { mbx = 0; mby++; } else mbx++;
+            __syncwarp();
+        }
+        first += nb;
+        mbx0 = mbx; mby0 = mby;
+    }
+}
+
+}  // namespace v3

@@ -34,6 +34,11 @@
 // The roofline that bounds this kernel and the byte counts are in DESIGN.md.
 #include "recon_kernels.cuh"
 
+#include <cudaTypedefs.h>
+
+#include <cstdlib>
+#include <mutex>
+
 #include "host/scan_tables.h"
 
 namespace mp2v {
@@ -681,41 +686,103 @@ __global__ void __launch_bounds__(kCtaThreads, MP2V_MINCTAS) recon_kernel(const 
     }
 }
 
-// __constant__ symbols are per device: remember which devices have been initialised
+}  // namespace mp2v
+
+namespace mp2v {
+#include "recon_kernel3.cuh"
+}
+
+namespace mp2v {
+
+// Which cut of the kernel launches: recon_kernel3 unless MP2V_RECON_KERNEL=2 (development A/B switch).
+static int kernel_generation() {
+    static const int gen = [] { const char* v = getenv("MP2V_RECON_KERNEL"); return (v && atoi(v) == 2) ? 2 : 3; }();
+    return gen;
+}
+
+template <int CF>
+static cudaError_t prepare_kernel3() {
+    return cudaFuncSetAttribute(v3::recon_kernel3<CF>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(sizeof(v3::cta_smem_t<CF>) + 128));
+}
+
+// __constant__ symbols and function attributes are per device: initialise each device once (any thread)
 static cudaError_t ensure_tables() {
+    static std::mutex mu;
     static bool done[64] = {};
     int dev = 0;
     cudaError_t e = cudaGetDevice(&dev);
     if (e != cudaSuccess) return e;
     if (dev < 0 || dev >= 64) return cudaErrorInvalidDevice;
+    std::lock_guard<std::mutex> lk(mu);
     if (!done[dev]) {
         const scan_tables_t& t = scan_tables();
         e = cudaMemcpyToSymbol(c_scan_trans, t.scan_trans, sizeof(t.scan_trans));
         if (e != cudaSuccess) return e;
+        if ((e = prepare_kernel3<1>()) != cudaSuccess || (e = prepare_kernel3<2>()) != cudaSuccess || (e = prepare_kernel3<3>()) != cudaSuccess) return e;
         done[dev] = true;
     }
     return cudaSuccess;
 }
 
-cudaError_t launch_recon(int chroma_format, const batch_desc_t& batch, cudaStream_t stream) {
+cudaError_t make_frame_tmaps(int chroma_format, uint8_t* frames, const mp2v_frame_layout_t& lay, size_t frame_alloc, int n_frames, recon_tmaps_t* out) {
+    // the driver entry point is resolved at run time: the library links against the CUDA runtime only
+    static PFN_cuTensorMapEncodeTiled_v12000 encode = [] {
+        void* fn = nullptr;
+        cudaDriverEntryPointQueryResult qres = cudaDriverEntryPointSymbolNotFound;
+        if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &fn, cudaEnableDefault, &qres) != cudaSuccess || qres != cudaDriverEntryPointSuccess) fn = nullptr;
+        return reinterpret_cast<PFN_cuTensorMapEncodeTiled_v12000>(fn);
+    }();
+    if (!encode) return cudaErrorNotSupported;
+    if (chroma_format < 1 || chroma_format > 3 || !out || n_frames < 1) return cudaErrorInvalidValue;
+    const cuuint32_t cbox_h = (chroma_format == 1 ? 8 : 16) + 1;      // v3::geo_t: every box is kBoxW = 32 bytes wide
+    for (int p = 0; p < 3; p++) {
+        const cuuint64_t gdim[3] = {(cuuint64_t)lay.width[p], (cuuint64_t)lay.height[p], (cuuint64_t)n_frames};
+        const cuuint64_t gstride[2] = {(cuuint64_t)lay.stride[p], (cuuint64_t)frame_alloc};      // bytes, dimensions 1 and 2
+        const cuuint32_t box[3] = {(cuuint32_t)v3::kBoxW, p == 0 ? 17u : cbox_h, 1u};
+        const cuuint32_t estr[3] = {1, 1, 1};
+        const CUresult r = encode(&out->plane[p], CU_TENSOR_MAP_DATA_TYPE_UINT8, 3, frames + lay.plane_offset[p], gdim, gstride, box, estr,
+                                  CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_NONE, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+        if (r != CUDA_SUCCESS) return cudaErrorInvalidValue;
+    }
+    return cudaSuccess;
+}
+
+cudaError_t launch_recon(int chroma_format, const batch_desc_t& batch, const recon_tmaps_t& tm, cudaStream_t stream) {
     cudaError_t e = ensure_tables();
     if (e != cudaSuccess) return e;
     if (batch.n_pics < 1 || batch.n_pics > kMaxBatch) return cudaErrorInvalidValue;
     const dim3 grid((unsigned)(batch.n_pics * batch.ctas_per_pic)), block(kCtaThreads);
-    switch (chroma_format) {
-        case 1: recon_kernel<1><<<grid, block, 0, stream>>>(batch); break;
-        case 2: recon_kernel<2><<<grid, block, 0, stream>>>(batch); break;
-        case 3: recon_kernel<3><<<grid, block, 0, stream>>>(batch); break;
-        default: return cudaErrorInvalidValue;
+    if (kernel_generation() == 2) {
+        switch (chroma_format) {
+            case 1: recon_kernel<1><<<grid, block, 0, stream>>>(batch); break;
+            case 2: recon_kernel<2><<<grid, block, 0, stream>>>(batch); break;
+            case 3: recon_kernel<3><<<grid, block, 0, stream>>>(batch); break;
+            default: return cudaErrorInvalidValue;
+        }
+    } else {
+        switch (chroma_format) {
+            case 1: v3::recon_kernel3<1><<<grid, block, sizeof(v3::cta_smem_t<1>) + 128, stream>>>(batch, tm); break;
+            case 2: v3::recon_kernel3<2><<<grid, block, sizeof(v3::cta_smem_t<2>) + 128, stream>>>(batch, tm); break;
+            case 3: v3::recon_kernel3<3><<<grid, block, sizeof(v3::cta_smem_t<3>) + 128, stream>>>(batch, tm); break;
+            default: return cudaErrorInvalidValue;
+        }
     }
     return cudaGetLastError();
 }
 
 cudaError_t recon_kernel_attributes(int chroma_format, cudaFuncAttributes* out) {
+    if (kernel_generation() == 2) {
+        switch (chroma_format) {
+            case 1: return cudaFuncGetAttributes(out, recon_kernel<1>);
+            case 2: return cudaFuncGetAttributes(out, recon_kernel<2>);
+            case 3: return cudaFuncGetAttributes(out, recon_kernel<3>);
+            default: return cudaErrorInvalidValue;
+        }
+    }
     switch (chroma_format) {
-        case 1: return cudaFuncGetAttributes(out, recon_kernel<1>);
-        case 2: return cudaFuncGetAttributes(out, recon_kernel<2>);
-        case 3: return cudaFuncGetAttributes(out, recon_kernel<3>);
+        case 1: return cudaFuncGetAttributes(out, v3::recon_kernel3<1>);
+        case 2: return cudaFuncGetAttributes(out, v3::recon_kernel3<2>);
+        case 3: return cudaFuncGetAttributes(out, v3::recon_kernel3<3>);
         default: return cudaErrorInvalidValue;
     }
 }

@@ -1,5 +1,6 @@
 // Device-side interface between recon_api.cu (context, scheduling) and recon_kernels.cu (kernels).
 #pragma once
+#include <cuda.h>
 #include <cuda_runtime.h>
 #include <cstdint>
 #include "mp2v_recon.h"
@@ -35,8 +36,7 @@ struct pic_desc_t {
     uint8_t* dst[3];
     const uint8_t* l0[3];
     const uint8_t* l1[3];
-    int32_t cta_begin;                 // first CTA of this picture inside the launch
-    int32_t pad;
+    int32_t l0_id, l1_id;              // the same references as frame ids: the z coordinate of the TMA boxes (-1: none)
 };
 
 struct batch_desc_t {
@@ -48,8 +48,15 @@ struct batch_desc_t {
     int32_t mbs_per_warp;
 };
 
+// TMA descriptors of the frame pool, one per plane: a [frame][row][pixel] tensor of bytes whose boxes are the
+// (w + 1) x (h + 1) reference windows of one macroblock (recon_kernel3.cuh)
+struct alignas(64) recon_tmaps_t { CUtensorMap plane[3]; };
+// frames: address of frame 0 plane 0; frames lie frame_alloc bytes apart.  Fails (cudaErrorNotSupported /
+// cudaErrorInvalidValue) when the driver cannot encode the maps.
+cudaError_t make_frame_tmaps(int chroma_format, uint8_t* frames, const mp2v_frame_layout_t& lay, size_t frame_alloc, int n_frames, recon_tmaps_t* out);
+
 // grid = n_pics * ctas_per_pic; returns the CUDA error of the launch
-cudaError_t launch_recon(int chroma_format, const batch_desc_t& batch, cudaStream_t stream);
+cudaError_t launch_recon(int chroma_format, const batch_desc_t& batch, const recon_tmaps_t& tm, cudaStream_t stream);
 
 // planar 4:2:0 frames -> NV12 (Y plane, then interleaved Cb/Cr rows) in the caller's device buffers (convert_kernel.cu)
 struct nv12_frame_t { const uint8_t* y; const uint8_t* cb; const uint8_t* cr; uint8_t* dst; };

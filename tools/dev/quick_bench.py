@@ -41,10 +41,19 @@ def run(name, w, h, cf, reps=20, max_batch=128, **kw):
 
 
 NAT = dict(mode=1, pct_coded=70)
+TEX = dict(mode=2, texture_noise=3, pct_intra_in_pb=3, q_scale_type=0, alternate_scan=0, intra_dc_precision=0)
 
 if __name__ == "__main__":
+    if "--intra-only" in sys.argv:
+        run("1080p420 intra texture", 1920, 1088, 1, reps=3, seed=2002, intra_only=1, gop_n=15, n_gops=2, gop_m=1, **TEX)
+        sys.exit(0)
+    if "--ipb-only" in sys.argv:
+        run("1080p420 IPB texture", 1920, 1088, 1, reps=3, seed=3003, gop_n=15, gop_m=3, n_gops=4, **TEX)
+        sys.exit(0)
     run("1080p420 intra natural", 1920, 1088, 1, seed=2, intra_only=1, gop_n=15, n_gops=2, gop_m=1, natural_mean_coefs=6, **NAT)
     run("1080p420 IPB natural", 1920, 1088, 1, seed=3, gop_n=15, gop_m=3, n_gops=4, natural_mean_coefs=5, **NAT)
+    run("1080p420 intra texture", 1920, 1088, 1, seed=2002, intra_only=1, gop_n=15, n_gops=2, gop_m=1, **TEX)
+    run("1080p420 IPB texture", 1920, 1088, 1, seed=3003, gop_n=15, gop_m=3, n_gops=4, **TEX)
     run("1080p420 intra fuzz", 1920, 1088, 1, seed=2, intra_only=1, gop_n=15, n_gops=2, gop_m=1)
     run("1080p420 IPB fuzz", 1920, 1088, 1, seed=3, gop_n=15, gop_m=3, n_gops=4)
     if "--all" in sys.argv:

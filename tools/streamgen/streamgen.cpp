@@ -3,8 +3,11 @@
 // (src/core/mp2v_hdr.cpp:4-152, mp2v_hdr.h:345-363, mb_decoder.cpp:341-641).
 #include "streamgen.h"
 
+#include <cstdio>
+#include <cstdlib>
 #include <cstring>
 #include <string>
+#include <utility>
 #include <vector>
 
 #include "scan_tables.h"
@@ -122,6 +125,10 @@ struct mp2v_gen {
         bw.put(1, 1); bw.put(p.chroma_format, 2);   // progressive_sequence = 1
         bw.put((p.width >> 12) & 3, 2); bw.put((p.height >> 12) & 3, 2);
         bw.put(0, 12); bw.put(1, 1); bw.put(0, 8); bw.put(0, 1); bw.put(0, 2); bw.put(0, 5);
+        if (p.user_data_bytes > 0) {                // user_data(): bytes that cannot emulate a start code
+            bw.start_code(0xB2);
+            for (int i = 0; i < p.user_data_bytes; i++) bw.put(0x80u | (uint32_t)rng.below(0x7f), 8);
+        }
     }
     void gop_header(int closed) {
         bw.start_code(0xB8);
@@ -130,6 +137,9 @@ struct mp2v_gen {
 
     // ------------------------------------------------------------------ one picture
     struct pic_hdr_t { int type, temporal_reference, f_code[2][2], alt_scan, q_scale_type, dc_prec; };
+
+    uint8_t gop_tx[4][64] = {};       // matrices_once: the matrices loaded by the GOP's first picture
+    bool gop_tx_valid = false;
 
     void picture_headers(const pic_hdr_t& h, picture_t& pic) {
         bw.start_code(0x00);
@@ -144,6 +154,14 @@ struct mp2v_gen {
         bw.put(0, 1); bw.put(1, 1); bw.put(0, 1);   // top_field_first, frame_pred_frame_dct, concealment_mv
         bw.put(h.q_scale_type, 1); bw.put(1, 1); bw.put(h.alt_scan, 1);   // intra_vlc_format = 1
         bw.put(0, 1); bw.put(p.chroma_format == 1 ? 1 : 0, 1); bw.put(1, 1); bw.put(0, 1);
+        if (p.matrices_once && gop_tx_valid) {      // no extension: the matrices of the GOP's first picture stay in force
+            for (int k = 0; k < 4; k++) {
+                memcpy(pic.tx[k], gop_tx[k], 64);
+                pic.tx_loaded[k] = 0;
+                build_scan_indexed_matrix(pic.tx[k], h.alt_scan, pic.params.W[k]);
+            }
+            return;
+        }
         bw.start_code(0xB5);                        // quant_matrix_extension, in EVERY picture
         bw.put(3, 4);
         const int nload = p.chroma_format == 1 ? 2 : 4;
@@ -154,12 +172,18 @@ struct mp2v_gen {
             if (!load) continue;
             for (int i = 0; i < 64; i++) {
                 int v;
-                if (p.mode == 1) v = (k & 1) ? 16 : kDefaultIntra[scan_tables().shuffle[0][i]];
+                if (p.mode >= 1) v = (k & 1) ? 16 : kDefaultIntra[scan_tables().shuffle[0][i]];
                 else v = rng.range(8, 80);
                 pic.tx[k][i] = (uint8_t)v;
                 bw.put(v, 8);
             }
             build_scan_indexed_matrix(pic.tx[k], h.alt_scan, pic.params.W[k]);
+        }
+        if (p.matrices_once) {
+            // 4:2:0 loads two matrices: the chroma pair follows the luminance pair (6.3.11)
+            for (int k = nload; k < 4; k++) { memcpy(pic.tx[k], pic.tx[k - 2], 64); build_scan_indexed_matrix(pic.tx[k], h.alt_scan, pic.params.W[k]); }
+            memcpy(gop_tx, pic.tx, sizeof(gop_tx));
+            gop_tx_valid = true;
         }
     }
 
@@ -236,6 +260,298 @@ struct mp2v_gen {
             pic.coef.push_back(MP2V_COEF(1, 0, b, MP2V_COEF_FIRST));
         }
         bw.put(intra ? kEobB15 : kEobB14);
+    }
+
+    // ------------------------------------------------------------------ mode 2: texture content
+    // A translating procedural texture plus per-frame noise is ENCODED: forward DCT of the source (intra) or of
+    // the motion-compensated difference against the SOURCE reference frames (open loop: the decoder drifts by the
+    // quantisation error, which is irrelevant here), quantised at quantiser_scale 4..8 with the default matrices.
+    // Everything is integer arithmetic, so a seed gives the same stream on every machine.
+    struct frame_t { int w[3], h[3]; std::vector<uint8_t> px[3]; };
+    struct wave_t { int fx, fy, phase, amp; };
+    wave_t waves[3][4];
+    int gvx = 0, gvy = 0;                      // global motion, luma half-pels per frame
+    frame_t ref_src[2];                        // source frames of the two live references (older, newer)
+    int ref_time[2] = {0, 0};
+    frame_t cur_src;
+
+    static int psin(int p) {                   // parabolic sine, period 1024, amplitude 1024
+        const int q = p & 511;
+        const int y = (q * (512 - q)) >> 6;
+        return (p & 512) ? -y : y;
+    }
+    void texture_setup() {
+        gvx = rng.range(-5, 5); gvy = rng.range(-3, 3);
+        if (gvx == 0 && gvy == 0) gvx = 3;
+        static const int period[4] = {220, 46, 11, 6};      // pixels
+        static const int amp[3][4] = {{38, 20, 9, 5}, {22, 10, 4, 0}, {22, 10, 4, 0}};
+        for (int pl = 0; pl < 3; pl++)
+            for (int i = 0; i < 4; i++) {
+                // phase advance per HALF-pel step so that one period spans period[i] pixels, split over x and y
+                const int f = 1024 / (2 * period[i]) + 1;
+                const int a = rng.range(0, f);
+                waves[pl][i] = {rng.pct(50) ? a : -a, rng.pct(50) ? f - a : a - f, rng.below(1024), amp[pl][i]};
+            }
+    }
+    static uint32_t hash32(uint64_t x) {
+        x ^= x >> 33; x *= 0xff51afd7ed558ccdull; x ^= x >> 33; x *= 0xc4ceb9fe1a85ec53ull; x ^= x >> 33;
+        return (uint32_t)x;
+    }
+    // source picture at display time t: plane sample (x, y) looks at texture position (sx * x + t * gv) in luma half-pels
+    void synth_frame(int t, frame_t& f) {
+        const int noise = p.texture_noise > 0 ? p.texture_noise : 3;
+        for (int pl = 0; pl < 3; pl++) {
+            const int w = pl == 0 ? p.width : (p.chroma_format == 3 ? p.width : p.width / 2);
+            const int h = pl == 0 ? p.height : (p.chroma_format == 1 ? p.height / 2 : p.height);
+            const int sx = 2 * p.width / w, sy = 2 * p.height / h;      // luma half-pels per sample of this plane
+            f.w[pl] = w; f.h[pl] = h;
+            f.px[pl].resize((size_t)w * h);
+            for (int y = 0; y < h; y++) {
+                const int Y = sy * y + t * gvy;
+                for (int x = 0; x < w; x++) {
+                    const int X = sx * x + t * gvx;
+                    int v = 0;
+                    for (int i = 0; i < 4; i++) { const wave_t& q = waves[pl][i]; v += q.amp * psin(q.fx * X + q.fy * Y + q.phase); }
+                    const uint32_t hsh = hash32(((uint64_t)p.seed << 40) ^ ((uint64_t)(t & 0xfff) << 28) ^ ((uint64_t)pl << 26) ^ ((uint64_t)y << 13) ^ (uint64_t)x);
+                    v = 128 + (v >> 10) + (int)(hsh % (uint32_t)(2 * noise + 1)) - noise;
+                    f.px[pl][(size_t)y * w + x] = (uint8_t)(v < 0 ? 0 : v > 255 ? 255 : v);
+                }
+            }
+        }
+    }
+    // forward 8x8 DCT (ISO/IEC 13818-2 Annex A normalisation), 14-bit fixed-point basis, out[v * 8 + u]
+    static void fdct8x8(const int in[64], int out[64]) {
+        static const int c16[9] = {16384, 16069, 15137, 13623, 11585, 9102, 6270, 3196, 0};      // 2^14 cos(k pi / 16)
+        auto cosi = [&](int i) { i &= 31; if (i > 16) i = 32 - i; return i <= 8 ? c16[i] : -c16[16 - i]; };
+        long long tmp[64];
+        for (int y = 0; y < 8; y++)
+            for (int u = 0; u < 8; u++) {
+                long long acc = 0;
+                for (int x = 0; x < 8; x++) acc += (long long)in[y * 8 + x] * (u ? cosi((2 * x + 1) * u) : 11585);
+                tmp[y * 8 + u] = acc;                                   // scale 2^14 (x C(u) with C(0) = 1/sqrt 2)
+            }
+        for (int u = 0; u < 8; u++)
+            for (int v = 0; v < 8; v++) {
+                long long acc = 0;
+                for (int y = 0; y < 8; y++) acc += tmp[y * 8 + u] * (v ? cosi((2 * y + 1) * v) : 11585);
+                out[v * 8 + u] = (int)((acc + (1ll << 29)) >> 30);      // / 2^28 for the two bases, / 4 for the 2/N factors
+            }
+    }
+    // half-pel prediction of a w x h block from a source reference plane, the reference decoder's arithmetic (mc_c.hpp:3-17)
+    static void predict_block(const frame_t& ref, int pl, int x0, int y0, int hx, int hy, int w, int h, int* out /* w*h */) {
+        const int W = ref.w[pl];
+        const uint8_t* px = ref.px[pl].data();
+        auto avg = [](int a, int b) { return (a + b + 1) >> 1; };
+        for (int y = 0; y < h; y++)
+            for (int x = 0; x < w; x++) {
+                const uint8_t* q = px + (size_t)(y0 + y) * W + x0 + x;
+                int v = q[0];
+                if (hx && !hy) v = avg(q[0], q[1]);
+                else if (!hx && hy) v = avg(q[0], q[W]);
+                else if (hx && hy) v = avg(avg(q[0], q[1]), avg(q[W], q[W + 1]));
+                out[y * w + x] = v;
+            }
+    }
+    // residual (or intra samples) of block b of macroblock (mbx, mby) -> quantised levels in SCAN order; returns true when any is non-zero.
+    // dc_out: intra only, the quantised DC (dct_dc as transmitted at this precision)
+    bool quantise_block(const picture_t& pic, int b, int mbx, int mby, bool intra, const int* pred_y, const int* pred_c[2], int alt, int dc_prec, int qs,
+                        int levels[64], int* dc_out) {
+        const int cf = p.chroma_format;
+        int pl, bx, by;                                                    // plane and pixel origin of the block (mb_decoder.cpp:177-195)
+        const int cw = cf == 3 ? 16 : 8;
+        if (b < 4) { pl = 0; bx = mbx * 16 + 8 * (b & 1); by = mby * 16 + 8 * (b >> 1); }
+        else {
+            pl = 1 + (b & 1);
+            const int k = (b - 4) >> 1;                                    // 0; 4:2:2 1 = lower; 4:4:4 2,3 = right column
+            bx = mbx * cw + (cf == 3 ? 8 * (k >> 1) : 0);
+            by = mby * (cf == 1 ? 8 : 16) + 8 * (k & 1);
+        }
+        const int W = cur_src.w[pl];
+        int blk[64], F[64];
+        for (int y = 0; y < 8; y++)
+            for (int x = 0; x < 8; x++) {
+                int v = cur_src.px[pl][(size_t)(by + y) * W + bx + x];
+                if (!intra) {
+                    if (pl == 0) v -= pred_y[(by - mby * 16 + y) * 16 + (bx - mbx * 16 + x)];
+                    else v -= pred_c[pl - 1][(by - mby * (cf == 1 ? 8 : 16) + y) * cw + (bx - mbx * cw + x)];
+                }
+                blk[y * 8 + x] = v;
+            }
+        fdct8x8(blk, F);
+        const scan_tables_t& st = scan_tables();
+        const uint8_t* Wq = pic.params.W[(b < 6 ? 0 : 2) + (intra ? 0 : 1)];   // the reference's matrix choice (blocks 4, 5 use the luminance pair)
+        bool any = false;
+        for (int i = 0; i < 64; i++) {
+            const int f = F[st.shuffle[alt][i]];
+            const int a = f < 0 ? -f : f;
+            int q;
+            if (intra && i == 0) {
+                const int mult = 8 >> dc_prec;
+                int dc = (F[0] + mult / 2) / mult;
+                const int maxdc = (1 << (8 + dc_prec)) - 1;
+                *dc_out = dc < 0 ? 0 : dc > maxdc ? maxdc : dc;
+                levels[0] = 0;
+                continue;
+            }
+            const int step16 = Wq[i] * qs;                                 // 16 x the reconstruction step
+            if (intra) q = (16 * a + (step16 * 3) / 8) / step16;           // (level * W * qs) >> 4 with a small dead zone
+            else q = (16 * a) / step16;                                    // ((2 level + 1) * W * qs) >> 5: centre of the cell
+            if (q > 2047) q = 2047;
+            levels[i] = f < 0 ? -q : q;
+            any = any || q != 0;
+        }
+        return any || intra;
+    }
+    // VLC-code one block from its quantised levels (scan order) and append the ground-truth records
+    void emit_block(picture_t& pic, int b, bool intra, int dc_prec, int dc, const int levels[64]) {
+        int i = 0;
+        if (intra) {
+            const int comp = b < 4 ? 0 : 1 + (b & 1);
+            const int diff = dc - dc_pred[comp];
+            dc_pred[comp] = dc;
+            int size = 0;
+            for (int a = diff < 0 ? -diff : diff; a; a >>= 1) size++;
+            bw.put(enc().dcsize[comp ? 1 : 0][size]);
+            if (size) bw.put((uint32_t)(diff > 0 ? diff : diff + (1 << size) - 1), size);
+            pic.coef.push_back(MP2V_COEF((int16_t)(uint16_t)((uint32_t)dc << (3 - dc_prec)), 0, b, MP2V_COEF_RAW));
+            i = 1;
+        }
+        int run = 0;
+        bool first = !intra;
+        for (; i < 64; i++) {
+            const int level = levels[i];
+            if (!level) { run++; continue; }
+            if (first && i == 0 && (level == 1 || level == -1)) {          // B.14 note 3: "1s"
+                bw.put("1"); bw.put(level < 0, 1);
+                pic.coef.push_back(MP2V_COEF(level, 0, b, MP2V_COEF_FIRST));
+            } else {
+                put_run_level(intra, run, level);
+                pic.coef.push_back(MP2V_COEF(level, i, b, 0));
+            }
+            first = false;
+            run = 0;
+        }
+        bw.put(intra ? kEobB15 : kEobB14);
+    }
+
+    void code_picture_texture(const pic_hdr_t& h, picture_t& pic, int t) {
+        const bool big = p.height > 2800;
+        const int cf = p.chroma_format, cw = cf == 3 ? 16 : 8, ch = cf == 1 ? 8 : 16;
+        // motion of this picture against its references: content moves gv per frame, so the matching block of a
+        // reference shown at time tr lies (t - tr) * gv half-pels away
+        int gmv[2][2] = {{0, 0}, {0, 0}};
+        if (h.type == 2) { gmv[0][0] = (t - ref_time[1]) * gvx; gmv[0][1] = (t - ref_time[1]) * gvy; }
+        if (h.type == 3) {
+            gmv[0][0] = (t - ref_time[0]) * gvx; gmv[0][1] = (t - ref_time[0]) * gvy;
+            gmv[1][0] = (t - ref_time[1]) * gvx; gmv[1][1] = (t - ref_time[1]) * gvy;
+        }
+        std::vector<int> py(256), pcb(16 * 16), pcr(16 * 16), tmp(256);
+        for (int mby = 0; mby < mbh; mby++) {
+            bw.start_code(big ? (mby & 127) + 1 : mby + 1);
+            if (big) bw.put(mby >> 7, 3);
+            qcode = h.q_scale_type ? rng.range(4, 8) : rng.range(2, 4);    // quantiser_scale 4 .. 8 with either mapping (decoder.cpp:140-145)
+            qscale = quantiser_scale_of(qcode, h.q_scale_type);
+            bw.put(qcode, 5); bw.put(0, 1);
+            memset(pmv, 0, sizeof(pmv));
+            for (int c = 0; c < 3; c++) dc_pred[c] = 1 << (h.dc_prec + 7);
+            prev_flags = 0;
+            int pending_skips = 0;
+            for (int mbx = 0; mbx < mbw; mbx++) {
+                mp2v_mb_info_t rec{};
+                rec.coef_off = (uint32_t)pic.coef.size();
+                const bool edge = mbx == 0 || mbx == mbw - 1;
+                // ---- prediction mode: the global vector(s) where the window stays inside the frame, intra otherwise
+                bool fwd = false, bwd = false;
+                if (h.type == 2) fwd = window_ok(mbx, mby, gmv[0][0], gmv[0][1]);
+                if (h.type == 3) {
+                    const bool okf = window_ok(mbx, mby, gmv[0][0], gmv[0][1]), okb = window_ok(mbx, mby, gmv[1][0], gmv[1][1]);
+                    const int d = (int)(hash32(((uint64_t)p.seed << 32) ^ ((uint64_t)pics.size() << 20) ^ (uint64_t)(mby * mbw + mbx)) % 10u);
+                    fwd = okf && d < 7;                                    // 30 % forward, 40 % both, 30 % backward
+                    bwd = okb && d >= 3;
+                    if (!fwd && !bwd) { fwd = okf; bwd = !okf && okb; }    // whichever window stays inside the frame
+                }
+                bool intra = h.type == 1 || (!fwd && !bwd) || (int)(hash32(((uint64_t)p.seed << 33) ^ ((uint64_t)pics.size() << 21) ^ (uint64_t)(mby * mbw + mbx) ^ 0x5bd1e995u) % 100u) < p.pct_intra_in_pb;
+                if (intra) fwd = bwd = false;
+                int mv[2][2] = {{0, 0}, {0, 0}};
+                const int* pc[2] = {pcb.data(), pcr.data()};
+                if (!intra) {
+                    bool have = false;
+                    for (int s2 = 0; s2 < 2; s2++) {
+                        if (!(s2 ? bwd : fwd)) continue;
+                        mv[s2][0] = gmv[s2][0]; mv[s2][1] = gmv[s2][1];
+                        const frame_t& ref = h.type == 2 ? ref_src[1] : ref_src[s2];
+                        const int cx = cf < 3 ? mv[s2][0] >> 1 : mv[s2][0], cy = cf < 2 ? mv[s2][1] >> 1 : mv[s2][1];   // floor (mb_decoder.cpp:198-206)
+                        for (int pl = 0; pl < 3; pl++) {
+                            const int w = pl ? cw : 16, hh = pl ? ch : 16, vx = pl ? cx : mv[s2][0], vy = pl ? cy : mv[s2][1];
+                            int* dst = pl == 0 ? py.data() : pl == 1 ? pcb.data() : pcr.data();
+                            predict_block(ref, pl, mbx * w + (vx >> 1), mby * hh + (vy >> 1), vx & 1, vy & 1, w, hh, have ? tmp.data() : dst);
+                            if (have) for (int k = 0; k < w * hh; k++) dst[k] = (tmp[k] + dst[k] + 1) >> 1;    // avg(backward, forward), mb_decoder.cpp:240-249
+                        }
+                        have = true;
+                    }
+                }
+                // ---- transform + quantise every block
+                int lv[12][64], dcq[12];
+                uint32_t cbp = 0;
+                for (int b = 0; b < nblk; b++)
+                    if (quantise_block(pic, b, mbx, mby, intra, py.data(), pc, h.alt_scan, h.dc_prec, qscale, lv[b], &dcq[b])) cbp |= 1u << b;
+                if (!intra && cf == 1 && cbp && (cbp & 63) == 0) cbp = 0;  // (cannot happen for 4:2:0; keeps the 4:2:0 pattern code valid)
+                // ---- skipped?  P: zero vector and nothing coded; B: same prediction as the previous macroblock and nothing coded
+                if (!intra && cbp == 0 && !edge) {
+                    bool skip = false;
+                    if (h.type == 2) skip = mv[0][0] == 0 && mv[0][1] == 0;
+                    else {
+                        const uint32_t fl = (fwd ? MP2V_MB_FWD : 0u) | (bwd ? MP2V_MB_BWD : 0u);
+                        skip = (prev_flags & (MP2V_MB_FWD | MP2V_MB_BWD)) == fl && !(prev_flags & MP2V_MB_INTRA) && prev_flags != 0;
+                        for (int s2 = 0; s2 < 2 && skip; s2++) if ((s2 ? bwd : fwd) && (pmv[s2][0] != mv[s2][0] || pmv[s2][1] != mv[s2][1])) skip = false;
+                    }
+                    if (skip) {
+                        const uint32_t fl = h.type == 2 ? MP2V_MB_FWD : (prev_flags & (MP2V_MB_FWD | MP2V_MB_BWD));
+                        if (h.type == 2) memset(pmv, 0, sizeof(pmv));      // mb_decoder.cpp:542-543
+                        rec.bits = MP2V_MB_BITS(0, qscale, 0, fl);
+                        for (int s2 = 0; s2 < 2; s2++) for (int k = 0; k < 2; k++) rec.mv[s2][k] = (int16_t)((fl & (s2 ? MP2V_MB_BWD : MP2V_MB_FWD)) ? mv[s2][k] : 0);
+                        pic.mb.push_back(rec);
+                        pending_skips++;
+                        continue;
+                    }
+                }
+                // ---- coded macroblock
+                int inc = pending_skips + 1;
+                const bool had_skips = pending_skips > 0;
+                pending_skips = 0;
+                while (inc > 33) { bw.put(enc().mba_escape); inc -= 33; }
+                bw.put(enc().mba[inc]);
+                const bool pattern = !intra && cbp != 0;
+                if (h.type == 2 && !intra && !pattern) fwd = true;         // "MC, not coded"
+                uint32_t type = intra ? 0x02 : (fwd ? 0x10 : 0) | (bwd ? 0x08 : 0) | (pattern ? 0x04 : 0);
+                bw.put(enc().mbtype[h.type][type]);
+                for (int s2 = 0; s2 < 2; s2++) {
+                    if (!(s2 ? bwd : fwd)) continue;
+                    put_mv_component(mv[s2][0], pmv[s2][0], h.f_code[s2][0]);
+                    put_mv_component(mv[s2][1], pmv[s2][1], h.f_code[s2][1]);
+                }
+                if (intra) memset(pmv, 0, sizeof(pmv));                    // mb_decoder.cpp:599-603
+                if (had_skips || !intra) for (int c = 0; c < 3; c++) dc_pred[c] = 1 << (h.dc_prec + 7);   // mb_decoder.cpp:623-626
+                if (intra) cbp = (1u << nblk) - 1;
+                else if (pattern) {
+                    uint32_t c420 = 0;
+                    for (int i = 0; i < 6; i++) if (cbp & (1u << i)) c420 |= 1u << (5 - i);
+                    bw.put(enc().cbp[c420]);
+                    if (cf == 2) bw.put((cbp >> 6 & 1) << 1 | (cbp >> 7 & 1), 2);
+                    if (cf == 3) for (int i = 6; i < 12; i++) bw.put((cbp >> i) & 1, 1);
+                }
+                for (int b = 0; b < nblk; b++) if (cbp & (1u << b)) emit_block(pic, b, intra, h.dc_prec, dcq[b], lv[b]);
+                uint32_t fl = intra ? MP2V_MB_INTRA : (fwd ? MP2V_MB_FWD : 0u) | (bwd ? MP2V_MB_BWD : 0u);
+                if (!intra) for (int s2 = 0; s2 < 2; s2++) for (int k = 0; k < 2; k++) rec.mv[s2][k] = (int16_t)mv[s2][k];
+                rec.bits = MP2V_MB_BITS(pic.coef.size() - rec.coef_off, qscale, cbp, fl);
+                pic.mb.push_back(rec);
+                prev_flags = fl;
+            }
+        }
+        pic.params.n_coef = (uint32_t)pic.coef.size();
+        if (getenv("MP2V_GEN_DEBUG"))
+            fprintf(stderr, "[gen] picture %zu type %d t %d gv (%d,%d) fwd mv (%d,%d) bwd mv (%d,%d) ref times %d %d: %u coefficients\n", pics.size() - 1, h.type, t, gvx, gvy,
+                    gmv[0][0], gmv[0][1], gmv[1][0], gmv[1][1], ref_time[0], ref_time[1], pic.params.n_coef);
     }
 
     // ------------------------------------------------------------------ motion vectors
@@ -387,12 +703,14 @@ struct mp2v_gen {
         }
         mbw = p.width / 16; mbh = p.height / 16;
         nblk = p.chroma_format == 1 ? 6 : p.chroma_format == 2 ? 8 : 12;
+        if (p.mode == 2) texture_setup();
         int display_base = 0;
         for (int g = 0; g < p.n_gops; g++) {
             bw.align();
             gop_off.push_back(bw.bytes.size());
             sequence_header();
             gop_header(1);
+            gop_tx_valid = false;                   // a sequence header resets the matrices
             // display positions of the references of this closed GOP: 0, m, 2m, ... and the last picture
             std::vector<int> refs;
             if (p.intra_only || p.gop_m == 1) for (int d = 0; d < p.gop_n; d++) refs.push_back(d);
@@ -413,6 +731,11 @@ struct mp2v_gen {
                     h.dc_prec = p.intra_dc_precision < 0 ? rng.below(4) : p.intra_dc_precision;
                     int need = 1;                           // smallest f_code covering +-(2*mv_range+1) half-pels
                     while ((16 << (need - 1)) <= 2 * p.mv_range + 1) need++;
+                    if (p.mode == 2) {                      // ... or the global motion over the longest reference distance
+                        const int far = (gvx < 0 ? -gvx : gvx) > (gvy < 0 ? -gvy : gvy) ? (gvx < 0 ? -gvx : gvx) : (gvy < 0 ? -gvy : gvy);
+                        need = 1;
+                        while ((16 << (need - 1)) <= far * (p.gop_m > p.gop_n ? p.gop_n : p.gop_m) + 1) need++;
+                    }
                     for (int s = 0; s < 2; s++) for (int t = 0; t < 2; t++) {
                         const bool used = (h.type == 2 && s == 0) || h.type == 3;
                         int fc = need + rng.below(3);
@@ -429,7 +752,14 @@ struct mp2v_gen {
                     pic.params.l0_frame = h.type == 2 ? prev_ref_coded : h.type == 3 ? prev_prev_ref_coded : -1;
                     pic.params.l1_frame = h.type == 3 ? prev_ref_coded : -1;
                     picture_headers(h, pic);
-                    code_picture(h, pic);
+                    if (p.mode == 2) {
+                        const int t = display_base + disp;
+                        synth_frame(t, cur_src);
+                        code_picture_texture(h, pic, t);
+                        if (is_ref) { std::swap(ref_src[0], ref_src[1]); std::swap(ref_src[1], cur_src); ref_time[0] = ref_time[1]; ref_time[1] = t; }
+                    } else {
+                        code_picture(h, pic);
+                    }
                     if (is_ref) { prev_prev_ref_coded = prev_ref_coded; prev_ref_coded = coded; }
                 }
             }

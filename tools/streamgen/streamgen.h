@@ -27,7 +27,8 @@ typedef struct mp2v_gen_params {
     int32_t  gop_m;                /* distance between references; 1 = no B pictures               */
     int32_t  intra_only;           /* every picture is an I picture                                  */
     uint64_t seed;
-    int32_t  mode;                 /* 0 fuzz (random syntax), 1 natural-like (decaying spectra)     */
+    int32_t  mode;                 /* 0 fuzz (random syntax), 1 statistical (decaying run/level spectra), 2 texture: a translating
+                                      procedural texture + noise, really encoded (forward DCT, quantiser_scale 4..8, global motion) */
     int32_t  mv_range;             /* max |integer luma displacement| in pixels                    */
     int32_t  qscale_code_max;      /* quantiser_scale_code drawn from 1..this (<= 31)              */
     int32_t  alternate_scan;       /* 0 / 1 fixed, -1 random per picture                            */
@@ -41,7 +42,10 @@ typedef struct mp2v_gen_params {
     int32_t  all_blocks_coded;     /* cbp = all ones whenever pattern is present                   */
     int32_t  natural_mean_coefs;   /* mode 1: mean number of AC coefficients per coded block (0 = 2.6) */
     int32_t  unclamped_mv;         /* 1: vectors may leave the frame (invalid streams for error-path tests) */
-    int32_t  reserved[2];
+    int32_t  user_data_bytes;      /* > 0: a user_data() of this many bytes follows every sequence_extension (the reference collects them, decoder.cpp:194-200) */
+    int32_t  texture_noise;        /* mode 2: per-frame noise amplitude (+-n grey levels, 0 = 3): sets the bit rate */
+    int32_t  matrices_once;        /* 1: quant_matrix_extension only in the first picture of every GOP; later pictures keep those matrices
+                                      (ISO/IEC 13818-2 6.3.11).  OUTSIDE the reference's envelope: it needs the extension in every picture */
 } mp2v_gen_params_t;
 
 typedef struct mp2v_gen mp2v_gen_t;
