@@ -161,6 +161,10 @@ typedef struct mp2v_recon_config {
                                       copies overlap later launches; mp2v_recon_map_frame then only
                                       waits for that copy (for decoders that show every frame)     */
 
+#define MP2V_RECON_THROUGHPUT 8    /* launch in full lots from the first picture on.  By default the lot size ramps up
+                                      (1, 2, 4, ... pictures) after every sync so that the first frames of a decode leave
+                                      early; consumers that only care about the rate (frames staying on the device) set this */
+
 typedef struct mp2v_recon mp2v_recon_t;
 
 /* frame geometry: the reference's frame_c rule (decoder.cpp:44-66) */
@@ -183,7 +187,8 @@ MP2V_API int  mp2v_recon_release_picture(mp2v_recon_t* ctx, mp2v_picture_t* pic)
 
 /* Queue one filled picture: H2D of its records + reconstruction.  Pictures must be submitted in
  * coded order (references before the pictures that use them).  Asynchronous; consecutive
- * submissions that do not depend on one another are fused into one launch. */
+ * submissions that do not depend on one another are fused into one launch, and launches are issued once
+ * max_batch pictures are queued (or by flush / sync / a wait for one of their frames). */
 MP2V_API int  mp2v_recon_submit(mp2v_recon_t* ctx, mp2v_picture_t* pic);
 /* Optional: run submit's record validation + byte accounting now, from any thread, without taking the
  * context lock (the picture still belongs to the caller); submit then skips it. */
@@ -221,6 +226,24 @@ MP2V_API int  mp2v_recon_submit_slices(mp2v_recon_t* ctx, mp2v_picture_t* pic, c
 MP2V_API int  mp2v_recon_stage_slices(mp2v_recon_t* ctx, mp2v_picture_t* pic, const mp2v_pic_syntax_t* syntax,
                                       const mp2v_slice_ref_t* slices, int n_slices);
 MP2V_API int  mp2v_recon_submit_staged(mp2v_recon_t* ctx, mp2v_picture_t* pic);
+
+/* ---- stream-resident front end (contexts created with MP2V_RECON_DEVICE_VLC) ------------------
+ * For callers that hold a whole elementary stream (the reference's decode(buffer, len), decoder.h:100): the stream is
+ * copied to the device ONCE, a kernel lists its start codes -- the reference's scan_start_codes (start_codes_search.hpp:7-26)
+ * -- and pictures are then handed over as byte offsets of their slices' start codes in that resident copy.  No byte of
+ * the stream is touched by the host besides the headers it parses, there is no per-picture staging copy, and one kernel
+ * launch parses the slices of every picture handed over since the previous launch.
+ *   stream_begin   copies data[0, bytes) (or only the given ranges of it: the other devices of a GOP-sharded decode) and,
+ *                  when `scan` is set, returns the ascending byte offsets of every 00 00 01 prefix (host memory owned by
+ *                  the context, valid until the next stream_begin).  `data` must stay valid until the pictures of this
+ *                  stream have been submitted (slice start codes are validated from it).  Pass page-locked memory for the
+ *                  full copy rate.  Waits for the device parses of the previous stream.
+ *   submit_stream_picture   like mp2v_recon_submit_slices with the slices named by offset; asynchronous, coded order. */
+typedef struct mp2v_byte_range { size_t offset, bytes; } mp2v_byte_range_t;
+MP2V_API int  mp2v_recon_stream_begin(mp2v_recon_t* ctx, const uint8_t* data, size_t bytes, const mp2v_byte_range_t* ranges, int n_ranges,
+                                      int scan, const uint32_t** codes, uint32_t* n_codes);
+MP2V_API int  mp2v_recon_submit_stream_picture(mp2v_recon_t* ctx, mp2v_picture_t* pic, const mp2v_pic_syntax_t* syntax,
+                                               const uint32_t* slice_offsets, int n_slices);
 
 MP2V_API int  mp2v_recon_flush(mp2v_recon_t* ctx);               /* launch whatever is queued       */
 MP2V_API int  mp2v_recon_sync(mp2v_recon_t* ctx);                /* flush + wait for the device     */
@@ -266,7 +289,8 @@ typedef struct mp2v_recon_stats {
     uint64_t algorithmic_bytes;    /* OUT + REF + COEF(128 B/coded block) + META   */
     double   kernel_ms;            /* CUDA-event time of the reconstruction launches (when
                                       timing is enabled)                                          */
-    uint64_t vlc_launches;         /* slice parser kernel launches (one per picture)              */
+    uint64_t vlc_launches;         /* slice parser kernel launches (one per picture handed over with submit_slices / submit_staged,
+                                      one per batch of pictures handed over with submit_stream_picture) */
     uint64_t vlc_slices;           /* slices handed to the device parser                          */
     uint64_t vlc_coefs;            /* coefficient records it wrote (parses completed so far)      */
 } mp2v_recon_stats_t;

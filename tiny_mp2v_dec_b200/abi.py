@@ -67,4 +67,5 @@ class SliceRef(C.Structure):
 RECON_VALIDATE = 1
 RECON_DEVICE_VLC = 2
 RECON_AUTO_DOWNLOAD = 4
+RECON_THROUGHPUT = 8
 OK, ERR_ARG, ERR_CUDA, ERR_NOMEM, ERR_STATE, ERR_RANGE = 0, -1, -2, -3, -4, -5

@@ -81,6 +81,8 @@ struct shared_t {
     mp2v_b200_options_t opt;
     std::function<void(frame_c*)> renderer;
     int mbw = 0, mbh = 0;
+    bool stream_mode = false;                // the stream is resident on the device(s): pictures are handed over as slice offsets
+    const uint8_t* stream_base = nullptr;
     // work distribution: pictures whose slices may be claimed (an atomic index per picture); workers
     // only take the lock to move on to the next picture or to sleep
     std::mutex qmu;
@@ -118,6 +120,7 @@ struct pipeline_t {
     std::condition_variable cv;
     int in_parse = 0;                        // acquired, not yet submitted
     int next_submit = 0;
+    int frame_cursor = 0;                    // next-fit: consecutive pictures get consecutive frame ids, so their copies to the host merge
     std::thread feeder_thread, output_thread;
 
     void feeder();
@@ -142,6 +145,7 @@ void shared_t::fail(const std::string& why) {
 
 void pipeline_t::feeder() {
     int refs[2] = {-1, -1};   // local task indices of the two live references
+    std::vector<uint32_t> slice_offsets;
     auto unref = [&](int k) { if (k >= 0) release_frame_use(tasks[k].dst); };
     for (size_t k = 0; k < tasks.size() && !sh->failed.load(); k++) {
         pic_task_t& t = tasks[k];
@@ -153,11 +157,12 @@ void pipeline_t::feeder() {
             cv.wait(lk, [&] {
                 if (sh->failed.load()) return true;
                 if (in_parse >= parse_window) return false;
-                for (int i = 0; i < n_frames; i++) if (frame_use[i] == 0) { f = i; return true; }
+                for (int i = 0; i < n_frames; i++) { const int c = (frame_cursor + i) % n_frames; if (frame_use[c] == 0) { f = c; return true; } }
                 return false;
             });
             if (sh->failed.load()) break;
             t.dst = f;
+            frame_cursor = (f + 1) % n_frames;
             frame_use[f] = 1;               // awaiting display
             in_parse++;
         }
@@ -181,6 +186,31 @@ void pipeline_t::feeder() {
         pp.picture_coding_type = info.picture_coding_type;
         pp.alternate_scan = info.alternate_scan;
         pp.dst_frame = t.dst; pp.l0_frame = t.l0; pp.l1_frame = t.l1;
+        if (sh->stream_mode) {
+            // stream-resident device parsing: the coded bytes are already on the device; the picture is its slices' offsets
+            if (!picture_in_envelope(info)) { sh->fail("only progressive frame pictures with frame prediction are supported (the reference's envelope)"); break; }
+            mp2v_pic_syntax_t sy{};
+            for (int a = 0; a < 2; a++) for (int b = 0; b < 2; b++) sy.f_code[a][b] = info.f_code[a][b];
+            sy.intra_dc_precision = info.intra_dc_precision;
+            sy.q_scale_type = info.q_scale_type;
+            sy.intra_vlc_format = info.intra_vlc_format;
+            slice_offsets.clear();
+            for (const slice_ref_t& sr : t.src->slices) slice_offsets.push_back((uint32_t)(sr.payload - 4 - sh->stream_base));
+            if (mp2v_recon_submit_stream_picture(recon, t.rp, &sy, slice_offsets.data(), (int)slice_offsets.size()) != MP2V_OK) {
+                sh->fail(std::string("picture ") + std::to_string(k) + ": " + mp2v_recon_last_error(recon));
+                break;
+            }
+            t.ts_queued = t.ts_submitted = sh->now_ms();
+            {
+                std::lock_guard<std::mutex> lk(mu);
+                t.parsed = t.submitted = true;
+                next_submit = (int)k + 1;
+                in_parse--;
+            }
+            cv.notify_all();
+            sh->feeder_work_ns.fetch_add(std::chrono::duration_cast<std::chrono::nanoseconds>(clock_t_::now() - tf1).count(), std::memory_order_relaxed);
+            continue;
+        }
         if (sh->opt.gpu_vlc) {
             // device-side parsing: a worker stages the coded slices (one job per picture), submission stays in coded order
             if (!picture_in_envelope(info)) { sh->fail("only progressive frame pictures with frame prediction are supported (the reference's envelope)"); break; }
@@ -387,11 +417,11 @@ struct mp2v_decoder_c::impl_t {
         }
     }
     bool prepare(bool gpu_vlc);
-    bool device_parser_can_take(const stream_index_t& index) const;
+    bool device_parser_can_take(const stream_index_t& index, bool staged) const;
 };
 
 // mp2v_recon_submit_slices' envelope: at most one slice per macroblock row, coded picture within the staging capacity
-bool mp2v_decoder_c::impl_t::device_parser_can_take(const stream_index_t& index) const {
+bool mp2v_decoder_c::impl_t::device_parser_can_take(const stream_index_t& index, bool staged) const {
     const int mbh = cfg.height / 16;
     const size_t cap = std::max<size_t>(2u << 20, (size_t)(cfg.width / 16) * mbh * 128u);   // the library's default bitstream_capacity
     std::vector<uint8_t> seen((size_t)mbh);
@@ -410,7 +440,7 @@ bool mp2v_decoder_c::impl_t::device_parser_can_take(const stream_index_t& index)
             lo = std::min(lo, sl.payload);
             hi = std::max(hi, sl.payload + sl.bytes);
         }
-        if ((size_t)(hi - lo) + 64 > cap) return false;
+        if (staged && (size_t)(hi - lo) + 64 > cap) return false;      // (a resident stream needs no staging capacity)
     }
     return true;
 }
@@ -435,7 +465,9 @@ bool mp2v_decoder_c::impl_t::prepare(bool gpu_vlc) {
         if (d.n_slots < 6) d.n_slots = 6;
         // a slice parses at the speed of one GPU thread: throughput comes from the number of pictures in flight
         if (gpu_vlc) {
-            int slots = 48, extra_frames = 40;
+            // ... about 128 pictures of 1080p, fewer of larger ones (a slot's worst-case coefficient arena is 1.5 KiB per macroblock)
+            int slots = (int)std::min<int64_t>(128, std::max<int64_t>(24, 128ll * 8160 / ((int64_t)mbw * mbh)));
+            int extra_frames = slots;
             if (const char* v = getenv("MP2V_VLC_SLOTS")) slots = atoi(v) > 0 ? atoi(v) : slots;             // dev knobs
             if (const char* v = getenv("MP2V_VLC_FRAMES")) extra_frames = atoi(v) > 0 ? atoi(v) : extra_frames;
             d.n_frames += extra_frames;
@@ -443,7 +475,9 @@ bool mp2v_decoder_c::impl_t::prepare(bool gpu_vlc) {
         }
         mp2v_recon_config_t rc{};
         rc.device = id; rc.width = c.width; rc.height = c.height; rc.chroma_format = c.chroma_format;
-        rc.n_frames = d.n_frames; rc.n_pictures = d.n_slots; rc.max_batch = opt.max_batch; rc.flags = MP2V_RECON_VALIDATE | (gpu_vlc ? MP2V_RECON_DEVICE_VLC : 0) | (opt.download_frames ? MP2V_RECON_AUTO_DOWNLOAD : 0);
+        rc.n_frames = d.n_frames; rc.n_pictures = d.n_slots; rc.max_batch = opt.max_batch;
+        if (gpu_vlc && rc.max_batch < 16) rc.max_batch = 16;     // device-parsed pictures: launches (parse and reconstruction) are issued per 16 queued pictures
+        rc.flags = MP2V_RECON_VALIDATE | (gpu_vlc ? MP2V_RECON_DEVICE_VLC : 0) | (opt.download_frames ? MP2V_RECON_AUTO_DOWNLOAD : MP2V_RECON_THROUGHPUT);
         rc.coef_capacity = (uint32_t)(cap > 0xffffffffull ? 0xffffffffull : cap);
         if (mp2v_recon_create(&rc, &d.recon) != MP2V_OK) {
             error = std::string("mp2v_recon_create (CUDA device ") + std::to_string(id) + "): " + mp2v_recon_last_error(nullptr);
@@ -506,7 +540,24 @@ bool mp2v_decoder_c::decode(uint8_t* buffer, int len) {
     const auto t_begin = clock_t_::now();
     m->error.clear();
     stream_index_t index;
-    if (!index_stream(buffer, (size_t)len, index, m->cfg.num_threads)) { m->error = index.error; return false; }
+    // Device front end: the stream goes to the first device in one copy and a kernel lists its start codes
+    // (start_codes_search.hpp:7-26); the host only parses the headers those offsets point at.
+    bool resident = false;
+    if (m->opt.gpu_vlc && len > 0) {
+        if (!m->prepare(true)) return false;
+        const uint32_t* codes = nullptr;
+        uint32_t n_codes = 0;
+        mp2v_recon_t* r0 = m->dev_sets[1][0].recon;
+        const int rc = mp2v_recon_stream_begin(r0, buffer, (size_t)len, nullptr, 0, 1, &codes, &n_codes);
+        if (rc == MP2V_OK) {
+            if (!index_stream_from_codes(buffer, (size_t)len, codes, n_codes, index)) { m->error = index.error; return false; }
+            resident = true;
+        } else if (rc != MP2V_ERR_RANGE) {        // (RANGE: a pathological number of start codes -- the host scan takes it)
+            m->error = std::string("stream upload: ") + mp2v_recon_last_error(r0);
+            return false;
+        }
+    }
+    if (!resident && !index_stream(buffer, (size_t)len, index, m->cfg.num_threads)) { m->error = index.error; return false; }
     publish_headers(*this, index.headers);
     const auto t_indexed = clock_t_::now();
     shared_t sh;
@@ -527,7 +578,9 @@ bool mp2v_decoder_c::decode(uint8_t* buffer, int len) {
     sh.gop_emitted.assign(sh.gop_size.size(), 0);
     for (const auto& pic : index.pictures) sh.gop_size[pic.gop]++;
     // one pipeline per device; GOP chain g -> device g mod N
-    sh.opt.gpu_vlc = m->opt.gpu_vlc && m->device_parser_can_take(index);
+    sh.opt.gpu_vlc = m->opt.gpu_vlc && m->device_parser_can_take(index, !resident);
+    sh.stream_mode = sh.opt.gpu_vlc && resident;
+    sh.stream_base = buffer;
     if (!m->prepare(sh.opt.gpu_vlc)) return false;
     const std::vector<device_ctx_t>& devs = m->dev_sets[sh.opt.gpu_vlc ? 1 : 0];
     std::deque<pipeline_t> pipes(devs.size());
@@ -546,11 +599,30 @@ bool mp2v_decoder_c::decode(uint8_t* buffer, int len) {
         pic_task_t& t = p.tasks.back();
         t.src = &pic; t.pipe = &p; t.local_index = (int)p.tasks.size() - 1;
     }
+    if (sh.stream_mode && pipes.size() > 1) {
+        // GOP sharding: every other device receives only the byte ranges of its own pictures (same offsets)
+        for (size_t d = 1; d < pipes.size(); d++) {
+            std::vector<mp2v_byte_range_t> ranges;
+            for (const pic_task_t& t : pipes[d].tasks) {
+                if (t.src->slices.empty()) continue;
+                const size_t lo = (size_t)(t.src->slices.front().payload - 4 - buffer);
+                const size_t hi = (size_t)(t.src->slices.back().payload + t.src->slices.back().bytes - buffer);
+                if (!ranges.empty() && lo <= ranges.back().offset + ranges.back().bytes + 4096) ranges.back().bytes = hi - ranges.back().offset;   // (picture headers in between)
+                else ranges.push_back({lo, hi - lo});
+            }
+            if (ranges.empty()) continue;
+            if (mp2v_recon_stream_begin(pipes[d].recon, buffer, (size_t)len, ranges.data(), (int)ranges.size(), 0, nullptr, nullptr) != MP2V_OK) {
+                m->error = std::string("stream upload (CUDA device ") + std::to_string(pipes[d].device) + "): " + mp2v_recon_last_error(pipes[d].recon);
+                return false;
+            }
+        }
+    }
     const auto t_setup = clock_t_::now();
     std::vector<std::thread> workers;
     {
         int nthreads = m->cfg.num_threads > MAX_NUM_THREADS ? MAX_NUM_THREADS : m->cfg.num_threads;
         if (sh.opt.gpu_vlc && nthreads > 4) nthreads = 4;        // no host slice parsing: workers only stage the coded bytes
+        if (sh.stream_mode) nthreads = 0;                        // ... and with the stream resident on the device there is nothing to stage
         for (int i = 0; i < nthreads; i++) workers.emplace_back(worker_main, &sh);
         for (auto& p : pipes) if (!p.tasks.empty()) {
             p.feeder_thread = std::thread(&pipeline_t::feeder, &p);

@@ -83,16 +83,21 @@ static void read_sequence_level_extension(const uint8_t* payload, stream_headers
 }
 
 bool index_stream(const uint8_t* buffer, size_t len, stream_index_t& out, int threads) {
+    const std::vector<uint32_t> codes = scan_start_codes(buffer, len, threads);
+    return index_stream_from_codes(buffer, len, codes.data(), codes.size(), out);
+}
+
+bool index_stream_from_codes(const uint8_t* buffer, size_t len, const uint32_t* codes, size_t n_codes, stream_index_t& out) {
     out.pictures.clear();
     out.headers = stream_headers_t();
     out.error.clear();
     const uint8_t* end = buffer + len;
-    const std::vector<uint32_t> codes = scan_start_codes(buffer, len, threads);
     sequence_info_t seq;
     coded_picture_t* cur = nullptr;
     int gop = 0;
     bool have_picture = false;      // a picture has been seen since the last chain boundary
-    for (size_t ci = 0; ci < codes.size(); ci++) {
+    for (size_t ci = 0; ci < n_codes; ci++) {
+        if (codes[ci] >= len || (ci && codes[ci] <= codes[ci - 1])) { out.error = "start code list is not ascending / inside the stream"; return false; }
         const uint8_t* p = buffer + codes[ci];
         if (p + 4 > end) break;
         const int code = p[3];
@@ -109,7 +114,7 @@ bool index_stream(const uint8_t* buffer, size_t len, stream_index_t& out, int th
             if (cur) cur->seq = seq;
             else read_sequence_level_extension(payload, out.headers);
         } else if (code == 0xB2) {                       // user_data_start_code: bytes up to the next start code
-            const uint8_t* next = ci + 1 < codes.size() ? buffer + codes[ci + 1] : end;
+            const uint8_t* next = ci + 1 < n_codes ? buffer + codes[ci + 1] : end;
             out.headers.user_data.insert(out.headers.user_data.end(), payload, next);
         } else if (code == 0xB8) {                       // group_start_code: time_code(25) closed_gop(1) broken_link(1)
             bitreader_t br(payload);
@@ -131,7 +136,7 @@ bool index_stream(const uint8_t* buffer, size_t len, stream_index_t& out, int th
             have_picture = true;
         } else if (code >= 0x01 && code <= 0xAF) {       // slice
             if (!cur) { out.error = "slice before any picture header"; return false; }
-            const uint8_t* next = ci + 1 < codes.size() ? buffer + codes[ci + 1] : end;
+            const uint8_t* next = ci + 1 < n_codes ? buffer + codes[ci + 1] : end;
             cur->slices.push_back({payload, code, (uint32_t)(next - payload)});
         } else if (code == 0xB7 || code == 0xB4) {       // sequence_end / sequence_error
             cur = nullptr;

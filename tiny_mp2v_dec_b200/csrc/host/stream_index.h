@@ -46,5 +46,7 @@ struct stream_index_t {
 // buffer must be followed by >= 64 readable bytes (decode() contract).  The start-code scan (the only
 // part that touches every byte) is split over `threads` threads; header parsing stays serial.
 bool index_stream(const uint8_t* buffer, size_t len, stream_index_t& out, int threads = 1);
+// the same from a given list of start-code offsets (ascending; e.g. the device-side scan of mp2v_recon_stream_begin)
+bool index_stream_from_codes(const uint8_t* buffer, size_t len, const uint32_t* codes, size_t n_codes, stream_index_t& out);
 
 }  // namespace mp2v

@@ -31,7 +31,7 @@ struct slot_t {
     uint8_t* h_arena = nullptr;
     uint8_t* d_arena = nullptr;
     slot_state_t state = SLOT_FREE;
-    cudaEvent_t done = nullptr;        // recorded on the compute stream after the launch that consumed the slot
+    cudaEvent_t done = nullptr;        // the event of the launch that consumed the slot (an entry of the context's launch-event ring)
     uint64_t alg_bytes = 0;
     bool prechecked = false;           // account_and_validate already ran for the records now in the slot
     uint64_t seq = 0;                  // submission order, to recycle the oldest in-flight slot first
@@ -47,6 +47,9 @@ struct slot_t {
     cudaStream_t s_vlc = nullptr;
     cudaEvent_t vlc_done = nullptr;    // H2D + parse + status read-back of the picture now in the slot
     bool vlc = false;                  // the slot's records come from the device parser
+    cudaEvent_t vlc_wait = nullptr;    // what the reconstruction launch waits for: vlc_done, or the event of the batched parse launch
+    bool stream_pic = false;           // handed over with mp2v_recon_submit_stream_picture: parsed by the next batched parse launch
+    bool need_blank = false;           // ... and some macroblock row has no slice: blank records first
     bool status_pending = false;       // h_status not yet folded into the statistics / error state
     uint64_t picture_no = 0;
 };
@@ -63,7 +66,12 @@ struct mp2v_recon {
     uint8_t* d_frames = nullptr;
     recon_tmaps_t tmaps{};                     // TMA descriptors of the frame pool (reference windows)
     std::vector<uint8_t*> h_frames;            // pinned mirrors, allocated on first map
-    std::vector<cudaEvent_t> frame_ev;         // last writer of each frame
+    // One event per reconstruction LAUNCH (a ring): frames and slots remember which launch wrote / consumed them.
+    // An entry re-recorded by a later launch only makes a waiter wait longer (same stream), never less.
+    std::vector<cudaEvent_t> launch_ev;
+    uint64_t launch_seq = 0;
+    std::vector<int> frame_launch;             // frame id -> index into launch_ev of its last writer (-1: none / an upload)
+    std::vector<cudaEvent_t> frame_ev;         // last writer of a frame filled by mp2v_recon_upload_frame
     std::vector<uint8_t> frame_written;
     // MP2V_RECON_AUTO_DOWNLOAD: every submitted picture's frame is copied to its pinned mirror right behind its launch
     bool auto_dl = false;
@@ -74,10 +82,13 @@ struct mp2v_recon {
     // a copy of a frame to the host (D2H stream) must finish before a later picture overwrites the frame (compute stream)
     std::vector<cudaEvent_t> read_ev;          // per frame: behind its last queued copy
     std::vector<uint8_t> read_pending;         // since the frame's last writer was launched: 1 = read_ev[f] recorded, 2 = a launch's mirror event covers a copy
-    cudaStream_t s_copy = nullptr, s_compute = nullptr, s_d2h = nullptr;
+    uint8_t* h_pool = nullptr;                 // the pinned mirrors as ONE block laid out like the device pool: runs of frame ids copy as one piece
+    cudaStream_t s_copy = nullptr, s_compute = nullptr, s_d2h = nullptr, s_d2h2 = nullptr;
     cudaEvent_t ev_h2d = nullptr, ev_t0 = nullptr, ev_t1 = nullptr;
     std::vector<slot_t> slots;
-    std::vector<int> pending;                  // queued slots, submit order
+    std::vector<int> pending;                  // the open launch group: queued slots, submit order
+    std::vector<std::vector<int>> closed;      // closed launch groups (a later picture depends on them), oldest first
+    int queued = 0;                            // pictures in closed + pending
     std::mutex mu;
     std::string err;
     uint64_t seq = 0;
@@ -101,6 +112,21 @@ struct mp2v_recon {
     std::vector<trace_rec_t> trace_log;
     std::deque<int> status_fifo;               // slots whose parse status has not been folded in yet, submission order
     std::string vlc_error;                     // sticky: first slice error reported by the device parser
+    // stream-resident front end (mp2v_recon_stream_begin / mp2v_recon_submit_stream_picture)
+    static constexpr int kParseStreams = 4, kParseBufs = 8;
+    uint8_t* d_stream = nullptr;               // device copy of the elementary stream
+    size_t stream_cap = 0, stream_len = 0;
+    const uint8_t* h_stream = nullptr;         // the caller's copy (valid until the next stream_begin): slice start codes are validated from it
+    uint32_t* d_codes = nullptr; uint32_t* h_codes = nullptr; uint32_t codes_cap = 0;
+    uint32_t* d_counts = nullptr; size_t counts_cap = 0;
+    uint32_t* h_total = nullptr; uint32_t* d_total = nullptr;   // pinned + mapped
+    cudaStream_t s_parse[kParseStreams] = {};
+    int parse_rr = 0;
+    cudaEvent_t ev_stream = nullptr;           // the upload (and scan) of the resident stream
+    struct parse_buf_t { uint8_t* h = nullptr; uint8_t* d = nullptr; cudaEvent_t done = nullptr; bool used = false; } parse_buf[kParseBufs];
+    int parse_buf_rr = 0;
+    size_t desc_stride = 0;
+    std::vector<int> parse_pending;            // stream pictures whose descriptors sit in parse_buf[parse_buf_rr], parse not launched yet
     uint64_t pictures_submitted = 0;
     int batch_ramp = 1;                        // launch batch limit right after a sync: 1, 2, 4, ... max_batch (first frames out early)
 
@@ -145,10 +171,19 @@ static void destroy_ctx(mp2v_recon* ctx) {
     if (ctx->s_compute) cudaStreamSynchronize(ctx->s_compute);
     if (ctx->s_copy) cudaStreamSynchronize(ctx->s_copy);
     if (ctx->s_d2h) cudaStreamSynchronize(ctx->s_d2h);
+    if (ctx->s_d2h2) cudaStreamSynchronize(ctx->s_d2h2);
+    for (auto st : ctx->s_parse) if (st) { cudaStreamSynchronize(st); cudaStreamDestroy(st); }
+    for (auto& b : ctx->parse_buf) { if (b.h) cudaFreeHost(b.h); if (b.d) cudaFree(b.d); if (b.done) cudaEventDestroy(b.done); }
+    if (ctx->d_stream) cudaFree(ctx->d_stream);
+    if (ctx->d_codes) cudaFree(ctx->d_codes);
+    if (ctx->h_codes) cudaFreeHost(ctx->h_codes);
+    if (ctx->d_counts) cudaFree(ctx->d_counts);
+    if (ctx->h_total) cudaFreeHost(ctx->h_total);
+    if (ctx->ev_stream) cudaEventDestroy(ctx->ev_stream);
+    for (auto e : ctx->launch_ev) if (e) cudaEventDestroy(e);
     for (auto& s : ctx->slots) {
         if (s.h_arena) cudaFreeHost(s.h_arena);
         if (s.d_arena) cudaFree(s.d_arena);
-        if (s.done) cudaEventDestroy(s.done);
         if (s.s_vlc) { cudaStreamSynchronize(s.s_vlc); cudaStreamDestroy(s.s_vlc); }
         if (s.vlc_done) cudaEventDestroy(s.vlc_done);
         if (s.h_staged) cudaFreeHost(s.h_staged);
@@ -157,7 +192,8 @@ static void destroy_ctx(mp2v_recon* ctx) {
     }
     if (ctx->d_tables) cudaFree(ctx->d_tables);
     if (ctx->d_blank_mb) cudaFree(ctx->d_blank_mb);
-    for (auto* h : ctx->h_frames) if (h) cudaFreeHost(h);
+    if (ctx->h_pool) cudaFreeHost(ctx->h_pool);
+    else for (auto* h : ctx->h_frames) if (h) cudaFreeHost(h);
     for (auto e : ctx->frame_ev) if (e) cudaEventDestroy(e);
     for (auto e : ctx->mirror_ev) if (e) cudaEventDestroy(e);
     for (auto e : ctx->read_ev) if (e) cudaEventDestroy(e);
@@ -171,6 +207,7 @@ static void destroy_ctx(mp2v_recon* ctx) {
     if (ctx->s_copy) cudaStreamDestroy(ctx->s_copy);
     if (ctx->s_compute) cudaStreamDestroy(ctx->s_compute);
     if (ctx->s_d2h) cudaStreamDestroy(ctx->s_d2h);
+    if (ctx->s_d2h2) cudaStreamDestroy(ctx->s_d2h2);
     delete ctx;
 }
 
@@ -202,6 +239,7 @@ static int create_impl(mp2v_recon* ctx) {
     CK(cudaStreamCreateWithFlags(&ctx->s_copy, cudaStreamNonBlocking), "stream");
     CK(cudaStreamCreateWithPriority(&ctx->s_compute, cudaStreamNonBlocking, prio_mid), "stream");
     CK(cudaStreamCreateWithPriority(&ctx->s_d2h, cudaStreamNonBlocking, prio_greatest), "stream");
+    CK(cudaStreamCreateWithPriority(&ctx->s_d2h2, cudaStreamNonBlocking, prio_greatest), "stream");
     CK(cudaEventCreateWithFlags(&ctx->ev_h2d, cudaEventDisableTiming), "event");
     CK(cudaEventCreate(&ctx->ev_t0), "event");
     CK(cudaEventCreate(&ctx->ev_t1), "event");
@@ -215,6 +253,9 @@ static int create_impl(mp2v_recon* ctx) {
     ctx->frame_ev.assign(c.n_frames, nullptr);
     ctx->frame_written.assign(c.n_frames, 0);
     for (auto& ev : ctx->frame_ev) CK(cudaEventCreateWithFlags(&ev, cudaEventDisableTiming), "event");
+    ctx->frame_launch.assign(c.n_frames, -1);
+    ctx->launch_ev.assign((size_t)c.n_pictures + c.n_frames + 16, nullptr);
+    for (auto& ev : ctx->launch_ev) CK(cudaEventCreateWithFlags(&ev, cudaEventDisableTiming), "event");
     if (const char* v = getenv("MP2V_TRACE")) ctx->trace = atoi(v) != 0;
     ctx->auto_dl = (c.flags & MP2V_RECON_AUTO_DOWNLOAD) != 0;
     ctx->mirror_valid.assign(c.n_frames, 0);
@@ -227,7 +268,8 @@ static int create_impl(mp2v_recon* ctx) {
         ctx->mirror_ev.assign(c.n_frames + 1, nullptr);
         ctx->mirror_ev_of.assign(c.n_frames, 0);
         for (auto& ev : ctx->mirror_ev) CK(cudaEventCreateWithFlags(&ev, cudaEventDisableTiming), "event");
-        for (auto& h : ctx->h_frames) CK(cudaHostAlloc(&h, ctx->lay.bytes, cudaHostAllocDefault), "cudaHostAlloc frame mirror");
+        CK(cudaHostAlloc(&ctx->h_pool, ctx->frame_alloc * c.n_frames, cudaHostAllocDefault), "cudaHostAlloc frame mirrors");
+        for (int f = 0; f < c.n_frames; f++) ctx->h_frames[f] = ctx->h_pool + (size_t)f * ctx->frame_alloc;
     }
     // picture slots
     const uint64_t worst = (uint64_t)ctx->mb_count * ctx->nblk * 64u;
@@ -260,7 +302,6 @@ static int create_impl(mp2v_recon* ctx) {
         slot_t& s = ctx->slots[i];
         CK(cudaHostAlloc(&s.h_arena, host_arena_bytes, cudaHostAllocDefault), "cudaHostAlloc picture arena");
         CK(cudaMalloc(&s.d_arena, ctx->arena_bytes), "cudaMalloc picture arena");
-        CK(cudaEventCreateWithFlags(&s.done, cudaEventDisableTiming), "event");
         s.pub.params = reinterpret_cast<mp2v_pic_params_t*>(s.h_arena);
         s.pub.mb = reinterpret_cast<mp2v_mb_info_t*>(s.h_arena + kParamsBytes);
         s.pub.coef = host_cap ? reinterpret_cast<mp2v_coef_t*>(s.h_arena + ctx->coef_off) : nullptr;
@@ -277,6 +318,19 @@ static int create_impl(mp2v_recon* ctx) {
             CK(cudaStreamCreateWithFlags(&s.s_vlc, cudaStreamNonBlocking), "stream");
             CK(cudaEventCreateWithFlags(&s.vlc_done, cudaEventDisableTiming), "event");
         }
+    }
+    if (ctx->vlc) {
+        // stream-resident front end: parse streams, descriptor buffers (one per batched parse launch in flight)
+        for (auto& st : ctx->s_parse) CK(cudaStreamCreateWithFlags(&st, cudaStreamNonBlocking), "stream");
+        CK(cudaEventCreateWithFlags(&ctx->ev_stream, cudaEventDisableTiming), "event");
+        ctx->desc_stride = vlc_stream_desc_bytes(ctx->mbh);
+        for (auto& b : ctx->parse_buf) {
+            CK(cudaHostAlloc(&b.h, ctx->desc_stride * kMaxStreamBatch, cudaHostAllocDefault), "cudaHostAlloc parse descriptors");
+            CK(cudaMalloc(&b.d, ctx->desc_stride * kMaxStreamBatch), "cudaMalloc parse descriptors");
+            CK(cudaEventCreateWithFlags(&b.done, cudaEventDisableTiming), "event");
+        }
+        CK(cudaHostAlloc(&ctx->h_total, 64, cudaHostAllocMapped), "cudaHostAlloc scan total");
+        CK(cudaHostGetDevicePointer(&ctx->d_total, ctx->h_total, 0), "cudaHostGetDevicePointer");
     }
     CK(cudaDeviceSynchronize(), "cudaDeviceSynchronize");
     return MP2V_OK;
@@ -359,44 +413,92 @@ static int launch_slots(mp2v_recon* ctx, const int* ids, int n, bool download = 
         CK(cudaEventRecord(t1, ctx->s_compute), "event record");
         ctx->timed.emplace_back(t0, t1);
     }
+    // ONE event for the whole launch: its frames and slots point at it
+    const int lidx = (int)(ctx->launch_seq++ % ctx->launch_ev.size());
+    CK(cudaEventRecord(ctx->launch_ev[lidx], ctx->s_compute), "event record");
     for (int i = 0; i < n; i++) {
         slot_t& s = ctx->slots[ids[i]];
         const int f = s.pub.params->dst_frame;
-        CK(cudaEventRecord(ctx->frame_ev[f], ctx->s_compute), "event record");
+        ctx->frame_launch[f] = lidx;
+        s.done = ctx->launch_ev[lidx];
         ctx->frame_written[f] = 1;
         ctx->mirror_valid[f] = 0;
         ctx->stats.algorithmic_bytes += s.alg_bytes;
         if (ctx->trace && s.vlc && s.trace_idx >= 0) CK(cudaEventRecord(ctx->trace_log[s.trace_idx].recon, ctx->s_compute), "event record");
     }
     if (download) {
-        // the copies queue up on the D2H stream behind this launch and overlap the launches that follow
-        CK(cudaStreamWaitEvent(ctx->s_d2h, ctx->frame_ev[ctx->slots[ids[n - 1]].pub.params->dst_frame], 0), "stream wait");
+        // The copies queue up behind this launch on one of two D2H streams (alternating, so that the copies of
+        // consecutive launches overlap their gaps) and overlap the launches that follow.  The mirrors are laid out
+        // like the device pool: a run of consecutive frame ids is ONE copy.
+        cudaStream_t sd = (ctx->mirror_batches & 1) ? ctx->s_d2h2 : ctx->s_d2h;
+        CK(cudaStreamWaitEvent(sd, ctx->launch_ev[lidx], 0), "stream wait");
         const int ev = (int)(ctx->mirror_batches++ % ctx->mirror_ev.size());
+        int fr[kMaxBatch];
+        for (int i = 0; i < n; i++) fr[i] = ctx->slots[ids[i]].pub.params->dst_frame;
+        std::sort(fr, fr + n);
+        for (int i = 0; i < n;) {
+            int j = i + 1;
+            while (j < n && fr[j] == fr[j - 1] + 1) j++;
+            const size_t bytes = (size_t)(j - i - 1) * ctx->frame_alloc + ctx->lay.bytes;
+            CK(cudaMemcpyAsync(ctx->h_frames[fr[i]], ctx->frame_ptr(fr[i], 0), bytes, cudaMemcpyDeviceToHost, sd), "D2H frames");
+            ctx->stats.d2h_bytes += (uint64_t)(j - i) * ctx->lay.bytes;
+            i = j;
+        }
         for (int i = 0; i < n; i++) {
-            const int f = ctx->slots[ids[i]].pub.params->dst_frame;
-            CK(cudaMemcpyAsync(ctx->h_frames[f], ctx->frame_ptr(f, 0), ctx->lay.bytes, cudaMemcpyDeviceToHost, ctx->s_d2h), "D2H frame");
+            const int f = fr[i];
             ctx->mirror_ev_of[f] = ev;
-            if (ctx->trace && ctx->slots[ids[i]].vlc && ctx->slots[ids[i]].trace_idx >= 0) CK(cudaEventRecord(ctx->trace_log[ctx->slots[ids[i]].trace_idx].d2h, ctx->s_d2h), "event record");
             ctx->mirror_valid[f] = 1;
             ctx->read_pending[f] |= 2;                     // covered by this launch's mirror event
-            ctx->stats.d2h_bytes += ctx->lay.bytes;
         }
-        CK(cudaEventRecord(ctx->mirror_ev[ev], ctx->s_d2h), "event record");
+        if (ctx->trace) for (int i = 0; i < n; i++) if (ctx->slots[ids[i]].vlc && ctx->slots[ids[i]].trace_idx >= 0) CK(cudaEventRecord(ctx->trace_log[ctx->slots[ids[i]].trace_idx].d2h, sd), "event record");
+        CK(cudaEventRecord(ctx->mirror_ev[ev], sd), "event record");
     }
     ctx->stats.pictures += n;
     ctx->stats.launches += 1;
     return MP2V_OK;
 }
 
-static int flush_locked(mp2v_recon* ctx) {
-    if (ctx->pending.empty()) return MP2V_OK;
-    CK(cudaSetDevice(ctx->cfg.device), "cudaSetDevice");
-    // H2D of every queued picture: params + macroblock records + the used part of the coefficient arena
+// one parse launch for every stream picture handed over since the last one (ctx->mu held)
+static int launch_parse_batch(mp2v_recon* ctx) {
+    if (ctx->parse_pending.empty()) return MP2V_OK;
+    mp2v_recon::parse_buf_t& b = ctx->parse_buf[ctx->parse_buf_rr];
+    cudaStream_t st = ctx->s_parse[ctx->parse_rr];
+    ctx->parse_rr = (ctx->parse_rr + 1) % mp2v_recon::kParseStreams;
+    const int n = (int)ctx->parse_pending.size();
+    CK(cudaStreamWaitEvent(st, ctx->ev_stream, 0), "stream wait");      // the resident stream has arrived
+    // rows without any slice (never in valid streams): blank records first
+    for (int id : ctx->parse_pending) {
+        slot_t& s = ctx->slots[id];
+        if (s.need_blank)
+            CK(cudaMemcpyAsync(s.d_arena + kParamsBytes, ctx->d_blank_mb, (size_t)ctx->mb_count * sizeof(mp2v_mb_info_t), cudaMemcpyDeviceToDevice, st), "blank records");
+    }
+    CK(cudaMemcpyAsync(b.d, b.h, (size_t)n * ctx->desc_stride, cudaMemcpyHostToDevice, st), "H2D parse descriptors");
+    CK(launch_vlc_stream(ctx->d_stream, b.d, ctx->desc_stride, n, ctx->mbh, ctx->d_tables, st), "slice parser kernel launch");
+    CK(cudaEventRecord(b.done, st), "event record");
+    b.used = true;
+    for (int id : ctx->parse_pending) ctx->slots[id].vlc_wait = b.done;
+    ctx->stats.h2d_bytes += (uint64_t)n * ctx->desc_stride;
+    ctx->stats.vlc_launches += 1;
+    ctx->parse_pending.clear();
+    // the next batch writes into the next buffer; wait (rare: kParseBufs launches deep) until its previous use has been read
+    ctx->parse_buf_rr = (ctx->parse_buf_rr + 1) % mp2v_recon::kParseBufs;
+    mp2v_recon::parse_buf_t& nb = ctx->parse_buf[ctx->parse_buf_rr];
+    if (nb.used) { CK(cudaEventSynchronize(nb.done), "event sync"); nb.used = false; }
+    return MP2V_OK;
+}
+
+// launch one group: H2D of host-parsed records / wait for device parses, then the reconstruction kernel (ctx->mu held)
+static int launch_group(mp2v_recon* ctx, const std::vector<int>& group) {
+    // H2D of every host-parsed picture: params + macroblock records + the used part of the coefficient arena
     // (pictures parsed on the device already have them there: the launch waits for their parse instead)
     bool any_h2d = false;
-    for (int id : ctx->pending) {
+    cudaEvent_t waited = nullptr;
+    for (int id : group) {
         slot_t& s = ctx->slots[id];
-        if (s.vlc) { CK(cudaStreamWaitEvent(ctx->s_compute, s.vlc_done, 0), "stream wait"); continue; }
+        if (s.vlc) {
+            if (s.vlc_wait != waited) { CK(cudaStreamWaitEvent(ctx->s_compute, s.vlc_wait, 0), "stream wait"); waited = s.vlc_wait; }
+            continue;
+        }
         const size_t bytes = ctx->coef_off + (size_t)s.pub.params->n_coef * sizeof(mp2v_coef_t);
         CK(cudaMemcpyAsync(s.d_arena, s.h_arena, bytes, cudaMemcpyHostToDevice, ctx->s_copy), "H2D picture records");
         ctx->stats.h2d_bytes += bytes;
@@ -406,16 +508,31 @@ static int flush_locked(mp2v_recon* ctx) {
         CK(cudaEventRecord(ctx->ev_h2d, ctx->s_copy), "event record");
         CK(cudaStreamWaitEvent(ctx->s_compute, ctx->ev_h2d, 0), "stream wait");
     }
-    const int rc = launch_slots(ctx, ctx->pending.data(), (int)ctx->pending.size(), ctx->auto_dl);
+    const int rc = launch_slots(ctx, group.data(), (int)group.size(), ctx->auto_dl);
     if (rc != MP2V_OK) return rc;
-    if (ctx->batch_ramp < ctx->max_batch) ctx->batch_ramp *= 2;
-    for (int id : ctx->pending) {
-        slot_t& s = ctx->slots[id];
-        CK(cudaEventRecord(s.done, ctx->s_compute), "event record");
-        s.state = SLOT_INFLIGHT;
-    }
-    ctx->pending.clear();
+    for (int id : group) ctx->slots[id].state = SLOT_INFLIGHT;
     return MP2V_OK;
+}
+
+// launch everything that is queued: the pending parses in one launch, then the groups in submit order
+static int flush_locked(mp2v_recon* ctx) {
+    if (ctx->queued == 0 && ctx->parse_pending.empty()) return MP2V_OK;
+    CK(cudaSetDevice(ctx->cfg.device), "cudaSetDevice");
+    int rc = launch_parse_batch(ctx);
+    if (rc != MP2V_OK) return rc;
+    for (auto& g : ctx->closed) { rc = launch_group(ctx, g); if (rc != MP2V_OK) return rc; }
+    ctx->closed.clear();
+    if (!ctx->pending.empty()) { rc = launch_group(ctx, ctx->pending); if (rc != MP2V_OK) return rc; }
+    ctx->pending.clear();
+    ctx->queued = 0;
+    if (ctx->batch_ramp < std::max(ctx->max_batch, 16)) ctx->batch_ramp *= 2;
+    return MP2V_OK;
+}
+
+static bool frame_is_queued(const mp2v_recon* ctx, int f) {
+    for (int id : ctx->pending) if (ctx->slots[id].pub.params->dst_frame == f) return true;
+    for (auto& g : ctx->closed) for (int id : g) if (ctx->slots[id].pub.params->dst_frame == f) return true;
+    return false;
 }
 
 // OUT + REF + COEF + META, and (optionally) the host-side validation of the records
@@ -483,7 +600,7 @@ static void fold_status(mp2v_recon* ctx, slot_t& s) {
 static void harvest_all(mp2v_recon* ctx) {
     while (!ctx->status_fifo.empty()) {
         slot_t& s = ctx->slots[ctx->status_fifo.front()];
-        if (cudaEventQuery(s.vlc_done) != cudaSuccess) break;
+        if (!s.vlc_wait || cudaEventQuery(s.vlc_wait) != cudaSuccess) break;      // (nullptr: its batched parse has not been launched yet)
         fold_status(ctx, s);
         ctx->status_fifo.pop_front();
     }
@@ -513,6 +630,7 @@ extern "C" MP2V_API int mp2v_recon_acquire_picture(mp2v_recon_t* ctx, mp2v_pictu
                 s.state = SLOT_FILLING;
                 s.prechecked = false;
                 s.vlc = false;
+                s.stream_pic = false;
                 s.staged = false;
                 memset(s.pub.params, 0, sizeof(mp2v_pic_params_t));
                 s.pub.params->l0_frame = s.pub.params->l1_frame = -1;
@@ -521,7 +639,7 @@ extern "C" MP2V_API int mp2v_recon_acquire_picture(mp2v_recon_t* ctx, mp2v_pictu
             }
             // otherwise wait (outside the lock) for that oldest in-flight slot; launch queued work first
             if (candidate < 0) {
-                if (ctx->pending.empty()) return ctx->fail(MP2V_ERR_STATE, "no picture slot available (all slots are being filled or resident)");
+                if (ctx->queued == 0) return ctx->fail(MP2V_ERR_STATE, "no picture slot available (all slots are being filled or resident)");
                 const int rc = flush_locked(ctx);
                 if (rc != MP2V_OK) return rc;
                 continue;
@@ -558,33 +676,38 @@ extern "C" MP2V_API int mp2v_recon_release_picture(mp2v_recon_t* ctx, mp2v_pictu
 static bool references_available(const mp2v_recon* ctx, const mp2v_pic_params_t& pp) {
     for (int d = 0; d < 2; d++) {
         const int fr = d ? pp.l1_frame : pp.l0_frame;
-        if (fr < 0 || ctx->frame_written[fr]) continue;
-        bool queued = false;
-        for (int id : ctx->pending) queued = queued || ctx->slots[id].pub.params->dst_frame == fr;
-        if (!queued) return false;
+        if (fr < 0 || ctx->frame_written[fr] || frame_is_queued(ctx, fr)) continue;
+        return false;
     }
     return true;
 }
 
-// queue a slot whose records are (or will be) complete; ctx->mu held
+// Queue a slot whose records are (or will be) complete; ctx->mu held.  A picture cannot share a launch with a
+// picture it reads from, nor with one touching its destination: such a conflict CLOSES the open group (it is
+// launched later, in order); everything queued is launched once `max_batch` pictures wait (1, 2, 4, ... right
+// after a sync, so that the first frames of a decode leave early).
 static int queue_slot(mp2v_recon* ctx, slot_t* s) {
     const mp2v_pic_params_t& pp = *s->pub.params;
-    // a picture cannot share a launch with a picture it reads from, nor with one touching its destination
-    bool conflict = (int)ctx->pending.size() >= std::min(ctx->max_batch, ctx->batch_ramp);
+    if (!references_available(ctx, pp)) return ctx->fail(MP2V_ERR_STATE, "reference frame has never been written");
+    bool conflict = (int)ctx->pending.size() >= ctx->max_batch;
     for (int id : ctx->pending) {
         const mp2v_pic_params_t& q = *ctx->slots[id].pub.params;
         if (q.dst_frame == pp.l0_frame || q.dst_frame == pp.l1_frame || q.dst_frame == pp.dst_frame ||
             q.l0_frame == pp.dst_frame || q.l1_frame == pp.dst_frame) conflict = true;
     }
-    if (conflict) { const int rc = flush_locked(ctx); if (rc != MP2V_OK) return rc; }
-    for (int d = 0; d < 2; d++) {
-        const int fr = d ? pp.l1_frame : pp.l0_frame;
-        if (fr >= 0 && !ctx->frame_written[fr]) return ctx->fail(MP2V_ERR_STATE, "reference frame has never been written");
-    }
+    if (conflict && !ctx->pending.empty()) { ctx->closed.emplace_back(std::move(ctx->pending)); ctx->pending.clear(); }
+    // a closed group that reads or writes this picture's destination must run first anyway (launch order = submit order)
     s->state = SLOT_QUEUED;
     s->seq = ++ctx->seq;
     s->picture_no = ctx->pictures_submitted++;
     ctx->pending.push_back(s->pub.slot);
+    ctx->queued++;
+    // Device-parsed stream pictures are launched in larger lots (4, 8, ... kMaxStreamBatch): a slice parses at the speed of
+    // ONE thread (about a millisecond for a dense 1080p row), so the parser's throughput is the number of pictures in flight.
+    // MP2V_RECON_THROUGHPUT: full lots from the first picture on (nobody is waiting for the first frame).
+    const int ramp = (ctx->cfg.flags & MP2V_RECON_THROUGHPUT) ? kMaxBatch : ctx->batch_ramp;
+    const int quota = s->stream_pic ? std::min(kMaxStreamBatch, 4 * ramp) : std::min(ctx->max_batch, ramp);
+    if (ctx->queued >= quota) return flush_locked(ctx);
     return MP2V_OK;
 }
 
@@ -697,6 +820,7 @@ extern "C" MP2V_API int mp2v_recon_submit_staged(mp2v_recon_t* ctx, mp2v_picture
                   ctx->vlc_lanes, s->s_vlc), "slice parser kernel launch");
     if (s->trace_idx >= 0) CK(cudaEventRecord(ctx->trace_log[s->trace_idx].vlc, s->s_vlc), "event record");
     CK(cudaEventRecord(s->vlc_done, s->s_vlc), "event record");
+    s->vlc_wait = s->vlc_done;
     ctx->stats.h2d_bytes += staged_end;
     ctx->stats.d2h_bytes += (uint64_t)n_slices * sizeof(vlc_slice_status_t);
     if (n_slices > 0) { ctx->stats.vlc_launches += 1; ctx->stats.vlc_slices += (uint64_t)n_slices; }
@@ -711,6 +835,144 @@ extern "C" MP2V_API int mp2v_recon_submit_slices(mp2v_recon_t* ctx, mp2v_picture
                                                  const mp2v_slice_ref_t* slices, int n_slices) {
     const int rc = mp2v_recon_stage_slices(ctx, pic, syntax, slices, n_slices);
     return rc != MP2V_OK ? rc : mp2v_recon_submit_staged(ctx, pic);
+}
+
+// ---------------------------------------------------------------------------------------------
+// stream-resident front end
+
+extern "C" MP2V_API int mp2v_recon_stream_begin(mp2v_recon_t* ctx, const uint8_t* data, size_t bytes, const mp2v_byte_range_t* ranges, int n_ranges,
+                                                int scan, const uint32_t** codes, uint32_t* n_codes) {
+    if (!ctx || (!data && bytes) || n_ranges < 0 || (n_ranges && !ranges) || (scan && (!codes || !n_codes))) return MP2V_ERR_ARG;
+    std::lock_guard<std::mutex> lk(ctx->mu);
+    if (!ctx->vlc) return ctx->fail(MP2V_ERR_STATE, "stream_begin: context was created without MP2V_RECON_DEVICE_VLC");
+    if (bytes > 0x7ffffff0ull) return ctx->fail(MP2V_ERR_ARG, "stream_begin: stream too large");
+    int rc = flush_locked(ctx);
+    if (rc != MP2V_OK) return rc;
+    CK(cudaSetDevice(ctx->cfg.device), "cudaSetDevice");
+    // parses of the previous stream may still be reading it
+    for (auto st : ctx->s_parse) CK(cudaStreamSynchronize(st), "stream sync");
+    const size_t need = ((bytes + 4095) & ~(size_t)4095) + 4096;         // the scan reads whole 4 KiB chunks + look-ahead; parsers read a few bytes past a slice
+    if (need > ctx->stream_cap) {
+        if (ctx->d_stream) CK(cudaFree(ctx->d_stream), "cudaFree");
+        ctx->d_stream = nullptr; ctx->stream_cap = 0;
+        const size_t cap = need + need / 4;
+        CK(cudaMalloc(&ctx->d_stream, cap), "cudaMalloc stream");
+        ctx->stream_cap = cap;
+    }
+    cudaStream_t st = ctx->s_parse[0];
+    if (n_ranges == 0) {
+        if (bytes) CK(cudaMemcpyAsync(ctx->d_stream, data, bytes, cudaMemcpyHostToDevice, st), "H2D stream");
+        ctx->stats.h2d_bytes += bytes;
+    } else {
+        for (int i = 0; i < n_ranges; i++) {
+            if (ranges[i].offset > bytes || ranges[i].bytes > bytes - ranges[i].offset) return ctx->fail(MP2V_ERR_ARG, "stream_begin: range outside the stream");
+            if (ranges[i].bytes) CK(cudaMemcpyAsync(ctx->d_stream + ranges[i].offset, data + ranges[i].offset, ranges[i].bytes, cudaMemcpyHostToDevice, st), "H2D stream");
+            ctx->stats.h2d_bytes += ranges[i].bytes;
+        }
+    }
+    CK(cudaMemsetAsync(ctx->d_stream + bytes, 0, need - bytes, st), "memset stream tail");
+    ctx->stream_len = bytes;
+    ctx->h_stream = data;
+    if (scan) {
+        const size_t nblk = vlc_scan_blocks(bytes);
+        if (nblk + 1 > ctx->counts_cap) {
+            if (ctx->d_counts) CK(cudaFree(ctx->d_counts), "cudaFree");
+            ctx->d_counts = nullptr; ctx->counts_cap = 0;
+            CK(cudaMalloc(&ctx->d_counts, (nblk + 1 + 1024) * sizeof(uint32_t)), "cudaMalloc scan scratch");
+            ctx->counts_cap = nblk + 1 + 1024;
+        }
+        // a code every 64 bytes on average is far beyond any real stream (a 1080p slice is kilobytes); more than that takes the host path
+        const uint32_t cap = (uint32_t)std::max<size_t>(1u << 16, bytes / 64);
+        if (cap > ctx->codes_cap) {
+            if (ctx->d_codes) CK(cudaFree(ctx->d_codes), "cudaFree");
+            if (ctx->h_codes) CK(cudaFreeHost(ctx->h_codes), "cudaFreeHost");
+            ctx->d_codes = nullptr; ctx->h_codes = nullptr; ctx->codes_cap = 0;
+            CK(cudaMalloc(&ctx->d_codes, (size_t)cap * sizeof(uint32_t)), "cudaMalloc start codes");
+            CK(cudaHostAlloc(&ctx->h_codes, (size_t)cap * sizeof(uint32_t), cudaHostAllocDefault), "cudaHostAlloc start codes");
+            ctx->codes_cap = cap;
+        }
+        CK(launch_start_code_scan(ctx->d_stream, bytes, ctx->d_counts, ctx->d_codes, ctx->codes_cap, ctx->d_total, st), "start code scan");
+        CK(cudaStreamSynchronize(st), "stream sync");
+        const uint32_t total = *ctx->h_total;
+        if (total > ctx->codes_cap) return ctx->fail(MP2V_ERR_RANGE, "stream_begin: more start codes than the scan list holds");
+        if (total) CK(cudaMemcpy(ctx->h_codes, ctx->d_codes, (size_t)total * sizeof(uint32_t), cudaMemcpyDeviceToHost), "D2H start codes");
+        ctx->stats.d2h_bytes += (uint64_t)total * sizeof(uint32_t);
+        *codes = ctx->h_codes;
+        *n_codes = total;
+    }
+    CK(cudaEventRecord(ctx->ev_stream, st), "event record");
+    return MP2V_OK;
+}
+
+extern "C" MP2V_API int mp2v_recon_submit_stream_picture(mp2v_recon_t* ctx, mp2v_picture_t* pic, const mp2v_pic_syntax_t* syntax,
+                                                         const uint32_t* slice_offsets, int n_slices) {
+    if (!ctx) return MP2V_ERR_ARG;
+    slot_t* s = slot_of(ctx, pic);
+    std::lock_guard<std::mutex> lk(ctx->mu);
+    if (!s || s->state != SLOT_FILLING) return ctx->fail(MP2V_ERR_STATE, "submit_stream_picture: picture was not acquired");
+    if (!ctx->vlc || !ctx->d_stream) return ctx->fail(MP2V_ERR_STATE, "submit_stream_picture: no resident stream (mp2v_recon_stream_begin)");
+    if (!syntax || (n_slices > 0 && !slice_offsets) || n_slices < 0) return ctx->fail(MP2V_ERR_ARG, "submit_stream_picture: bad arguments");
+    const mp2v_pic_params_t& pp = *s->pub.params;
+    const int nf = ctx->cfg.n_frames;
+    if (pp.dst_frame < 0 || pp.dst_frame >= nf || pp.l0_frame >= nf || pp.l1_frame >= nf) return ctx->fail(MP2V_ERR_ARG, "frame id out of range");
+    if (pp.picture_coding_type < 1 || pp.picture_coding_type > 3) return ctx->fail(MP2V_ERR_ARG, "picture_coding_type must be 1 (I), 2 (P) or 3 (B)");
+    if ((pp.picture_coding_type >= 2 && pp.l0_frame < 0) || (pp.picture_coding_type == 3 && pp.l1_frame < 0))
+        return ctx->fail(MP2V_ERR_STATE, "prediction from a missing reference frame");
+    if (syntax->intra_dc_precision < 0 || syntax->intra_dc_precision > 3) return ctx->fail(MP2V_ERR_ARG, "intra_dc_precision out of range");
+    if (n_slices > ctx->mbh) return ctx->fail(MP2V_ERR_RANGE, "the device parser takes at most one slice per macroblock row");
+    CHECK_VLC_ERROR();
+    if (!references_available(ctx, pp)) return ctx->fail(MP2V_ERR_STATE, "reference frame has never been written");
+    if ((int)ctx->parse_pending.size() >= kMaxStreamBatch) { const int rc = flush_locked(ctx); if (rc != MP2V_OK) return rc; }
+    // ---- the picture's descriptor, in the buffer of the next parse launch
+    vlc_stream_pic_t& d = *reinterpret_cast<vlc_stream_pic_t*>(ctx->parse_buf[ctx->parse_buf_rr].h + ctx->parse_pending.size() * ctx->desc_stride);
+    int rows_covered = 0;
+    {
+        uint64_t seen[16] = {};                               // mbh <= 1024 rows
+        if (ctx->mbh > 1024) return ctx->fail(MP2V_ERR_RANGE, "picture too tall for the device parser");
+        for (int i = 0; i < n_slices; i++) {
+            const uint32_t off = slice_offsets[i];
+            if ((size_t)off + 8 > ctx->stream_len) return ctx->fail(MP2V_ERR_ARG, "submit_stream_picture: slice offset outside the stream");
+            const uint8_t* sc = ctx->h_stream + off;
+            if (sc[0] != 0 || sc[1] != 0 || sc[2] != 1 || sc[3] < 1 || sc[3] > 0xAF) return ctx->fail(MP2V_ERR_ARG, "submit_stream_picture: not a slice start code");
+            int row = sc[3] - 1;
+            if (ctx->cfg.height > 2800) row += (sc[4] >> 5) << 7;
+            if (row < 0 || row >= ctx->mbh) return ctx->fail(MP2V_ERR_RANGE, "slice row outside the picture");
+            if (seen[row >> 6] >> (row & 63) & 1) return ctx->fail(MP2V_ERR_RANGE, "the device parser takes at most one slice per macroblock row");
+            seen[row >> 6] |= 1ull << (row & 63);
+            rows_covered++;
+            d.slice_off[i] = off;
+        }
+    }
+    d.params = pp;
+    d.params.n_coef = 0;
+    memset(&d.sx, 0, sizeof(d.sx));
+    d.sx.picture_coding_type = pp.picture_coding_type;
+    for (int a = 0; a < 2; a++) for (int b = 0; b < 2; b++) d.sx.f_code[a][b] = syntax->f_code[a][b];
+    d.sx.intra_dc_precision = syntax->intra_dc_precision;
+    d.sx.q_scale_type = syntax->q_scale_type != 0;
+    d.sx.intra_vlc_format = syntax->intra_vlc_format != 0;
+    d.sx.chroma_format = ctx->cfg.chroma_format;
+    d.sx.vertical_size = ctx->cfg.height;                 // only compared with 2800 (slice_vertical_position_extension)
+    d.sx.mbw = ctx->mbw; d.sx.mbh = ctx->mbh;
+    d.n_slices = (uint32_t)n_slices;
+    d.slice_region = ctx->slice_region;
+    d.params_out = reinterpret_cast<mp2v_pic_params_t*>(s->d_staged);
+    d.mb = reinterpret_cast<mp2v_mb_info_t*>(s->d_arena + kParamsBytes);
+    d.coef = reinterpret_cast<mp2v_coef_t*>(s->d_arena + ctx->coef_off);
+    d.status = s->d_status;
+    s->n_slices = n_slices;
+    s->need_blank = rows_covered < ctx->mbh;
+    s->vlc = true;
+    s->stream_pic = true;
+    s->vlc_wait = nullptr;
+    s->status_pending = true;
+    s->trace_idx = -1;
+    s->alg_bytes = 0;                                     // folded in from the parse status (fold_status)
+    ctx->status_fifo.push_back(s->pub.slot);
+    ctx->parse_pending.push_back(s->pub.slot);
+    ctx->stats.d2h_bytes += (uint64_t)n_slices * sizeof(vlc_slice_status_t);
+    ctx->stats.vlc_slices += (uint64_t)n_slices;
+    return queue_slot(ctx, s);
 }
 
 extern "C" MP2V_API int mp2v_recon_precheck(mp2v_recon_t* ctx, mp2v_picture_t* pic) {
@@ -739,6 +1001,8 @@ extern "C" MP2V_API int mp2v_recon_sync(mp2v_recon_t* ctx) {
     CK(cudaStreamSynchronize(ctx->s_copy), "stream sync");
     CK(cudaStreamSynchronize(ctx->s_compute), "stream sync");
     CK(cudaStreamSynchronize(ctx->s_d2h), "stream sync");      // queued frame copies (auto download, downloads of other threads)
+    CK(cudaStreamSynchronize(ctx->s_d2h2), "stream sync");
+    for (auto& b : ctx->parse_buf) b.used = false;
     std::fill(ctx->read_pending.begin(), ctx->read_pending.end(), 0);
     for (auto& s : ctx->slots) if (s.state == SLOT_INFLIGHT) s.state = SLOT_FREE;
     ctx->batch_ramp = 1;
@@ -776,9 +1040,15 @@ extern "C" MP2V_API int mp2v_recon_reset(mp2v_recon_t* ctx) {
     CK(cudaStreamSynchronize(ctx->s_copy), "stream sync");
     CK(cudaStreamSynchronize(ctx->s_compute), "stream sync");
     CK(cudaStreamSynchronize(ctx->s_d2h), "stream sync");
+    CK(cudaStreamSynchronize(ctx->s_d2h2), "stream sync");
+    for (auto st : ctx->s_parse) if (st) CK(cudaStreamSynchronize(st), "stream sync");
     ctx->pending.clear();
+    ctx->closed.clear();
+    ctx->queued = 0;
+    ctx->parse_pending.clear();
+    for (auto& b : ctx->parse_buf) b.used = false;
     ctx->status_fifo.clear();
-    for (auto& s : ctx->slots) { s.state = SLOT_FREE; s.staged = false; s.status_pending = false; s.prechecked = false; s.vlc = false; }
+    for (auto& s : ctx->slots) { s.state = SLOT_FREE; s.staged = false; s.status_pending = false; s.prechecked = false; s.vlc = false; s.stream_pic = false; }
     std::fill(ctx->frame_written.begin(), ctx->frame_written.end(), 0);
     std::fill(ctx->mirror_valid.begin(), ctx->mirror_valid.end(), 0);
     std::fill(ctx->read_pending.begin(), ctx->read_pending.end(), 0);
@@ -845,11 +1115,10 @@ extern "C" MP2V_API int mp2v_recon_run_resident(mp2v_recon_t* ctx, mp2v_picture_
 // for *done outside the lock so that submissions and launches keep flowing while the copy runs.
 static int enqueue_frame_copy(mp2v_recon* ctx, int frame_id, uint8_t* const dst[3], const int32_t dst_stride[3], cudaEvent_t* done) {
     if (frame_id < 0 || frame_id >= ctx->cfg.n_frames) return ctx->fail(MP2V_ERR_ARG, "frame id out of range");
-    int rc = flush_locked(ctx);
-    if (rc != MP2V_OK) return rc;
+    if (frame_is_queued(ctx, frame_id)) { const int rc = flush_locked(ctx); if (rc != MP2V_OK) return rc; }
     if (!ctx->frame_written[frame_id]) return ctx->fail(MP2V_ERR_STATE, "frame has never been written");
     CK(cudaSetDevice(ctx->cfg.device), "cudaSetDevice");
-    CK(cudaStreamWaitEvent(ctx->s_d2h, ctx->frame_ev[frame_id], 0), "stream wait");
+    CK(cudaStreamWaitEvent(ctx->s_d2h, ctx->frame_launch[frame_id] >= 0 ? ctx->launch_ev[ctx->frame_launch[frame_id]] : ctx->frame_ev[frame_id], 0), "stream wait");
     // destination laid out exactly like the device frame (the pinned mirrors are): one copy for all planes
     bool same = true;
     for (int p = 0; p < 3; p++)
@@ -899,12 +1168,12 @@ extern "C" MP2V_API int mp2v_recon_map_frame(mp2v_recon_t* ctx, int frame_id, ui
     {
         std::lock_guard<std::mutex> lk(ctx->mu);
         if (frame_id < 0 || frame_id >= ctx->cfg.n_frames) return ctx->fail(MP2V_ERR_ARG, "frame id out of range");
-        if (!ctx->h_frames[frame_id]) {
+        if (!ctx->h_frames[frame_id]) {      // (contexts with MP2V_RECON_AUTO_DOWNLOAD own all mirrors from the start)
             CK(cudaSetDevice(ctx->cfg.device), "cudaSetDevice");
             CK(cudaHostAlloc(&ctx->h_frames[frame_id], ctx->lay.bytes, cudaHostAllocDefault), "cudaHostAlloc frame mirror");
         }
         for (int p = 0; p < 3; p++) { planes[p] = ctx->h_frames[frame_id] + ctx->lay.plane_offset[p]; strides[p] = ctx->lay.stride[p]; }
-        if (ctx->auto_dl) { const int rc = flush_locked(ctx); if (rc != MP2V_OK) return rc; }
+        if (frame_is_queued(ctx, frame_id)) { const int rc = flush_locked(ctx); if (rc != MP2V_OK) return rc; }
         if (ctx->auto_dl && ctx->mirror_valid[frame_id]) {
             done = ctx->mirror_ev[ctx->mirror_ev_of[frame_id]];   // the copy was queued with the picture's launch
             pooled = false;
@@ -929,6 +1198,7 @@ extern "C" MP2V_API int mp2v_recon_upload_frame(mp2v_recon_t* ctx, int frame_id,
                         (size_t)ctx->lay.width[p], (size_t)ctx->lay.height[p], cudaMemcpyHostToDevice), "H2D frame");
     ctx->frame_written[frame_id] = 1;
     ctx->mirror_valid[frame_id] = 0;
+    ctx->frame_launch[frame_id] = -1;
     CK(cudaEventRecord(ctx->frame_ev[frame_id], ctx->s_compute), "event record");
     return MP2V_OK;
 }

@@ -33,6 +33,32 @@ struct vlc_slice_status_t {
     uint32_t ref_dirs;          // prediction directions summed over the slice's macroblocks
 };
 
+// ---- stream-resident front end: the whole elementary stream lies in device memory, a scan kernel lists its start
+// codes, and pictures are handed over as descriptors (a few hundred bytes each, one H2D copy per parse launch) that
+// name their slices by byte offset.  One launch parses every slice of up to kMaxStreamBatch pictures.
+constexpr int kMaxStreamBatch = 64;
+struct vlc_stream_pic_t {
+    mp2v_pic_params_t params;           // copied into the slot's device parameter block by the kernel (the reconstruction kernel reads W from there)
+    slice_syntax_t sx;
+    uint32_t n_slices;
+    uint32_t slice_region;              // coefficient records reserved per slice
+    mp2v_pic_params_t* params_out;      // device addresses of the picture slot
+    mp2v_mb_info_t* mb;
+    mp2v_coef_t* coef;
+    vlc_slice_status_t* status;         // pinned + mapped, one entry per slice
+    uint32_t slice_off[1];              // n_slices byte offsets of the slices' start codes in the resident stream (the struct is over-allocated)
+};
+inline size_t vlc_stream_desc_bytes(int max_slices) { return (sizeof(vlc_stream_pic_t) + (size_t)max_slices * sizeof(uint32_t) + 15) & ~(size_t)15; }
+
+// parse every slice of n_pics pictures described at desc (device copy, desc_stride bytes apart) out of the resident stream
+cudaError_t launch_vlc_stream(const uint8_t* d_stream, const uint8_t* d_desc, size_t desc_stride, int n_pics, int max_slices, const void* d_tables, cudaStream_t stream);
+
+// start-code scan of a device-resident stream (the reference's scan_start_codes, start_codes_search.hpp:7-26): byte offsets of
+// every 00 00 01 prefix in [0, len), ascending, into d_codes (capacity cap entries); *d_total = number found (may exceed cap: then
+// only the first cap were stored).  d_counts: scratch of vlc_scan_blocks(len) + 1 entries.  d_stream must be readable up to len + 32.
+size_t vlc_scan_blocks(size_t len);
+cudaError_t launch_start_code_scan(const uint8_t* d_stream, size_t len, uint32_t* d_counts, uint32_t* d_codes, uint32_t cap, uint32_t* d_total, cudaStream_t stream);
+
 // the tables are copied to the device once per context
 cudaError_t vlc_upload_tables(void** d_tables);
 cudaError_t vlc_kernel_attributes(cudaFuncAttributes* out);

@@ -15,7 +15,7 @@ _lib = None
 
 EXPORTS = [
     "mp2v_frame_layout", "mp2v_recon_create", "mp2v_recon_destroy", "mp2v_recon_last_error",
-    "mp2v_recon_acquire_picture", "mp2v_recon_release_picture", "mp2v_recon_submit", "mp2v_recon_submit_slices", "mp2v_recon_stage_slices", "mp2v_recon_submit_staged", "mp2v_recon_precheck", "mp2v_recon_flush",
+    "mp2v_recon_acquire_picture", "mp2v_recon_release_picture", "mp2v_recon_submit", "mp2v_recon_submit_slices", "mp2v_recon_stage_slices", "mp2v_recon_submit_staged", "mp2v_recon_stream_begin", "mp2v_recon_submit_stream_picture", "mp2v_recon_precheck", "mp2v_recon_flush",
     "mp2v_recon_sync", "mp2v_recon_reset", "mp2v_recon_upload", "mp2v_recon_run_resident", "mp2v_recon_download_frame",
     "mp2v_recon_map_frame", "mp2v_recon_upload_frame", "mp2v_recon_frame_device_ptrs", "mp2v_recon_convert_frame_nv12", "mp2v_recon_convert_frames_nv12",
     "mp2v_recon_set_timing", "mp2v_recon_get_stats", "mp2v_recon_timer_start", "mp2v_recon_timer_stop",
@@ -46,6 +46,8 @@ def lib():
         L.mp2v_recon_submit_slices.argtypes = [C.c_void_p, P(Picture), P(PicSyntax), P(SliceRef), C.c_int]
         L.mp2v_recon_stage_slices.argtypes = [C.c_void_p, P(Picture), P(PicSyntax), P(SliceRef), C.c_int]
         L.mp2v_recon_submit_staged.argtypes = [C.c_void_p, P(Picture)]
+        L.mp2v_recon_stream_begin.argtypes = [C.c_void_p, C.c_void_p, C.c_size_t, C.c_void_p, C.c_int, C.c_int, P(P(C.c_uint32)), P(C.c_uint32)]
+        L.mp2v_recon_submit_stream_picture.argtypes = [C.c_void_p, P(Picture), P(PicSyntax), P(C.c_uint32), C.c_int]
         L.mp2v_recon_precheck.argtypes = [C.c_void_p, P(Picture)]
         L.mp2v_recon_flush.argtypes = [C.c_void_p]
         L.mp2v_recon_sync.argtypes = [C.c_void_p]
@@ -145,6 +147,29 @@ class Recon:
         buf = np.ascontiguousarray(data, np.uint8)
         refs = (SliceRef * max(len(slices), 1))(*[SliceRef(buf.ctypes.data + off, n, code) for off, n, code in slices])
         self._ck(self.L.mp2v_recon_submit_slices(self.h, pic, C.byref(sy), refs, len(slices)))
+
+    def stream_begin(self, data, size, scan=True):
+        """stream-resident front end: copy data[:size] (uint8 array, kept alive by the caller until the pictures are
+        submitted) to the device; with scan -> ascending offsets of every 00 00 01 prefix (numpy copy)"""
+        self._stream = np.ascontiguousarray(data, np.uint8)
+        codes = C.POINTER(C.c_uint32)()
+        n = C.c_uint32()
+        self._ck(self.L.mp2v_recon_stream_begin(self.h, self._stream.ctypes.data, size, None, 0, 1 if scan else 0,
+                                                C.byref(codes) if scan else None, C.byref(n) if scan else None))
+        if not scan:
+            return None
+        return np.ctypeslib.as_array(codes, shape=(n.value,)).copy() if n.value else np.zeros(0, np.uint32)
+
+    def submit_stream_picture(self, pic, params, slice_offsets, f_code, intra_dc_precision=0, q_scale_type=0, intra_vlc_format=1,
+                              dst=0, l0=-1, l1=-1):
+        """slice_offsets: byte offsets of the slices' START CODES in the resident stream"""
+        p = pic.contents
+        C.memmove(p.params, C.byref(params), C.sizeof(PicParams))
+        p.params.contents.dst_frame, p.params.contents.l0_frame, p.params.contents.l1_frame = dst, l0, l1
+        sy = PicSyntax(((C.c_int32 * 2) * 2)((C.c_int32 * 2)(*f_code[0]), (C.c_int32 * 2)(*f_code[1])),
+                       intra_dc_precision, q_scale_type, intra_vlc_format, 0)
+        offs = (C.c_uint32 * max(len(slice_offsets), 1))(*[int(o) for o in slice_offsets])
+        self._ck(self.L.mp2v_recon_submit_stream_picture(self.h, pic, C.byref(sy), offs, len(slice_offsets)))
 
     def upload(self, pic):
         self._ck(self.L.mp2v_recon_upload(self.h, pic))

@@ -1,27 +1,43 @@
-"""Dev-time: where the end-to-end decode pipeline spends its time (MP2V_PROFILE=1 prints per-stage totals).
-usage: e2e_profile.py [workload ...] ; env DOWNLOAD=0/1, REPS, HOST=1 (host parser too)"""
+"""Dev-time: end-to-end decode of the 1080p IPB texture workload with the decoder's stage profile (MP2V_PROFILE=1)."""
 import os
 import sys
 import time
 
-os.environ["MP2V_PROFILE"] = "1"
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.dirname(os.path.abspath(__file__)))))
-import bench
+os.environ.setdefault("CUDA_DEVICE_MAX_CONNECTIONS", "32")
 from tiny_mp2v_dec_b200.decoder import Decoder
+from tiny_mp2v_dec_b200.streamgen import Stream
 
-dl = os.environ.get("DOWNLOAD", "1") != "0"
-reps = int(os.environ.get("REPS", "3"))
-for name in sys.argv[1:] or ["1080p420_intra", "1080p420_ipb"]:
-    wl = bench.WORKLOADS[name]
-    s = bench.make_stream(wl, 0)
+TEX = dict(mode=2, texture_noise=3, pct_intra_in_pb=3, q_scale_type=0, alternate_scan=0, intra_dc_precision=0)
+
+
+def run(name, w, h, cf, reps=5, **kw):
+    s = Stream(w, h, cf, **kw)
     n = len(s.pictures)
-    modes = [True] + ([False] if os.environ.get("HOST") else [])
-    for gpu_vlc in modes:
-        d = Decoder(wl["width"], wl["height"], wl["chroma_format"], num_threads=14, max_batch=8, output_lag=6, gpu_vlc=gpu_vlc).prepare(download=dl)
+    import torch
+    pinned = torch.empty(len(s.padded), dtype=torch.uint8).pin_memory()
+    pinned.numpy()[:] = s.padded
+    s.padded = pinned.numpy()
+    print("== %s: %d pictures, %.0f kB/frame" % (name, n, s.size / n / 1e3), flush=True)
+    for dl, batch, lag, gv in [(True, 8, 6, True), (False, 8, 6, True), (True, 16, 16, True), (False, 16, 16, True), (False, 32, 32, True), (True, 8, 6, False)]:
+        d = Decoder(w, h, cf, num_threads=14, max_batch=batch, output_lag=lag, gpu_vlc=gv).prepare(download=dl)
         d.decode(s.padded, s.size, want_output=False, download=dl)
+        os.environ.pop("MP2V_PROFILE", None)
+        t0 = time.perf_counter()
         for _ in range(reps):
-            t0 = time.perf_counter()
             d.decode(s.padded, s.size, want_output=False, download=dl)
-            dt = time.perf_counter() - t0
-            print("%s gpu_vlc=%d download=%d: %.0f fps (%.1f ms)  launches %d + %d" % (name, gpu_vlc, dl, n / dt, dt * 1e3, d.stats.launches, d.stats.vlc_launches), flush=True)
+        dt = (time.perf_counter() - t0) / reps
+        st = d.stats
+        print("   gpu_vlc=%d download=%d batch=%2d lag=%2d: %6.0f fps  %.2f ms/call  launches %3d + %3d parse  kernel %.2f ms  h2d %.1f MB d2h %.1f MB"
+              % (gv, dl, batch, lag, n / dt, dt * 1e3, st.launches, st.vlc_launches, st.kernel_ms, st.h2d_bytes / 1e6, st.d2h_bytes / 1e6), flush=True)
+        os.environ["MP2V_PROFILE"] = "1"
+        d.decode(s.padded, s.size, want_output=False, download=dl)
+        os.environ.pop("MP2V_PROFILE", None)
         d.close()
+
+
+if __name__ == "__main__":
+    run("1080p420 IPB texture", 1920, 1088, 1, seed=3003, n_gops=8, gop_n=15, gop_m=3, **TEX)
+    if "--all" in sys.argv:
+        run("1080p420 intra texture", 1920, 1088, 1, seed=2002, n_gops=8, gop_n=15, gop_m=1, intra_only=1, **TEX)
+        run("720p420 IPB texture", 1280, 720, 1, seed=5005, n_gops=8, gop_n=15, gop_m=3, **TEX)
