@@ -167,7 +167,7 @@ static std::vector<uint8_t> load(const char* path) {
     return v;
 }
 
-// ref_decode <serial|mt> in.m2v width height chroma_format [out.yuv] [threads] [pool] [repeat]
+// ref_decode <serial|mt> in.m2v width height chroma_format [out.yuv | - | hash] [threads] [pool] [repeat]
 int main(int argc, char** argv) {
     if (argc < 6) { fprintf(stderr, "usage: %s serial|mt in.m2v W H CF [out.yuv|-] [threads] [pool] [repeat]\n", argv[0]); return 2; }
     std::string mode = argv[1];
@@ -175,7 +175,9 @@ int main(int argc, char** argv) {
     if (bs.empty()) { fprintf(stderr, "cannot read %s\n", argv[2]); return 1; }
     int len = (int)bs.size() - 256;
     int w = atoi(argv[3]), h = atoi(argv[4]), cf = atoi(argv[5]);
-    const char* outp = (argc > 6 && strcmp(argv[6], "-")) ? argv[6] : nullptr;
+    // "hash": the renderer hashes every frame (FNV-1a over the cropped planes) but nothing is stored or written
+    const bool hash_only = argc > 6 && !strcmp(argv[6], "hash");
+    const char* outp = (argc > 6 && strcmp(argv[6], "-") && !hash_only) ? argv[6] : nullptr;
     int threads = argc > 7 ? atoi(argv[7]) : 8, pool = argc > 8 ? atoi(argv[8]) : 10, repeat = argc > 9 ? atoi(argv[9]) : 1;
     size_t fb = (size_t)w * h * (cf == 1 ? 3 : cf == 2 ? 4 : 6) / 2;
     std::vector<uint8_t> out;
@@ -188,7 +190,7 @@ int main(int argc, char** argv) {
             frames = ref_decode_serial(bs.data(), len, w, h, cf, outp ? out.data() : nullptr, out.size(), &nbytes, &hash);
             s = std::chrono::duration<double>(std::chrono::steady_clock::now() - t0).count();
         } else {
-            frames = ref_decode_mt(bs.data(), len, w, h, cf, pool, threads, outp ? 1 : 0, outp ? out.data() : nullptr, out.size(), &nbytes, &hash, &s);
+            frames = ref_decode_mt(bs.data(), len, w, h, cf, pool, threads, (outp || hash_only) ? 1 : 0, outp ? out.data() : nullptr, out.size(), &nbytes, &hash, &s);
         }
         if (s < best) best = s;
     }

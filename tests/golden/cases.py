@@ -9,6 +9,10 @@ CASES = {
     "sd422_longmv": (720, 480, 2, dict(seed=107, gop_n=7, gop_m=3, mv_range=120, pct_skipped=30)),
     "tiny420_m1": (48, 32, 1, dict(seed=108, gop_n=10, gop_m=1)),
     "natural420": (640, 368, 1, dict(seed=109, mode=1, n_gops=2, gop_n=15, gop_m=3)),
+    # texture mode: a translating procedural texture + noise, really encoded (forward DCT, quantiser_scale 4..8)
+    "texture420": (640, 368, 1, dict(seed=113, mode=2, n_gops=2, gop_n=9, gop_m=3, pct_intra_in_pb=3)),
+    "texture444": (352, 288, 3, dict(seed=114, mode=2, n_gops=1, gop_n=7, gop_m=3, q_scale_type=1, alternate_scan=1)),
+    "cif420_userdata": (352, 288, 1, dict(seed=115, n_gops=2, gop_n=6, gop_m=3, user_data_bytes=37)),
     "tall420_vpos_ext": (32, 2816, 1, dict(seed=112, gop_n=4, gop_m=3)),
     "hd420_ipb": (1920, 1088, 1, dict(seed=110, gop_n=7, gop_m=3)),
     "hd422_ipb": (1920, 1088, 2, dict(seed=111, gop_n=4, gop_m=3)),

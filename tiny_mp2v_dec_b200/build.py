@@ -85,7 +85,7 @@ def build_streamgen(force=False):
     src = os.path.join(ROOT, "tools", "streamgen", "streamgen.cpp")
     deps = [src, os.path.join(ROOT, "tools", "streamgen", "streamgen.h")] + _deps(os.path.join(CSRC, "host"), os.path.join(ROOT, "include"))
     if force or _stale(STREAMGEN_LIB, deps):
-        _run(["g++", "-std=c++17", "-O2", "-Wall", "-fPIC", "-shared", "-fvisibility=hidden",
+        _run(["g++", "-std=c++17", "-O2", "-Wall", "-fPIC", "-shared", "-fvisibility=hidden", "-pthread",
               "-I", os.path.join(ROOT, "include"), "-I", os.path.join(CSRC, "host"), "-o", STREAMGEN_LIB, src])
     return STREAMGEN_LIB
 

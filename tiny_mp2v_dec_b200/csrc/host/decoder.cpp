@@ -476,7 +476,7 @@ bool mp2v_decoder_c::impl_t::prepare(bool gpu_vlc) {
         mp2v_recon_config_t rc{};
         rc.device = id; rc.width = c.width; rc.height = c.height; rc.chroma_format = c.chroma_format;
         rc.n_frames = d.n_frames; rc.n_pictures = d.n_slots; rc.max_batch = opt.max_batch;
-        if (gpu_vlc && rc.max_batch < 16) rc.max_batch = 16;     // device-parsed pictures: launches (parse and reconstruction) are issued per 16 queued pictures
+        if (gpu_vlc && rc.max_batch < 64) rc.max_batch = 64;     // device-parsed pictures are launched in lots of up to 64, one launch per dependency level
         rc.flags = MP2V_RECON_VALIDATE | (gpu_vlc ? MP2V_RECON_DEVICE_VLC : 0) | (opt.download_frames ? MP2V_RECON_AUTO_DOWNLOAD : MP2V_RECON_THROUGHPUT);
         rc.coef_capacity = (uint32_t)(cap > 0xffffffffull ? 0xffffffffull : cap);
         if (mp2v_recon_create(&rc, &d.recon) != MP2V_OK) {

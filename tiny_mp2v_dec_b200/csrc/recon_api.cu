@@ -86,9 +86,8 @@ struct mp2v_recon {
     cudaStream_t s_copy = nullptr, s_compute = nullptr, s_d2h = nullptr, s_d2h2 = nullptr;
     cudaEvent_t ev_h2d = nullptr, ev_t0 = nullptr, ev_t1 = nullptr;
     std::vector<slot_t> slots;
-    std::vector<int> pending;                  // the open launch group: queued slots, submit order
-    std::vector<std::vector<int>> closed;      // closed launch groups (a later picture depends on them), oldest first
-    int queued = 0;                            // pictures in closed + pending
+    std::vector<int> pending;                  // queued slots, submit order; launched by dependency level (flush_locked)
+    int queued = 0;                            // = pending.size()
     std::mutex mu;
     std::string err;
     uint64_t seq = 0;
@@ -107,6 +106,8 @@ struct mp2v_recon {
     uint8_t* d_blank_mb = nullptr;             // mb_count blank records, copied over a slot's records before each parse
     // MP2V_TRACE=1 (development): device timestamps per picture, dumped to stderr by mp2v_recon_sync
     struct trace_rec_t { uint64_t picture_no; cudaEvent_t h2d, vlc, recon, d2h; };
+    struct launch_trace_t { int n; cudaEvent_t begin, end, copied; };      // MP2V_TRACE: one per reconstruction launch
+    std::vector<launch_trace_t> launch_log;
     bool trace = false;
     cudaEvent_t trace_base = nullptr;
     std::vector<trace_rec_t> trace_log;
@@ -321,7 +322,8 @@ static int create_impl(mp2v_recon* ctx) {
     }
     if (ctx->vlc) {
         // stream-resident front end: parse streams, descriptor buffers (one per batched parse launch in flight)
-        for (auto& st : ctx->s_parse) CK(cudaStreamCreateWithFlags(&st, cudaStreamNonBlocking), "stream");
+        const bool parse_first = getenv("MP2V_PARSE_PRIO") && atoi(getenv("MP2V_PARSE_PRIO"));      // dev knob
+        for (auto& st : ctx->s_parse) CK(cudaStreamCreateWithPriority(&st, cudaStreamNonBlocking, parse_first ? prio_greatest : prio_least), "stream");
         CK(cudaEventCreateWithFlags(&ctx->ev_stream, cudaEventDisableTiming), "event");
         ctx->desc_stride = vlc_stream_desc_bytes(ctx->mbh);
         for (auto& b : ctx->parse_buf) {
@@ -408,7 +410,14 @@ static int launch_slots(mp2v_recon* ctx, const int* ids, int n, bool download = 
         }
         CK(cudaEventRecord(t0, ctx->s_compute), "event record");
     }
+    mp2v_recon::launch_trace_t lt{n, nullptr, nullptr, nullptr};
+    if (ctx->trace) {
+        if (!ctx->trace_base) { CK(cudaEventCreate(&ctx->trace_base), "event"); CK(cudaEventRecord(ctx->trace_base, ctx->s_compute), "event record"); }
+        CK(cudaEventCreate(&lt.begin), "event"); CK(cudaEventCreate(&lt.end), "event"); CK(cudaEventCreate(&lt.copied), "event");
+        CK(cudaEventRecord(lt.begin, ctx->s_compute), "event record");
+    }
     CK(launch_recon(ctx->cfg.chroma_format, b, ctx->tmaps, ctx->s_compute), "reconstruction kernel launch");
+    if (ctx->trace) CK(cudaEventRecord(lt.end, ctx->s_compute), "event record");
     if (ctx->timing) {
         CK(cudaEventRecord(t1, ctx->s_compute), "event record");
         ctx->timed.emplace_back(t0, t1);
@@ -452,7 +461,9 @@ static int launch_slots(mp2v_recon* ctx, const int* ids, int n, bool download = 
         }
         if (ctx->trace) for (int i = 0; i < n; i++) if (ctx->slots[ids[i]].vlc && ctx->slots[ids[i]].trace_idx >= 0) CK(cudaEventRecord(ctx->trace_log[ctx->slots[ids[i]].trace_idx].d2h, sd), "event record");
         CK(cudaEventRecord(ctx->mirror_ev[ev], sd), "event record");
+        if (ctx->trace) CK(cudaEventRecord(lt.copied, sd), "event record");
     }
+    if (ctx->trace) ctx->launch_log.push_back(lt);
     ctx->stats.pictures += n;
     ctx->stats.launches += 1;
     return MP2V_OK;
@@ -514,15 +525,40 @@ static int launch_group(mp2v_recon* ctx, const std::vector<int>& group) {
     return MP2V_OK;
 }
 
-// launch everything that is queued: the pending parses in one launch, then the groups in submit order
+// Launch everything that is queued: the pending parses in one launch, then the pictures by DEPENDENCY LEVEL.
+// A picture's level is one more than the deepest queued picture it reads from, or whose frame accesses it must
+// not overtake (it overwrites a frame that one reads or writes); pictures of one level are independent and share
+// a launch, whatever GOP chain they belong to -- the I pictures of every queued GOP, then their P pictures, ...
+// This is the reference's add_dependency order (decoder.cpp:294-305) taken over the whole lot.
 static int flush_locked(mp2v_recon* ctx) {
-    if (ctx->queued == 0 && ctx->parse_pending.empty()) return MP2V_OK;
+    if (ctx->pending.empty() && ctx->parse_pending.empty()) return MP2V_OK;
     CK(cudaSetDevice(ctx->cfg.device), "cudaSetDevice");
     int rc = launch_parse_batch(ctx);
     if (rc != MP2V_OK) return rc;
-    for (auto& g : ctx->closed) { rc = launch_group(ctx, g); if (rc != MP2V_OK) return rc; }
-    ctx->closed.clear();
-    if (!ctx->pending.empty()) { rc = launch_group(ctx, ctx->pending); if (rc != MP2V_OK) return rc; }
+    const int n = (int)ctx->pending.size();
+    std::vector<int> level((size_t)n, 0);
+    int top = 0;
+    for (int i = 0; i < n; i++) {
+        const mp2v_pic_params_t& p = *ctx->slots[ctx->pending[i]].pub.params;
+        int lv = 0;
+        for (int j = 0; j < i; j++) {
+            const mp2v_pic_params_t& q = *ctx->slots[ctx->pending[j]].pub.params;
+            if (q.dst_frame == p.l0_frame || q.dst_frame == p.l1_frame || q.dst_frame == p.dst_frame ||
+                q.l0_frame == p.dst_frame || q.l1_frame == p.dst_frame) lv = std::max(lv, level[j] + 1);
+        }
+        level[i] = lv;
+        top = std::max(top, lv);
+    }
+    std::vector<int> group;
+    for (int lv = 0; lv <= top && n; lv++) {
+        group.clear();
+        for (int i = 0; i < n; i++) {
+            if (level[i] != lv) continue;
+            group.push_back(ctx->pending[i]);
+            if ((int)group.size() == ctx->max_batch) { rc = launch_group(ctx, group); if (rc != MP2V_OK) return rc; group.clear(); }
+        }
+        if (!group.empty()) { rc = launch_group(ctx, group); if (rc != MP2V_OK) return rc; }
+    }
     ctx->pending.clear();
     ctx->queued = 0;
     if (ctx->batch_ramp < std::max(ctx->max_batch, 16)) ctx->batch_ramp *= 2;
@@ -531,7 +567,6 @@ static int flush_locked(mp2v_recon* ctx) {
 
 static bool frame_is_queued(const mp2v_recon* ctx, int f) {
     for (int id : ctx->pending) if (ctx->slots[id].pub.params->dst_frame == f) return true;
-    for (auto& g : ctx->closed) for (int id : g) if (ctx->slots[id].pub.params->dst_frame == f) return true;
     return false;
 }
 
@@ -682,31 +717,25 @@ static bool references_available(const mp2v_recon* ctx, const mp2v_pic_params_t&
     return true;
 }
 
-// Queue a slot whose records are (or will be) complete; ctx->mu held.  A picture cannot share a launch with a
-// picture it reads from, nor with one touching its destination: such a conflict CLOSES the open group (it is
-// launched later, in order); everything queued is launched once `max_batch` pictures wait (1, 2, 4, ... right
-// after a sync, so that the first frames of a decode leave early).
+// Queue a slot whose records are (or will be) complete; ctx->mu held.  Everything queued is launched once a lot
+// of pictures waits: `max_batch` of them -- 1, 2, 4, ... right after a sync, so that the first frames of a decode
+// leave early -- or by flush / sync / a wait for one of their frames.
 static int queue_slot(mp2v_recon* ctx, slot_t* s) {
     const mp2v_pic_params_t& pp = *s->pub.params;
     if (!references_available(ctx, pp)) return ctx->fail(MP2V_ERR_STATE, "reference frame has never been written");
-    bool conflict = (int)ctx->pending.size() >= ctx->max_batch;
-    for (int id : ctx->pending) {
-        const mp2v_pic_params_t& q = *ctx->slots[id].pub.params;
-        if (q.dst_frame == pp.l0_frame || q.dst_frame == pp.l1_frame || q.dst_frame == pp.dst_frame ||
-            q.l0_frame == pp.dst_frame || q.l1_frame == pp.dst_frame) conflict = true;
-    }
-    if (conflict && !ctx->pending.empty()) { ctx->closed.emplace_back(std::move(ctx->pending)); ctx->pending.clear(); }
-    // a closed group that reads or writes this picture's destination must run first anyway (launch order = submit order)
     s->state = SLOT_QUEUED;
     s->seq = ++ctx->seq;
     s->picture_no = ctx->pictures_submitted++;
     ctx->pending.push_back(s->pub.slot);
-    ctx->queued++;
+    ctx->queued = (int)ctx->pending.size();
     // Device-parsed stream pictures are launched in larger lots (4, 8, ... kMaxStreamBatch): a slice parses at the speed of
     // ONE thread (about a millisecond for a dense 1080p row), so the parser's throughput is the number of pictures in flight.
     // MP2V_RECON_THROUGHPUT: full lots from the first picture on (nobody is waiting for the first frame).
-    const int ramp = (ctx->cfg.flags & MP2V_RECON_THROUGHPUT) ? kMaxBatch : ctx->batch_ramp;
-    const int quota = s->stream_pic ? std::min(kMaxStreamBatch, 4 * ramp) : std::min(ctx->max_batch, ramp);
+    // Otherwise lots of 4, 8, 16, 16, ...: the frame copies to the host (the slower stage) start early and never run dry
+    // (measured: a last lot of 60 pictures left the copy engine idle for 2 ms of a 12 ms decode).
+    const bool rate = (ctx->cfg.flags & MP2V_RECON_THROUGHPUT) != 0;
+    const int ramp = rate ? kMaxBatch : ctx->batch_ramp;
+    const int quota = s->stream_pic ? std::min(rate ? kMaxStreamBatch : 16, 4 * ramp) : std::min(ctx->max_batch, ramp);
     if (ctx->queued >= quota) return flush_locked(ctx);
     return MP2V_OK;
 }
@@ -1007,6 +1036,19 @@ extern "C" MP2V_API int mp2v_recon_sync(mp2v_recon_t* ctx) {
     for (auto& s : ctx->slots) if (s.state == SLOT_INFLIGHT) s.state = SLOT_FREE;
     ctx->batch_ramp = 1;
     ctx->pictures_submitted = 0;                         // slice errors name pictures by their number since the last sync
+    if (ctx->trace && !ctx->launch_log.empty()) {
+        int i = 0;
+        for (auto& lt : ctx->launch_log) {
+            float a = -1, b = -1, c = -1;
+            cudaEventElapsedTime(&a, ctx->trace_base, lt.begin); cudaEventElapsedTime(&b, ctx->trace_base, lt.end);
+            if (cudaEventQuery(lt.copied) == cudaSuccess) cudaEventElapsedTime(&c, ctx->trace_base, lt.copied);
+            fprintf(stderr, "[mp2v trace] launch %3d  %3d pictures  kernel %7.3f .. %7.3f  frames on the host %7.3f ms\n", i++, lt.n, a, b, c);
+            cudaEventDestroy(lt.begin); cudaEventDestroy(lt.end); cudaEventDestroy(lt.copied);
+        }
+        cudaGetLastError();
+        ctx->launch_log.clear();
+        if (ctx->trace_log.empty()) { cudaEventDestroy(ctx->trace_base); ctx->trace_base = nullptr; }
+    }
     if (ctx->trace && !ctx->trace_log.empty()) {
         cudaStreamSynchronize(ctx->s_d2h);
         for (auto& tr : ctx->trace_log) {
@@ -1043,7 +1085,6 @@ extern "C" MP2V_API int mp2v_recon_reset(mp2v_recon_t* ctx) {
     CK(cudaStreamSynchronize(ctx->s_d2h2), "stream sync");
     for (auto st : ctx->s_parse) if (st) CK(cudaStreamSynchronize(st), "stream sync");
     ctx->pending.clear();
-    ctx->closed.clear();
     ctx->queued = 0;
     ctx->parse_pending.clear();
     for (auto& b : ctx->parse_buf) b.used = false;

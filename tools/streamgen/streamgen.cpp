@@ -6,7 +6,9 @@
 #include <cstdio>
 #include <cstdlib>
 #include <cstring>
+#include <algorithm>
 #include <string>
+#include <thread>
 #include <utility>
 #include <vector>
 
@@ -306,7 +308,8 @@ struct mp2v_gen {
             const int sx = 2 * p.width / w, sy = 2 * p.height / h;      // luma half-pels per sample of this plane
             f.w[pl] = w; f.h[pl] = h;
             f.px[pl].resize((size_t)w * h);
-            for (int y = 0; y < h; y++) {
+            uint8_t* const dstpx = f.px[pl].data();
+            parallel_rows(h, [=](int y) {
                 const int Y = sy * y + t * gvy;
                 for (int x = 0; x < w; x++) {
                     const int X = sx * x + t * gvx;
@@ -314,9 +317,9 @@ struct mp2v_gen {
                     for (int i = 0; i < 4; i++) { const wave_t& q = waves[pl][i]; v += q.amp * psin(q.fx * X + q.fy * Y + q.phase); }
                     const uint32_t hsh = hash32(((uint64_t)p.seed << 40) ^ ((uint64_t)(t & 0xfff) << 28) ^ ((uint64_t)pl << 26) ^ ((uint64_t)y << 13) ^ (uint64_t)x);
                     v = 128 + (v >> 10) + (int)(hsh % (uint32_t)(2 * noise + 1)) - noise;
-                    f.px[pl][(size_t)y * w + x] = (uint8_t)(v < 0 ? 0 : v > 255 ? 255 : v);
+                    dstpx[(size_t)y * w + x] = (uint8_t)(v < 0 ? 0 : v > 255 ? 255 : v);
                 }
-            }
+            });
         }
     }
     // forward 8x8 DCT (ISO/IEC 13818-2 Annex A normalisation), 14-bit fixed-point basis, out[v * 8 + u]
@@ -434,6 +437,20 @@ struct mp2v_gen {
         bw.put(intra ? kEobB15 : kEobB14);
     }
 
+    // rows of a picture are analysed on several threads (results do not depend on the thread count)
+    template <class F>
+    static void parallel_rows(int n, F fn) {
+        unsigned hw = std::thread::hardware_concurrency();
+        const int nt = (int)std::min<unsigned>(hw ? hw : 4u, 32u);
+        if (nt <= 1 || n < 4) { for (int i = 0; i < n; i++) fn(i); return; }
+        std::vector<std::thread> th;
+        for (int k = 0; k < nt; k++) th.emplace_back([=] { for (int i = k; i < n; i += nt) fn(i); });
+        for (auto& x : th) x.join();
+    }
+
+    struct mb_plan_t { bool intra, fwd, bwd; int mv[2][2]; uint32_t cbp; int dcq[12]; int16_t lv[12][64]; };
+    std::vector<mb_plan_t> plan;
+
     void code_picture_texture(const pic_hdr_t& h, picture_t& pic, int t) {
         const bool big = p.height > 2800;
         const int cf = p.chroma_format, cw = cf == 3 ? 16 : 8, ch = cf == 1 ? 8 : 16;
@@ -445,44 +462,42 @@ struct mp2v_gen {
             gmv[0][0] = (t - ref_time[0]) * gvx; gmv[0][1] = (t - ref_time[0]) * gvy;
             gmv[1][0] = (t - ref_time[1]) * gvx; gmv[1][1] = (t - ref_time[1]) * gvy;
         }
-        std::vector<int> py(256), pcb(16 * 16), pcr(16 * 16), tmp(256);
-        for (int mby = 0; mby < mbh; mby++) {
-            bw.start_code(big ? (mby & 127) + 1 : mby + 1);
-            if (big) bw.put(mby >> 7, 3);
-            qcode = h.q_scale_type ? rng.range(4, 8) : rng.range(2, 4);    // quantiser_scale 4 .. 8 with either mapping (decoder.cpp:140-145)
-            qscale = quantiser_scale_of(qcode, h.q_scale_type);
-            bw.put(qcode, 5); bw.put(0, 1);
-            memset(pmv, 0, sizeof(pmv));
-            for (int c = 0; c < 3; c++) dc_pred[c] = 1 << (h.dc_prec + 7);
-            prev_flags = 0;
-            int pending_skips = 0;
+        // ---- quantiser per slice: quantiser_scale 4 .. 8 with either mapping (decoder.cpp:140-145)
+        std::vector<int> row_qcode((size_t)mbh);
+        for (int mby = 0; mby < mbh; mby++) row_qcode[mby] = h.q_scale_type ? rng.range(4, 8) : rng.range(2, 4);
+        // ---- analysis (parallel): prediction mode, prediction, transform, quantisation of every macroblock
+        plan.resize((size_t)mbw * mbh);
+        const size_t pic_no = pics.size();
+        parallel_rows(mbh, [&, pic_no](int mby) {
+            std::vector<int> py(256), pcb(16 * 16), pcr(16 * 16), tmp(256);
+            const int qs = quantiser_scale_of(row_qcode[mby], h.q_scale_type);
             for (int mbx = 0; mbx < mbw; mbx++) {
-                mp2v_mb_info_t rec{};
-                rec.coef_off = (uint32_t)pic.coef.size();
-                const bool edge = mbx == 0 || mbx == mbw - 1;
-                // ---- prediction mode: the global vector(s) where the window stays inside the frame, intra otherwise
+                mb_plan_t& m = plan[(size_t)mby * mbw + mbx];
+                // the global vector(s) where the window stays inside the frame, intra otherwise
                 bool fwd = false, bwd = false;
                 if (h.type == 2) fwd = window_ok(mbx, mby, gmv[0][0], gmv[0][1]);
                 if (h.type == 3) {
                     const bool okf = window_ok(mbx, mby, gmv[0][0], gmv[0][1]), okb = window_ok(mbx, mby, gmv[1][0], gmv[1][1]);
-                    const int d = (int)(hash32(((uint64_t)p.seed << 32) ^ ((uint64_t)pics.size() << 20) ^ (uint64_t)(mby * mbw + mbx)) % 10u);
+                    const int d = (int)(hash32(((uint64_t)p.seed << 32) ^ ((uint64_t)pic_no << 20) ^ (uint64_t)(mby * mbw + mbx)) % 10u);
                     fwd = okf && d < 7;                                    // 30 % forward, 40 % both, 30 % backward
                     bwd = okb && d >= 3;
                     if (!fwd && !bwd) { fwd = okf; bwd = !okf && okb; }    // whichever window stays inside the frame
                 }
-                bool intra = h.type == 1 || (!fwd && !bwd) || (int)(hash32(((uint64_t)p.seed << 33) ^ ((uint64_t)pics.size() << 21) ^ (uint64_t)(mby * mbw + mbx) ^ 0x5bd1e995u) % 100u) < p.pct_intra_in_pb;
+                const bool intra = h.type == 1 || (!fwd && !bwd) ||
+                                   (int)(hash32(((uint64_t)p.seed << 33) ^ ((uint64_t)pic_no << 21) ^ (uint64_t)(mby * mbw + mbx) ^ 0x5bd1e995u) % 100u) < p.pct_intra_in_pb;
                 if (intra) fwd = bwd = false;
-                int mv[2][2] = {{0, 0}, {0, 0}};
+                m.intra = intra; m.fwd = fwd; m.bwd = bwd;
+                memset(m.mv, 0, sizeof(m.mv));
                 const int* pc[2] = {pcb.data(), pcr.data()};
                 if (!intra) {
                     bool have = false;
                     for (int s2 = 0; s2 < 2; s2++) {
                         if (!(s2 ? bwd : fwd)) continue;
-                        mv[s2][0] = gmv[s2][0]; mv[s2][1] = gmv[s2][1];
+                        m.mv[s2][0] = gmv[s2][0]; m.mv[s2][1] = gmv[s2][1];
                         const frame_t& ref = h.type == 2 ? ref_src[1] : ref_src[s2];
-                        const int cx = cf < 3 ? mv[s2][0] >> 1 : mv[s2][0], cy = cf < 2 ? mv[s2][1] >> 1 : mv[s2][1];   // floor (mb_decoder.cpp:198-206)
+                        const int cx = cf < 3 ? m.mv[s2][0] >> 1 : m.mv[s2][0], cy = cf < 2 ? m.mv[s2][1] >> 1 : m.mv[s2][1];   // floor (mb_decoder.cpp:198-206)
                         for (int pl = 0; pl < 3; pl++) {
-                            const int w = pl ? cw : 16, hh = pl ? ch : 16, vx = pl ? cx : mv[s2][0], vy = pl ? cy : mv[s2][1];
+                            const int w = pl ? cw : 16, hh = pl ? ch : 16, vx = pl ? cx : m.mv[s2][0], vy = pl ? cy : m.mv[s2][1];
                             int* dst = pl == 0 ? py.data() : pl == 1 ? pcb.data() : pcr.data();
                             predict_block(ref, pl, mbx * w + (vx >> 1), mby * hh + (vy >> 1), vx & 1, vy & 1, w, hh, have ? tmp.data() : dst);
                             if (have) for (int k = 0; k < w * hh; k++) dst[k] = (tmp[k] + dst[k] + 1) >> 1;    // avg(backward, forward), mb_decoder.cpp:240-249
@@ -490,12 +505,35 @@ struct mp2v_gen {
                         have = true;
                     }
                 }
-                // ---- transform + quantise every block
-                int lv[12][64], dcq[12];
-                uint32_t cbp = 0;
-                for (int b = 0; b < nblk; b++)
-                    if (quantise_block(pic, b, mbx, mby, intra, py.data(), pc, h.alt_scan, h.dc_prec, qscale, lv[b], &dcq[b])) cbp |= 1u << b;
-                if (!intra && cf == 1 && cbp && (cbp & 63) == 0) cbp = 0;  // (cannot happen for 4:2:0; keeps the 4:2:0 pattern code valid)
+                m.cbp = 0;
+                int lv[64];
+                for (int b = 0; b < nblk; b++) {
+                    if (quantise_block(pic, b, mbx, mby, intra, py.data(), pc, h.alt_scan, h.dc_prec, qs, lv, &m.dcq[b])) m.cbp |= 1u << b;
+                    for (int i = 0; i < 64; i++) m.lv[b][i] = (int16_t)lv[i];
+                }
+            }
+        });
+        // ---- syntax (serial): skipped macroblocks, VLC codes, ground-truth records
+        int lvi[64];
+        for (int mby = 0; mby < mbh; mby++) {
+            bw.start_code(big ? (mby & 127) + 1 : mby + 1);
+            if (big) bw.put(mby >> 7, 3);
+            qcode = row_qcode[mby];
+            qscale = quantiser_scale_of(qcode, h.q_scale_type);
+            bw.put(qcode, 5); bw.put(0, 1);
+            memset(pmv, 0, sizeof(pmv));
+            for (int c = 0; c < 3; c++) dc_pred[c] = 1 << (h.dc_prec + 7);
+            prev_flags = 0;
+            int pending_skips = 0;
+            for (int mbx = 0; mbx < mbw; mbx++) {
+                const mb_plan_t& m = plan[(size_t)mby * mbw + mbx];
+                mp2v_mb_info_t rec{};
+                rec.coef_off = (uint32_t)pic.coef.size();
+                const bool edge = mbx == 0 || mbx == mbw - 1;
+                const bool intra = m.intra;
+                bool fwd = m.fwd, bwd = m.bwd;
+                uint32_t cbp = m.cbp;
+                const int (*mv)[2] = m.mv;
                 // ---- skipped?  P: zero vector and nothing coded; B: same prediction as the previous macroblock and nothing coded
                 if (!intra && cbp == 0 && !edge) {
                     bool skip = false;
@@ -540,7 +578,10 @@ struct mp2v_gen {
                     if (cf == 2) bw.put((cbp >> 6 & 1) << 1 | (cbp >> 7 & 1), 2);
                     if (cf == 3) for (int i = 6; i < 12; i++) bw.put((cbp >> i) & 1, 1);
                 }
-                for (int b = 0; b < nblk; b++) if (cbp & (1u << b)) emit_block(pic, b, intra, h.dc_prec, dcq[b], lv[b]);
+                for (int b = 0; b < nblk; b++) if (cbp & (1u << b)) {
+                    for (int i = 0; i < 64; i++) lvi[i] = m.lv[b][i];
+                    emit_block(pic, b, intra, h.dc_prec, m.dcq[b], lvi);
+                }
                 uint32_t fl = intra ? MP2V_MB_INTRA : (fwd ? MP2V_MB_FWD : 0u) | (bwd ? MP2V_MB_BWD : 0u);
                 if (!intra) for (int s2 = 0; s2 < 2; s2++) for (int k = 0; k < 2; k++) rec.mv[s2][k] = (int16_t)mv[s2][k];
                 rec.bits = MP2V_MB_BITS(pic.coef.size() - rec.coef_off, qscale, cbp, fl);
