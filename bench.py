@@ -1,23 +1,28 @@
 #!/usr/bin/env python
-"""Benchmark of the MPEG-2 reconstruction hot path (BASELINE.json metric: 1080p decode frames/s).
+"""Benchmark of the MPEG-2 decode hot path (BASELINE.json metric: 1080p decode frames/s, Mpixel/s, kernel GB/s vs peak).
 
   python bench.py [--gpus N] [--steps K] [--warmup W] [--workload NAME] [--impl reference]
 
 One step = one pass of the hot path over the whole workload stream (all its pictures).
-  value     frames/s with every picture's records already resident in HBM: device time of K steps of
-            batched reconstruction launches (CUDA events on the launching stream), max over ranks
-  e2e       frames/s through the reference-facing decode API (mp2v_decoder_c via the C ABI) from a host
-            buffer: start-code index + H2D of the coded slices + device slice parsing + reconstruction +
-            D2H of every frame, wall clock (the host-parser mode of the same API is timed beside it)
-  roofline  algorithmic bytes (OUT + REF + 128 B/coded block + 16 B/MB) / per-launch
-            CUDA-event time of the reconstruction kernel, against the measured HBM peak
-  cpu_baseline  the unmodified reference (oracle/_ref, its own multi-threaded decoder) on this box's
-            host cores, same stream, no-op renderer
-Under torchrun (N > 1) every rank decodes its own shard of closed GOPs (weak scaling, no collective
-on the data path); times are the max over ranks.
+  value     decode frames/s with the coded stream already RESIDENT in HBM: slice parsing + reconstruction on the device
+            (mp2v_decoder_c::decode_resident: no upload, no frame download), device time by CUDA events on the stream
+            every launch runs in or is awaited by, max over ranks
+  e2e       frames/s through the reference-facing decode API (mp2v_decoder_c::decode via the C ABI) from a pinned HOST
+            buffer: H2D of the stream + start-code scan + device slice parsing + reconstruction + D2H of every frame
+            into pinned host frames, wall clock (THE headline; the same call without the frame download and with the
+            host slice parser are timed beside it)
+  roofline  the reconstruction kernel timed alone over device-resident records: algorithmic bytes (SURVEY.md 8d:
+            OUT + REF + 128 B/coded block + 16 B/MB) / per-launch CUDA-event time, against the measured HBM peak
+  cpu_baseline  the unmodified reference (oracle/_ref, its own multi-threaded decoder) on this box's host cores, same
+            stream, no-op renderer; its YUV is checked once against the reference's serial driver
+Streams are generated in-repo (texture mode: a translating procedural texture + noise, really encoded at
+quantiser_scale 4..8).  Under torchrun (N > 1) every rank decodes its own shard of closed GOPs (weak scaling, no
+collective on the data path); times are the max over ranks; rank 0 then runs the two multi-GPU configurations of
+BASELINE.json in ONE process over all N devices (closed GOPs of a 4K 4:4:4 stream dealt round-robin, 64 x 720p streams).
 `--impl reference` times the reference's CPU decoder on the same workload instead (rank 0 only).
 """
 import argparse
+import ctypes as C
 import json
 import os
 import statistics
@@ -27,42 +32,30 @@ import tempfile
 import threading
 import time
 
-# the decoder parses every picture in flight on its own CUDA stream: give the streams their own hardware
-# work queues (must be set before the process's first CUDA call; the library does the same when it is first)
+# (must be set before the process's first CUDA call; the library does the same when it is first)
 os.environ.setdefault("CUDA_DEVICE_MAX_CONNECTIONS", "32")
 
 ROOT = os.path.dirname(os.path.abspath(__file__))
 sys.path.insert(0, ROOT)
 
 # BASELINE.json configs -> generator parameters.  seed = stream_id*1000 + config_id.
-# Throughput runs use the generator's natural-like mode (decaying run/level statistics, default
-# matrices, quantiser_scale_code 1..12) at about 40 Mbit/s for 1080p IPB, as SURVEY.md 8(d) asks;
-# the random-syntax fuzz mode is what the parity tests use.
-NATURAL = dict(mode=1, pct_coded=70)
+TEX = dict(mode=2, texture_noise=3, pct_intra_in_pb=3, q_scale_type=0, alternate_scan=0, intra_dc_precision=0)
 WORKLOADS = {
+    # configs[2]: 1080p 4:2:0 IPB, GOP N=15 M=3, half-pel bidirectional MC (about 48 Mbit/s)
+    "1080p420_ipb": dict(width=1920, height=1088, chroma_format=1, config_id=3, gen=dict(n_gops=8, gop_n=15, gop_m=3, **TEX)),
     # configs[1]: 1080p 4:2:0 intra-only, every block coded (IQ + IDCT path)
-    "1080p420_intra": dict(width=1920, height=1088, chroma_format=1, config_id=2,
-                           gen=dict(n_gops=8, gop_n=15, gop_m=1, intra_only=1, natural_mean_coefs=6, **NATURAL)),
-    # configs[2]: 1080p 4:2:0 IPB, GOP N=15 M=3, half-pel bidirectional MC
-    "1080p420_ipb": dict(width=1920, height=1088, chroma_format=1, config_id=3,
-                         gen=dict(n_gops=8, gop_n=15, gop_m=3, natural_mean_coefs=5, **NATURAL)),
+    "1080p420_intra": dict(width=1920, height=1088, chroma_format=1, config_id=2, gen=dict(n_gops=8, gop_n=15, gop_m=1, intra_only=1, **TEX)),
     # configs[0]: 1080p 4:2:2 IPB (the reference sample's hard-wired geometry)
-    "1080p422_ipb": dict(width=1920, height=1088, chroma_format=2, config_id=1,
-                         gen=dict(n_gops=4, gop_n=15, gop_m=3, natural_mean_coefs=5, **NATURAL)),
-    # configs[3]: 4K 4:4:4 IPB
-    "2160p444_ipb": dict(width=3840, height=2160, chroma_format=3, config_id=4,
-                         gen=dict(n_gops=2, gop_n=15, gop_m=3, natural_mean_coefs=5, **NATURAL)),
-    # configs[4]: 720p 4:2:0 streams (per-GPU share of the 64-stream batch is run as consecutive GOP chains)
-    "720p420_ipb": dict(width=1280, height=720, chroma_format=1, config_id=5,
-                        gen=dict(n_gops=8, gop_n=15, gop_m=3, natural_mean_coefs=5, **NATURAL)),
-    # the same two 1080p shapes in random-syntax fuzz mode (stress: escapes, saturating levels)
-    "1080p420_intra_fuzz": dict(width=1920, height=1088, chroma_format=1, config_id=2,
-                                gen=dict(n_gops=4, gop_n=15, gop_m=1, intra_only=1)),
-    "1080p420_ipb_fuzz": dict(width=1920, height=1088, chroma_format=1, config_id=3,
-                              gen=dict(n_gops=4, gop_n=15, gop_m=3)),
+    "1080p422_ipb": dict(width=1920, height=1088, chroma_format=2, config_id=1, gen=dict(n_gops=4, gop_n=15, gop_m=3, **TEX)),
+    # configs[3]: 4K 4:4:4 IPB, 16 closed GOPs (sharded over the GPUs in one process when N > 1)
+    "2160p444_ipb": dict(width=3840, height=2160, chroma_format=3, config_id=4, gen=dict(n_gops=16, gop_n=6, gop_m=3, **TEX)),
+    # configs[4]: one of the 64 concurrent 720p 4:2:0 streams
+    "720p420_ipb": dict(width=1280, height=720, chroma_format=1, config_id=5, gen=dict(n_gops=2, gop_n=15, gop_m=3, **TEX)),
+    # the two 1080p shapes in random-syntax fuzz mode (stress: escapes, saturating levels, random matrices)
+    "1080p420_intra_fuzz": dict(width=1920, height=1088, chroma_format=1, config_id=2, gen=dict(n_gops=4, gop_n=15, gop_m=1, intra_only=1)),
+    "1080p420_ipb_fuzz": dict(width=1920, height=1088, chroma_format=1, config_id=3, gen=dict(n_gops=4, gop_n=15, gop_m=3)),
 }
-DEFAULT_WORKLOAD = "1080p420_intra"
-
+DEFAULT_WORKLOAD = "1080p420_ipb"
 
 # The contract is ONE JSON line on stdout.  Libraries write there too (NCCL prints its version banner to fd 1 on
 # the GPU boxes), so the real stdout is kept aside for that line and fd 1 is pointed at stderr for everything else.
@@ -89,10 +82,10 @@ def log(*a):
 
 
 def measured_traffic(workload, pictures_per_launch):
-    """DRAM bytes per launch of the dominant kernel from the committed ncu --set full capture
-    (profiles/r1_traffic.json), scaled to this run's average launch size; None when no capture exists."""
+    """DRAM bytes per launch of the reconstruction kernel from the committed ncu --set full capture
+    (profiles/r2_traffic.json), scaled to this run's average launch size; None when no capture exists."""
     try:
-        t = json.load(open(os.path.join(ROOT, "profiles", "r1_traffic.json")))[workload]
+        t = json.load(open(os.path.join(ROOT, "profiles", "r2_traffic.json")))[workload]
         per_picture = (t["dram_read_bytes"] + t["dram_write_bytes"]) / t["pictures_in_launch"]
         return round(per_picture * pictures_per_launch)
     except Exception:
@@ -160,6 +153,14 @@ def make_stream(wl, stream_id):
     return Stream(wl["width"], wl["height"], wl["chroma_format"], seed=stream_id * 1000 + wl["config_id"], **wl["gen"])
 
 
+def pinned_copy(stream):
+    """the coded stream (+ padding) in page-locked host memory: what the e2e copies to the device every step"""
+    import torch
+    t = torch.empty(len(stream.padded), dtype=torch.uint8).pin_memory()
+    t.numpy()[:] = stream.padded
+    return t
+
+
 def dependency_levels(pics):
     lvl, out = {}, []
     for i, p in enumerate(pics):
@@ -178,11 +179,20 @@ def host_threads(world):
     return max(1, n // world)
 
 
+def workload_config(wl_name, wl, n_frames, world):
+    """the `config` block: identical in both arms (the driver compares them)"""
+    frame_mb = wl["width"] * wl["height"] * {1: 1.5, 2: 2, 3: 3}[wl["chroma_format"]] / 1e6
+    return {"workload": wl_name, "width": wl["width"], "height": wl["height"], "chroma_format": wl["chroma_format"],
+            "frames_per_step_per_gpu": n_frames, "gop": wl["gen"],
+            "parallelism": "closed GOPs sharded over %d GPU(s), no collective" % world,
+            "l2_policy": "working set per step (%d frames = %.0f MB of pixels + the coded stream / records) exceeds the 126 MB L2" % (n_frames, n_frames * frame_mb)}
+
+
 # ------------------------------------------------------------------------------------------------ reference arm
 
-def run_reference_cli(stream, threads, pool=10, repeat=3, timeout=600):
-    """oracle/_ref/ref_decode (the unmodified reference library + its MT decoder) in a subprocess, so a
-    scheduler hang cannot take the benchmark down.  Returns (fps, seconds, frames)."""
+def run_reference_cli(stream, threads, mode="mt", out="-", pool=10, repeat=1, timeout=600):
+    """oracle/_ref/ref_decode (the unmodified reference library + its MT decoder / the serial driver) in a subprocess,
+    so a scheduler hang cannot take the benchmark down.  Returns the tool's JSON line or None."""
     exe = os.path.join(ROOT, "oracle", "_ref", "ref_decode")
     if not os.path.exists(exe):
         return None
@@ -190,12 +200,11 @@ def run_reference_cli(stream, threads, pool=10, repeat=3, timeout=600):
         f.write(stream.data.tobytes())
         path = f.name
     try:
-        out = subprocess.run([exe, "mt", path, str(stream.width), str(stream.height), str(stream.chroma_format), "-",
+        res = subprocess.run([exe, mode, path, str(stream.width), str(stream.height), str(stream.chroma_format), out,
                               str(threads), str(pool), str(repeat)], capture_output=True, text=True, timeout=timeout)
-        if out.returncode != 0:
+        if res.returncode != 0:
             return None
-        d = json.loads(out.stdout.strip().splitlines()[-1])
-        return d["fps"], d["seconds"], d["frames"]
+        return json.loads(res.stdout.strip().splitlines()[-1])
     except Exception as e:  # timeout / hang / bad output
         log("reference run failed:", e)
         return None
@@ -203,18 +212,41 @@ def run_reference_cli(stream, threads, pool=10, repeat=3, timeout=600):
         os.unlink(path)
 
 
-def reference_best(stream, repeat=3):
-    """thread sweep {nproc/2, nproc-2, nproc} (busy-spinning workers: never oversubscribe), best fps"""
+def reference_pick_threads(stream):
+    """thread sweep {nproc/2, nproc-2, nproc, 8, 16, 32} (busy-spinning workers: never oversubscribe) -> best thread count"""
     n = host_threads(1)
-    cands = sorted(set(max(1, min(256, t)) for t in (n // 2, n - 2, n, 8, 16, 32)))
-    cands = [t for t in cands if t <= n]
+    cands = sorted(set(t for t in (n // 2, n - 2, n, 8, 16, 32) if 1 <= t <= min(n, 256)))
     best = None
     for t in cands:
-        r = run_reference_cli(stream, t, repeat=repeat)
-        log("  reference MT threads=%d ->" % t, r)
-        if r and (best is None or r[0] > best[0]):
-            best = (r[0], r[1], r[2], t)
-    return best
+        r = run_reference_cli(stream, t)
+        log("  reference MT threads=%d ->" % t, r and (r["fps"], r["seconds"]))
+        if r and (best is None or r["fps"] > best[0]):
+            best = (r["fps"], t)
+    return best[1] if best else None
+
+
+def reference_measure(stream, steps, warmup):
+    """the SAME statistic in both arms: thread sweep, then the mean of `steps` decodes at the best thread count;
+    the MT decoder's YUV hash is checked against the serial driver once (the MT scheduler races on small pictures)"""
+    threads = reference_pick_threads(stream)
+    if threads is None:
+        return None
+    times = []
+    for i in range(warmup + steps):
+        r = run_reference_cli(stream, threads)
+        if r is None:
+            break
+        if i >= warmup:
+            times.append(r["seconds"])
+    if not times:
+        return None
+    mt = run_reference_cli(stream, threads, out="hash")
+    serial = run_reference_cli(stream, 1, mode="serial", out="hash")
+    same = bool(mt and serial and mt["hash"] == serial["hash"] and mt["frames"] == serial["frames"])
+    n = len(stream.pictures)
+    sec = sum(times) / len(times)
+    return {"fps": n / sec, "seconds": sec, "threads": threads, "runs": len(times), "mt_yuv_equals_serial_driver": same,
+            "serial_fps": serial["fps"] if serial else None}
 
 
 def cpu_model():
@@ -227,38 +259,33 @@ def cpu_model():
     return "unknown"
 
 
+def cpu_baseline_block(stream, steps, warmup):
+    ref = reference_measure(stream, steps, warmup)
+    if ref:
+        return {"value": round(ref["fps"], 2), "unit": "frames/s", "cores": ref["threads"], "kind": "reference",
+                "sample": "whole workload stream (%d frames), unmodified reference MT decoder (oracle/_ref), no-op renderer, mean of %d runs at the "
+                          "best thread count of a sweep up to %d host threads; CPU: %s" % (len(stream.pictures), ref["runs"], host_threads(1), cpu_model()),
+                "mt_yuv_equals_serial_driver": ref["mt_yuv_equals_serial_driver"],
+                "serial_driver_fps_1_core": round(ref["serial_fps"], 2) if ref["serial_fps"] else None}
+    return {"value": round(oracle_port_fps(stream), 2), "unit": "frames/s", "cores": 1, "kind": "port",
+            "sample": "oracle C restatement on 4 pictures of the workload stream (oracle/_ref not present)"}
+
+
 def reference_arm(args, wl_name, wl):
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
         return 0
     stream = make_stream(wl, 0)
     n_frames = len(stream.pictures)
-    best = reference_best(stream, repeat=1)
-    if best is None:
-        # the compiled reference did not travel: time the oracle's C restatement (1 core) instead
-        fps, kind, cores, sample = oracle_port_fps(stream), "port", 1, "oracle C restatement on 4 pictures of the stream"
-        ms = 1000.0 * n_frames / fps
-    else:
-        threads = best[3]
-        times = []
-        for i in range(args.warmup + args.steps):
-            r = run_reference_cli(stream, threads, repeat=1)
-            if r is None:
-                break
-            if i >= args.warmup:
-                times.append(r[1])
-        sec = sum(times) / max(1, len(times))
-        fps, kind, cores, ms = n_frames / sec, "reference", threads, sec * 1000.0
-        sample = "whole workload stream (%d frames) per step, unmodified reference MT decoder, no-op renderer" % n_frames
-    mpix = fps * wl["width"] * wl["height"] / 1e6
-    line = {"impl": "reference", "metric": "decode_frames_per_second", "value": round(fps, 2), "unit": "frames/s", "n_gpus": args.gpus,
-            "steps": args.steps, "warmup": args.warmup, "ms_per_step": round(ms, 3), "higher_is_better": True, "scaling": "weak",
+    cpu = cpu_baseline_block(stream, args.steps, args.warmup)
+    fps = cpu["value"]
+    line = {"impl": "reference", "metric": "decode_frames_per_second", "value": fps, "unit": "frames/s", "n_gpus": args.gpus,
+            "steps": args.steps, "warmup": args.warmup, "ms_per_step": round(1000.0 * n_frames / fps, 3), "higher_is_better": True, "scaling": "weak",
             "vs_baseline": None, "dtype": "int16", "data": "synthetic",
-            "config": {"workload": wl_name, "width": wl["width"], "height": wl["height"], "chroma_format": wl["chroma_format"],
-                       "frames_per_step": n_frames, "gop": wl["gen"], "cpu": cpu_model()},
-            "mpixel_per_s": round(mpix, 1),
-            "cpu_baseline": {"value": round(fps, 2), "unit": "frames/s", "cores": cores, "kind": kind, "sample": sample},
-            "e2e": {"value": round(fps, 2), "unit": "frames/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
+            "config": workload_config(wl_name, wl, n_frames, args.gpus),
+            "mpixel_per_s": round(fps * wl["width"] * wl["height"] / 1e6, 1),
+            "cpu_baseline": cpu,
+            "e2e": {"value": fps, "unit": "frames/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
     emit(line)
     return 0
 
@@ -266,7 +293,6 @@ def reference_arm(args, wl_name, wl):
 def oracle_port_fps(stream, n=4):
     """1-core timing of the oracle's C restatement on the first pictures of the stream (fallback only)"""
     sys.path.insert(0, os.path.join(ROOT, "tests"))
-    import ctypes as C
     import oracle_lib as O
     L = O.oracle()
     frames = {}
@@ -285,8 +311,9 @@ def oracle_port_fps(stream, n=4):
 
 # ------------------------------------------------------------------------------------------------ our arm
 
-def measure_resident(wl, stream, steps, warmup, device, world=1):
-    """value + roofline: records parsed by the product's host parser, uploaded once, reconstructed K times"""
+def kernel_roofline(wl, stream, steps, warmup, device, peak, world=1):
+    """the reconstruction kernel alone: records parsed by the product's host parser, uploaded once, reconstructed K times
+    (every launch timed with a CUDA event pair on the launching stream)"""
     from tiny_mp2v_dec_b200.decoder import parse_stream
     from tiny_mp2v_dec_b200.recon import Recon
     w, h, cf = wl["width"], wl["height"], wl["chroma_format"]
@@ -304,8 +331,139 @@ def measure_resident(wl, stream, steps, warmup, device, world=1):
     r.sync()
     r.stats(reset=True)
     r.set_timing(True)
-    rec_bytes = sum(p.mb.nbytes + p.coef.nbytes for p in pics)
-    return r, hnds, levels, n, dict(parse_wall=parse_wall, parse_cpu=parse_cpu, record_bytes=rec_bytes)
+    r.timer_start()
+    for _ in range(steps):
+        r.run_resident(hnds, levels)
+    dev_ms = r.timer_stop()
+    st = r.stats()
+    r.close()
+    launches = int(st.launches)
+    achieved = st.algorithmic_bytes / (st.kernel_ms * 1e-3) / 1e9
+    return {"bound": "hbm", "achieved": round(achieved, 1), "peak": peak, "unit": "GB/s", "frac": round(achieved / peak, 4),
+            "kernel": "recon_kernel3<%d>" % cf, "launches_per_step": launches // steps,
+            "algorithmic_bytes_per_launch": round(st.algorithmic_bytes / launches), "launch_ms": round(st.kernel_ms / launches, 4),
+            "frames_per_s_kernel_only": round(n * steps / (dev_ms * 1e-3), 1),
+            "timed": "kernel alone over device-resident records, %d steps, CUDA event pair around every launch" % steps,
+            "host_parse": {"wall_s": round(parse_wall, 4), "cpu_s": round(parse_cpu, 4), "fps_per_core": round(n / parse_cpu, 1) if parse_cpu > 0 else None}}, \
+        n * steps / launches
+
+
+def time_decoder(wl, stream, pinned, threads, device, steps, barrier, max_over_ranks, gpu_vlc=True, download=True, resident=False):
+    """K decode() calls of one persistent decoder through the C ABI.  Returns (seconds max over ranks, device ms, stats)"""
+    import torch
+    from tiny_mp2v_dec_b200.decoder import Decoder
+    dec = Decoder(wl["width"], wl["height"], wl["chroma_format"], pictures_pool_size=10, num_threads=threads,
+                  devices=(device,), max_batch=8, output_lag=6, gpu_vlc=gpu_vlc).prepare(download=download)
+    buf = pinned.numpy()
+    for _ in range(3):
+        dec.decode(buf, stream.size, want_output=False, download=download)
+    barrier()
+    t0 = time.perf_counter()
+    dev_ms, rows = 0.0, []
+    for _ in range(steps):
+        if resident:
+            dec.decode_resident()
+        else:
+            dec.decode(buf, stream.size, want_output=False, download=download)
+        s = dec.stats
+        dev_ms += s.device_ms
+        rows.append((s.h2d_bytes, s.d2h_bytes, s.parse_cpu_seconds, s.kernel_ms, s.launches + s.vlc_launches))
+    torch.cuda.synchronize()
+    secs = max_over_ranks(time.perf_counter() - t0)
+    barrier()
+    dec.close()
+    return secs, max_over_ranks(dev_ms), [sum(x[i] for x in rows) / len(rows) for i in range(5)]
+
+
+def workload_block(wl_name, wl, stream, args, local, world, peak, barrier, max_over_ranks, sum_over_ranks, with_host_parser=True):
+    """value + roofline + e2e of one workload on this rank's device"""
+    n_frames = len(stream.pictures)
+    pinned = pinned_copy(stream)
+    threads = max(1, host_threads(world) - 2)      # two cores stay free for the decoder's feeder and output threads
+    total_frames = sum_over_ranks(float(n_frames)) * args.steps
+    # ---- value: the stream is resident on the device; slice parsing + reconstruction, nothing crosses PCIe but descriptors
+    res_s, res_dev_ms, (_, _, _, res_kernel_ms, res_launches) = time_decoder(wl, stream, pinned, threads, local, args.steps, barrier, max_over_ranks,
+                                                                            download=False, resident=True)
+    value = total_frames / (res_dev_ms * 1e-3)
+    # ---- roofline: the reconstruction kernel alone
+    roof, pics_per_launch = kernel_roofline(wl, stream, args.steps, args.warmup, local, peak, world)
+    roof["traffic"] = measured_traffic(wl_name, pics_per_launch)
+    roof["share_of_resident_decode_step"] = round(res_kernel_ms / (res_dev_ms / args.steps), 3)
+    # ---- e2e: the decode API from a pinned host buffer
+    e2e_s, _, (h2d, d2h, _, _, e2e_launches) = time_decoder(wl, stream, pinned, threads, local, args.steps, barrier, max_over_ranks)
+    nodl_s, _, (h2d_n, d2h_n, _, _, _) = time_decoder(wl, stream, pinned, threads, local, args.steps, barrier, max_over_ranks, download=False)
+    e2e = {"value": round(total_frames / e2e_s, 1), "unit": "frames/s", "h2d_bytes_per_step": int(h2d), "d2h_bytes_per_step": int(d2h),
+           "slice_parser": "device, out of the device-resident stream (mp2v_b200_options_t.gpu_vlc, the API default)",
+           "gpu_launches_per_step": int(e2e_launches), "d2h_gbs": round(d2h * args.steps / e2e_s / 1e9, 1),
+           "without_frame_download": {"value": round(total_frames / nodl_s, 1), "unit": "frames/s", "h2d_bytes_per_step": int(h2d_n), "d2h_bytes_per_step": int(d2h_n),
+                                      "note": "same call, download_frames=false (frames stay in the device pool for a GPU consumer)"}}
+    if with_host_parser:
+        host_s, _, (host_h2d, _, parse_cpu, _, _) = time_decoder(wl, stream, pinned, threads, local, max(2, args.steps // 2), barrier, max_over_ranks, gpu_vlc=False)
+        e2e["host_parser_mode"] = {"value": round(total_frames / args.steps * max(2, args.steps // 2) / host_s, 1), "unit": "frames/s", "host_threads": threads,
+                                   "h2d_bytes_per_step": int(host_h2d), "host_parse_cpu_s_per_step": round(parse_cpu, 4),
+                                   "host_parse_fps_per_core": round(n_frames / parse_cpu, 1) if parse_cpu > 0 else None}
+    return {"value": round(value, 1), "ms_per_step": round(res_dev_ms / args.steps, 4), "wall_ms_per_step": round(res_s / args.steps * 1e3, 4),
+            "gpu_launches": int(res_launches) * args.steps, "roofline": roof, "e2e": e2e,
+            "mpixel_per_s": round(value * wl["width"] * wl["height"] / 1e6, 1)}
+
+
+def sharded_block(n_dev, steps):
+    """BASELINE.json configs[3] and [4] in ONE process over n_dev devices (run by rank 0 while the other ranks wait):
+    a 4K 4:4:4 stream whose closed GOPs are dealt round-robin to the devices and gathered in display order, and 64
+    concurrent 720p streams, stream s on device s mod n_dev.  Output hashes are checked against a 1-device decode."""
+    from tiny_mp2v_dec_b200.decoder import Decoder
+    out = {}
+    wl = WORKLOADS["2160p444_ipb"]
+    s = make_stream(wl, 0)
+    pinned = pinned_copy(s)
+    n = len(s.pictures)
+
+    def run(devices, download, reps, hash_out=False):
+        d = Decoder(wl["width"], wl["height"], wl["chroma_format"], num_threads=8, devices=tuple(devices), max_batch=8, output_lag=6)
+        d.p.hash_output = 1 if hash_out else 0
+        d.prepare(download=download)
+        d.decode(pinned.numpy(), s.size, want_output=False, download=download)
+        h = d.stats.hash
+        t0 = time.perf_counter()
+        for _ in range(reps):
+            d.decode(pinned.numpy(), s.size, want_output=False, download=download)
+        dt = (time.perf_counter() - t0) / reps
+        d.close()
+        return n / dt, h
+    _, h1 = run([0], True, 0, hash_out=True)
+    _, hn = run(range(n_dev), True, 0, hash_out=True)
+    fps_dl, _ = run(range(n_dev), True, steps)
+    fps_nodl, _ = run(range(n_dev), False, steps)
+    fps1_dl, _ = run([0], True, max(1, steps // 2))
+    fps1_nodl, _ = run([0], False, max(1, steps // 2))
+    out["2160p444_ipb_gop_sharded"] = {
+        "frames": n, "closed_gops": wl["gen"]["n_gops"], "devices": n_dev, "e2e_frames_per_s": round(fps_dl, 1), "e2e_without_frame_download": round(fps_nodl, 1),
+        "one_device_e2e_frames_per_s": round(fps1_dl, 1), "one_device_without_frame_download": round(fps1_nodl, 1),
+        "mpixel_per_s": round(fps_dl * wl["width"] * wl["height"] / 1e6, 1), "display_order_yuv_hash_equals_one_device": bool(h1 == hn),
+        "host_copy_ceiling": "every decoded frame (24.9 MB) is copied to pinned host memory: with download the figure is bounded by the box's D2H rate"}
+    # 64 x 720p: one decoder object and one host thread per stream
+    wl5 = WORKLOADS["720p420_ipb"]
+    streams = [make_stream(wl5, k) for k in range(8)]                 # 8 distinct streams, reused round-robin for the 64 sessions
+    pins = [pinned_copy(x) for x in streams]
+    for download in (True, False):
+        decs = [Decoder(wl5["width"], wl5["height"], 1, num_threads=2, devices=(k % n_dev,), max_batch=8, output_lag=6).prepare(download=download) for k in range(64)]
+        for k, d in enumerate(decs[:n_dev]):
+            d.decode(pins[k % 8].numpy(), streams[k % 8].size, want_output=False, download=download)
+        frames = [0]
+
+        def session(k):
+            for _ in range(max(1, steps // 2)):
+                decs[k].decode(pins[k % 8].numpy(), streams[k % 8].size, want_output=False, download=download)
+                frames[0] += len(streams[k % 8].pictures)
+        t0 = time.perf_counter()
+        th = [threading.Thread(target=session, args=(k,)) for k in range(64)]
+        [t.start() for t in th]
+        [t.join() for t in th]
+        dt = time.perf_counter() - t0
+        for d in decs:
+            d.close()
+        out.setdefault("64x720p420_streams", {"devices": n_dev, "streams": 64})["e2e_frames_per_s" if download else "e2e_without_frame_download"] = round(frames[0] / dt, 1)
+    return out
 
 
 def main():
@@ -316,7 +474,7 @@ def main():
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--workload", default=DEFAULT_WORKLOAD, choices=sorted(WORKLOADS))
     ap.add_argument("--no-cpu-baseline", action="store_true")
-    ap.add_argument("--no-extra", action="store_true", help="skip the additional IPB kernel measurement")
+    ap.add_argument("--no-extra", action="store_true", help="skip the additional workloads (intra, fuzz, NV12) and the multi-GPU configurations")
     ap.add_argument("--cpu-dryrun", action="store_true",
                     help="host-only: shard generation + slice parsing per rank over gloo (exercises the N>1 plumbing without a GPU)")
     args = ap.parse_args()
@@ -376,9 +534,8 @@ def main():
         ncoef = sum_over_ranks(float(sum(len(p.coef) for p in pics)))
         if rank == 0:
             emit({"dryrun": True, "metric": "host_parse_frames_per_second", "value": round(total / secs, 1),
-                              "unit": "frames/s", "n_ranks": world, "steps": args.steps, "frames_per_step": int(total / args.steps),
-                              "coef_records_all_ranks": int(ncoef), "scaling": "weak",
-                              "config": {"workload": args.workload}})
+                  "unit": "frames/s", "n_ranks": world, "steps": args.steps, "frames_per_step": int(total / args.steps),
+                  "coef_records_all_ranks": int(ncoef), "scaling": "weak", "config": {"workload": args.workload}})
         if world > 1:
             dist.destroy_process_group()
         return 0
@@ -387,137 +544,98 @@ def main():
     # every rank decodes its own shard: the N-GPU job is N x the GOPs (closed GOPs g = rank mod N)
     stream = make_stream(wl, rank)
     n_frames = len(stream.pictures)
-    r, hnds, levels, n, parse_info = measure_resident(wl, stream, args.steps, args.warmup, local, world)
-
-    # ---- value: K steps, device time on the launching stream
     sampler = ClockSampler(local)
     barrier()
     sampler.start()
-    r.timer_start()
-    for _ in range(args.steps):
-        r.run_resident(hnds, levels)
-    dev_ms = r.timer_stop()
-    barrier()
-    st = r.stats()
-    t_ms = max_over_ranks(dev_ms)
-    total_frames = sum_over_ranks(float(n_frames)) * args.steps
-    value = total_frames / (t_ms * 1e-3)
-    kernel_ms = st.kernel_ms                     # sum of per-launch event durations on this rank
-    launches = int(st.launches)
-    achieved = st.algorithmic_bytes / (kernel_ms * 1e-3) / 1e9
-    alg_per_launch = st.algorithmic_bytes / launches
-    r.close()
+    main_blk = workload_block(args.workload, wl, stream, args, local, world, peak, barrier, max_over_ranks, sum_over_ranks)
+    clocks = sampler.stop()          # sampled across the timed regions (a resident step lasts a few ms)
+    main_blk["roofline"]["peak_source"] = peak_src
 
-    # ---- e2e: the reference-facing decode API from a host buffer (H2D + parse + kernels + D2H of every frame).
-    # The API's default parses slices on the device; the host-parser mode of the same API is timed beside it.
-    from tiny_mp2v_dec_b200.decoder import Decoder
-    threads = max(1, host_threads(world) - 2)      # two cores stay free for the decoder's feeder and output threads
-
-    def time_decoder(gpu_vlc, steps, download=True):
-        dec = Decoder(wl["width"], wl["height"], wl["chroma_format"], pictures_pool_size=10, num_threads=threads,
-                      devices=(local,), max_batch=8, output_lag=6, gpu_vlc=gpu_vlc).prepare(download=download)
-        for _ in range(2):
-            dec.decode(stream.padded, stream.size, want_output=False, download=download)
-        barrier()
-        t0 = time.perf_counter()
-        stats = []
-        for _ in range(steps):
-            dec.decode(stream.padded, stream.size, want_output=False, download=download)
-            stats.append((dec.stats.h2d_bytes, dec.stats.d2h_bytes, dec.stats.parse_cpu_seconds, dec.stats.kernel_ms,
-                          dec.stats.launches + dec.stats.vlc_launches))
-        torch.cuda.synchronize()
-        secs = max_over_ranks(time.perf_counter() - t0)
-        barrier()
-        dec.close()
-        return secs, [sum(x[i] for x in stats) / len(stats) for i in range(5)]
-
-    e2e_s, (h2d, d2h, _, _, e2e_launches) = time_decoder(True, args.steps)
-    host_s, (host_h2d, _, parse_cpu, _, _) = time_decoder(False, args.steps)
-    nodl_s, _ = time_decoder(True, args.steps, download=False)      # frames stay on the device (zero-copy consumer)
-    clocks = sampler.stop()          # sampled across the timed regions (the resident steps alone last a few ms)
-    e2e_value = total_frames / e2e_s
-    host_e2e_value = total_frames / host_s
-
-    # ---- extra (N = 1): the IPB workload's kernel-only numbers, so the MC path is on the record too
-    extra = None
-    if world == 1 and not args.no_extra and args.workload != "1080p420_ipb":
-        wl2 = WORKLOADS["1080p420_ipb"]
-        s2 = make_stream(wl2, 0)
-        r2, h2, l2, n2, _ = measure_resident(wl2, s2, args.steps, args.warmup, local)
-        r2.timer_start()
-        for _ in range(args.steps):
-            r2.run_resident(h2, l2)
-        ms2 = r2.timer_stop()
-        st2 = r2.stats()
-        extra = {"workload": "1080p420_ipb", "value": round(n2 * args.steps / (ms2 * 1e-3), 1), "unit": "frames/s",
-                 "launches_per_step": int(st2.launches) // args.steps,
-                 "roofline_achieved_gbs": round(st2.algorithmic_bytes / (st2.kernel_ms * 1e-3) / 1e9, 1),
-                 "roofline_frac": round(st2.algorithmic_bytes / (st2.kernel_ms * 1e-3) / 1e9 / peak, 4)}
-        # the output-path kernel (planar 4:2:0 -> NV12 for GPU consumers) on the frames that run left in the pool
+    extra = {}
+    if world == 1 and not args.no_extra:
+        # the other single-GPU configuration of BASELINE.json as a complete block, and the fuzz-mode stress workloads (kernel only)
+        other = "1080p420_intra" if args.workload != "1080p420_intra" else "1080p420_ipb"
+        s2 = make_stream(WORKLOADS[other], 0)
+        extra[other] = workload_block(other, WORKLOADS[other], s2, args, local, 1, peak, barrier, max_over_ranks, sum_over_ranks, with_host_parser=False)
+        for name in ("1080p420_intra_fuzz", "1080p420_ipb_fuzz"):
+            roof, _ = kernel_roofline(WORKLOADS[name], make_stream(WORKLOADS[name], 0), max(3, args.steps // 2), 3, local, peak)
+            extra[name] = {"roofline": roof}
+        # the output-path kernels on reconstructed frames
         try:
-            import ctypes as C
-            fw, fh = wl2["width"], wl2["height"]
-            nv = torch.empty((n2, fh * 3 // 2, fw), dtype=torch.uint8, device="cuda:%d" % local)
-            ids = (C.c_int32 * n2)(*range(n2))
-            ptrs = (C.c_void_p * n2)(*[nv[f].data_ptr() for f in range(n2)])
-            reps = 20
-            for timed in (False, True):
-                r2.timer_start()
-                for _ in range(reps):
-                    r2._ck(r2.L.mp2v_recon_convert_frames_nv12(r2.h, ids, ptrs, n2, fw))
-                ms_nv = r2.timer_stop()
-            gbs_nv = 2 * (fw * fh * 3 // 2) * n2 * reps / (ms_nv * 1e-3) / 1e9
-            extra["nv12_output_kernel"] = {"frames_per_s": round(n2 * reps / (ms_nv * 1e-3), 1), "achieved_gbs": round(gbs_nv, 1),
-                                           "frac_of_hbm_peak": round(gbs_nv / peak, 4), "bytes": "read + write = 2 x frame bytes"}
-            del nv
+            extra["output_kernels"] = output_kernels(WORKLOADS["1080p420_ipb"], local, peak)
         except Exception as e:      # an extra, never the bench line's reason to fail
-            extra["nv12_output_kernel"] = {"error": repr(e)}
-        r2.close()
+            extra["output_kernels"] = {"error": repr(e)}
+    sharded = None
+    if world > 1 and not args.no_extra:
+        # rank 0 drives ALL devices from one process; the others wait on a HOST barrier (an NCCL barrier would park a
+        # spinning kernel on every device for the duration)
+        host_group = dist.new_group(backend="gloo")
+        barrier()
+        if rank == 0:
+            try:
+                sharded = sharded_block(world, max(2, args.steps // 3))
+            except Exception as e:
+                sharded = {"error": repr(e)}
+        dist.barrier(group=host_group)
 
-    # ---- CPU baseline beside it (rank 0, N = 1 only): the unmodified reference on this box's cores
     cpu = None
     if rank == 0 and world == 1 and not args.no_cpu_baseline:
-        best = reference_best(stream, repeat=3)
-        if best:
-            cpu = {"value": round(best[0], 2), "unit": "frames/s", "cores": best[3], "kind": "reference",
-                   "sample": "whole workload stream (%d frames), unmodified reference MT decoder (oracle/_ref), no-op renderer, best of 3, "
-                             "thread sweep up to %d host threads; CPU: %s" % (best[2], host_threads(1), cpu_model())}
-        else:
-            cpu = {"value": round(oracle_port_fps(stream), 2), "unit": "frames/s", "cores": 1, "kind": "port",
-                   "sample": "oracle C restatement on 4 pictures of the workload stream (oracle/_ref not present)"}
+        cpu = cpu_baseline_block(stream, max(3, args.steps), 1)
 
     if rank == 0:
         line = {
-            "metric": "decode_frames_per_second", "value": round(value, 1), "unit": "frames/s", "n_gpus": world,
-            "steps": args.steps, "warmup": args.warmup, "ms_per_step": round(t_ms / args.steps, 4), "higher_is_better": True,
+            "metric": "decode_frames_per_second", "value": main_blk["value"], "unit": "frames/s", "n_gpus": world,
+            "steps": args.steps, "warmup": args.warmup, "ms_per_step": main_blk["ms_per_step"], "higher_is_better": True,
             "scaling": "weak", "vs_baseline": None, "dtype": "int16", "data": "synthetic",
-            "config": {"workload": args.workload, "width": wl["width"], "height": wl["height"], "chroma_format": wl["chroma_format"],
-                       "frames_per_step_per_gpu": n_frames, "gop": wl["gen"], "parallelism": "closed GOPs sharded over %d GPU(s), no collective" % world,
-                       "l2_policy": "working set per step (frames + records, %.0f MB) exceeds the 126 MB L2" % (
-                           (n_frames * (wl["width"] * wl["height"] * {1: 1.5, 2: 2, 3: 3}[wl["chroma_format"]]) + parse_info["record_bytes"]) / 1e6)},
-            "mpixel_per_s": round(value * wl["width"] * wl["height"] / 1e6, 1),
-            "roofline": {"bound": "hbm", "achieved": round(achieved, 1), "peak": peak, "unit": "GB/s", "frac": round(achieved / peak, 4),
-                         "traffic": measured_traffic(args.workload, n_frames * args.steps / launches), "peak_source": peak_src, "kernel": "recon_kernel<%d>" % wl["chroma_format"],
-                         "algorithmic_bytes_per_launch": round(alg_per_launch), "launch_ms": round(kernel_ms / launches, 4)},
-            "e2e": {"value": round(e2e_value, 1), "unit": "frames/s", "h2d_bytes_per_step": int(h2d), "d2h_bytes_per_step": int(d2h),
-                    "slice_parser": "device (mp2v_b200_options_t.gpu_vlc, the API default)", "gpu_launches_per_step": int(e2e_launches),
-                    "d2h_gbs": round(d2h * args.steps / e2e_s / 1e9, 1),
-                    "without_frame_download": {"value": round(total_frames / nodl_s, 1), "unit": "frames/s",
-                                               "note": "same call, download_frames=false: what the D2H of every frame costs"},
-                    "host_parser_mode": {"value": round(host_e2e_value, 1), "unit": "frames/s", "host_threads": threads,
-                                         "h2d_bytes_per_step": int(host_h2d), "host_parse_cpu_s_per_step": round(parse_cpu, 4),
-                                         "host_parse_fps_per_core": round(n_frames / parse_cpu, 1) if parse_cpu > 0 else None,
-                                         "host_parse_only_fps": round(n_frames / parse_info["parse_wall"], 1)}},
-            "gpu_launches": launches,
-            "clocks": clocks,
-            "cpu_baseline": cpu,
+            "value_is": "decode (device slice parsing + reconstruction) of a stream already resident in HBM, frames left in the device pool; "
+                        "the end-to-end figure from host memory with every frame copied back is `e2e`",
+            "config": workload_config(args.workload, wl, n_frames, world),
+            "mpixel_per_s": main_blk["mpixel_per_s"],
+            "roofline": main_blk["roofline"], "e2e": main_blk["e2e"], "gpu_launches": main_blk["gpu_launches"],
+            "clocks": clocks, "cpu_baseline": cpu,
         }
         if extra:
             line["also_measured"] = extra
+        if sharded:
+            line["multi_gpu_in_process"] = sharded
         emit(line)
     if world > 1:
         dist.destroy_process_group()
     return 0
+
+
+def output_kernels(wl, device, peak):
+    """planar 4:2:0 -> NV12 / P010 and 4:2:2 -> UYVY conversion of reconstructed frames on the device"""
+    import torch
+    from tiny_mp2v_dec_b200.recon import Recon
+    from tiny_mp2v_dec_b200.streamgen import Stream
+    out = {}
+    fw, fh, n = wl["width"], wl["height"], 60
+    for fmt, cf, bytes_out in (("nv12", 1, fw * fh * 3 // 2), ("p010", 1, fw * fh * 3), ("uyvy", 2, fw * fh * 2)):
+        s = Stream(fw, fh, cf, seed=77, gop_n=2, gop_m=1, n_gops=1, mode=1)
+        with Recon(fw, fh, cf, n_frames=n, n_pictures=4, device=device) as r:
+            if not hasattr(r, "convert_batch"):
+                return out
+            for f in range(n):      # any reconstructed content will do: the kernels only move bytes
+                h = r.acquire()
+                p = s.pictures[0]
+                r.fill(h, p.params, p.mb, p.coef, dst=f)
+                r.submit(h)
+            r.sync()
+            dst = torch.empty((n, bytes_out), dtype=torch.uint8, device="cuda:%d" % device)
+            ptrs = [dst[f].data_ptr() for f in range(n)]
+            pitch = {"nv12": fw, "p010": fw * 2, "uyvy": fw * 2}[fmt]
+            reps = 20
+            for _ in range(2):
+                r.timer_start()
+                for _ in range(reps):
+                    r.convert_batch(fmt, list(range(n)), ptrs, pitch)
+                ms = r.timer_stop()
+            frame_in = fw * fh * (3 if cf == 1 else 4) // 2
+            gbs = (frame_in + bytes_out) * n * reps / (ms * 1e-3) / 1e9
+            out[fmt] = {"frames_per_s": round(n * reps / (ms * 1e-3), 1), "achieved_gbs": round(gbs, 1), "frac_of_hbm_peak": round(gbs / peak, 4),
+                        "bytes": "read + write = frame bytes in + %s bytes out" % fmt}
+    return out
 
 
 if __name__ == "__main__":

@@ -31,11 +31,17 @@ typedef struct mp2v_decode_stats {
     double kernel_ms, parse_cpu_seconds, wall_seconds;
     uint64_t hash;                          /* FNV-1a 64 of the cropped planar output, display order        */
     uint64_t vlc_launches;                  /* slice parser kernel launches (0: the host parser was used)   */
+    double device_ms;                       /* CUDA-event time between the call's first and last device work  */
 } mp2v_decode_stats_t;
 
 /* per-frame callback, invoked on the decoder's output thread in display order */
 typedef void (*mp2v_frame_fn)(void* user, uint8_t* const planes[3], const int32_t strides[3],
                               const int32_t widths[3], const int32_t heights[3]);
+
+/* per-frame callback with the frame's planes in DEVICE memory (mp2v_b200_options_t::device_renderer): complete and valid
+ * during the call; recon / frame_id name the frame for mp2v_recon_convert_frames */
+typedef void (*mp2v_device_frame_fn)(void* user, void* const planes[3], const int32_t strides[3], const int32_t widths[3],
+                                     const int32_t heights[3], int32_t device, int32_t frame_id, mp2v_recon_t* recon);
 
 /* Decode a whole elementary stream (buffer padded with >= 64 readable bytes).  Frames go to `fn` when
  * given; when `out` is given the cropped planar YUV (Y, Cb, Cr per frame, display order) is also
@@ -52,6 +58,11 @@ MP2V_API int mp2v_decoder_create(const mp2v_decode_params_t* params, mp2v_decode
 MP2V_API int mp2v_decoder_decode(mp2v_decoder_t* dec, uint8_t* buffer, int len, mp2v_frame_fn fn, void* user,
                                  uint8_t* out, size_t out_cap, size_t* out_bytes, mp2v_decode_stats_t* stats,
                                  char* err, size_t err_len);
+/* decode once more the stream the last mp2v_decoder_decode left resident on the device (mp2v_decoder_c::decode_resident) */
+MP2V_API int mp2v_decoder_decode_resident(mp2v_decoder_t* dec, mp2v_frame_fn fn, void* user, uint8_t* out, size_t out_cap, size_t* out_bytes,
+                                          mp2v_decode_stats_t* stats, char* err, size_t err_len);
+/* install (fn != NULL) or remove the device-side consumer of the decoder's frames; keeps the device contexts */
+MP2V_API int mp2v_decoder_set_device_renderer(mp2v_decoder_t* dec, mp2v_device_frame_fn fn, void* user);
 MP2V_API void mp2v_decoder_destroy(mp2v_decoder_t* dec);
 
 /* Host-only: index + slice-parse a stream into reconstruction records on `threads` threads, no GPU

@@ -62,12 +62,28 @@ private:
     bool m_owner = false;
 };
 
+// A decoded frame where it was reconstructed: plane pointers in DEVICE memory of CUDA device `device`, complete (the
+// reconstruction has finished) and valid until the callback returns.  `recon` / `frame_id` name it for
+// mp2v_recon_convert_frames (NV12 / P010 / UYVY into the consumer's own device buffer, mp2v_recon.h).
+struct mp2v_recon;
+struct mp2v_device_frame_t {
+    void* planes[3];
+    int strides[3], width[3], height[3];
+    int device;
+    int frame_id;
+    mp2v_recon* recon;
+};
+
 // Knobs the reference does not have; all optional.
 struct mp2v_b200_options_t {
     std::vector<int> devices = {0};   // CUDA ordinals; more than one = closed GOPs round-robin over the devices
     int max_batch = 8;                // pictures fused into one launch
     int output_lag = 4;               // pictures the display side stays behind the submit side (lets launches batch)
     bool download_frames = true;      // false: renderer gets frames whose planes were not copied back (benchmarks)
+    // Consumer on the GPU: called on the output thread for every frame in display order, like the renderer, but with
+    // the frame's DEVICE planes -- set download_frames = false and no decoded pixel crosses PCIe (the reference's only
+    // output path is the host-side planar write of its sample, tiny_decoder/tiny_mp2v_dec.cpp:11-17).
+    std::function<void(const mp2v_device_frame_t&)> device_renderer;
     bool gpu_vlc = true;              // slices are parsed on the device (mp2v_recon_submit_slices): the host only finds
                                       // start codes and parses headers.  Streams outside the device parser's envelope
                                       // (several slices in one macroblock row, oversized pictures) and gpu_vlc = false
@@ -97,7 +113,12 @@ public:
     group_of_pictures_header_t* m_group_of_pictures_header = nullptr;
 
     // extensions
+    // Decode once more the stream the last successful decode() left resident on the device(s) (device slice parsing
+    // only): no upload, no start-code scan, the renderer is called for every frame again.  The buffer given to that
+    // decode() must still be valid.  (Re-decode, and the device-side figure of the benchmark.)
+    bool decode_resident();
     void set_options(const mp2v_b200_options_t& opt);
+    void set_device_renderer(std::function<void(const mp2v_device_frame_t&)> r);   // mp2v_b200_options_t::device_renderer alone; keeps the device contexts
     bool prepare();                   // allocate the device contexts now (otherwise the first decode() does)
     const char* last_error() const;
     struct stats_t {
@@ -106,6 +127,7 @@ public:
         uint64_t vlc_launches = 0;     // slice parser kernel launches (0: the host parser was used)
         double parse_cpu_seconds = 0;  // summed over worker threads: slice parsing only
         double wall_seconds = 0;       // decode() wall clock
+        double device_ms = 0;          // CUDA-event time from the call's first to its last device work (max over devices)
     };
     stats_t stats() const;
 

@@ -270,15 +270,22 @@ MP2V_API int  mp2v_recon_upload_frame(mp2v_recon_t* ctx, int frame_id, const uin
 /* Device pointers of a frame's planes (zero-copy consumers, e.g. a CUDA renderer). */
 MP2V_API int  mp2v_recon_frame_device_ptrs(mp2v_recon_t* ctx, int frame_id, void* planes[3], int32_t strides[3]);
 
-/* Output path for GPU consumers: convert a reconstructed 4:2:0 frame to NV12 -- `height`
- * rows of Y, then `height / 2` rows of interleaved Cb/Cr pairs, every row `dst_pitch` bytes apart -- into
- * the caller's DEVICE buffer, ordered on the context's compute stream behind the picture that writes
- * the frame; mp2v_recon_sync (or any later work on that stream) completes it.  Replaces the host-side
- * planar write of the reference's sample (tiny_decoder/tiny_mp2v_dec.cpp:11-17) for pipelines whose next
- * stage is on the GPU; with mp2v_b200_options_t::download_frames = false no frame crosses PCIe.       */
+/* Output path for GPU consumers: convert reconstructed frames into the layout the next stage on
+ * the GPU takes, into the caller's DEVICE buffers (one pointer per frame, rows `dst_pitch` bytes apart), ordered on
+ * the context's compute stream behind the pictures that write the frames; mp2v_recon_sync (or any later work on that
+ * stream) completes it.  Replaces the host-side planar write of the reference's sample
+ * (tiny_decoder/tiny_mp2v_dec.cpp:11-17); with mp2v_b200_options_t::download_frames = false no frame crosses PCIe.
+ *   MP2V_OUT_NV12  4:2:0: `height` rows of Y, then `height / 2` rows of interleaved Cb/Cr pairs (row = width bytes)
+ *   MP2V_OUT_P010  4:2:0: the same layout with 16-bit little-endian samples, the decoded 8 bits in the high byte
+ *                  (row = 2 * width bytes)
+ *   MP2V_OUT_UYVY  4:2:2: `height` rows of packed Cb Y0 Cr Y1 (row = 2 * width bytes)                              */
+enum { MP2V_OUT_NV12 = 0, MP2V_OUT_P010 = 1, MP2V_OUT_UYVY = 2 };
+MP2V_API int  mp2v_recon_convert_frames(mp2v_recon_t* ctx, int format, const int32_t* frame_ids, void* const* dst_device, int n, int32_t dst_pitch);
 MP2V_API int  mp2v_recon_convert_frame_nv12(mp2v_recon_t* ctx, int frame_id, void* dst_device, int32_t dst_pitch);
-/* n frames (any number; 32 per launch), one destination pointer per frame, same pitch */
 MP2V_API int  mp2v_recon_convert_frames_nv12(mp2v_recon_t* ctx, const int32_t* frame_ids, void* const* dst_device, int n, int32_t dst_pitch);
+/* Block until the reconstruction of a frame has finished on the device (consumers that read
+ * mp2v_recon_frame_device_ptrs' planes from their own streams); reports a slice error of its picture. */
+MP2V_API int  mp2v_recon_wait_frame(mp2v_recon_t* ctx, int frame_id);
 
 /* Statistics of the context since creation / last reset. */
 typedef struct mp2v_recon_stats {

@@ -23,7 +23,7 @@ def run(nproc):
 def test_two_ranks_decode_two_distinct_shards():
     one = run(1)
     two = run(2)
-    assert one["frames_per_step"] == 120 and two["frames_per_step"] == 240
+    assert one["frames_per_step"] == 30 and two["frames_per_step"] == 60
     assert two["n_ranks"] == 2 and two["scaling"] == "weak"
     # rank 1's shard is a different stream (seed = stream_id*1000 + config_id), not a copy of rank 0's
     assert two["coef_records_all_ranks"] != 2 * one["coef_records_all_ranks"]

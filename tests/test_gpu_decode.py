@@ -7,6 +7,7 @@ import pytest
 import oracle_lib as O
 from helpers import GOLDEN, GOLDEN_CASES, sha
 from tiny_mp2v_dec_b200.decoder import Decoder, frame_bytes
+from tiny_mp2v_dec_b200.recon import ReconError
 from tiny_mp2v_dec_b200.streamgen import Stream
 
 pytestmark = pytest.mark.gpu
@@ -65,8 +66,9 @@ def test_decode_without_download_still_reconstructs(gpu_vlc):
     s = Stream(352, 288, 1, seed=63, gop_n=9, gop_m=3)
     d = Decoder(352, 288, 1, num_threads=2, gpu_vlc=gpu_vlc)
     assert d.decode(s.padded, s.size, want_output=False, download=False) is None
-    # nothing comes back but, with the device parser, its 16-byte status per slice
-    assert d.stats.frames == 9 and d.stats.pictures == 9 and d.stats.d2h_bytes == (9 * 18 * 16 if gpu_vlc else 0)
+    # nothing comes back but, with the device parser, its 16-byte status per slice and the list of start-code offsets
+    assert d.stats.frames == 9 and d.stats.pictures == 9
+    assert (9 * 18 * 16 <= d.stats.d2h_bytes < 9 * 18 * 16 + 4096) if gpu_vlc else d.stats.d2h_bytes == 0
 
 
 def test_malformed_stream_is_an_error_not_a_crash(gpu_vlc):
@@ -196,3 +198,21 @@ def test_concurrent_decoders_share_one_gpu(gpu_vlc):
     for t in threads:
         t.join()
     assert got == want
+
+
+def test_decode_resident_repeats_the_decode_without_an_upload():
+    """mp2v_decoder_c::decode_resident: the stream of the last decode() is still on the device; decoding it again gives
+    the same frames, copies no stream bytes and reports the device time of the call"""
+    s = Stream(352, 288, 1, seed=77, n_gops=3, gop_n=9, gop_m=3)
+    want = O.oracle_decode_stream(s)
+    d = Decoder(352, 288, 1, num_threads=2)
+    assert d.decode(s.padded, s.size) == want
+    first_h2d = d.stats.h2d_bytes
+    assert first_h2d >= s.size
+    assert d.decode_resident(want_output=True) == want
+    assert d.stats.h2d_bytes < first_h2d - s.size // 2 and d.stats.device_ms > 0 and d.stats.vlc_launches > 0
+    # the host-parser mode leaves nothing resident
+    h = Decoder(352, 288, 1, num_threads=2, gpu_vlc=False)
+    assert h.decode(s.padded, s.size) == want
+    with pytest.raises(ReconError, match="resident"):
+        h.decode_resident()

@@ -308,6 +308,19 @@ void pipeline_t::output() {
             sh->gcv.wait(lk, [&] { return sh->failed.load() || sh->emit_gop == t.src->gop; });
             if (sh->failed.load()) return false;
         }
+        if (sh->opt.device_renderer) {
+            mp2v_device_frame_t df{};
+            int32_t dstr[3] = {0, 0, 0};
+            if (mp2v_recon_wait_frame(recon, t.dst) != MP2V_OK || mp2v_recon_frame_device_ptrs(recon, t.dst, df.planes, dstr) != MP2V_OK) {
+                sh->fail(std::string("device frame: ") + mp2v_recon_last_error(recon));
+                return false;
+            }
+            mp2v_frame_layout_t lay;
+            mp2v_frame_layout(sh->cfg.width, sh->cfg.height, sh->cfg.chroma_format, &lay);
+            for (int p = 0; p < 3; p++) { df.strides[p] = dstr[p]; df.width[p] = lay.width[p]; df.height[p] = lay.height[p]; }
+            df.device = device; df.frame_id = t.dst; df.recon = recon;
+            sh->opt.device_renderer(df);
+        }
         if (sh->renderer) {
             const int st[3] = {strides[0], strides[1], strides[2]};
             frame_c view(sh->cfg.width, sh->cfg.height, sh->cfg.chroma_format, planes, st);
@@ -418,6 +431,20 @@ struct mp2v_decoder_c::impl_t {
     }
     bool prepare(bool gpu_vlc);
     bool device_parser_can_take(const stream_index_t& index, bool staged) const;
+
+    // the stream of the last decode(): its index, and whether it is resident on the device(s) (decode_resident re-decodes it)
+    struct stream_state_t {
+        stream_index_t index;
+        uint8_t* buffer = nullptr;
+        int len = 0;
+        bool resident = false;        // uploaded to and scanned on the first device
+        bool gpu_vlc = false;         // slices are parsed on the device
+        bool stream_mode = false;     // ... straight out of the resident copy
+        double index_ms = 0;
+    };
+    std::unique_ptr<stream_state_t> last;
+    bool open_stream(mp2v_decoder_c& owner, uint8_t* buffer, int len);
+    bool run(mp2v_decoder_c& owner, clock_t_::time_point t_begin, bool fresh_stats);
 };
 
 // mp2v_recon_submit_slices' envelope: at most one slice per macroblock row, coded picture within the staging capacity
@@ -530,6 +557,7 @@ bool mp2v_decoder_c::decoder_init(const decoder_config_t& config, std::function<
 }
 
 void mp2v_decoder_c::set_options(const mp2v_b200_options_t& opt) { m->release(); m->opt = opt; }
+void mp2v_decoder_c::set_device_renderer(std::function<void(const mp2v_device_frame_t&)> r) { m->opt.device_renderer = std::move(r); }
 bool mp2v_decoder_c::prepare() { return m->initialised && m->prepare(m->opt.gpu_vlc); }
 const char* mp2v_decoder_c::last_error() const { return m->error.c_str(); }
 mp2v_decoder_c::stats_t mp2v_decoder_c::stats() const { return m->stats; }
@@ -539,50 +567,100 @@ bool mp2v_decoder_c::decode(uint8_t* buffer, int len) {
     if (!m->initialised) return false;
     const auto t_begin = clock_t_::now();
     m->error.clear();
-    stream_index_t index;
+    for (auto& devs : m->dev_sets) for (auto& d : devs) { mp2v_recon_stats_t st; mp2v_recon_get_stats(d.recon, &st, 1); }   // statistics are per decode() call
+    if (!m->open_stream(*this, buffer, len)) return false;
+    return m->run(*this, t_begin, false);
+}
+
+bool mp2v_decoder_c::decode_resident() {
+    if (!m->initialised) return false;
+    m->error.clear();
+    if (!m->last || !m->last->stream_mode) { m->error = "decode_resident: the last decode() did not leave a stream resident on the device"; return false; }
+    return m->run(*this, clock_t_::now(), true);
+}
+
+// index the stream (on the device when slices are parsed there), publish its headers, check it against the configuration
+bool mp2v_decoder_c::impl_t::open_stream(mp2v_decoder_c& owner, uint8_t* buffer, int len) {
+    const auto t_begin = clock_t_::now();
+    last.reset(new stream_state_t);
+    stream_state_t& S = *last;
+    S.buffer = buffer; S.len = len;
+    stream_index_t& index = S.index;
     // Device front end: the stream goes to the first device in one copy and a kernel lists its start codes
     // (start_codes_search.hpp:7-26); the host only parses the headers those offsets point at.
-    bool resident = false;
-    if (m->opt.gpu_vlc && len > 0) {
-        if (!m->prepare(true)) return false;
+    if (opt.gpu_vlc && len > 0) {
+        if (!prepare(true)) { last.reset(); return false; }
         const uint32_t* codes = nullptr;
         uint32_t n_codes = 0;
-        mp2v_recon_t* r0 = m->dev_sets[1][0].recon;
+        mp2v_recon_t* r0 = dev_sets[1][0].recon;
         const int rc = mp2v_recon_stream_begin(r0, buffer, (size_t)len, nullptr, 0, 1, &codes, &n_codes);
         if (rc == MP2V_OK) {
-            if (!index_stream_from_codes(buffer, (size_t)len, codes, n_codes, index)) { m->error = index.error; return false; }
-            resident = true;
+            if (!index_stream_from_codes(buffer, (size_t)len, codes, n_codes, index)) { error = index.error; last.reset(); return false; }
+            S.resident = true;
         } else if (rc != MP2V_ERR_RANGE) {        // (RANGE: a pathological number of start codes -- the host scan takes it)
-            m->error = std::string("stream upload: ") + mp2v_recon_last_error(r0);
+            error = std::string("stream upload: ") + mp2v_recon_last_error(r0);
+            last.reset();
             return false;
         }
     }
-    if (!resident && !index_stream(buffer, (size_t)len, index, m->cfg.num_threads)) { m->error = index.error; return false; }
-    publish_headers(*this, index.headers);
+    if (!S.resident && !index_stream(buffer, (size_t)len, index, cfg.num_threads)) { error = index.error; last.reset(); return false; }
+    publish_headers(owner, index.headers);
+    for (const auto& pic : index.pictures) {
+        if (pic.seq.chroma_format != cfg.chroma_format) { error = "stream chroma_format differs from decoder_config_t.chroma_format"; last.reset(); return false; }
+        // the reference trusts decoder_config_t blindly (decoder.cpp:44-66); a stream of another coded size would be
+        // reconstructed into the wrong geometry, so it is refused here
+        if (pic.seq.have_sequence_header && (((pic.seq.horizontal_size + 15) & ~15) != cfg.width || ((pic.seq.vertical_size + 15) & ~15) != cfg.height)) {
+            error = "stream coded size " + std::to_string(pic.seq.horizontal_size) + "x" + std::to_string(pic.seq.vertical_size) +
+                    " (rounded up to macroblocks) differs from decoder_config_t " + std::to_string(cfg.width) + "x" + std::to_string(cfg.height);
+            last.reset();
+            return false;
+        }
+    }
+    S.gpu_vlc = opt.gpu_vlc && device_parser_can_take(index, !S.resident);
+    S.stream_mode = S.gpu_vlc && S.resident;
+    if (!prepare(S.gpu_vlc)) { last.reset(); return false; }
+    const std::vector<device_ctx_t>& devs = dev_sets[S.gpu_vlc ? 1 : 0];
+    if (S.stream_mode && devs.size() > 1) {
+        // GOP sharding (chain g -> device g mod N): every other device receives only the byte ranges of its own pictures, at the same offsets
+        for (size_t d = 1; d < devs.size(); d++) {
+            std::vector<mp2v_byte_range_t> ranges;
+            for (const coded_picture_t& pic : index.pictures) {
+                if ((size_t)pic.gop % devs.size() != d || pic.slices.empty()) continue;
+                const size_t lo = (size_t)(pic.slices.front().payload - 4 - buffer);
+                const size_t hi = (size_t)(pic.slices.back().payload + pic.slices.back().bytes - buffer);
+                if (!ranges.empty() && lo <= ranges.back().offset + ranges.back().bytes + 4096) ranges.back().bytes = hi - ranges.back().offset;   // (picture headers in between)
+                else ranges.push_back({lo, hi - lo});
+            }
+            if (ranges.empty()) continue;
+            if (mp2v_recon_stream_begin(devs[d].recon, buffer, (size_t)len, ranges.data(), (int)ranges.size(), 0, nullptr, nullptr) != MP2V_OK) {
+                error = std::string("stream upload (CUDA device ") + std::to_string(devs[d].device) + "): " + mp2v_recon_last_error(devs[d].recon);
+                last.reset();
+                return false;
+            }
+        }
+    }
+    S.index_ms = std::chrono::duration<double, std::milli>(clock_t_::now() - t_begin).count();
+    return true;
+}
+
+// decode the opened stream: one pipeline per device; GOP chain g -> device g mod N
+bool mp2v_decoder_c::impl_t::run(mp2v_decoder_c& owner, clock_t_::time_point t_begin, bool fresh_stats) {
+    (void)owner;
+    impl_t* m = this;
+    const stream_state_t& S = *last;
+    const stream_index_t& index = S.index;
     const auto t_indexed = clock_t_::now();
     shared_t sh;
     sh.t_origin = t_begin;
-    sh.cfg = m->cfg; sh.opt = m->opt; sh.renderer = m->renderer;
-    sh.mbw = m->cfg.width / 16; sh.mbh = m->cfg.height / 16;
-    for (const auto& pic : index.pictures) {
-        if (pic.seq.chroma_format != m->cfg.chroma_format) { m->error = "stream chroma_format differs from decoder_config_t.chroma_format"; return false; }
-        // the reference trusts decoder_config_t blindly (decoder.cpp:44-66); a stream of another coded size would be
-        // reconstructed into the wrong geometry, so it is refused here
-        if (pic.seq.have_sequence_header && (((pic.seq.horizontal_size + 15) & ~15) != m->cfg.width || ((pic.seq.vertical_size + 15) & ~15) != m->cfg.height)) {
-            m->error = "stream coded size " + std::to_string(pic.seq.horizontal_size) + "x" + std::to_string(pic.seq.vertical_size) +
-                       " (rounded up to macroblocks) differs from decoder_config_t " + std::to_string(m->cfg.width) + "x" + std::to_string(m->cfg.height);
-            return false;
-        }
-    }
+    sh.cfg = cfg; sh.opt = opt; sh.renderer = renderer;
+    sh.mbw = cfg.width / 16; sh.mbh = cfg.height / 16;
     sh.gop_size.assign(index.n_gops > 0 ? index.n_gops : 1, 0);
     sh.gop_emitted.assign(sh.gop_size.size(), 0);
     for (const auto& pic : index.pictures) sh.gop_size[pic.gop]++;
-    // one pipeline per device; GOP chain g -> device g mod N
-    sh.opt.gpu_vlc = m->opt.gpu_vlc && m->device_parser_can_take(index, !resident);
-    sh.stream_mode = sh.opt.gpu_vlc && resident;
-    sh.stream_base = buffer;
-    if (!m->prepare(sh.opt.gpu_vlc)) return false;
-    const std::vector<device_ctx_t>& devs = m->dev_sets[sh.opt.gpu_vlc ? 1 : 0];
+    sh.opt.gpu_vlc = S.gpu_vlc;
+    sh.stream_mode = S.stream_mode;
+    sh.stream_base = S.buffer;
+    const std::vector<device_ctx_t>& devs = dev_sets[sh.opt.gpu_vlc ? 1 : 0];
     std::deque<pipeline_t> pipes(devs.size());
     for (size_t d = 0; d < pipes.size(); d++) {
         pipeline_t& p = pipes[d];
@@ -591,31 +669,14 @@ bool mp2v_decoder_c::decode(uint8_t* buffer, int len) {
         p.frame_use.assign(p.n_frames, 0);
         sh.pipes.push_back(&p);
         mp2v_recon_stats_t st;
-        mp2v_recon_get_stats(p.recon, &st, 1);   // statistics are per decode() call
+        if (fresh_stats) mp2v_recon_get_stats(p.recon, &st, 1);   // statistics are per call (decode() has reset them before its upload)
+        mp2v_recon_timer_start(p.recon);         // device time of the call: CUDA events on the stream every launch waits on / runs in
     }
     for (const auto& pic : index.pictures) {
         pipeline_t& p = pipes[(size_t)pic.gop % pipes.size()];
         p.tasks.emplace_back();
         pic_task_t& t = p.tasks.back();
         t.src = &pic; t.pipe = &p; t.local_index = (int)p.tasks.size() - 1;
-    }
-    if (sh.stream_mode && pipes.size() > 1) {
-        // GOP sharding: every other device receives only the byte ranges of its own pictures (same offsets)
-        for (size_t d = 1; d < pipes.size(); d++) {
-            std::vector<mp2v_byte_range_t> ranges;
-            for (const pic_task_t& t : pipes[d].tasks) {
-                if (t.src->slices.empty()) continue;
-                const size_t lo = (size_t)(t.src->slices.front().payload - 4 - buffer);
-                const size_t hi = (size_t)(t.src->slices.back().payload + t.src->slices.back().bytes - buffer);
-                if (!ranges.empty() && lo <= ranges.back().offset + ranges.back().bytes + 4096) ranges.back().bytes = hi - ranges.back().offset;   // (picture headers in between)
-                else ranges.push_back({lo, hi - lo});
-            }
-            if (ranges.empty()) continue;
-            if (mp2v_recon_stream_begin(pipes[d].recon, buffer, (size_t)len, ranges.data(), (int)ranges.size(), 0, nullptr, nullptr) != MP2V_OK) {
-                m->error = std::string("stream upload (CUDA device ") + std::to_string(pipes[d].device) + "): " + mp2v_recon_last_error(pipes[d].recon);
-                return false;
-            }
-        }
     }
     const auto t_setup = clock_t_::now();
     std::vector<std::thread> workers;
@@ -640,6 +701,8 @@ bool mp2v_decoder_c::decode(uint8_t* buffer, int len) {
     m->stats = stats_t();
     for (auto& p : pipes) {
         if (mp2v_recon_sync(p.recon) != MP2V_OK && !sh.failed.load()) sh.fail(std::string("sync: ") + mp2v_recon_last_error(p.recon));
+        double dev_ms = 0;
+        if (mp2v_recon_timer_stop(p.recon, &dev_ms) == MP2V_OK && dev_ms > m->stats.device_ms) m->stats.device_ms = dev_ms;
         mp2v_recon_stats_t st;
         if (mp2v_recon_get_stats(p.recon, &st, 0) == MP2V_OK) {
             m->stats.pictures += st.pictures; m->stats.launches += st.launches; m->stats.h2d_bytes += st.h2d_bytes;
@@ -650,7 +713,7 @@ bool mp2v_decoder_c::decode(uint8_t* buffer, int len) {
     m->stats.parse_cpu_seconds = sh.parse_ns.load() * 1e-9;
     if (getenv("MP2V_PROFILE")) {
         auto ms = [](clock_t_::time_point a, clock_t_::time_point b) { return std::chrono::duration<double, std::milli>(b - a).count(); };
-        fprintf(stderr, "[mp2v profile] index %.2f ms  setup %.2f ms  pipeline %.2f ms  drain+stats %.2f ms\n", ms(t_begin, t_indexed), ms(t_indexed, t_setup),
+        fprintf(stderr, "[mp2v profile] index %.2f ms  setup %.2f ms  pipeline %.2f ms  drain+stats %.2f ms\n", S.index_ms, ms(t_indexed, t_setup),
                 ms(t_setup, t_joined), ms(t_joined, clock_t_::now()));
     }
     if (getenv("MP2V_PROFILE"))

@@ -72,15 +72,24 @@ extern "C" MP2V_API int mp2v_decoder_create(const mp2v_decode_params_t* p, mp2v_
     return MP2V_OK;
 }
 
+extern "C" MP2V_API int mp2v_decoder_set_device_renderer(mp2v_decoder_t* d, mp2v_device_frame_fn fn, void* user) {
+    if (!d) return MP2V_ERR_ARG;
+    std::function<void(const mp2v_device_frame_t&)> r;
+    if (fn) r = [fn, user](const mp2v_device_frame_t& f) {
+        const int32_t st[3] = {f.strides[0], f.strides[1], f.strides[2]}, w[3] = {f.width[0], f.width[1], f.width[2]}, h[3] = {f.height[0], f.height[1], f.height[2]};
+        fn(user, f.planes, st, w, h, f.device, f.frame_id, f.recon);
+    };
+    d->dec.set_device_renderer(r);
+    return MP2V_OK;
+}
+
 extern "C" MP2V_API void mp2v_decoder_destroy(mp2v_decoder_t* d) { delete d; }
 
-extern "C" MP2V_API int mp2v_decoder_decode(mp2v_decoder_t* d, uint8_t* buffer, int len, mp2v_frame_fn fn, void* user,
-                                            uint8_t* out, size_t out_cap, size_t* out_bytes, mp2v_decode_stats_t* stats,
-                                            char* err, size_t err_len) {
-    if (!d || !buffer || len < 0) return MP2V_ERR_ARG;
+static int run_decode(mp2v_decoder_t* d, uint8_t* buffer, int len, bool resident, mp2v_frame_fn fn, void* user,
+                      uint8_t* out, size_t out_cap, size_t* out_bytes, mp2v_decode_stats_t* stats, char* err, size_t err_len) {
     d->fn = fn; d->user = user; d->out = out; d->out_cap = out_cap; d->pos = 0;
     d->hash = 1469598103934665603ull; d->frames = 0;
-    const bool ok = d->dec.decode(buffer, len);
+    const bool ok = resident ? d->dec.decode_resident() : d->dec.decode(buffer, len);
     if (out_bytes) *out_bytes = d->pos;
     if (stats) {
         const auto s = d->dec.stats();
@@ -89,12 +98,26 @@ extern "C" MP2V_API int mp2v_decoder_decode(mp2v_decoder_t* d, uint8_t* buffer, 
         stats->kernel_ms = s.kernel_ms; stats->parse_cpu_seconds = s.parse_cpu_seconds; stats->wall_seconds = s.wall_seconds;
         stats->hash = d->hash;
         stats->vlc_launches = s.vlc_launches;
+        stats->device_ms = s.device_ms;
     }
     if (!ok) {
         set_err(err, err_len, d->dec.last_error());
         return (strstr(d->dec.last_error(), "CUDA") || strstr(d->dec.last_error(), "recon_create")) ? MP2V_ERR_CUDA : MP2V_ERR_RANGE;
     }
     return MP2V_OK;
+}
+
+extern "C" MP2V_API int mp2v_decoder_decode(mp2v_decoder_t* d, uint8_t* buffer, int len, mp2v_frame_fn fn, void* user,
+                                            uint8_t* out, size_t out_cap, size_t* out_bytes, mp2v_decode_stats_t* stats,
+                                            char* err, size_t err_len) {
+    if (!d || !buffer || len < 0) return MP2V_ERR_ARG;
+    return run_decode(d, buffer, len, false, fn, user, out, out_cap, out_bytes, stats, err, err_len);
+}
+
+extern "C" MP2V_API int mp2v_decoder_decode_resident(mp2v_decoder_t* d, mp2v_frame_fn fn, void* user, uint8_t* out, size_t out_cap, size_t* out_bytes,
+                                                     mp2v_decode_stats_t* stats, char* err, size_t err_len) {
+    if (!d) return MP2V_ERR_ARG;
+    return run_decode(d, nullptr, 0, true, fn, user, out, out_cap, out_bytes, stats, err, err_len);
 }
 
 extern "C" MP2V_API int mp2v_decode_stream(const mp2v_decode_params_t* p, uint8_t* buffer, int len,

@@ -122,7 +122,7 @@ struct mp2v_recon {
     uint32_t* d_counts = nullptr; size_t counts_cap = 0;
     uint32_t* h_total = nullptr; uint32_t* d_total = nullptr;   // pinned + mapped
     cudaStream_t s_parse[kParseStreams] = {};
-    int parse_rr = 0;
+    int parse_rr = 0, n_parse_streams = kParseStreams, lot_cap = 0;      // dev knobs MP2V_PARSE_STREAMS / MP2V_LOT
     cudaEvent_t ev_stream = nullptr;           // the upload (and scan) of the resident stream
     struct parse_buf_t { uint8_t* h = nullptr; uint8_t* d = nullptr; cudaEvent_t done = nullptr; bool used = false; } parse_buf[kParseBufs];
     int parse_buf_rr = 0;
@@ -323,6 +323,8 @@ static int create_impl(mp2v_recon* ctx) {
     if (ctx->vlc) {
         // stream-resident front end: parse streams, descriptor buffers (one per batched parse launch in flight)
         const bool parse_first = getenv("MP2V_PARSE_PRIO") && atoi(getenv("MP2V_PARSE_PRIO"));      // dev knob
+        if (const char* v = getenv("MP2V_PARSE_STREAMS")) { const int k = atoi(v); if (k >= 1 && k <= mp2v_recon::kParseStreams) ctx->n_parse_streams = k; }
+        if (const char* v = getenv("MP2V_LOT")) { const int k = atoi(v); if (k >= 1 && k <= kMaxStreamBatch) ctx->lot_cap = k; }
         for (auto& st : ctx->s_parse) CK(cudaStreamCreateWithPriority(&st, cudaStreamNonBlocking, parse_first ? prio_greatest : prio_least), "stream");
         CK(cudaEventCreateWithFlags(&ctx->ev_stream, cudaEventDisableTiming), "event");
         ctx->desc_stride = vlc_stream_desc_bytes(ctx->mbh);
@@ -474,7 +476,7 @@ static int launch_parse_batch(mp2v_recon* ctx) {
     if (ctx->parse_pending.empty()) return MP2V_OK;
     mp2v_recon::parse_buf_t& b = ctx->parse_buf[ctx->parse_buf_rr];
     cudaStream_t st = ctx->s_parse[ctx->parse_rr];
-    ctx->parse_rr = (ctx->parse_rr + 1) % mp2v_recon::kParseStreams;
+    ctx->parse_rr = (ctx->parse_rr + 1) % ctx->n_parse_streams;
     const int n = (int)ctx->parse_pending.size();
     CK(cudaStreamWaitEvent(st, ctx->ev_stream, 0), "stream wait");      // the resident stream has arrived
     // rows without any slice (never in valid streams): blank records first
@@ -731,11 +733,11 @@ static int queue_slot(mp2v_recon* ctx, slot_t* s) {
     // Device-parsed stream pictures are launched in larger lots (4, 8, ... kMaxStreamBatch): a slice parses at the speed of
     // ONE thread (about a millisecond for a dense 1080p row), so the parser's throughput is the number of pictures in flight.
     // MP2V_RECON_THROUGHPUT: full lots from the first picture on (nobody is waiting for the first frame).
-    // Otherwise lots of 4, 8, 16, 16, ...: the frame copies to the host (the slower stage) start early and never run dry
+    // Otherwise lots of 4, 8, 16, 32, 32, ...: the frame copies to the host (the slower stage) start early and never run dry
     // (measured: a last lot of 60 pictures left the copy engine idle for 2 ms of a 12 ms decode).
     const bool rate = (ctx->cfg.flags & MP2V_RECON_THROUGHPUT) != 0;
     const int ramp = rate ? kMaxBatch : ctx->batch_ramp;
-    const int quota = s->stream_pic ? std::min(rate ? kMaxStreamBatch : 16, 4 * ramp) : std::min(ctx->max_batch, ramp);
+    const int quota = s->stream_pic ? std::min(ctx->lot_cap ? ctx->lot_cap : (rate ? kMaxStreamBatch : 32), 4 * ramp) : std::min(ctx->max_batch, ramp);
     if (ctx->queued >= quota) return flush_locked(ctx);
     return MP2V_OK;
 }
@@ -879,7 +881,7 @@ extern "C" MP2V_API int mp2v_recon_stream_begin(mp2v_recon_t* ctx, const uint8_t
     if (rc != MP2V_OK) return rc;
     CK(cudaSetDevice(ctx->cfg.device), "cudaSetDevice");
     // parses of the previous stream may still be reading it
-    for (auto st : ctx->s_parse) CK(cudaStreamSynchronize(st), "stream sync");
+    for (auto st : ctx->s_parse) if (st) CK(cudaStreamSynchronize(st), "stream sync");
     const size_t need = ((bytes + 4095) & ~(size_t)4095) + 4096;         // the scan reads whole 4 KiB chunks + look-ahead; parsers read a few bytes past a slice
     if (need > ctx->stream_cap) {
         if (ctx->d_stream) CK(cudaFree(ctx->d_stream), "cudaFree");
@@ -1251,38 +1253,65 @@ extern "C" MP2V_API int mp2v_recon_frame_device_ptrs(mp2v_recon_t* ctx, int fram
     return MP2V_OK;
 }
 
-extern "C" MP2V_API int mp2v_recon_convert_frames_nv12(mp2v_recon_t* ctx, const int32_t* frame_ids, void* const* dst_device, int n, int32_t dst_pitch) {
+extern "C" MP2V_API int mp2v_recon_convert_frames(mp2v_recon_t* ctx, int format, const int32_t* frame_ids, void* const* dst_device, int n, int32_t dst_pitch) {
     if (!ctx || !frame_ids || !dst_device || n < 0) return MP2V_ERR_ARG;
     std::lock_guard<std::mutex> lk(ctx->mu);
-    if (ctx->cfg.chroma_format != 1) return ctx->fail(MP2V_ERR_ARG, "NV12 is a 4:2:0 format");
-    if (dst_pitch < ctx->cfg.width || (dst_pitch & 15)) return ctx->fail(MP2V_ERR_ARG, "NV12 destination must be 16-byte aligned with a pitch that is a multiple of 16 and >= width");
-    const int rc = flush_locked(ctx);
-    if (rc != MP2V_OK) return rc;
+    const int cf = ctx->cfg.chroma_format;
+    if (format == MP2V_OUT_NV12 || format == MP2V_OUT_P010) { if (cf != 1) return ctx->fail(MP2V_ERR_ARG, "NV12 / P010 are 4:2:0 formats"); }
+    else if (format == MP2V_OUT_UYVY) { if (cf != 2) return ctx->fail(MP2V_ERR_ARG, "UYVY is a 4:2:2 format"); }
+    else return ctx->fail(MP2V_ERR_ARG, "unknown output format");
+    const int row_bytes = ctx->cfg.width * (format == MP2V_OUT_NV12 ? 1 : 2);
+    if (dst_pitch < row_bytes || (dst_pitch & 15)) return ctx->fail(MP2V_ERR_ARG, "destination must be 16-byte aligned with a pitch that is a multiple of 16 and >= the row bytes");
     for (int i = 0; i < n; i++) {
         if (frame_ids[i] < 0 || frame_ids[i] >= ctx->cfg.n_frames) return ctx->fail(MP2V_ERR_ARG, "frame id out of range");
-        if (!dst_device[i] || ((uintptr_t)dst_device[i] & 15)) return ctx->fail(MP2V_ERR_ARG, "NV12 destination must be 16-byte aligned with a pitch that is a multiple of 16 and >= width");
-        if (!ctx->frame_written[frame_ids[i]]) return ctx->fail(MP2V_ERR_STATE, "frame has never been written");
+        if (!dst_device[i] || ((uintptr_t)dst_device[i] & 15)) return ctx->fail(MP2V_ERR_ARG, "destination must be 16-byte aligned with a pitch that is a multiple of 16 and >= the row bytes");
+        if (!ctx->frame_written[frame_ids[i]] && !frame_is_queued(ctx, frame_ids[i])) return ctx->fail(MP2V_ERR_STATE, "frame has never been written");
     }
+    const int rc = flush_locked(ctx);
+    if (rc != MP2V_OK) return rc;
     CK(cudaSetDevice(ctx->cfg.device), "cudaSetDevice");
     // on the compute stream: ordered behind the launches that write the frames and ahead of any that overwrites them
-    for (int first = 0; first < n; first += kMaxNv12Batch) {
-        nv12_batch_t b{};
-        b.n_frames = std::min(n - first, (int)kMaxNv12Batch);
+    for (int first = 0; first < n; first += kMaxConvertBatch) {
+        convert_batch_t b{};
+        b.n_frames = std::min(n - first, (int)kMaxConvertBatch);
         b.width = ctx->cfg.width; b.height = ctx->cfg.height;
         b.stride_y = ctx->lay.stride[0]; b.stride_c = ctx->lay.stride[1]; b.dst_pitch = dst_pitch;
         for (int i = 0; i < b.n_frames; i++)
             b.frame[i] = {ctx->frame_ptr(frame_ids[first + i], 0), ctx->frame_ptr(frame_ids[first + i], 1), ctx->frame_ptr(frame_ids[first + i], 2),
                           static_cast<uint8_t*>(dst_device[first + i])};
-        CK(launch_nv12(b, ctx->s_compute), "NV12 conversion launch");
+        CK(launch_convert(format, b, ctx->s_compute), "output conversion launch");
         ctx->stats.launches += 1;
     }
     return MP2V_OK;
 }
 
+extern "C" MP2V_API int mp2v_recon_convert_frames_nv12(mp2v_recon_t* ctx, const int32_t* frame_ids, void* const* dst_device, int n, int32_t dst_pitch) {
+    return mp2v_recon_convert_frames(ctx, MP2V_OUT_NV12, frame_ids, dst_device, n, dst_pitch);
+}
+
 extern "C" MP2V_API int mp2v_recon_convert_frame_nv12(mp2v_recon_t* ctx, int frame_id, void* dst_device, int32_t dst_pitch) {
     const int32_t id = frame_id;
     void* const dst = dst_device;
-    return mp2v_recon_convert_frames_nv12(ctx, &id, &dst, 1, dst_pitch);
+    return mp2v_recon_convert_frames(ctx, MP2V_OUT_NV12, &id, &dst, 1, dst_pitch);
+}
+
+// Wait until a frame's reconstruction has finished (device consumers that read the planes with their own streams).
+extern "C" MP2V_API int mp2v_recon_wait_frame(mp2v_recon_t* ctx, int frame_id) {
+    if (!ctx) return MP2V_ERR_ARG;
+    cudaEvent_t ev = nullptr;
+    {
+        std::lock_guard<std::mutex> lk(ctx->mu);
+        if (frame_id < 0 || frame_id >= ctx->cfg.n_frames) return ctx->fail(MP2V_ERR_ARG, "frame id out of range");
+        if (frame_is_queued(ctx, frame_id)) { const int rc = flush_locked(ctx); if (rc != MP2V_OK) return rc; }
+        if (!ctx->frame_written[frame_id]) return ctx->fail(MP2V_ERR_STATE, "frame has never been written");
+        ev = ctx->frame_launch[frame_id] >= 0 ? ctx->launch_ev[ctx->frame_launch[frame_id]] : ctx->frame_ev[frame_id];
+    }
+    const cudaError_t e = cudaEventSynchronize(ev);
+    std::lock_guard<std::mutex> lk(ctx->mu);
+    if (e != cudaSuccess) return ctx->cuda_fail(e, "event sync");
+    harvest_all(ctx);      // the frame's picture has been parsed by now: a slice error surfaces with its frame
+    CHECK_VLC_ERROR();
+    return MP2V_OK;
 }
 
 // ---------------------------------------------------------------------------------------------

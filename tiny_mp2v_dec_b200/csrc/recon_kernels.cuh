@@ -8,7 +8,7 @@
 namespace mp2v {
 
 constexpr int kMaxBatch = 128;       // pictures fused into one launch (descriptors travel as kernel arguments: 104 B each, 13 KB of the 32 KB limit)
-constexpr int kMaxNv12Batch = 32;    // frames per NV12 conversion launch
+constexpr int kMaxConvertBatch = 32; // frames per output-conversion launch
 constexpr int kCtaThreads = 128;
 
 // A warp owns `mbs_per_warp` consecutive macroblocks and walks them in batches of <= MP2V_SLOTS coded
@@ -58,13 +58,13 @@ cudaError_t make_frame_tmaps(int chroma_format, uint8_t* frames, const mp2v_fram
 // grid = n_pics * ctas_per_pic; returns the CUDA error of the launch
 cudaError_t launch_recon(int chroma_format, const batch_desc_t& batch, const recon_tmaps_t& tm, cudaStream_t stream);
 
-// planar 4:2:0 frames -> NV12 (Y plane, then interleaved Cb/Cr rows) in the caller's device buffers (convert_kernel.cu)
-struct nv12_frame_t { const uint8_t* y; const uint8_t* cb; const uint8_t* cr; uint8_t* dst; };
-struct nv12_batch_t {
-    nv12_frame_t frame[kMaxNv12Batch];
+// planar frames -> NV12 / P010 / UYVY (MP2V_OUT_*, mp2v_recon.h) in the caller's device buffers (convert_kernel.cu)
+struct convert_frame_t { const uint8_t* y; const uint8_t* cb; const uint8_t* cr; uint8_t* dst; };
+struct convert_batch_t {
+    convert_frame_t frame[kMaxConvertBatch];
     int32_t n_frames, width, height, stride_y, stride_c, dst_pitch;
 };
-cudaError_t launch_nv12(const nv12_batch_t& batch, cudaStream_t stream);
+cudaError_t launch_convert(int format, const convert_batch_t& batch, cudaStream_t stream);
 
 // registers / shared memory of the kernels as compiled, for DESIGN.md and the occupancy report
 cudaError_t recon_kernel_attributes(int chroma_format, cudaFuncAttributes* out);

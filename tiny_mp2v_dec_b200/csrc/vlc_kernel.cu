@@ -23,7 +23,10 @@ namespace mp2v {
 
 namespace {
 
-constexpr int kVlcCtaThreads = 128;
+#ifndef MP2V_VLC_CTA
+#define MP2V_VLC_CTA 128
+#endif
+constexpr int kVlcCtaThreads = MP2V_VLC_CTA;
 
 __global__ void __launch_bounds__(kVlcCtaThreads)
 parse_slices_kernel(const uint8_t* __restrict__ staged, const vlc_decode_tables_t* __restrict__ tables, mp2v_mb_info_t* __restrict__ mb,
@@ -64,8 +67,9 @@ parse_stream_slices_kernel(const uint8_t* __restrict__ stream, const uint8_t* __
     const vlc_stream_pic_t& d = *reinterpret_cast<const vlc_stream_pic_t*>(desc_base + (size_t)blockIdx.y * desc_stride);
     // the picture's parameter block (W, scan, frame ids) travels in the descriptor: the first CTA drops it where the
     // reconstruction kernel reads it (that launch is ordered behind this one)
-    if (blockIdx.x == 0 && threadIdx.x < sizeof(mp2v_pic_params_t) / 4)
-        reinterpret_cast<uint32_t*>(d.params_out)[threadIdx.x] = reinterpret_cast<const uint32_t*>(&d.params)[threadIdx.x];
+    if (blockIdx.x == 0)
+        for (unsigned i = threadIdx.x; i < sizeof(mp2v_pic_params_t) / 4; i += kVlcCtaThreads)
+            reinterpret_cast<uint32_t*>(d.params_out)[i] = reinterpret_cast<const uint32_t*>(&d.params)[i];
     const int lane = threadIdx.x & 31;
     const int slice = (blockIdx.x * kVlcCtaThreads + threadIdx.x) >> 5;
     if (lane != 0 || slice >= (int)d.n_slices) return;

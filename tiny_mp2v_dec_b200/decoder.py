@@ -22,10 +22,14 @@ class DecodeStats(C.Structure):
     _fields_ = [("frames", C.c_uint64), ("pictures", C.c_uint64), ("launches", C.c_uint64), ("h2d_bytes", C.c_uint64),
                 ("d2h_bytes", C.c_uint64), ("algorithmic_bytes", C.c_uint64), ("kernel_ms", C.c_double),
                 ("parse_cpu_seconds", C.c_double), ("wall_seconds", C.c_double), ("hash", C.c_uint64),
-                ("vlc_launches", C.c_uint64)]
+                ("vlc_launches", C.c_uint64), ("device_ms", C.c_double)]
 
 
-DECODE_EXPORTS = ["mp2v_decode_stream", "mp2v_decoder_create", "mp2v_decoder_decode", "mp2v_decoder_destroy", "mp2v_parse_stream", "mp2v_parsed_num_pictures", "mp2v_parsed_picture",
+# void (*)(void* user, void* const planes[3], const int32 strides[3], const int32 widths[3], const int32 heights[3], int32 device, int32 frame_id, mp2v_recon_t*)
+DEVICE_FRAME_FN = C.CFUNCTYPE(None, C.c_void_p, C.POINTER(C.c_void_p), C.POINTER(C.c_int32), C.POINTER(C.c_int32), C.POINTER(C.c_int32),
+                              C.c_int32, C.c_int32, C.c_void_p)
+
+DECODE_EXPORTS = ["mp2v_decode_stream", "mp2v_decoder_create", "mp2v_decoder_decode", "mp2v_decoder_decode_resident", "mp2v_decoder_set_device_renderer", "mp2v_decoder_destroy", "mp2v_parse_stream", "mp2v_parsed_num_pictures", "mp2v_parsed_picture",
                   "mp2v_parsed_wall_seconds", "mp2v_parsed_cpu_seconds", "mp2v_parsed_free"]
 
 _bound = False
@@ -41,6 +45,9 @@ def lib():
         L.mp2v_decoder_create.argtypes = [P(DecodeParams), P(C.c_void_p), C.c_char_p, C.c_size_t]
         L.mp2v_decoder_decode.argtypes = [C.c_void_p, C.c_void_p, C.c_int, C.c_void_p, C.c_void_p, C.c_void_p, C.c_size_t,
                                           P(C.c_size_t), P(DecodeStats), C.c_char_p, C.c_size_t]
+        L.mp2v_decoder_decode_resident.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_size_t, P(C.c_size_t), P(DecodeStats),
+                                                   C.c_char_p, C.c_size_t]
+        L.mp2v_decoder_set_device_renderer.argtypes = [C.c_void_p, DEVICE_FRAME_FN, C.c_void_p]
         L.mp2v_decoder_destroy.argtypes = [C.c_void_p]
         L.mp2v_decoder_destroy.restype = None
         L.mp2v_parse_stream.argtypes = [C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, P(C.c_void_p), C.c_char_p, C.c_size_t]
@@ -121,6 +128,8 @@ class Decoder:
             n_pics = 0 if size < 4 else int(np.count_nonzero((buf[:size - 3] == 0) & (buf[1:size - 2] == 0) & (buf[2:size - 1] == 1) & (buf[3:size] == 0)))
             cap = n_pics * frame_bytes(self.p.width, self.p.height, self.p.chroma_format)
             out = np.empty(max(cap, 1), np.uint8)
+        self._last_cap = cap        # (0 unless this call produced output: decode_resident(want_output=True) then counts the pictures itself)
+        self._keep, self._keep_size = buf, size      # decode_resident needs the bytes to stay alive
         nbytes = C.c_size_t()
         rc = L.mp2v_decoder_decode(h, buf.ctypes.data, size, None, None, out.ctypes.data if out is not None else None,
                                    cap, C.byref(nbytes), C.byref(st), err, 512)
@@ -131,6 +140,44 @@ class Decoder:
             return None
         assert nbytes.value <= cap, (nbytes.value, cap)
         return out[:nbytes.value].tobytes()
+
+
+def _decode_resident(self, want_output=False):
+    """mp2v_decoder_c::decode_resident: decode once more the stream the last decode() left on the device (no upload, no
+    start-code scan); the buffer given to that decode() must still be alive.  Returns the YUV when want_output."""
+    L = lib()
+    st = DecodeStats()
+    err = C.create_string_buffer(512)
+    out, cap = None, 0
+    if want_output and self._download:
+        if not self._last_cap:
+            b = self._keep[:self._keep_size]
+            n_pics = 0 if len(b) < 4 else int(np.count_nonzero((b[:-3] == 0) & (b[1:-2] == 0) & (b[2:-1] == 1) & (b[3:] == 0)))
+            self._last_cap = n_pics * frame_bytes(self.p.width, self.p.height, self.p.chroma_format)
+        cap = self._last_cap
+        out = np.empty(max(cap, 1), np.uint8)
+    nbytes = C.c_size_t()
+    rc = L.mp2v_decoder_decode_resident(self.h, None, None, out.ctypes.data if out is not None else None, cap, C.byref(nbytes),
+                                        C.byref(st), err, 512)
+    self.stats = st
+    if rc != OK:
+        raise ReconError("decode_resident failed (%d): %s" % (rc, err.value.decode()))
+    return out[:nbytes.value].tobytes() if out is not None else None
+
+
+Decoder.decode_resident = _decode_resident
+
+
+def _set_device_renderer(self, fn, download=False):
+    """fn(planes[3] device pointers, strides[3], widths[3], heights[3], device, frame_id, recon handle) is called on the
+    decoder's output thread for every frame in display order (mp2v_b200_options_t::device_renderer); None removes it"""
+    h = self._handle(download)
+    self._dev_cb = DEVICE_FRAME_FN(lambda user, pl, st, w, hh, dev, fid, rc: fn([pl[i] for i in range(3)], [st[i] for i in range(3)],
+                                                                          [w[i] for i in range(3)], [hh[i] for i in range(3)], dev, fid, rc)) if fn else DEVICE_FRAME_FN()
+    lib().mp2v_decoder_set_device_renderer(h, self._dev_cb, None)
+
+
+Decoder.set_device_renderer = _set_device_renderer
 
 
 class ParsedPicture:

@@ -17,7 +17,7 @@ EXPORTS = [
     "mp2v_frame_layout", "mp2v_recon_create", "mp2v_recon_destroy", "mp2v_recon_last_error",
     "mp2v_recon_acquire_picture", "mp2v_recon_release_picture", "mp2v_recon_submit", "mp2v_recon_submit_slices", "mp2v_recon_stage_slices", "mp2v_recon_submit_staged", "mp2v_recon_stream_begin", "mp2v_recon_submit_stream_picture", "mp2v_recon_precheck", "mp2v_recon_flush",
     "mp2v_recon_sync", "mp2v_recon_reset", "mp2v_recon_upload", "mp2v_recon_run_resident", "mp2v_recon_download_frame",
-    "mp2v_recon_map_frame", "mp2v_recon_upload_frame", "mp2v_recon_frame_device_ptrs", "mp2v_recon_convert_frame_nv12", "mp2v_recon_convert_frames_nv12",
+    "mp2v_recon_map_frame", "mp2v_recon_upload_frame", "mp2v_recon_frame_device_ptrs", "mp2v_recon_convert_frames", "mp2v_recon_convert_frame_nv12", "mp2v_recon_convert_frames_nv12", "mp2v_recon_wait_frame",
     "mp2v_recon_set_timing", "mp2v_recon_get_stats", "mp2v_recon_timer_start", "mp2v_recon_timer_stop",
 ]
 
@@ -60,6 +60,8 @@ def lib():
         L.mp2v_recon_frame_device_ptrs.argtypes = [C.c_void_p, C.c_int, C.c_void_p * 3, C.c_int32 * 3]
         L.mp2v_recon_convert_frame_nv12.argtypes = [C.c_void_p, C.c_int, C.c_void_p, C.c_int32]
         L.mp2v_recon_convert_frames_nv12.argtypes = [C.c_void_p, P(C.c_int32), P(C.c_void_p), C.c_int, C.c_int32]
+        L.mp2v_recon_convert_frames.argtypes = [C.c_void_p, C.c_int, P(C.c_int32), P(C.c_void_p), C.c_int, C.c_int32]
+        L.mp2v_recon_wait_frame.argtypes = [C.c_void_p, C.c_int]
         L.mp2v_recon_set_timing.argtypes = [C.c_void_p, C.c_int]
         L.mp2v_recon_get_stats.argtypes = [C.c_void_p, P(ReconStats), C.c_int]
         L.mp2v_recon_timer_start.argtypes = [C.c_void_p]
@@ -217,6 +219,18 @@ class Recon:
         ids = (C.c_int32 * n)(*frame_ids)
         ptrs = (C.c_void_p * n)(*dst_device_ptrs)
         self._ck(self.L.mp2v_recon_convert_frames_nv12(self.h, ids, ptrs, n, dst_pitch))
+
+    OUT_FORMATS = {"nv12": 0, "p010": 1, "uyvy": 2}
+
+    def convert_batch(self, fmt, frame_ids, dst_device_ptrs, dst_pitch):
+        """frames -> NV12 / P010 (4:2:0) or UYVY (4:2:2) in device buffers of the caller; asynchronous, 32 frames per launch"""
+        n = len(frame_ids)
+        ids = (C.c_int32 * n)(*frame_ids)
+        ptrs = (C.c_void_p * n)(*dst_device_ptrs)
+        self._ck(self.L.mp2v_recon_convert_frames(self.h, self.OUT_FORMATS[fmt], ids, ptrs, n, dst_pitch))
+
+    def wait_frame(self, frame_id):
+        self._ck(self.L.mp2v_recon_wait_frame(self.h, frame_id))
 
     # ---- statistics
     def set_timing(self, on=True):
