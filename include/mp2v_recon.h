@@ -98,12 +98,15 @@ typedef struct mp2v_mb_info {
  *   [26]    RAW     intra DC: stored as is, excluded from the mismatch sum (mb_decoder.cpp:160)
  *   [27]    FIRST   non-intra first coefficient coded "1s" (mb_decoder.cpp:79-88):
  *                   val = (3*W[0]*qscale)>>5 with sign, NOT clamped, included in the mismatch sum
+ *   [31:28] mbx     the macroblock's column modulo 16: the reconstruction kernel walks the records of up to 16
+ *                   consecutive macroblocks of a row as one flat list and finds each record's macroblock from it
  */
 typedef uint32_t mp2v_coef_t;
 #define MP2V_COEF_RAW    (1u << 26)
 #define MP2V_COEF_FIRST  (1u << 27)
 #define MP2V_COEF(level, pos, blk, flags) \
     (((uint32_t)(uint16_t)(int16_t)(level)) | ((uint32_t)(pos) << 16) | ((uint32_t)(blk) << 22) | (flags))
+#define MP2V_COEF_MB(mbx)  (((uint32_t)(mbx) & 15u) << 28)
 #define MP2V_COEF_LEVEL(c) ((int)(int16_t)((c) & 0xffffu))
 #define MP2V_COEF_POS(c)   (((c) >> 16) & 63u)
 #define MP2V_COEF_BLK(c)   (((c) >> 22) & 15u)

@@ -103,8 +103,8 @@ MP2V_HDI bool decode_mv_component(bitreader_t& br, const vlc_decode_tables_t& T,
 
 // one block: DC (intra) + run/level list; returns false on a syntax error
 MP2V_HDI bool parse_block(bitreader_t& br, mp2v_coef_t*& out, const vlc_decode_tables_t& T, const slice_syntax_t& sx,
-                          uint16_t (&dc_pred)[3], int b, bool intra) {
-    const uint32_t blk_bits = (uint32_t)b << 22;
+                          uint16_t (&dc_pred)[3], int b, bool intra, uint32_t mb_bits) {
+    const uint32_t blk_bits = ((uint32_t)b << 22) | mb_bits;      // block index + the macroblock column tag of every record
     int i = 0;
     const coef_vlc_t* table = &T.b14;
     br.refill();
@@ -124,14 +124,14 @@ MP2V_HDI bool parse_block(bitreader_t& br, mp2v_coef_t*& out, const vlc_decode_t
         }
         dc_pred[comp] = (uint16_t)(dc_pred[comp] + diff);
         const int16_t dc = (int16_t)(uint16_t)((uint32_t)dc_pred[comp] << (3 - sx.intra_dc_precision));
-        *out++ = MP2V_COEF(dc, 0, b, MP2V_COEF_RAW);
+        *out++ = MP2V_COEF(dc, 0, b, MP2V_COEF_RAW) | mb_bits;
         i = 1;
         if (sx.intra_vlc_format) table = &T.b15;
         br.refill();
     } else if (br.peek(1)) {                                   // first coefficient "1s" (mb_decoder.cpp:79-88)
         const int neg = (int)br.peek(2) & 1;
         br.skip(2);
-        *out++ = MP2V_COEF(neg ? -1 : 1, 0, b, MP2V_COEF_FIRST);
+        *out++ = MP2V_COEF(neg ? -1 : 1, 0, b, MP2V_COEF_FIRST) | mb_bits;
         i = 1;
     }
 #ifdef __CUDA_ARCH__
@@ -154,7 +154,7 @@ MP2V_HDI bool parse_block(bitreader_t& br, mp2v_coef_t*& out, const vlc_decode_t
                 if ((int32_t)e < 0) break;
                 br.skip((int)(e >> 24));
                 rec = q + (e & 0x007fffffu);
-                if ((rec >> 22) != (uint32_t)b) break;         // i + run > 63
+                if ((rec >> 22) != (blk_bits >> 22)) break;         // i + run > 63
                 o0[n++] = rec;
                 q = rec & 0xffff0000u;
             }
@@ -184,7 +184,7 @@ MP2V_HDI bool parse_block(bitreader_t& br, mp2v_coef_t*& out, const vlc_decode_t
                 break;
             }
             rec = q + ((uint32_t)(run + 1) << 16) + (uint32_t)(uint16_t)level;
-            if ((rec >> 22) != (uint32_t)b) break;             // i + run > 63
+            if ((rec >> 22) != (blk_bits >> 22)) break;             // i + run > 63
             o0[n++] = rec;
             q = rec & 0xffff0000u;
         }
@@ -348,7 +348,7 @@ MP2V_HDI int parse_slice_core(const uint8_t* payload, int slice_start_code, cons
         const uint32_t off = (uint32_t)(out - out_base);
         for (int b = 0; b < nblk; b++)
             if (cbp & (1u << b))
-                if (!parse_block(br, out, T, sx, dc_pred, b, intra)) { err = SLICE_ERR_COEF; break; }
+                if (!parse_block(br, out, T, sx, dc_pred, b, intra, MP2V_COEF_MB(mbx))) { err = SLICE_ERR_COEF; break; }
         if (err) break;
         uint32_t flags = 0;
         if (intra) flags = MP2V_MB_INTRA;

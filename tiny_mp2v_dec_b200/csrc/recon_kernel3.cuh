@@ -58,9 +58,8 @@ template <int CF>
 struct alignas(128) warp_smem_t {
     alignas(128) uint8_t win[kWinBuf][2][geo_t<CF>::DIR_BYTES];   // [buffer][direction]
     alignas(16) int16_t tile[kTileRows][kTilePitch];
-    // macroblocks of the batch that carry records: {first record index in the batch, coef_off - that index,
-    // cbp | W row offset << 16, first slot | qscale << 8 | shift << 16}
-    alignas(16) uint4 mb_ctx[32];
+    // the (up to 16) macroblocks of the batch, by position: {cbp | W row offset << 16, first slot | qscale << 8 | shift << 16}
+    alignas(16) uint2 mb_ctx[16];
     alignas(16) int bound[kTileRows + 3];  // saturation bound per slot
     alignas(8) uint64_t mbar[kWinBuf];
 };
@@ -175,7 +174,6 @@ recon_kernel3(const __grid_constant__ batch_desc_t batch, const __grid_constant_
     const int mb_begin = (grp * kWarps + warp) * run;
     const int mb_end = min(mb_begin + run, batch.mb_count);
     if (mb_begin >= mb_end) return;
-    const uint32_t lt_mask = (1u << lane) - 1u, le_mask = 0xffffffffu >> (31 - lane);
 
     // ---- per-lane constants of the output stage.  4:2:0: lane = one whole row (16 luma rows, 8 Cb, 8 Cr: one
     // trip of four-word units, the chroma lanes drop two words).  4:2:2 / 4:4:4: trips of 8-pixel half rows.
@@ -212,7 +210,7 @@ recon_kernel3(const __grid_constant__ batch_desc_t batch, const __grid_constant_
 
     uint32_t wphase = 0;                                   // bit b: parity the next wait on buffer b expects
     uint4 rec_next = (mb_begin + lane < mb_end) ? __ldg(reinterpret_cast<const uint4*>(pd.mb) + mb_begin + lane) : make_uint4(0, 0, 0, 0);
-    // guess of the next batch's first 32 coefficient records (right when its records are contiguous, which they are inside a slice)
+    // the 32 coefficient records behind the previous batch's last one: the next batch's first trip when its list continues there
     uint32_t pref_idx = 0xffffffffu, pref_c = 0;
 
     // boxes of one macroblock (its record broadcast in m_*), issued by one lane into window buffer `buf`
@@ -237,7 +235,9 @@ recon_kernel3(const __grid_constant__ batch_desc_t batch, const __grid_constant_
 
     int16_t* const tile0 = &ws.tile[0][0];
     for (int first = mb_begin; first < mb_end;) {
-        // ---- 1. macroblock records of the batch: as many as fit the tile's coded-block slots
+        // ---- 1. macroblock records of the batch: as many as fit the tile's coded-block slots, at most 16, inside one
+        // macroblock row (a coefficient record names its macroblock by its column modulo 16), with their coefficient
+        // records contiguous in the arena (they are inside a slice; anything else only shortens the batch)
         const int idx = first + lane;
         const bool have = idx < mb_end;
         const uint4 rec = rec_next;
@@ -250,40 +250,32 @@ recon_kernel3(const __grid_constant__ batch_desc_t batch, const __grid_constant_
             if (lane >= d) scan2 += t;
         }
         const int incl = scan2 & 0xffff;
-        const int nb = max(__popc(__ballot_sync(0xffffffffu, have && incl <= kSlots)), 1);
+        const int start = (scan2 >> 16) - ncoef_all;                     // this macroblock's first record in the batch's flat list
+        int nb = max(__popc(__ballot_sync(0xffffffffu, have && incl <= kSlots && lane < 16 && lane < mbw - mbx0)), 1);
+        uint32_t base_off = 0;                                           // arena index of flat record 0
+        bool any_records;
+        {
+            const uint32_t ne_mask = __ballot_sync(0xffffffffu, lane < nb && ncoef_all > 0);
+            any_records = ne_mask != 0;
+            const int f_ne = ne_mask ? __ffs(ne_mask) - 1 : 0;
+            base_off = __shfl_sync(0xffffffffu, rec.x - (uint32_t)start, f_ne);
+            const uint32_t gap = __ballot_sync(0xffffffffu, lane < nb && ncoef_all > 0 && rec.x - (uint32_t)start != base_off);
+            if (gap) nb = __ffs(gap) - 1;                                // (>= 1: the first macroblock with records defines base_off)
+        }
         const int base = incl - cnt;
         const int nslots = __shfl_sync(0xffffffffu, incl, nb - 1);
+        const int total = __shfl_sync(0xffffffffu, scan2, nb - 1) >> 16;
         rec_next = (idx + nb < mb_end) ? __ldg(reinterpret_cast<const uint4*>(pd.mb) + idx + nb) : make_uint4(0, 0, 0, 0);
 
-        // ---- 2. per-macroblock context of the flat dequantisation loop, and the first trip's records on their way
-        const int ncoef = lane < nb ? ncoef_all : 0;
-        const int total = __shfl_sync(0xffffffffu, scan2, nb - 1) >> 16;
-        const int start = (scan2 >> 16) - ncoef_all;
-        const bool ne = ncoef > 0;
-        {
-            const uint32_t ne_mask = __ballot_sync(0xffffffffu, ne);
+        // ---- 2. the first trip's records on their way (usually already requested during the previous batch), and the
+        // per-macroblock context of the dequantisation loop: {cbp | W row offset, first slot | qscale << 8 | shift << 16}
+        uint32_t c_nx = 0;
+        if (lane < total) c_nx = (base_off + (uint32_t)lane == pref_idx) ? pref_c : __ldg(pd.coef + base_off + lane);
+        if (lane < 16) {
             const uint32_t ni = (rec.y & MP2V_MB_INTRA) ? 0u : 1u;
-            if (ne) ws.mb_ctx[__popc(ne_mask & lt_mask)] = make_uint4((uint32_t)start, rec.x - (uint32_t)start, MP2V_MB_CBP(rec.y) | (ni << 22),
-                                                                      (uint32_t)base | (MP2V_MB_QSCALE(rec.y) << 8) | ((4u + ni) << 16));
+            ws.mb_ctx[lane] = lane < nb ? make_uint2(MP2V_MB_CBP(rec.y) | (ni << 22), (uint32_t)base | (MP2V_MB_QSCALE(rec.y) << 8) | ((4u + ni) << 16))
+                                        : make_uint2(0u, 0u);            // (a record with a wrong column tag lands in slot 0 of the batch: garbage in, no fault)
         }
-        __syncwarp();
-        // All records of the batch are ONE flat index space (lane = record).  The owner of record f is the last
-        // macroblock whose first record index is <= f: per trip of 32 records the lanes that HOLD macroblocks mark
-        // where theirs starts inside the trip (REDUX.OR) and count those that started before it (ballot).
-        auto fetch = [&](int f0, uint32_t& c, uint4& ctx, bool use_pref) {
-            const int rel = start - f0;
-            const uint32_t starts = __reduce_or_sync(0xffffffffu, (ne && (unsigned)rel < 32u) ? 1u << rel : 0u);
-            const int before = __popc(__ballot_sync(0xffffffffu, ne && rel < 0));
-            c = 0; ctx = make_uint4(0, 0, 0, 0);
-            if (f0 + lane < total) {
-                ctx = ws.mb_ctx[before + __popc(starts & le_mask) - 1];
-                const uint32_t ci = ctx.y + (uint32_t)(f0 + lane);
-                c = (use_pref && ci == pref_idx) ? pref_c : __ldg(pd.coef + ci);
-            }
-        };
-        uint32_t c_nx;
-        uint4 ctx_nx;
-        fetch(0, c_nx, ctx_nx, true);
 
         // ---- 3. the first macroblocks' boxes start loading now; they land while we dequantise and transform
         {
@@ -295,18 +287,22 @@ recon_kernel3(const __grid_constant__ batch_desc_t batch, const __grid_constant_
             }
         }
 
-        // ---- 4. clear the used slots (QFS[64] = {0}, mb_decoder.cpp:159) and bounds; dequantise
+        // ---- 4. clear the used slots (QFS[64] = {0}, mb_decoder.cpp:159) and bounds; dequantise.  All records of the
+        // batch are ONE flat list (lane = record), so sparse P/B macroblocks do not cost a loop trip each.
         for (int i = lane; i < nslots * 8; i += 32) reinterpret_cast<uint4*>(tile0)[(i >> 3) * (kTilePitch / 8) + (i & 7)] = make_uint4(0, 0, 0, 0);
         if (lane < 7) reinterpret_cast<uint4*>(ws.bound)[lane] = make_uint4(0, 0, 0, 0);
         __syncwarp();
         uint32_t parity = 0;                 // bit s = parity of the coefficient sum of tile slot s
         uint32_t col7 = 0;                   // bit s = column 7 of slot s holds a coefficient
+        const uint32_t mb0 = (uint32_t)mbx0 & 15u;
         for (int f0 = 0; f0 < total; f0 += 32) {
-            const uint32_t c = c_nx, cz = ctx_nx.z, pk = ctx_nx.w;
+            const uint32_t c = c_nx;
             const bool live = f0 + lane < total;
-            fetch(f0 + 32, c_nx, ctx_nx, false);
+            c_nx = (f0 + 32 + lane < total) ? __ldg(pd.coef + base_off + (uint32_t)(f0 + 32 + lane)) : 0u;      // next trip's record
             uint32_t pbit = 0, c7bit = 0;
             if (live) {
+                const uint2 ctx = ws.mb_ctx[((c >> 28) - mb0) & 15u];
+                const uint32_t cz = ctx.x, pk = ctx.y;
                 const int blk = (c >> 22) & 15;
                 const int slot = (int)(pk & 0xffu) + __popc(cz & 0xfffu & ((1u << blk) - 1u));      // <= kSlots even for a record naming an uncoded block
                 const int qs = (pk >> 8) & 0xff, sh = pk >> 16;
@@ -332,13 +328,10 @@ recon_kernel3(const __grid_constant__ batch_desc_t batch, const __grid_constant_
             parity ^= __reduce_xor_sync(0xffffffffu, pbit);
             col7 |= __reduce_or_sync(0xffffffffu, c7bit);
         }
-        // the next batch's first records: requested now, used after this batch's transform and output
-        {
-            const uint32_t nxt = __ballot_sync(0xffffffffu, MP2V_MB_NCOEF(rec_next.y) != 0);
-            const uint32_t off = __shfl_sync(0xffffffffu, rec_next.x, nxt ? __ffs(nxt) - 1 : 0);
-            pref_idx = nxt ? off + (uint32_t)lane : 0xffffffffu;
-            if (nxt) pref_c = __ldg(pd.coef + pref_idx);      // (arenas are padded: 32 records past the last one stay inside the allocation)
-        }
+        // the next batch's first records (its list continues where this one ends, inside a slice): requested now, used
+        // after this batch's transform and output.  (Arenas are padded: 32 records past the last one stay inside the allocation.)
+        pref_idx = any_records ? base_off + (uint32_t)total + (uint32_t)lane : 0xffffffffu;
+        if (any_records) pref_c = __ldg(pd.coef + pref_idx);
         __syncwarp();
         // qfs[63] ^= (sum & 1) ^ 1 (:150-152) -- only where column 7 already holds something (see the header)
         if (lane < nslots && (col7 >> lane & 1u)) tile0[lane * kTilePitch + 63] ^= (int16_t)(((parity >> lane) & 1u) ^ 1u);
@@ -349,28 +342,26 @@ recon_kernel3(const __grid_constant__ batch_desc_t batch, const __grid_constant_
         const bool p2_exact = __any_sync(0xffffffffu, bnd > kBoundLimit);
         __syncwarp();
         // pass 1: one lane per column, in place; the transform runs across the vector index k (idct_sse2.hpp:98)
+        // (no predication: the lanes of a last, partly filled trip transform whatever the tile rows behind the used
+        // slots hold -- every trip stays inside the tile's kTileRows -- and nobody reads those rows)
         for (int i0 = 0; i0 < nslots * 8; i0 += 32) {
             const int i = i0 + lane;
-            const bool act = i < nslots * 8;
-            int16_t* p = tile0 + (act ? i >> 3 : 0) * kTilePitch + (i & 7);
+            int16_t* p = tile0 + (i >> 3) * kTilePitch + (i & 7);
             int x[8];
 #pragma unroll
-            for (int k = 0; k < 8; k++) x[k] = act ? (int)p[k * 8] : 0;
+            for (int k = 0; k < 8; k++) x[k] = (int)p[k * 8];
             if (p1_exact) idct_lane<0>(x[0], x[1], x[2], x[3], x[4], x[5], x[6], x[7]);
             else if (p2_exact) idct_lane<1>(x[0], x[1], x[2], x[3], x[4], x[5], x[6], x[7]);
             else idct_lane<2>(x[0], x[1], x[2], x[3], x[4], x[5], x[6], x[7]);     // the bound that clears pass 2 also bounds every pass-1 output
-            if (act) {
 #pragma unroll
-                for (int k = 0; k < 8; k++) p[k * 8] = (int16_t)x[k];
-            }
+            for (int k = 0; k < 8; k++) p[k * 8] = (int16_t)x[k];
         }
         __syncwarp();
         // pass 2: one lane per row of the transposed block (transpose_8x8_sse2 is the addressing); output r of
         // row k is res[r][k], shifted down by 6 (idct_sse2.hpp:100-107)
         for (int i0 = 0; i0 < nslots * 8; i0 += 32) {
             const int i = i0 + lane;
-            const bool act = i < nslots * 8;
-            int16_t* t = tile0 + (act ? i >> 3 : 0) * kTilePitch;
+            int16_t* t = tile0 + (i >> 3) * kTilePitch;
             const int k = i & 7;
             const uint4 q = *reinterpret_cast<const uint4*>(t + k * 8);      // a quarter warp reads the 128 contiguous bytes of one block
             int x[8] = {(int)(short)(q.x & 0xffffu), (int)q.x >> 16, (int)(short)(q.y & 0xffffu), (int)q.y >> 16,
@@ -378,10 +369,8 @@ recon_kernel3(const __grid_constant__ batch_desc_t batch, const __grid_constant_
             __syncwarp();      // the eight rows of a block sit in one trip: all are in registers before any is overwritten
             if (p2_exact) idct_lane<0>(x[0], x[1], x[2], x[3], x[4], x[5], x[6], x[7]);
             else idct_lane<2>(x[0], x[1], x[2], x[3], x[4], x[5], x[6], x[7]);
-            if (act) {
 #pragma unroll
-                for (int r = 0; r < 8; r++) t[r * 8 + k] = (int16_t)(x[r] >> 6);      // _mm_srai_epi16(., 6)
-            }
+            for (int r = 0; r < 8; r++) t[r * 8 + k] = (int16_t)(x[r] >> 6);      // _mm_srai_epi16(., 6)
         }
         __syncwarp();
 

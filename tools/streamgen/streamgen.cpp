@@ -111,6 +111,7 @@ struct mp2v_gen {
     int dc_pred[3];
     int qcode = 1, qscale = 2;
     uint32_t prev_flags = 0;
+    int cur_mbx = 0;                   // column of the macroblock being coded (tag of its coefficient records)
 
     explicit mp2v_gen(const mp2v_gen_params_t& params) : p(params), rng(params.seed) {}
 
@@ -239,7 +240,7 @@ struct mp2v_gen {
             for (int a = diff < 0 ? -diff : diff; a; a >>= 1) size++;
             bw.put(enc().dcsize[comp ? 1 : 0][size]);
             if (size) bw.put((uint32_t)(diff > 0 ? diff : diff + (1 << size) - 1), size);
-            pic.coef.push_back(MP2V_COEF((int16_t)(uint16_t)((uint32_t)dc << (3 - dc_prec)), 0, b, MP2V_COEF_RAW));
+            pic.coef.push_back(MP2V_COEF((int16_t)(uint16_t)((uint32_t)dc << (3 - dc_prec)), 0, b, MP2V_COEF_RAW) | MP2V_COEF_MB(cur_mbx));
             i = 1;
         }
         const int n = draw_count(!intra);
@@ -250,16 +251,16 @@ struct mp2v_gen {
             i += run;
             if (!intra && i == 0 && k == 0 && (level == 1 || level == -1)) {   // B.14 note 3: "1s"
                 bw.put("1"); bw.put(level < 0, 1);
-                pic.coef.push_back(MP2V_COEF(level, 0, b, MP2V_COEF_FIRST));
+                pic.coef.push_back(MP2V_COEF(level, 0, b, MP2V_COEF_FIRST) | MP2V_COEF_MB(cur_mbx));
             } else {
                 put_run_level(intra, run, level);
-                pic.coef.push_back(MP2V_COEF(level, i, b, 0));
+                pic.coef.push_back(MP2V_COEF(level, i, b, 0) | MP2V_COEF_MB(cur_mbx));
             }
             i++;
         }
         if (!intra && i == 0) {   // every run overshot: a coded non-intra block still needs one coefficient
             bw.put("1"); bw.put(0, 1);
-            pic.coef.push_back(MP2V_COEF(1, 0, b, MP2V_COEF_FIRST));
+            pic.coef.push_back(MP2V_COEF(1, 0, b, MP2V_COEF_FIRST) | MP2V_COEF_MB(cur_mbx));
         }
         bw.put(intra ? kEobB15 : kEobB14);
     }
@@ -416,7 +417,7 @@ struct mp2v_gen {
             for (int a = diff < 0 ? -diff : diff; a; a >>= 1) size++;
             bw.put(enc().dcsize[comp ? 1 : 0][size]);
             if (size) bw.put((uint32_t)(diff > 0 ? diff : diff + (1 << size) - 1), size);
-            pic.coef.push_back(MP2V_COEF((int16_t)(uint16_t)((uint32_t)dc << (3 - dc_prec)), 0, b, MP2V_COEF_RAW));
+            pic.coef.push_back(MP2V_COEF((int16_t)(uint16_t)((uint32_t)dc << (3 - dc_prec)), 0, b, MP2V_COEF_RAW) | MP2V_COEF_MB(cur_mbx));
             i = 1;
         }
         int run = 0;
@@ -426,10 +427,10 @@ struct mp2v_gen {
             if (!level) { run++; continue; }
             if (first && i == 0 && (level == 1 || level == -1)) {          // B.14 note 3: "1s"
                 bw.put("1"); bw.put(level < 0, 1);
-                pic.coef.push_back(MP2V_COEF(level, 0, b, MP2V_COEF_FIRST));
+                pic.coef.push_back(MP2V_COEF(level, 0, b, MP2V_COEF_FIRST) | MP2V_COEF_MB(cur_mbx));
             } else {
                 put_run_level(intra, run, level);
-                pic.coef.push_back(MP2V_COEF(level, i, b, 0));
+                pic.coef.push_back(MP2V_COEF(level, i, b, 0) | MP2V_COEF_MB(cur_mbx));
             }
             first = false;
             run = 0;
@@ -527,6 +528,7 @@ struct mp2v_gen {
             int pending_skips = 0;
             for (int mbx = 0; mbx < mbw; mbx++) {
                 const mb_plan_t& m = plan[(size_t)mby * mbw + mbx];
+                cur_mbx = mbx;
                 mp2v_mb_info_t rec{};
                 rec.coef_off = (uint32_t)pic.coef.size();
                 const bool edge = mbx == 0 || mbx == mbw - 1;
@@ -639,6 +641,7 @@ struct mp2v_gen {
             prev_flags = 0;
             int pending_skips = 0;
             for (int mbx = 0; mbx < mbw; mbx++) {
+                cur_mbx = mbx;
                 mp2v_mb_info_t rec{};
                 rec.coef_off = (uint32_t)pic.coef.size();
                 const bool edge = mbx == 0 || mbx == mbw - 1;
