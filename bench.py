@@ -427,9 +427,9 @@ def sharded_block(n_dev, steps):
         t0 = time.perf_counter()
         for _ in range(reps):
             d.decode(pinned.numpy(), s.size, want_output=False, download=download)
-        dt = (time.perf_counter() - t0) / reps
+        dt = (time.perf_counter() - t0) / max(reps, 1)
         d.close()
-        return n / dt, h
+        return (n / dt if reps else 0.0), h
     _, h1 = run([0], True, 0, hash_out=True)
     _, hn = run(range(n_dev), True, 0, hash_out=True)
     fps_dl, _ = run(range(n_dev), True, steps)
@@ -449,12 +449,12 @@ def sharded_block(n_dev, steps):
         decs = [Decoder(wl5["width"], wl5["height"], 1, num_threads=2, devices=(k % n_dev,), max_batch=8, output_lag=6).prepare(download=download) for k in range(64)]
         for k, d in enumerate(decs[:n_dev]):
             d.decode(pins[k % 8].numpy(), streams[k % 8].size, want_output=False, download=download)
-        frames = [0]
+        reps = max(1, steps // 2)
+        frames = [sum(reps * len(streams[k % 8].pictures) for k in range(64))]
 
         def session(k):
-            for _ in range(max(1, steps // 2)):
+            for _ in range(reps):
                 decs[k].decode(pins[k % 8].numpy(), streams[k % 8].size, want_output=False, download=download)
-                frames[0] += len(streams[k % 8].pictures)
         t0 = time.perf_counter()
         th = [threading.Thread(target=session, args=(k,)) for k in range(64)]
         [t.start() for t in th]

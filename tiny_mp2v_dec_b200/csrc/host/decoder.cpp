@@ -247,6 +247,8 @@ void pipeline_t::feeder() {
     }
     unref(refs[0]);
     unref(refs[1]);
+    // the last pictures rarely fill a launch lot: hand them over now instead of when the output thread asks for them
+    if (sh->stream_mode && !sh->failed.load() && mp2v_recon_flush(recon) != MP2V_OK) sh->fail(std::string("flush: ") + mp2v_recon_last_error(recon));
 }
 
 // called by the worker that finished the last slice of a picture

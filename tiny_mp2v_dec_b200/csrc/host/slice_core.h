@@ -61,11 +61,32 @@ inline const char* slice_error_string(int e) {
 #define MP2V_UNROLL2 _Pragma("GCC unroll 2")
 #endif
 
+// (the two-trip loops over prediction direction / vector component: fully unrolled so that pmv[][] , mv[][] and
+// f_code[][] are indexed by constants and live in registers -- the device compiler otherwise parks them in local memory)
+#define MP2V_UNROLL_ALL MP2V_UNROLL2
+
 #if defined(__CUDACC__)
 #define MP2V_HDI __host__ __device__ __forceinline__
 #else
 #define MP2V_HDI inline __attribute__((always_inline))
 #endif
+
+MP2V_HDI uint32_t reverse_bits(uint32_t x, int n) {           // the low n bits of x, mirrored
+#ifdef __CUDA_ARCH__
+    return __brev(x) >> (32 - n);
+#else
+    uint32_t r = 0;
+    for (int i = 0; i < n; i++) r |= ((x >> i) & 1u) << (n - 1 - i);
+    return r;
+#endif
+}
+MP2V_HDI int lowest_bit(uint32_t x) {                           // index of the lowest set bit (x != 0)
+#ifdef __CUDA_ARCH__
+    return __ffs((int)x) - 1;
+#else
+    return __builtin_ctz(x);
+#endif
+}
 
 MP2V_HDI int quantiser_scale_of(int code, int q_scale_type) {   // decoder.cpp:140-145, mb_decoder.cpp:555-563
     if (!q_scale_type) return code << 1;
@@ -101,9 +122,30 @@ MP2V_HDI bool decode_mv_component(bitreader_t& br, const vlc_decode_tables_t& T,
     return true;
 }
 
+// intra DC predictors (mb_decoder.cpp:46-72) as three scalars: a block's component is only known at run time, and an
+// array indexed by it would live in local memory on the device
+struct dc_pred_t {
+    uint32_t y, cb, cr;
+    MP2V_HDI void reset(uint32_t v) { y = cb = cr = v; }
+    MP2V_HDI uint32_t get(int comp) const { return comp == 0 ? y : comp == 1 ? cb : cr; }
+    MP2V_HDI void set(int comp, uint32_t v) { if (comp == 0) y = v; else if (comp == 1) cb = v; else cr = v; }
+};
+
+constexpr int kDevTableWords = (2 << kFastBits) + (2 << coef_vlc_t::kLongBits);
+
+#ifdef __CUDA_ARCH__
+__device__ __forceinline__ uint32_t lds_word(uint32_t shared_base, uint32_t index) {      // word `index` of a table in shared memory
+    uint32_t v;
+    asm("{\n\t.reg .u32 a;\n\tmad.lo.u32 a, %2, 4, %1;\n\tld.shared.u32 %0, [a];\n\t}" : "=r"(v) : "r"(shared_base), "r"(index));
+    return v;
+}
+#endif
+
 // one block: DC (intra) + run/level list; returns false on a syntax error
+// dev_fast: shared-window address of the device parser's copy of {b14.gpu_fast, b15.gpu_fast, b14.gpu_long, b15.gpu_long}
+// (kDevTableWords words; unused on the host)
 MP2V_HDI bool parse_block(bitreader_t& br, mp2v_coef_t*& out, const vlc_decode_tables_t& T, const slice_syntax_t& sx,
-                          uint16_t (&dc_pred)[3], int b, bool intra, uint32_t mb_bits) {
+                          dc_pred_t& dc_pred, int b, bool intra, uint32_t mb_bits, uint32_t dev_fast) {
     const uint32_t blk_bits = ((uint32_t)b << 22) | mb_bits;      // block index + the macroblock column tag of every record
     int i = 0;
     const coef_vlc_t* table = &T.b14;
@@ -122,8 +164,9 @@ MP2V_HDI bool parse_block(bitreader_t& br, mp2v_coef_t*& out, const vlc_decode_t
             const int half = 1 << (e.val - 1);
             diff = v >= half ? v : v + 1 - 2 * half;           // mb_decoder.cpp:59-68
         }
-        dc_pred[comp] = (uint16_t)(dc_pred[comp] + diff);
-        const int16_t dc = (int16_t)(uint16_t)((uint32_t)dc_pred[comp] << (3 - sx.intra_dc_precision));
+        const uint32_t pred = (dc_pred.get(comp) + (uint32_t)diff) & 0xffffu;
+        dc_pred.set(comp, pred);
+        const int16_t dc = (int16_t)(uint16_t)(pred << (3 - sx.intra_dc_precision));
         *out++ = MP2V_COEF(dc, 0, b, MP2V_COEF_RAW) | mb_bits;
         i = 1;
         if (sx.intra_vlc_format) table = &T.b15;
@@ -135,61 +178,66 @@ MP2V_HDI bool parse_block(bitreader_t& br, mp2v_coef_t*& out, const vlc_decode_t
         i = 1;
     }
 #ifdef __CUDA_ARCH__
-    // Device loop.  A slice thread's time is its instruction count (one warp, no ILP to speak of), so a
-    // fast symbol is: look up one pre-assembled word, add it to the running {position, block} word q --
-    // that IS the record -- store, keep its upper half as the next q.  q = ((i - 1) << 16 | block << 22)
-    // modulo 2^32; a position past 63 carries into the block field, which is the range check.
+    // Device loop.  A slice thread's time is its instruction count (one lane of a warp, no ILP to speak of), so a
+    // fast symbol is: look up one pre-assembled word (shared memory), add it to the running {position, block}
+    // word q -- that IS the record -- store, keep its upper half as the next q.  q = ((i - 1) << 16 | block << 22
+    // | macroblock tag) modulo 2^32: a position past 63 carries into the block field and stays there, so the
+    // range check is ONE compare of q at the end of the block; what bounds the writes meanwhile is the record
+    // count (a block has at most 64 coefficients and every symbol is one).  Fast symbols are at most kFastBits
+    // = 11 bits long, so three of them fit the 33 bits a refill guarantees: one refill check per three symbols.
     {
-        const uint32_t* gfast = table->gpu_fast;
+        const bool b15 = table == &T.b15;
+        const uint32_t fast = dev_fast + (b15 ? (4u << kFastBits) : 0u);
+        const uint32_t long_codes = dev_fast + (8u << kFastBits) + (b15 ? (4u << coef_vlc_t::kLongBits) : 0u);
         uint32_t q = (((uint32_t)i << 16) | blk_bits) - 0x10000u;
         mp2v_coef_t* const o0 = out;
-        uint32_t n = 0;                                        // 32-bit record index: one add per record, not a 64-bit pointer bump
+        uint32_t n = 0;                                        // records stored by this loop; 32-bit index, not a 64-bit pointer bump
+        const uint32_t n_max = 64u - (uint32_t)i;
         bool ok = false;
         for (;;) {
             // tight loop over fast symbols only (its own loop so that the rare paths below do not shape its code)
-            uint32_t e, rec;
+            uint32_t e;
             for (;;) {
-                br.refill();                                   // >= 33 bits: any one symbol (escape = 24)
-                e = __ldg(gfast + br.peek(kFastBits));
-                if ((int32_t)e < 0) break;
-                br.skip((int)(e >> 24));
-                rec = q + (e & 0x007fffffu);
-                if ((rec >> 22) != (blk_bits >> 22)) break;         // i + run > 63
-                o0[n++] = rec;
-                q = rec & 0xffff0000u;
+                br.refill();
+#define MP2V_FAST_SYMBOL                                                                   \
+                e = lds_word(fast, br.peek(kFastBits));                                   \
+                if ((int32_t)e < 0 || n == n_max) break;   /* not fast, or a 65th coefficient */ \
+                br.skip((int)(e >> 24));                                                   \
+                { const uint32_t rec = q + (e & 0x007fffffu); o0[n++] = rec; q = rec & 0xffff0000u; }
+                MP2V_FAST_SYMBOL
+                MP2V_FAST_SYMBOL
+                MP2V_FAST_SYMBOL
+#undef MP2V_FAST_SYMBOL
             }
-            if ((int32_t)e >= 0) break;                        // range error inside the tight loop
+            if ((int32_t)e >= 0) break;                        // count error inside the tight loop
             if (e & 0x40000000u) {                             // end of block
                 br.skip((int)((e >> 24) & 15u));
                 ok = true;
                 break;
             }
-            const coef_entry_t s = table->look(br.peek(17));
-            int run, level;
-            if (s.level > 0) {
-                br.skip(s.len);
-                const int neg = (int)br.peek(1);
-                br.skip(1);
-                run = s.run;
-                level = (s.level ^ -neg) + neg;
-            } else if (s.level == kCoefEob && s.len) {
-                br.skip(s.len);
-                ok = true;
-                break;
-            } else if (s.level == kCoefEsc && s.len) {         // 6-bit run, 12-bit two's complement level
-                br.skip(6);
-                run = (int)br.peek(6); br.skip(6);
-                level = ((int)br.peek(12) ^ 0x800) - 0x800; br.skip(12);
+            // the rare symbols: an escape (000001, 6-bit run, 12-bit two's complement level) or one of the long codes
+            br.refill();                                       // up to 22 bits went since the loop's refill; an escape is 24
+            const uint32_t w = br.peek(24);
+            uint32_t inc, len;
+            if ((w >> 18) == 1u) {
+                inc = ((((w >> 12) & 63u) + 1u) << 16) | ((((w & 0xfffu) ^ 0x800u) - 0x800u) & 0xffffu);
+                len = 24u;
+            } else if ((w >> (24 - coef_vlc_t::kLongZeros)) == 0u) {
+                const uint32_t l = lds_word(long_codes, (w >> (24 - coef_vlc_t::kLongZeros - coef_vlc_t::kLongBits)) & ((1u << coef_vlc_t::kLongBits) - 1u));
+                if ((int32_t)l < 0) break;                     // no such code
+                inc = l & 0x007fffffu;
+                len = l >> 24;
             } else {
                 break;
             }
-            rec = q + ((uint32_t)(run + 1) << 16) + (uint32_t)(uint16_t)level;
-            if ((rec >> 22) != (blk_bits >> 22)) break;             // i + run > 63
+            if (n == n_max) break;
+            br.skip((int)len);
+            const uint32_t rec = q + inc;
             o0[n++] = rec;
             q = rec & 0xffff0000u;
         }
         out = o0 + n;
-        return ok;
+        return ok && ((q ^ blk_bits) >> 22) == 0;              // i + run never passed 63
     }
 #else
     // Host loop.  Symbols decoded per refill: an escape is 24 bits, so two of any kind fit the 56 bits a
@@ -248,15 +296,15 @@ MP2V_HDI bool mv_inside(int mbx, int mby, int mvx, int mvy, int width, int heigh
 template <bool CHECK_MV>
 MP2V_HDI int parse_slice_core(const uint8_t* payload, int slice_start_code, const slice_syntax_t& sx, const vlc_decode_tables_t& T,
                               mp2v_mb_info_t* mb, mp2v_coef_t* out_base, uint32_t coef_off_base,
-                              uint32_t* n_out, int* first_mbx_out, int* last_mbx_out, int* mb_row_out) {
+                              uint32_t* n_out, int* first_mbx_out, int* last_mbx_out, int* mb_row_out, uint32_t dev_fast = 0) {
     const int cf = sx.chroma_format, mbw = sx.mbw;
     const int nblk = cf == 1 ? 6 : cf == 2 ? 8 : 12;
     mp2v_coef_t* out = out_base;
     bitreader_t br(payload);
     int pmv[2][2] = {{0, 0}, {0, 0}};
-    uint16_t dc_pred[3];
-    const uint16_t dc_reset = (uint16_t)(1u << (sx.intra_dc_precision + 7));
-    dc_pred[0] = dc_pred[1] = dc_pred[2] = dc_reset;
+    dc_pred_t dc_pred;
+    const uint32_t dc_reset = 1u << (sx.intra_dc_precision + 7);
+    dc_pred.reset(dc_reset);
     int mb_row = slice_start_code - 1;
     if (sx.vertical_size > 2800) mb_row += (int)br.get(3) << 7;        // slice_vertical_position_extension
     *n_out = 0; *first_mbx_out = 0; *last_mbx_out = -1; *mb_row_out = mb_row;
@@ -308,11 +356,10 @@ MP2V_HDI int parse_slice_core(const uint8_t* payload, int slice_start_code, cons
                 done_mbx = mbx;
             }
             if (err) break;
-            dc_pred[0] = dc_pred[1] = dc_pred[2] = dc_reset;
+            dc_pred.reset(dc_reset);
         }
         mp2v_mb_info_t& r = row[++mbx];
-        // ---- macroblock_type
-        br.refill();
+        // ---- macroblock_type (no refill: the last increment code took at most 11 of the 33 bits, type and quantiser 11 more)
         const vlc_entry_t te = T.mbtype[pct].look(br.peek(6));
         if (!te.len) { err = SLICE_ERR_MBTYPE; break; }
         br.skip(te.len);
@@ -321,17 +368,20 @@ MP2V_HDI int parse_slice_core(const uint8_t* payload, int slice_start_code, cons
         if (type & 0x20) { qscale = quantiser_scale_of((int)br.peek(5), sx.q_scale_type); br.skip(5); }
         // ---- motion vectors (frame prediction: one vector per direction)
         int mv[2][2] = {{0, 0}, {0, 0}};
-        for (int s = 0; s < 2 && !err; s++) {
-            if (!(s ? bwd : fwd)) continue;
+        MP2V_UNROLL_ALL
+        for (int s = 0; s < 2; s++) {
+            if (err || !(s ? bwd : fwd)) continue;
+            MP2V_UNROLL_ALL
             for (int t = 0; t < 2; t++) {
+                if (err) continue;
                 const int fc = sx.f_code[s][t];
-                if (fc < 1 || fc > 9) { err = SLICE_ERR_FCODE; break; }
-                if (!decode_mv_component(br, T, fc, pmv[s][t], mv[s][t])) { err = SLICE_ERR_MOTION; break; }
+                if (fc < 1 || fc > 9) { err = SLICE_ERR_FCODE; continue; }
+                if (!decode_mv_component(br, T, fc, pmv[s][t], mv[s][t])) err = SLICE_ERR_MOTION;
             }
         }
         if (err) break;
         if (intra || (pct == 2 && !fwd)) { pmv[0][0] = pmv[0][1] = pmv[1][0] = pmv[1][1] = 0; }   // mb_decoder.cpp:599-603
-        if (!intra) dc_pred[0] = dc_pred[1] = dc_pred[2] = dc_reset;                                // mb_decoder.cpp:623-626
+        if (!intra) dc_pred.reset(dc_reset);                                // mb_decoder.cpp:623-626
         // ---- coded_block_pattern
         uint32_t cbp = 0;
         if (intra) cbp = (1u << nblk) - 1u;
@@ -340,15 +390,16 @@ MP2V_HDI int parse_slice_core(const uint8_t* payload, int slice_start_code, cons
             const vlc_entry_t ce = T.cbp.look(br.peek(9));
             if (!ce.len) { err = SLICE_ERR_CBP; break; }
             br.skip(ce.len);
-            for (int i = 0; i < 6; i++) if (ce.val & (1 << (5 - i))) cbp |= 1u << i;          // mb_decoder.cpp:435-436
+            cbp = reverse_bits((uint32_t)ce.val, 6);                                           // mb_decoder.cpp:435-436: block 0 is the code's MSB
             if (cf == 2) { const uint32_t x = br.peek(2); br.skip(2); cbp |= ((x >> 1) & 1u) << 6 | (x & 1u) << 7; }
-            if (cf == 3) { const uint32_t x = br.peek(6); br.skip(6); for (int i = 0; i < 6; i++) cbp |= ((x >> (5 - i)) & 1u) << (6 + i); }
+            if (cf == 3) { const uint32_t x = br.peek(6); br.skip(6); cbp |= reverse_bits(x, 6) << 6; }
         }
         // ---- blocks
         const uint32_t off = (uint32_t)(out - out_base);
-        for (int b = 0; b < nblk; b++)
-            if (cbp & (1u << b))
-                if (!parse_block(br, out, T, sx, dc_pred, b, intra, MP2V_COEF_MB(mbx))) { err = SLICE_ERR_COEF; break; }
+        // (coded blocks by the set bits of cbp, not by block number: slices that share a warp on the device then walk
+        // their k-th coded block together whichever block that is)
+        for (uint32_t left = cbp; left; left &= left - 1u)
+            if (!parse_block(br, out, T, sx, dc_pred, lowest_bit(left), intra, MP2V_COEF_MB(mbx), dev_fast)) { err = SLICE_ERR_COEF; break; }
         if (err) break;
         uint32_t flags = 0;
         if (intra) flags = MP2V_MB_INTRA;

@@ -83,7 +83,20 @@ struct coef_vlc_t {
     //   [15:0] level (two's complement)  [22:16] run + 1  [27:24] bits consumed (incl. sign)
     //   [31] not a fast symbol -> [30] end of block (then [27:24] = its length), else take the two-level table
     uint32_t gpu_fast[1 << kFastBits];
+    // ... and the codes the fast table does not hold: besides the escape (prefix 000001) they all start with seven
+    // zeros and are 12..16 bits long, so the ten bits behind the zeros resolve code and sign:
+    //   [15:0] level  [22:16] run + 1  [28:24] bits consumed (incl. the zeros and the sign)  [31] no such code
+    static constexpr int kLongZeros = 7, kLongBits = 10;
+    uint32_t gpu_long[1 << kLongBits];
     void build_fast() {
+        for (uint32_t i = 0; i < (1u << kLongBits); i++) {
+            const coef_entry_t e = look(i);                       // a 17-bit window whose top seven bits are zero
+            gpu_long[i] = 0x80000000u;
+            if (e.len > kLongZeros && e.len <= 16 && e.level > 0) {
+                const int neg = (int)(i >> (16 - e.len)) & 1;
+                gpu_long[i] = (uint32_t)(uint16_t)(neg ? -e.level : e.level) | ((uint32_t)(e.run + 1) << 16) | ((uint32_t)(e.len + 1) << 24);
+            }
+        }
         for (uint32_t i = 0; i < (1u << kFastBits); i++) {
             const coef_entry_t e = look(i << (17 - kFastBits));
             coef_fast_t f{0, kFastSlow, 0};

@@ -108,6 +108,7 @@ struct mp2v_recon {
     struct trace_rec_t { uint64_t picture_no; cudaEvent_t h2d, vlc, recon, d2h; };
     struct launch_trace_t { int n; cudaEvent_t begin, end, copied; };      // MP2V_TRACE: one per reconstruction launch
     std::vector<launch_trace_t> launch_log;
+    std::vector<launch_trace_t> parse_log;      // (begin, end of a parse launch; copied = the resident stream's arrival)
     bool trace = false;
     cudaEvent_t trace_base = nullptr;
     std::vector<trace_rec_t> trace_log;
@@ -122,8 +123,10 @@ struct mp2v_recon {
     uint32_t* d_counts = nullptr; size_t counts_cap = 0;
     uint32_t* h_total = nullptr; uint32_t* d_total = nullptr;   // pinned + mapped
     cudaStream_t s_parse[kParseStreams] = {};
-    int parse_rr = 0, n_parse_streams = kParseStreams, lot_cap = 0;      // dev knobs MP2V_PARSE_STREAMS / MP2V_LOT
+    int sm_count = 148;
+    int parse_rr = 0, n_parse_streams = 2, lot_cap = 0, parse_lanes = 0;      // dev knobs MP2V_PARSE_STREAMS / MP2V_LOT
     cudaEvent_t ev_stream = nullptr;           // the upload (and scan) of the resident stream
+    cudaEvent_t ev_stream_timed = nullptr;     // MP2V_TRACE: the same moment with a timestamp
     struct parse_buf_t { uint8_t* h = nullptr; uint8_t* d = nullptr; cudaEvent_t done = nullptr; bool used = false; } parse_buf[kParseBufs];
     int parse_buf_rr = 0;
     size_t desc_stride = 0;
@@ -181,6 +184,7 @@ static void destroy_ctx(mp2v_recon* ctx) {
     if (ctx->d_counts) cudaFree(ctx->d_counts);
     if (ctx->h_total) cudaFreeHost(ctx->h_total);
     if (ctx->ev_stream) cudaEventDestroy(ctx->ev_stream);
+    if (ctx->ev_stream_timed) cudaEventDestroy(ctx->ev_stream_timed);
     for (auto e : ctx->launch_ev) if (e) cudaEventDestroy(e);
     for (auto& s : ctx->slots) {
         if (s.h_arena) cudaFreeHost(s.h_arena);
@@ -258,6 +262,7 @@ static int create_impl(mp2v_recon* ctx) {
     ctx->launch_ev.assign((size_t)c.n_pictures + c.n_frames + 16, nullptr);
     for (auto& ev : ctx->launch_ev) CK(cudaEventCreateWithFlags(&ev, cudaEventDisableTiming), "event");
     if (const char* v = getenv("MP2V_TRACE")) ctx->trace = atoi(v) != 0;
+    CK(cudaDeviceGetAttribute(&ctx->sm_count, cudaDevAttrMultiProcessorCount, c.device), "device attribute");
     ctx->auto_dl = (c.flags & MP2V_RECON_AUTO_DOWNLOAD) != 0;
     ctx->mirror_valid.assign(c.n_frames, 0);
     ctx->read_ev.assign(c.n_frames, nullptr);
@@ -324,6 +329,7 @@ static int create_impl(mp2v_recon* ctx) {
         // stream-resident front end: parse streams, descriptor buffers (one per batched parse launch in flight)
         const bool parse_first = getenv("MP2V_PARSE_PRIO") && atoi(getenv("MP2V_PARSE_PRIO"));      // dev knob
         if (const char* v = getenv("MP2V_PARSE_STREAMS")) { const int k = atoi(v); if (k >= 1 && k <= mp2v_recon::kParseStreams) ctx->n_parse_streams = k; }
+        if (const char* v = getenv("MP2V_PARSE_LANES")) { const int k = atoi(v); if (k >= 0 && k <= 32) ctx->parse_lanes = k; }
         if (const char* v = getenv("MP2V_LOT")) { const int k = atoi(v); if (k >= 1 && k <= kMaxStreamBatch) ctx->lot_cap = k; }
         for (auto& st : ctx->s_parse) CK(cudaStreamCreateWithPriority(&st, cudaStreamNonBlocking, parse_first ? prio_greatest : prio_least), "stream");
         CK(cudaEventCreateWithFlags(&ctx->ev_stream, cudaEventDisableTiming), "event");
@@ -486,8 +492,25 @@ static int launch_parse_batch(mp2v_recon* ctx) {
             CK(cudaMemcpyAsync(s.d_arena + kParamsBytes, ctx->d_blank_mb, (size_t)ctx->mb_count * sizeof(mp2v_mb_info_t), cudaMemcpyDeviceToDevice, st), "blank records");
     }
     CK(cudaMemcpyAsync(b.d, b.h, (size_t)n * ctx->desc_stride, cudaMemcpyHostToDevice, st), "H2D parse descriptors");
-    CK(launch_vlc_stream(ctx->d_stream, b.d, ctx->desc_stride, n, ctx->mbh, ctx->d_tables, st), "slice parser kernel launch");
+    if (ctx->trace && ctx->trace_base) {
+        mp2v_recon::launch_trace_t lt{n, nullptr, nullptr, nullptr};
+        CK(cudaEventCreate(&lt.begin), "event"); CK(cudaEventCreate(&lt.end), "event");
+        CK(cudaEventRecord(lt.begin, st), "event record");
+        ctx->parse_log.push_back(lt);
+    }
+    // Slices per warp: a parser thread's registers are held by its whole warp, and a lot of single-lane warps fills every
+    // SM's register file (8 CTAs of 128 threads x 64 registers) for a millisecond -- the reconstruction launches of the
+    // lots before it then wait for room.  Two CTAs per SM and lot is the budget; larger lots put 2 or 4 slices in a warp
+    // (lanes of a warp that sit on different slices serialise where their paths differ, measured: no loss up to 4).
+    int lanes = ctx->parse_lanes;
+    if (lanes == 0) {
+        const int warps_budget = 2 * ctx->sm_count * 4;
+        const int slices = n * ctx->mbh;
+        lanes = slices <= warps_budget ? 1 : slices <= 2 * warps_budget ? 2 : 4;
+    }
+    CK(launch_vlc_stream(ctx->d_stream, b.d, ctx->desc_stride, n, ctx->mbh, lanes, ctx->d_tables, st), "slice parser kernel launch");
     CK(cudaEventRecord(b.done, st), "event record");
+    if (ctx->trace && !ctx->parse_log.empty() && ctx->parse_log.back().end) CK(cudaEventRecord(ctx->parse_log.back().end, st), "event record");
     b.used = true;
     for (int id : ctx->parse_pending) ctx->slots[id].vlc_wait = b.done;
     ctx->stats.h2d_bytes += (uint64_t)n * ctx->desc_stride;
@@ -737,7 +760,7 @@ static int queue_slot(mp2v_recon* ctx, slot_t* s) {
     // (measured: a last lot of 60 pictures left the copy engine idle for 2 ms of a 12 ms decode).
     const bool rate = (ctx->cfg.flags & MP2V_RECON_THROUGHPUT) != 0;
     const int ramp = rate ? kMaxBatch : ctx->batch_ramp;
-    const int quota = s->stream_pic ? std::min(ctx->lot_cap ? ctx->lot_cap : (rate ? kMaxStreamBatch : 32), 4 * ramp) : std::min(ctx->max_batch, ramp);
+    const int quota = s->stream_pic ? std::min(ctx->lot_cap ? ctx->lot_cap : (rate ? 64 : 32), 4 * ramp) : std::min(ctx->max_batch, ramp);
     if (ctx->queued >= quota) return flush_locked(ctx);
     return MP2V_OK;
 }
@@ -891,6 +914,7 @@ extern "C" MP2V_API int mp2v_recon_stream_begin(mp2v_recon_t* ctx, const uint8_t
         ctx->stream_cap = cap;
     }
     cudaStream_t st = ctx->s_parse[0];
+    if (ctx->trace && !ctx->trace_base) { CK(cudaEventCreate(&ctx->trace_base), "event"); CK(cudaEventRecord(ctx->trace_base, st), "event record"); }
     if (n_ranges == 0) {
         if (bytes) CK(cudaMemcpyAsync(ctx->d_stream, data, bytes, cudaMemcpyHostToDevice, st), "H2D stream");
         ctx->stats.h2d_bytes += bytes;
@@ -932,6 +956,10 @@ extern "C" MP2V_API int mp2v_recon_stream_begin(mp2v_recon_t* ctx, const uint8_t
         *n_codes = total;
     }
     CK(cudaEventRecord(ctx->ev_stream, st), "event record");
+    if (ctx->trace) {
+        if (!ctx->ev_stream_timed) CK(cudaEventCreate(&ctx->ev_stream_timed), "event");
+        CK(cudaEventRecord(ctx->ev_stream_timed, st), "event record");
+    }
     return MP2V_OK;
 }
 
@@ -1038,6 +1066,19 @@ extern "C" MP2V_API int mp2v_recon_sync(mp2v_recon_t* ctx) {
     for (auto& s : ctx->slots) if (s.state == SLOT_INFLIGHT) s.state = SLOT_FREE;
     ctx->batch_ramp = 1;
     ctx->pictures_submitted = 0;                         // slice errors name pictures by their number since the last sync
+    if (ctx->trace && !ctx->parse_log.empty()) {
+        float up = -1;
+        if (ctx->ev_stream_timed) cudaEventElapsedTime(&up, ctx->trace_base, ctx->ev_stream_timed);
+        fprintf(stderr, "[mp2v trace] resident stream uploaded + scanned at %7.3f ms\n", up);
+        int i = 0;
+        for (auto& lt : ctx->parse_log) {
+            float a = -1, b = -1;
+            cudaEventElapsedTime(&a, ctx->trace_base, lt.begin); cudaEventElapsedTime(&b, ctx->trace_base, lt.end);
+            fprintf(stderr, "[mp2v trace] parse  %3d  %3d pictures  kernel %7.3f .. %7.3f ms\n", i++, lt.n, a, b);
+            cudaEventDestroy(lt.begin); cudaEventDestroy(lt.end);
+        }
+        ctx->parse_log.clear();
+    }
     if (ctx->trace && !ctx->launch_log.empty()) {
         int i = 0;
         for (auto& lt : ctx->launch_log) {

@@ -28,9 +28,25 @@ namespace {
 #endif
 constexpr int kVlcCtaThreads = MP2V_VLC_CTA;
 
-__global__ void __launch_bounds__(kVlcCtaThreads)
+// the run/level tables of the symbol loop (B.14, B.15: 8 KB of fast entries and 4 KB of long codes each) live in
+// shared memory: a look-up per coefficient
+__device__ __forceinline__ void load_fast_tables(uint32_t* s_tab, const vlc_decode_tables_t* __restrict__ tables) {
+    const uint32_t* src[4] = {tables->b14.gpu_fast, tables->b15.gpu_fast, tables->b14.gpu_long, tables->b15.gpu_long};
+    constexpr int words[4] = {1 << kFastBits, 1 << kFastBits, 1 << coef_vlc_t::kLongBits, 1 << coef_vlc_t::kLongBits};
+    uint32_t* d = s_tab;
+#pragma unroll
+    for (int t = 0; t < 4; t++) {
+        for (int i = threadIdx.x; i < words[t]; i += kVlcCtaThreads) d[i] = __ldg(src[t] + i);
+        d += words[t];
+    }
+    __syncthreads();
+}
+
+__global__ void __launch_bounds__(kVlcCtaThreads, 1024 / kVlcCtaThreads)
 parse_slices_kernel(const uint8_t* __restrict__ staged, const vlc_decode_tables_t* __restrict__ tables, mp2v_mb_info_t* __restrict__ mb,
                     mp2v_coef_t* __restrict__ coef, vlc_slice_status_t* __restrict__ status, int lanes) {
+    __shared__ __align__(16) uint32_t s_fast[kDevTableWords];
+    load_fast_tables(s_fast, tables);
     const vlc_pic_header_t& hdr = *reinterpret_cast<const vlc_pic_header_t*>(staged + kVlcParamsBytes);
     const int lane = threadIdx.x & 31;
     const int warp = (blockIdx.x * kVlcCtaThreads + threadIdx.x) >> 5;
@@ -41,7 +57,7 @@ parse_slices_kernel(const uint8_t* __restrict__ staged, const vlc_decode_tables_
     const uint32_t base = (uint32_t)slice * hdr.slice_region;
     uint32_t n = 0;
     int first_mbx = 0, last_mbx = -1, mb_row = 0;
-    const int err = parse_slice_core<true>(staged + hdr.data_off + sl.byte_off, sl.code, sx, *tables, mb, coef + base, base, &n, &first_mbx, &last_mbx, &mb_row);
+    const int err = parse_slice_core<true>(staged + hdr.data_off + sl.byte_off, sl.code, sx, *tables, mb, coef + base, base, &n, &first_mbx, &last_mbx, &mb_row, (uint32_t)__cvta_generic_to_shared(s_fast));
     uint32_t coded = 0, dirs = 0;
     if (mb_row >= 0 && mb_row < sx.mbh) {          // (the host checked the row before staging the slice)
         mp2v_mb_info_t* row = mb + (size_t)mb_row * sx.mbw;
@@ -61,9 +77,11 @@ parse_slices_kernel(const uint8_t* __restrict__ staged, const vlc_decode_tables_
 }
 
 // ---- stream-resident variant: grid.y = picture of the batch, one warp per slice, descriptors in device memory
-__global__ void __launch_bounds__(kVlcCtaThreads)
+__global__ void __launch_bounds__(kVlcCtaThreads, 1024 / kVlcCtaThreads)
 parse_stream_slices_kernel(const uint8_t* __restrict__ stream, const uint8_t* __restrict__ desc_base, size_t desc_stride,
-                           const vlc_decode_tables_t* __restrict__ tables) {
+                           const vlc_decode_tables_t* __restrict__ tables, int lanes) {
+    __shared__ __align__(16) uint32_t s_fast[kDevTableWords];
+    load_fast_tables(s_fast, tables);
     const vlc_stream_pic_t& d = *reinterpret_cast<const vlc_stream_pic_t*>(desc_base + (size_t)blockIdx.y * desc_stride);
     // the picture's parameter block (W, scan, frame ids) travels in the descriptor: the first CTA drops it where the
     // reconstruction kernel reads it (that launch is ordered behind this one)
@@ -71,14 +89,14 @@ parse_stream_slices_kernel(const uint8_t* __restrict__ stream, const uint8_t* __
         for (unsigned i = threadIdx.x; i < sizeof(mp2v_pic_params_t) / 4; i += kVlcCtaThreads)
             reinterpret_cast<uint32_t*>(d.params_out)[i] = reinterpret_cast<const uint32_t*>(&d.params)[i];
     const int lane = threadIdx.x & 31;
-    const int slice = (blockIdx.x * kVlcCtaThreads + threadIdx.x) >> 5;
-    if (lane != 0 || slice >= (int)d.n_slices) return;
+    const int slice = ((blockIdx.x * kVlcCtaThreads + threadIdx.x) >> 5) * lanes + lane;
+    if (lane >= lanes || slice >= (int)d.n_slices) return;
     const slice_syntax_t sx = d.sx;
     const uint8_t* sc = stream + d.slice_off[slice];             // 00 00 01 <slice_start_code> payload...
     const uint32_t base = (uint32_t)slice * d.slice_region;
     uint32_t n = 0;
     int first_mbx = 0, last_mbx = -1, mb_row = 0;
-    const int err = parse_slice_core<true>(sc + 4, (int)sc[3], sx, *tables, d.mb, d.coef + base, base, &n, &first_mbx, &last_mbx, &mb_row);
+    const int err = parse_slice_core<true>(sc + 4, (int)sc[3], sx, *tables, d.mb, d.coef + base, base, &n, &first_mbx, &last_mbx, &mb_row, (uint32_t)__cvta_generic_to_shared(s_fast));
     uint32_t coded = 0, dirs = 0;
     if (mb_row >= 0 && mb_row < sx.mbh) {
         mp2v_mb_info_t* row = d.mb + (size_t)mb_row * sx.mbw;
@@ -190,11 +208,12 @@ cudaError_t launch_start_code_scan(const uint8_t* d_stream, size_t len, uint32_t
     return cudaGetLastError();
 }
 
-cudaError_t launch_vlc_stream(const uint8_t* d_stream, const uint8_t* d_desc, size_t desc_stride, int n_pics, int max_slices, const void* d_tables, cudaStream_t stream) {
+cudaError_t launch_vlc_stream(const uint8_t* d_stream, const uint8_t* d_desc, size_t desc_stride, int n_pics, int max_slices, int lanes, const void* d_tables, cudaStream_t stream) {
     if (n_pics <= 0 || max_slices <= 0) return cudaSuccess;
-    if (n_pics > kMaxStreamBatch) return cudaErrorInvalidValue;
-    const dim3 grid((unsigned)((max_slices * 32 + kVlcCtaThreads - 1) / kVlcCtaThreads), (unsigned)n_pics);
-    parse_stream_slices_kernel<<<grid, kVlcCtaThreads, 0, stream>>>(d_stream, d_desc, desc_stride, static_cast<const vlc_decode_tables_t*>(d_tables));
+    if (n_pics > kMaxStreamBatch || lanes < 1 || lanes > 32) return cudaErrorInvalidValue;
+    const int warps = (max_slices + lanes - 1) / lanes;
+    const dim3 grid((unsigned)((warps * 32 + kVlcCtaThreads - 1) / kVlcCtaThreads), (unsigned)n_pics);
+    parse_stream_slices_kernel<<<grid, kVlcCtaThreads, 0, stream>>>(d_stream, d_desc, desc_stride, static_cast<const vlc_decode_tables_t*>(d_tables), lanes);
     return cudaGetLastError();
 }
 

@@ -36,7 +36,7 @@ struct vlc_slice_status_t {
 // ---- stream-resident front end: the whole elementary stream lies in device memory, a scan kernel lists its start
 // codes, and pictures are handed over as descriptors (a few hundred bytes each, one H2D copy per parse launch) that
 // name their slices by byte offset.  One launch parses every slice of up to kMaxStreamBatch pictures.
-constexpr int kMaxStreamBatch = 64;
+constexpr int kMaxStreamBatch = 128;
 struct vlc_stream_pic_t {
     mp2v_pic_params_t params;           // copied into the slot's device parameter block by the kernel (the reconstruction kernel reads W from there)
     slice_syntax_t sx;
@@ -51,7 +51,7 @@ struct vlc_stream_pic_t {
 inline size_t vlc_stream_desc_bytes(int max_slices) { return (sizeof(vlc_stream_pic_t) + (size_t)max_slices * sizeof(uint32_t) + 15) & ~(size_t)15; }
 
 // parse every slice of n_pics pictures described at desc (device copy, desc_stride bytes apart) out of the resident stream
-cudaError_t launch_vlc_stream(const uint8_t* d_stream, const uint8_t* d_desc, size_t desc_stride, int n_pics, int max_slices, const void* d_tables, cudaStream_t stream);
+cudaError_t launch_vlc_stream(const uint8_t* d_stream, const uint8_t* d_desc, size_t desc_stride, int n_pics, int max_slices, int lanes, const void* d_tables, cudaStream_t stream);
 
 // start-code scan of a device-resident stream (the reference's scan_start_codes, start_codes_search.hpp:7-26): byte offsets of
 // every 00 00 01 prefix in [0, len), ascending, into d_codes (capacity cap entries); *d_total = number found (may exceed cap: then

@@ -19,4 +19,11 @@ for _ in range(int(sys.argv[1]) if len(sys.argv) > 1 else 2):
     t0 = time.perf_counter()
     d.decode(pinned.numpy(), s.size, want_output=False, download=dl)
     print("decode %.2f ms" % ((time.perf_counter() - t0) * 1e3), file=sys.stderr)
+if "--resident" in sys.argv:
+    best = 1e9
+    for _ in range(int(sys.argv[1]) if len(sys.argv) > 1 else 2):
+        d.decode_resident()
+        best = min(best, d.stats.device_ms)
+        print("resident %.3f ms (device)" % d.stats.device_ms, file=sys.stderr)
+    print("resident best %.3f ms = %.0f frames/s" % (best, len(s.pictures) / best * 1e3), file=sys.stderr)
 print("ok", d.stats.launches, d.stats.vlc_launches)
