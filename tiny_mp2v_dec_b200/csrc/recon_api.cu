@@ -327,11 +327,11 @@ static int create_impl(mp2v_recon* ctx) {
     }
     if (ctx->vlc) {
         // stream-resident front end: parse streams, descriptor buffers (one per batched parse launch in flight)
-        const bool parse_first = getenv("MP2V_PARSE_PRIO") && atoi(getenv("MP2V_PARSE_PRIO"));      // dev knob
+        // (development knobs of tools/dev/*_sweep.sh: concurrent parse launches, slices per warp, pictures per parse launch)
         if (const char* v = getenv("MP2V_PARSE_STREAMS")) { const int k = atoi(v); if (k >= 1 && k <= mp2v_recon::kParseStreams) ctx->n_parse_streams = k; }
         if (const char* v = getenv("MP2V_PARSE_LANES")) { const int k = atoi(v); if (k >= 0 && k <= 32) ctx->parse_lanes = k; }
         if (const char* v = getenv("MP2V_LOT")) { const int k = atoi(v); if (k >= 1 && k <= kMaxStreamBatch) ctx->lot_cap = k; }
-        for (auto& st : ctx->s_parse) CK(cudaStreamCreateWithPriority(&st, cudaStreamNonBlocking, parse_first ? prio_greatest : prio_least), "stream");
+        for (auto& st : ctx->s_parse) CK(cudaStreamCreateWithPriority(&st, cudaStreamNonBlocking, prio_least), "stream");
         CK(cudaEventCreateWithFlags(&ctx->ev_stream, cudaEventDisableTiming), "event");
         ctx->desc_stride = vlc_stream_desc_bytes(ctx->mbh);
         for (auto& b : ctx->parse_buf) {

@@ -4,32 +4,45 @@
 // back (the CPU reference writes it with mc_pred*/mc_bidir* and re-reads it in
 // inverse_dct_template<true>, idct_sse2.hpp:110-114).
 //
-// Work decomposition (v2, "warp-autonomous"): a warp owns a run of consecutive macroblocks of one
-// picture and walks it in batches of <= 32 coded blocks.  There is ONE __syncthreads() per CTA (after
-// the picture tables are staged); everything else is __syncwarp(), so warps of a CTA drift apart and
-// the memory latency of one overlaps the integer work of the others.  Per batch:
-//   1  lanes load the macroblock records (one 16-byte record per lane); a warp scan of popc(cbp)
-//      assigns every coded block one of 32 residual-tile slots (144 B each) -- and one IDCT lane
-//   2  the first macroblock's reference windows start flowing into shared memory (cp.async)
-//   3  dequantise: the warp streams each macroblock's coefficient records with coalesced 32-bit
-//      loads, applies parse_block's arithmetic (mb_decoder.cpp:139-146) and scatters int16 values to
-//      tile[slot][g_scan_trans[pos]]; mismatch parity of all (<= 12) blocks of a macroblock is one
-//      REDUX.XOR per 32 records; a weighted L1 norm per block feeds the saturation bound below
-//   4  IDCT: four lanes per coded block, 8 blocks per round, values as packed int16 pairs in the
-//      tile (the 8x8 transpose between the passes, idct_sse2.hpp:67-94, is the conflict-free shared
-//      memory round trip).  Three bit-exact variants of the lane arithmetic, chosen per round of 8
-//      blocks from rigorous range bounds (tools/dev/idct_bounds.py):
+// Work decomposition ("warp-autonomous"): a warp owns a run of consecutive macroblocks of one picture
+// and walks it in batches of <= 24 coded blocks / <= 16 macroblocks of one macroblock row.  There is
+// ONE __syncthreads() per CTA (after the picture tables are staged); everything else is __syncwarp()
+// and per-warp mbarriers, so the warps of a CTA drift apart and the memory latency of one overlaps the
+// integer work of the others.  Per batch:
+//   1  lanes load the macroblock records (one 16-byte record per lane, requested during the previous
+//      batch); a warp scan of popc(cbp) assigns every coded block a 144-byte slot of the warp's
+//      residual tile; lane 0 issues the first macroblock's reference boxes
+//   2  dequantise: the coefficient records of the batch are ONE contiguous list (lane = record,
+//      coalesced 32-bit loads, the next trip requested before this one is processed).  A record names
+//      its macroblock by the column tag in bits 31:28 (include/mp2v_recon.h), so its context
+//      {cbp, first slot, quantiser scale, shift} is one 8-byte shared-memory load.  parse_block's
+//      arithmetic (mb_decoder.cpp:139-146), scatter to tile[slot][g_scan_trans[pos]]; mismatch parity
+//      of all slots is one REDUX.XOR per 32 records; a weighted L1 norm per block feeds the
+//      saturation bound below.  A mismatch toggle that only turns F[63] from 0 into 1 is dropped:
+//      column 7 of pass 1 maps x7 = 1 to (1 * 25570) >> 16 = 0, an all-zero column
+//      (idct_sse2.hpp:32,41) -- the block is bit-identical without it
+//   3  IDCT: one lane per column in pass 1 and one lane per row in pass 2 (8 lanes per block, 4
+//      blocks per trip); 16-bit shared-memory loads sign-extend, 16-bit stores pack, pass 2 reads its
+//      row with one conflict-free 128-bit load -- the 8x8 transpose between the passes
+//      (idct_sse2.hpp:67-94) is that shared-memory round trip.  Three bit-exact variants of the lane
+//      arithmetic, chosen per batch from rigorous range bounds (tools/dev/idct_bounds.py):
 //        pass 1  dequantised inputs (|F| <= 2048, first coefficient <= 3036) cannot saturate or wrap
 //                anywhere except in the last 8 additions -> plain int32 ops + 8 saturating adds
-//        pass 2  if sum |F[k][c]| * Omax[k] * G[c] of every block in the warp stays below the
+//        pass 2  if sum |F[k][c]| * Omax[k] * G[c] of every block in the batch stays below the
 //                threshold no intermediate can leave int16 -> plain int32 ops; otherwise the exact form
 //        exact   every SSE2 lane op reproduced: adds/subs = VIADDMNMX+VIMNMX, mulhi = IMAD+SHF,
 //                slli = shift pair with 16-bit wrap
-//   5  prediction: per macroblock the (w+1)x(h+1) reference windows of all planes / directions are
-//      staged as aligned 16-byte chunks (cp.async, double buffered: the next macroblock's windows load
-//      while this one is computed), then every lane produces one output row: funnel-shift
-//      realignment, __vavgu4 rounding averages in the reference's order (mc_c.hpp:3-17), residual
-//      add + unsigned saturation as VIADDMNMX.S16x2.RELU, one 128-bit (or 64-bit) store.
+//   4  prediction: per macroblock, ONE TMA box load per plane and direction
+//      (cp.async.bulk.tensor.3d over the frame pool viewed as [frame][row][pixel], completion on a
+//      per-warp mbarrier).  A box must start on a 16-byte boundary of the innermost dimension
+//      (measured: any other x coordinate raises an illegal-instruction fault), so a box is 32 bytes
+//      wide from (x & ~15) and its rows are read at the byte offset x & 15.  Boxes that leave the
+//      plane are zero-filled by the TMA unit: a bad vector cannot fault.  Every lane then produces one
+//      output row (4:2:0; half rows for the wider formats): 32-bit loads at the dynamic word offset,
+//      funnel-shift realignment, packed rounding averages in the reference's order (mc_c.hpp:3-17),
+//      residual add + unsigned saturation as VIADDMNMX.S16x2.RELU, one 128-bit (or 64-bit) store.
+//      Every lane owns the same (plane, row) of every macroblock: block indices, box offsets and the
+//      destination pointer are per-lane constants / running pointers.
 //
 // The roofline that bounds this kernel and the byte counts are in DESIGN.md.
 #include "recon_kernels.cuh"
@@ -59,54 +72,7 @@ constexpr int kBoundLimit = 16 * 30000;
 constexpr int kBoundWild = 1 << 28;       // added when a block must take the fully exact path
 constexpr int kMaxFirstCoef = 3036;       // (3 * 255 * 127) >> 5: largest unclamped pass-1 input the analysis covers
 
-// Window row pitch: 2 data chunks + 1 chunk of padding.  With 48 bytes the 128-bit row reads of 8
-// consecutive rows (a quarter warp) fall into 8 disjoint 4-bank groups (12*r mod 32), i.e. they are
-// bank-conflict free; the natural 32-byte pitch measured 4.1 wavefronts per shared load.
-constexpr int kWinPitch = 48;
-
-template <int CF>
-struct fmt_t {
-    static constexpr int NBLK = CF == 1 ? 6 : CF == 2 ? 8 : 12;
-    static constexpr int CW = CF == 3 ? 16 : 8;     // chroma macroblock width
-    static constexpr int CH = CF == 1 ? 8 : 16;     // chroma macroblock height
-    static constexpr int WIN_LUMA = 17 * kWinPitch; // 17 rows x 2 aligned 16-byte chunks (+ 16 B of pitch padding)
-    static constexpr int WIN_CHROMA = (CH + 1) * kWinPitch;
-    static constexpr int WIN_DIR = WIN_LUMA + 2 * WIN_CHROMA;
-    static constexpr int N_ITEMS = 2 * 17 + 2 * 2 * (CH + 1);   // 16-byte chunks per direction
-    static constexpr int N_UNITS = 16 + 2 * CH;                 // output rows per macroblock
-};
-
 constexpr int kTilePitch = 72;   // int16 per slot: 64 + 8 pad -> 144 B, conflict-free 128-bit row access
-#ifndef MP2V_SLOTS
-#define MP2V_SLOTS 24      // measured best: 24 slots (4:2:0 4 MBs, 4:2:2 3, 4:4:4 2 all-coded macroblocks fill it exactly)
-#endif
-#ifndef MP2V_WINBUF
-#define MP2V_WINBUF 1      // one window buffer: 29 KB / CTA -> 8 CTAs per SM; two buffers measured 3-6 % slower
-#endif
-#ifndef MP2V_MINCTAS
-#define MP2V_MINCTAS 6
-#endif
-constexpr int kSlots = MP2V_SLOTS;   // coded blocks per batch (multiple of 8: the IDCT runs 8 blocks per round)
-constexpr int kWinBuf = MP2V_WINBUF; // 2: the next macroblock's windows load while this one is computed
-constexpr int kWarps = kCtaThreads / 32;
-
-template <int CF>
-struct warp_smem_t {
-    alignas(16) int16_t tile[kSlots][kTilePitch];
-    alignas(16) uint8_t win[kWinBuf][2][fmt_t<CF>::WIN_DIR];   // [buffer][direction]
-    int bound[kSlots];
-    // per-batch context of the macroblocks that carry records, for the flat dequantisation loop:
-    // {first record index in the batch, coef_off, bits, first tile slot}
-    alignas(16) uint4 mb_ctx[32];
-};
-
-template <int CF>
-struct smem_t {
-    warp_smem_t<CF> w[kWarps];
-    alignas(16) uint8_t W[4][64];
-    alignas(16) uint8_t scan[64];
-    alignas(16) uint16_t bw[64];
-};
 
 // ------------------------------------------------------------------------------------------------
 // Exact 16-bit lane arithmetic on sign-extended int32 (idct_sse2.hpp:7-21 helpers).
@@ -194,121 +160,11 @@ __device__ __forceinline__ void idct_lane(int& x0, int& x1, int& x2, int& x3, in
     }
 }
 
-// inverse_dct_template up to the >>6 (idct_sse2.hpp:96-107) for 8 tile slots at a time, in place:
-// in  F[k*8+c] (the transposed-raster layout parse_block writes), out res[r*8+c].
-// FOUR lanes share a block; lane j owns columns 2j,2j+1 in pass 1 and rows 2j,2j+1 in pass 2, always
-// as packed int16 pairs (one 32-bit word), so a lane holds 16 values, the 8x8 transpose between the
-// passes (transpose_8x8_sse2, idct_sse2.hpp:67-94) is the shared-memory round trip, and with the
-// 36-word slot pitch every access pattern below is bank-conflict free:
-//   word k*4+j of 8 slots x 4 lanes -> banks 4*slot + 4*k + j, all distinct;
-//   128-bit rows 2j, 2j+1           -> quarter-warps cover 8 disjoint 4-bank groups.
-// p1_exact / p2_exact are uniform over the warp.
-__device__ __forceinline__ void idct_round(int16_t* slot_base, int j, bool active, bool p1_exact, bool p2_exact) {
-    uint32_t* t = reinterpret_cast<uint32_t*>(slot_base);
-    int a[8], b[8];
-    // ---- pass 1: the transform runs across the vector index k for columns 2j and 2j+1
-    if (active) {
-#pragma unroll
-        for (int k = 0; k < 8; k++) { const uint32_t w = t[k * 4 + j]; a[k] = (int)(short)(w & 0xffffu); b[k] = (int)w >> 16; }
-    } else {
-#pragma unroll
-        for (int k = 0; k < 8; k++) a[k] = b[k] = 0;
-    }
-    if (p1_exact) {
-        idct_lane<0>(a[0], a[1], a[2], a[3], a[4], a[5], a[6], a[7]);
-        idct_lane<0>(b[0], b[1], b[2], b[3], b[4], b[5], b[6], b[7]);
-    } else if (p2_exact) {
-        idct_lane<1>(a[0], a[1], a[2], a[3], a[4], a[5], a[6], a[7]);
-        idct_lane<1>(b[0], b[1], b[2], b[3], b[4], b[5], b[6], b[7]);
-    } else {
-        // the bound that clears pass 2 also bounds every pass-1 OUTPUT: |y_c| <= bound / (16 G[c]) + E with
-        // G[c] >= 1, i.e. below 30 100 -- the 8 output additions cannot saturate either
-        idct_lane<2>(a[0], a[1], a[2], a[3], a[4], a[5], a[6], a[7]);
-        idct_lane<2>(b[0], b[1], b[2], b[3], b[4], b[5], b[6], b[7]);
-    }
-    if (active) {
-#pragma unroll
-        for (int k = 0; k < 8; k++) t[k * 4 + j] = __byte_perm(a[k], b[k], 0x5410);
-    }
-    __syncwarp();
-    // ---- pass 2: rows 2j and 2j+1 of the first-pass result are lanes 2j, 2j+1 of the transposed block
-    if (active) {
-        const uint4 r0 = reinterpret_cast<const uint4*>(t)[2 * j], r1 = reinterpret_cast<const uint4*>(t)[2 * j + 1];
-        a[0] = (int)(short)(r0.x & 0xffffu); a[1] = (int)r0.x >> 16; a[2] = (int)(short)(r0.y & 0xffffu); a[3] = (int)r0.y >> 16;
-        a[4] = (int)(short)(r0.z & 0xffffu); a[5] = (int)r0.z >> 16; a[6] = (int)(short)(r0.w & 0xffffu); a[7] = (int)r0.w >> 16;
-        b[0] = (int)(short)(r1.x & 0xffffu); b[1] = (int)r1.x >> 16; b[2] = (int)(short)(r1.y & 0xffffu); b[3] = (int)r1.y >> 16;
-        b[4] = (int)(short)(r1.z & 0xffffu); b[5] = (int)r1.z >> 16; b[6] = (int)(short)(r1.w & 0xffffu); b[7] = (int)r1.w >> 16;
-    }
-    __syncwarp();      // every lane has its rows in registers before anyone overwrites the slot
-    if (p2_exact) {
-        idct_lane<0>(a[0], a[1], a[2], a[3], a[4], a[5], a[6], a[7]);
-        idct_lane<0>(b[0], b[1], b[2], b[3], b[4], b[5], b[6], b[7]);
-    } else {
-        idct_lane<2>(a[0], a[1], a[2], a[3], a[4], a[5], a[6], a[7]);
-        idct_lane<2>(b[0], b[1], b[2], b[3], b[4], b[5], b[6], b[7]);
-    }
-    // output r of row k is res[r][k]: rows 2j, 2j+1 give the adjacent columns 2j, 2j+1 of every result row
-    if (active) {
-#pragma unroll
-        for (int r = 0; r < 8; r++) t[r * 4 + j] = __byte_perm(a[r] >> 6, b[r] >> 6, 0x5410);   // _mm_srai_epi16(.,6)
-    }
-}
-
-// ------------------------------------------------------------------------------------------------
-// prediction row: NW words (4 pixels each) of one row of a staged window, realigned from byte offset
-// o, with the reference's half-pel averaging order (mc_c.hpp:3-17).  The 32 data bytes of a row come
-// in as two conflict-free 128-bit loads; the word offset (o >> 2) is resolved by a two-level
-// register mux, the byte offset by funnel shifts.
 // _mm_avg_epu8 on 4 packed bytes: (a + b + 1) >> 1 = (a | b) - (((a ^ b) & 0xfe..) >> 1), 4 ops (LOP3 fuses xor+and)
 __device__ __forceinline__ uint32_t avg4(uint32_t a, uint32_t b) {
     uint32_t t;
     asm("lop3.b32 %0, %1, %2, 0xfefefefe, 0x28;" : "=r"(t) : "r"(a), "r"(b));    // (a ^ b) & c
     return (a | b) - (t >> 1);
-}
-
-#ifndef MP2V_WINREAD128
-#define MP2V_WINREAD128 0
-#endif
-template <int NW>
-__device__ __forceinline__ void window_words(const uint8_t* win_row, int k, uint32_t (&u)[NW + 1]) {
-    if (!MP2V_WINREAD128) {     // NW+1 32-bit loads at the dynamic word offset (at most 2-way conflicts with the 48-byte pitch)
-        const uint32_t* p = reinterpret_cast<const uint32_t*>(win_row) + k;
-#pragma unroll
-        for (int i = 0; i <= NW; i++) u[i] = p[i];
-        return;
-    }
-    const uint4 a = *reinterpret_cast<const uint4*>(win_row), b = *reinterpret_cast<const uint4*>(win_row + 16);
-    const uint32_t w[8] = {a.x, a.y, a.z, a.w, b.x, b.y, b.z, b.w};
-    uint32_t t[NW + 2];
-#pragma unroll
-    for (int i = 0; i < NW + 2; i++) t[i] = (k & 2) ? w[i + 2] : w[i];
-#pragma unroll
-    for (int i = 0; i <= NW; i++) u[i] = (k & 1) ? t[i + 1] : t[i];
-}
-
-template <int NW>
-__device__ __forceinline__ void pred_row(const uint8_t* win_row, int o, int hx, int hy, uint32_t (&out)[NW]) {
-    const int sh = (o & 3) * 8;
-    uint32_t w[NW + 1];
-    window_words<NW>(win_row, o >> 2, w);
-#pragma unroll
-    for (int j = 0; j < NW; j++) out[j] = __funnelshift_rc(w[j], w[j + 1], sh);
-    if (hx) {
-#pragma unroll
-        for (int j = 0; j < NW; j++) out[j] = avg4(out[j], __funnelshift_rc(w[j], w[j + 1], sh + 8));
-    }
-    if (hy) {
-        uint32_t b[NW];
-        window_words<NW>(win_row + kWinPitch, o >> 2, w);   // next window row
-#pragma unroll
-        for (int j = 0; j < NW; j++) b[j] = __funnelshift_rc(w[j], w[j + 1], sh);
-        if (hx) {
-#pragma unroll
-            for (int j = 0; j < NW; j++) b[j] = avg4(b[j], __funnelshift_rc(w[j], w[j + 1], sh + 8));
-        }
-#pragma unroll
-        for (int j = 0; j < NW; j++) out[j] = avg4(out[j], b[j]);
-    }
 }
 
 // pred (4 pixels) + residual (two int16x2 words), unsigned-saturated: packus(adds_epi16(zext(dst), res))
@@ -323,386 +179,431 @@ __device__ __forceinline__ uint32_t clip4(uint32_t r01, uint32_t r23) {
     return __byte_perm(__vimin_s16x2_relu(r01, 0x00ff00ffu), __vimin_s16x2_relu(r23, 0x00ff00ffu), 0x6420);
 }
 
-__device__ __forceinline__ int chroma_mv(int mv, bool halve) { return halve ? (mv >> 1) : mv; }   // floor, mb_decoder.cpp:198-206
 
-__device__ __forceinline__ void cp_async16(void* smem, const void* gmem) {
-    const unsigned s = (unsigned)__cvta_generic_to_shared(smem);
-    asm volatile("cp.async.cg.shared.global [%0], [%1], 16;\n" ::"r"(s), "l"(gmem) : "memory");   // L2 only: window chunks are not re-read through L1
-}
-__device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;\n" ::: "memory"); }
-template <int N> __device__ __forceinline__ void cp_async_wait() { asm volatile("cp.async.wait_group %0;\n" ::"n"(N) : "memory"); }
 
-// Stage the reference windows of one macroblock: aligned 16-byte chunks, 2 per row, (h+1) rows per
-// plane.  Lane l always copies chunk (l & 1) of row (l >> 1) of some plane, so its source offset inside
-// a plane (lane_off = row * stride + 16 * chunk) is a per-kernel constant and a trip is just
-// "plane base + lane_off -> window + 16 * lane".  Trips: luma rows 0-15; chroma rows 0-15 (4:2:0: Cb
-// rows 0-7 on lanes 0-15, Cr on lanes 16-31); and, only for vertical half-pel vectors, the extra
-// bottom rows.
+#ifndef MP2V_V3_WINBUF
+#define MP2V_V3_WINBUF 1
+#endif
+#ifndef MP2V_V3_MINCTAS
+#define MP2V_V3_MINCTAS 8
+#endif
+constexpr int kSlots = 24;                 // coded blocks per batch
+constexpr int kTileRows = kSlots + 1;      // + one spare row: a record naming an uncoded block lands there at worst
+constexpr int kWinBuf = MP2V_V3_WINBUF;    // window buffers per warp (2: the next macroblock's boxes load during this one)
+constexpr int kWarps = kCtaThreads / 32;
+constexpr int kBoxW = 32;                  // bytes per box row: 16-byte aligned start + up to 15 bytes of offset + 17 pixels
+
+constexpr int align128(int x) { return (x + 127) & ~127; }
+
 template <int CF>
-__device__ __forceinline__ void stage_windows(const pic_desc_t& pd, const batch_desc_t& batch, uint4 m, int mbx, int mby,
-                                              uint8_t* win /* [2][WIN_DIR] */, int lane, int lane_off_y, int lane_off_c) {
-    const int lane_woff = (lane >> 1) * kWinPitch + (lane & 1) * 16;      // window position of this lane's chunk
-    using F = fmt_t<CF>;
-    if (m.y & MP2V_MB_INTRA) return;
+struct geo_t {
+    static constexpr int NBLK = CF == 1 ? 6 : CF == 2 ? 8 : 12;
+    static constexpr int CW = CF == 3 ? 16 : 8;      // chroma macroblock width
+    static constexpr int CH = CF == 1 ? 8 : 16;      // chroma macroblock height
+    static constexpr int Y_BYTES = kBoxW * 17, C_BYTES = kBoxW * (CH + 1);
+    static constexpr int CB_OFF = align128(Y_BYTES), CR_OFF = CB_OFF + align128(C_BYTES);
+    static constexpr int DIR_BYTES = CR_OFF + align128(C_BYTES);      // every box 128-byte aligned
+    static constexpr uint32_t TX_BYTES = Y_BYTES + 2 * C_BYTES;      // bytes one direction's three boxes deliver
+};
+
+template <int CF>
+struct alignas(128) warp_smem_t {
+    alignas(128) uint8_t win[kWinBuf][2][geo_t<CF>::DIR_BYTES];   // [buffer][direction]
+    alignas(16) int16_t tile[kTileRows][kTilePitch];
+    // the (up to 16) macroblocks of the batch, by position: {cbp | W row offset << 16, first slot | qscale << 8 | shift << 16}
+    alignas(16) uint2 mb_ctx[16];
+    alignas(16) int bound[kTileRows + 3];  // saturation bound per slot
+    alignas(8) uint64_t mbar[kWinBuf];
+};
+
+template <int CF>
+struct cta_smem_t {
+    warp_smem_t<CF> w[kWarps];
+    alignas(16) uint8_t W[4][64];          // quantiser matrices by scan position
+    alignas(16) uint8_t scan[64];          // scan position -> tile index (g_scan_trans)
+    alignas(16) uint16_t bwp[64];          // bound weight by scan position
+};
+
+// ---- mbarrier / TMA wrappers (PTX ISA 8.6, sm_100a)
+__device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+__device__ __forceinline__ void mbar_init(uint64_t* bar, uint32_t count) {
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count) : "memory");
+}
+__device__ __forceinline__ void mbar_fence_init() { asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory"); }
+__device__ __forceinline__ void mbar_expect_tx(uint64_t* bar, uint32_t bytes) {
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
+}
+// Bounded: a box that never arrives traps instead of hanging the device.
+__device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
+    uint32_t done = 0;
+    for (int spins = 0; spins < (1 << 22); spins++) {
+        asm volatile(
+            "{\n\t.reg .pred p;\n\t"
+            "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
+            "selp.u32 %0, 1, 0, p;\n\t}"
+            : "=r"(done) : "r"(smem_u32(bar)), "r"(parity) : "memory");
+        if (done) return;
+    }
+    __trap();
+}
+// one box of a [frame][row][pixel] plane tensor; coordinates in elements, innermost first; x must be a multiple of 16
+__device__ __forceinline__ void tma_box_3d(void* dst, const CUtensorMap* tm, int x, int y, int z, uint64_t* bar) {
+    asm volatile("cp.async.bulk.tensor.3d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%2, %3, %4}], [%5];"
+                 ::"r"(smem_u32(dst)), "l"(reinterpret_cast<uint64_t>(tm)), "r"(x), "r"(y), "r"(z), "r"(smem_u32(bar)) : "memory");
+}
+
+// prediction of one unit (NW words = 4 * NW pixels) from a staged box row at byte offset o; half-pel
+// averaging in the reference's order (mc_c.hpp:3-17): H = avg(p[x], p[x+1]), V = avg(p[x], p[x+stride]),
+// HV = avg(H(row), H(row + 1)).  32-bit loads at the dynamic word offset, funnel shifts for the byte part.
+template <int NW>
+__device__ __forceinline__ void pred_unit(const uint8_t* row, int o, int hx, int hy, uint32_t (&out)[NW]) {
+    const int sh = (o & 3) * 8;
+    const uint32_t* p = reinterpret_cast<const uint32_t*>(row + (o & ~3));
+    uint32_t w[NW + 1];
 #pragma unroll
-    for (int d = 0; d < 2; d++) {
-        if (!(m.y & (d ? MP2V_MB_BWD : MP2V_MB_FWD))) continue;
-        const uint32_t mvw = d ? m.w : m.z;
-        const int mvx = (int)(short)(mvw & 0xffffu), mvy = (int)mvw >> 16;
-        const int cx = chroma_mv(mvx, CF < 3), cy = chroma_mv(mvy, CF < 2);
-        const uint8_t* const* ref = d ? pd.l1 : pd.l0;
-        uint8_t* w = win + d * F::WIN_DIR;
-        const int x0 = mbx * 16 + (mvx >> 1), y0 = mby * 16 + (mvy >> 1);
-        const int cx0 = mbx * F::CW + (cx >> 1), cy0 = mby * F::CH + (cy >> 1);
-        const uint8_t* by = ref[0] + (size_t)y0 * batch.stride[0] + (x0 & ~15);
-        const size_t coff = (size_t)cy0 * batch.stride[1] + (cx0 & ~15);
-        const uint8_t* bcb = ref[1] + coff;
-        const uint8_t* bcr = ref[2] + coff;
-        cp_async16(w + lane_woff, by + lane_off_y);                                   // luma rows 0..15
-        if (CF == 1) {
-            const int l = lane & 15;                                                   // Cb rows 0..7 | Cr rows 0..7
-            cp_async16(w + F::WIN_LUMA + (lane >> 4) * F::WIN_CHROMA + (l >> 1) * kWinPitch + (l & 1) * 16, (lane < 16 ? bcb : bcr) + (l >> 1) * batch.stride[1] + (l & 1) * 16);
-        } else {
-            cp_async16(w + F::WIN_LUMA + lane_woff, bcb + lane_off_c);                 // Cb rows 0..15
-            cp_async16(w + F::WIN_LUMA + F::WIN_CHROMA + lane_woff, bcr + lane_off_c); // Cr rows 0..15
+    for (int i = 0; i <= NW; i++) w[i] = p[i];
+#pragma unroll
+    for (int j = 0; j < NW; j++) out[j] = __funnelshift_rc(w[j], w[j + 1], sh);
+    if (hx) {
+#pragma unroll
+        for (int j = 0; j < NW; j++) out[j] = avg4(out[j], __funnelshift_rc(w[j], w[j + 1], sh + 8));
+    }
+    if (hy) {
+        uint32_t b[NW];
+#pragma unroll
+        for (int i = 0; i <= NW; i++) w[i] = p[i + kBoxW / 4];      // next box row
+#pragma unroll
+        for (int j = 0; j < NW; j++) b[j] = __funnelshift_rc(w[j], w[j + 1], sh);
+        if (hx) {
+#pragma unroll
+            for (int j = 0; j < NW; j++) b[j] = avg4(b[j], __funnelshift_rc(w[j], w[j + 1], sh + 8));
         }
-        if (((mvy | cy) & 1) && lane < 6) {                                            // bottom rows for vertical half-pel
-            const int pl = lane >> 1, ch = lane & 1;
-            const uint8_t* src = pl == 0 ? by + (size_t)16 * batch.stride[0] : (pl == 1 ? bcb : bcr) + (size_t)F::CH * batch.stride[1];
-            uint8_t* dst = w + (pl == 0 ? 16 * kWinPitch : F::WIN_LUMA + (pl - 1) * F::WIN_CHROMA + F::CH * kWinPitch);
-            cp_async16(dst + 16 * ch, src + 16 * ch);
-        }
+#pragma unroll
+        for (int j = 0; j < NW; j++) out[j] = avg4(out[j], b[j]);
     }
 }
 
-// prediction + residual + clip + store of one macroblock; windows already staged in `win`.
-// Whole-row variant (4:2:0): 16 luma rows of 16 pixels + 2 x 8 chroma rows of 8 pixels = exactly 32 lanes,
-// one trip; the luma and chroma half warps run different word counts one after the other.
-template <int CF>
-__device__ __forceinline__ void reconstruct_mb_rows(const pic_desc_t& pd, const batch_desc_t& batch, uint4 m, int mbx, int mby, int base,
-                                               const uint8_t* win, const int16_t (*tile)[kTilePitch], int lane) {
-    using F = fmt_t<CF>;
-    const uint32_t cbp = MP2V_MB_CBP(m.y);
-    const bool fwd = (m.y & MP2V_MB_FWD) != 0, bwd = (m.y & MP2V_MB_BWD) != 0, intra = (m.y & MP2V_MB_INTRA) != 0;
-    for (int u = lane; u < F::N_UNITS; u += 32) {
-        int p, r;
-        if (u < 16) { p = 0; r = u; }
-        else if (u < 16 + F::CH) { p = 1; r = u - 16; }
-        else { p = 2; r = u - 16 - F::CH; }
-        const bool wide = (p == 0) || (CF == 3);
-        const int pw = p ? F::CW : 16, ph = p ? F::CH : 16;
-        uint32_t pred[4] = {0, 0, 0, 0};
-        bool have = false;
-        if (!intra) {
-#pragma unroll
-            for (int d = 0; d < 2; d++) {
-                if (!(d ? bwd : fwd)) continue;
-                const uint32_t mvw = d ? m.w : m.z;
-                const int mvx = (int)(short)(mvw & 0xffffu), mvy = (int)mvw >> 16;
-                const int cx = p ? chroma_mv(mvx, CF < 3) : mvx, cy = p ? chroma_mv(mvy, CF < 2) : mvy;
-                const int o = (mbx * pw + (cx >> 1)) & 15;
-                const uint8_t* row = win + d * F::WIN_DIR + (p == 0 ? 0 : F::WIN_LUMA + (p - 1) * F::WIN_CHROMA) + r * kWinPitch;
-                // one four-word path for all 32 lanes: the 8-pixel chroma lanes compute (and drop) two words of
-                // padding instead of making the warp run a second, two-word path after the luma one
-                uint32_t q[4];
-                pred_row<4>(row, o, cx & 1, cy & 1, q);
-                if (have) {
-#pragma unroll
-                    for (int j = 0; j < 4; j++) pred[j] = avg4(q[j], pred[j]);   // bidirectional rounding average
-                } else {
-#pragma unroll
-                    for (int j = 0; j < 4; j++) pred[j] = q[j];
-                }
-                have = true;
-            }
-        }
-        // residual blocks covering this row (block geometry: mb_decoder.cpp:177-195)
-        int bl, br = -1;
-        if (p == 0) { bl = (r >> 3) * 2; br = bl + 1; }
-        else if (CF == 1) bl = 3 + p;
-        else if (CF == 2) bl = 3 + p + ((r >> 3) << 1);
-        else { bl = 3 + p + ((r >> 3) << 1); br = bl + 4; }
-        const int rr = r & 7;
-        uint32_t out[4] = {pred[0], pred[1], pred[2], pred[3]};
-        if (cbp >> bl & 1) {
-            const uint4 res = *reinterpret_cast<const uint4*>(&tile[base + __popc(cbp & ((1u << bl) - 1u))][rr * 8]);
-            if (intra) { out[0] = clip4(res.x, res.y); out[1] = clip4(res.z, res.w); }      // add=false: packus(res)
-            else { out[0] = add_clip4(pred[0], res.x, res.y); out[1] = add_clip4(pred[1], res.z, res.w); }
-        }
-        uint8_t* drow = pd.dst[p] + (size_t)(mby * ph + r) * batch.stride[p] + mbx * pw;
-        if (wide) {
-            if (cbp >> br & 1) {
-                const uint4 res = *reinterpret_cast<const uint4*>(&tile[base + __popc(cbp & ((1u << br) - 1u))][rr * 8]);
-                if (intra) { out[2] = clip4(res.x, res.y); out[3] = clip4(res.z, res.w); }
-                else { out[2] = add_clip4(pred[2], res.x, res.y); out[3] = add_clip4(pred[3], res.z, res.w); }
-            }
-            *reinterpret_cast<uint4*>(drow) = make_uint4(out[0], out[1], out[2], out[3]);
-        } else {
-            *reinterpret_cast<uint2*>(drow) = make_uint2(out[0], out[1]);
-        }
+// residual of block `blk` (row rr) on top of two words of prediction, or alone for intra macroblocks
+__device__ __forceinline__ void add_residual(const int16_t (*tile)[kTilePitch], int base, uint32_t cbp, uint32_t below, int blk, int rr8, bool intra,
+                                             uint32_t& o0, uint32_t& o1) {
+    if (cbp >> blk & 1) {
+        const uint4 res = *reinterpret_cast<const uint4*>(&tile[base + __popc(cbp & below)][rr8]);
+        if (intra) { o0 = clip4(res.x, res.y); o1 = clip4(res.z, res.w); }      // add=false: packus(res), idct_sse2.hpp:108-109
+        else { o0 = add_clip4(o0, res.x, res.y); o1 = add_clip4(o1, res.z, res.w); }
     }
 }
 
-// Half-row variant (4:2:2, 4:4:4), same contract.
-// The unit of work is an 8-pixel half row = one row of ONE 8x8 block, for luma and chroma alike, so all
-// lanes run the same two-word code path (a 16-pixel / 8-pixel split made the luma and chroma half
-// warps execute two different paths one after the other).  Units: 32 luma (16 rows x 2 halves), then
-// 2 planes x CH rows x (CW/8) halves of chroma.
 template <int CF>
-__device__ __forceinline__ void reconstruct_mb_halfrows(const pic_desc_t& pd, const batch_desc_t& batch, uint4 m, int mbx, int mby, int base,
-                                                        const uint8_t* win, const int16_t (*tile)[kTilePitch], int lane) {
-    using F = fmt_t<CF>;
-    constexpr int CHALF = F::CW / 8;                       // 8-pixel halves per chroma row
-    constexpr int N_UNITS = 32 + 2 * F::CH * CHALF;
-    const uint32_t cbp = MP2V_MB_CBP(m.y);
-    const bool fwd = (m.y & MP2V_MB_FWD) != 0, bwd = (m.y & MP2V_MB_BWD) != 0, intra = (m.y & MP2V_MB_INTRA) != 0;
-#pragma unroll 1
-    for (int u = lane; u < N_UNITS; u += 32) {
-        int p, r, half;
-        if (u < 32) { p = 0; r = u >> 1; half = u & 1; }
-        else {
-            const int v = u - 32;
-            p = 1 + v / (F::CH * CHALF);
-            const int w = v - (p - 1) * (F::CH * CHALF);
-            r = CHALF == 2 ? w >> 1 : w; half = CHALF == 2 ? w & 1 : 0;
-        }
-        const int pw = p ? F::CW : 16, ph = p ? F::CH : 16;
-        uint32_t pred[2] = {0, 0};
-        if (!intra) {
-            bool have = false;
-#pragma unroll
-            for (int d = 0; d < 2; d++) {
-                if (!(d ? bwd : fwd)) continue;
-                const uint32_t mvw = d ? m.w : m.z;
-                const int mvx = (int)(short)(mvw & 0xffffu), mvy = (int)mvw >> 16;
-                const int cx = p ? chroma_mv(mvx, CF < 3) : mvx, cy = p ? chroma_mv(mvy, CF < 2) : mvy;
-                const int o = ((mbx * pw + (cx >> 1)) & 15) + 8 * half;                 // byte offset of this half row in the window row
-                const uint8_t* row = win + d * F::WIN_DIR + (p == 0 ? 0 : F::WIN_LUMA + (p - 1) * F::WIN_CHROMA) + r * kWinPitch;
-                uint32_t q[2];
-                pred_row<2>(row, o, cx & 1, cy & 1, q);
-                if (have) { pred[0] = avg4(q[0], pred[0]); pred[1] = avg4(q[1], pred[1]); }   // bidirectional rounding average
-                else { pred[0] = q[0]; pred[1] = q[1]; }
-                have = true;
-            }
-        }
-        // the 8x8 block this half row belongs to (block geometry: mb_decoder.cpp:177-195)
-        int blk;
-        if (p == 0) blk = (r >> 3) * 2 + half;
-        else if (CF == 1) blk = 3 + p;
-        else if (CF == 2) blk = 3 + p + ((r >> 3) << 1);
-        else blk = 3 + p + ((r >> 3) << 1) + 4 * half;
-        uint32_t out0 = pred[0], out1 = pred[1];
-        if (cbp >> blk & 1) {
-            const uint4 res = *reinterpret_cast<const uint4*>(&tile[base + __popc(cbp & ((1u << blk) - 1u))][(r & 7) * 8]);
-            if (intra) { out0 = clip4(res.x, res.y); out1 = clip4(res.z, res.w); }          // add=false: packus(res)
-            else { out0 = add_clip4(pred[0], res.x, res.y); out1 = add_clip4(pred[1], res.z, res.w); }
-        }
-        *reinterpret_cast<uint2*>(pd.dst[p] + (size_t)(mby * ph + r) * batch.stride[p] + mbx * pw + 8 * half) = make_uint2(out0, out1);
-    }
-}
-
-// 4:2:0 fills one trip of whole rows exactly (measured 9 % faster than 1.5 trips of half rows); 4:2:2 and
-// 4:4:4 fill 2 / 3 trips of half rows exactly (measured 17 % / 24 % faster than whole rows)
-template <int CF>
-__device__ __forceinline__ void reconstruct_mb(const pic_desc_t& pd, const batch_desc_t& batch, uint4 m, int mbx, int mby, int base,
-                                               const uint8_t* win, const int16_t (*tile)[kTilePitch], int lane) {
-    if (CF == 1) reconstruct_mb_rows<CF>(pd, batch, m, mbx, mby, base, win, tile, lane);
-    else reconstruct_mb_halfrows<CF>(pd, batch, m, mbx, mby, base, win, tile, lane);
-}
-
-template <int CF>
-__global__ void __launch_bounds__(kCtaThreads, MP2V_MINCTAS) recon_kernel(const __grid_constant__ batch_desc_t batch) {
-    using F = fmt_t<CF>;
-    __shared__ smem_t<CF> s;
+__global__ void __launch_bounds__(kCtaThreads, MP2V_V3_MINCTAS)
+recon_kernel3(const __grid_constant__ batch_desc_t batch, const __grid_constant__ recon_tmaps_t tm) {
+    using G = geo_t<CF>;
+    extern __shared__ uint8_t smem_raw[];
+    cta_smem_t<CF>& s = *reinterpret_cast<cta_smem_t<CF>*>(smem_raw + ((128u - (smem_u32(smem_raw) & 127u)) & 127u));
 
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     const int pi = blockIdx.x / batch.ctas_per_pic;
     const int grp = blockIdx.x - pi * batch.ctas_per_pic;
     const pic_desc_t& pd = batch.pic[pi];
+    warp_smem_t<CF>& ws = s.w[warp];
 
-    // ---- picture tables (the only CTA-wide barrier)
+    // ---- picture tables + this warp's barriers (the only CTA-wide barrier)
     if (tid < 64) {
         reinterpret_cast<uint32_t*>(&s.W[0][0])[tid] = reinterpret_cast<const uint32_t*>(&pd.params->W[0][0])[tid];
-    } else if (tid < 80) {
         const int alt = pd.params->alternate_scan ? 1 : 0;
-        reinterpret_cast<uint32_t*>(s.scan)[tid - 64] = reinterpret_cast<const uint32_t*>(c_scan_trans[alt])[tid - 64];
-    } else if (tid < 112) {
-        reinterpret_cast<uint32_t*>(s.bw)[tid - 80] = reinterpret_cast<const uint32_t*>(c_bound_w)[tid - 80];
+        const int t = c_scan_trans[alt][tid];
+        s.scan[tid] = (uint8_t)t;
+        s.bwp[tid] = c_bound_w[t];
+    }
+    if (lane == 0) {
+#pragma unroll
+        for (int b = 0; b < kWinBuf; b++) mbar_init(&ws.mbar[b], 1);
+        mbar_fence_init();
     }
     __syncthreads();
 
-    warp_smem_t<CF>& ws = s.w[warp];
     const int mbw = batch.mbw;
-    const int lane_off_y = (lane >> 1) * batch.stride[0] + (lane & 1) * 16;     // window staging: row lane/2, chunk lane&1
-    const int lane_off_c = (lane >> 1) * batch.stride[1] + (lane & 1) * 16;
     const int run = batch.mbs_per_warp;
     const int mb_begin = (grp * kWarps + warp) * run;
     const int mb_end = min(mb_begin + run, batch.mb_count);
+    if (mb_begin >= mb_end) return;
 
+    // ---- per-lane constants of the output stage.  4:2:0: lane = one whole row (16 luma rows, 8 Cb, 8 Cr: one
+    // trip of four-word units, the chroma lanes drop two words).  4:2:2 / 4:4:4: trips of 8-pixel half rows.
+    constexpr int NT = CF == 1 ? 1 : CF == 2 ? 2 : 3;      // trips per macroblock
+    constexpr int NW = CF == 1 ? 4 : 2;                    // words per unit
+    int u_woff[NT], u_xoff[NT], u_blk[NT], u_rr8[NT], u_adv[NT], u_wrap[NT];
+    uint32_t u_below[NT];
+    uint8_t* u_dst[NT];
+    bool u_chroma[NT];
+    int mby0 = mb_begin / mbw, mbx0 = mb_begin - mby0 * mbw;      // the only division of the warp
+#pragma unroll
+    for (int t = 0; t < NT; t++) {
+        int p, r, half;
+        if (CF == 1) { p = lane < 16 ? 0 : lane < 24 ? 1 : 2; r = lane < 16 ? lane : (lane & 7); half = 0; }
+        else if (CF == 2) { p = t == 0 ? 0 : 1 + (lane >> 4); r = t == 0 ? lane >> 1 : lane & 15; half = t == 0 ? lane & 1 : 0; }
+        else { p = t; r = lane >> 1; half = lane & 1; }
+        u_chroma[t] = p != 0;
+        u_woff[t] = (p == 0 ? 0 : p == 1 ? G::CB_OFF : G::CR_OFF) + r * kBoxW;
+        u_xoff[t] = 8 * half;
+        // the 8x8 block this unit's (left) half belongs to (block geometry: mb_decoder.cpp:177-195)
+        int blk;
+        if (p == 0) blk = (r >> 3) * 2 + half;
+        else if (CF == 1) blk = 3 + p;
+        else if (CF == 2) blk = 3 + p + ((r >> 3) << 1);
+        else blk = 3 + p + ((r >> 3) << 1) + 4 * half;
+        u_blk[t] = blk;
+        u_below[t] = (1u << blk) - 1u;
+        u_rr8[t] = (r & 7) * 8;
+        const int pw = p ? G::CW : 16, ph = p ? G::CH : 16;
+        u_dst[t] = pd.dst[p] + (size_t)(mby0 * ph + r) * batch.stride[p] + mbx0 * pw + 8 * half;
+        u_adv[t] = pw;                                                     // destination step to the next macroblock of the row ...
+        u_wrap[t] = ph * batch.stride[p] - (mbw - 1) * pw;                 // ... and from the last one to the first of the next row
+    }
+
+    uint32_t wphase = 0;                                   // bit b: parity the next wait on buffer b expects
     uint4 rec_next = (mb_begin + lane < mb_end) ? __ldg(reinterpret_cast<const uint4*>(pd.mb) + mb_begin + lane) : make_uint4(0, 0, 0, 0);
-    int mby0 = mb_begin / mbw, mbx0 = mb_begin - mby0 * mbw;      // the only division of the warp; batches advance it
+    // the 32 coefficient records behind the previous batch's last one: the next batch's first trip when its list continues there
+    uint32_t pref_idx = 0xffffffffu, pref_c = 0;
+
+    // boxes of one macroblock (its record broadcast in m_*), issued by one lane into window buffer `buf`
+    auto issue_windows = [&](uint32_t m_y, uint32_t m_z, uint32_t m_w, int ix, int iy, int buf) {
+        if ((m_y & MP2V_MB_INTRA) || lane != 0) return;
+        const uint32_t ndir = ((m_y & MP2V_MB_FWD) ? 1u : 0u) + ((m_y & MP2V_MB_BWD) ? 1u : 0u);
+        mbar_expect_tx(&ws.mbar[buf], ndir * G::TX_BYTES);
+#pragma unroll
+        for (int d = 0; d < 2; d++) {
+            if (!(m_y & (d ? MP2V_MB_BWD : MP2V_MB_FWD))) continue;
+            const uint32_t mvw = d ? m_w : m_z;
+            const int mvx = (int)(short)(mvw & 0xffffu), mvy = (int)mvw >> 16;
+            const int cx = CF < 3 ? mvx >> 1 : mvx, cy = CF < 2 ? mvy >> 1 : mvy;     // chroma vector: floor (mb_decoder.cpp:198-206)
+            const int z = d ? pd.l1_id : pd.l0_id;
+            const int cxa = (ix * G::CW + (cx >> 1)) & ~15, cya = iy * G::CH + (cy >> 1);
+            uint8_t* w = &ws.win[buf][d][0];
+            tma_box_3d(w, &tm.plane[0], (ix * 16 + (mvx >> 1)) & ~15, iy * 16 + (mvy >> 1), z, &ws.mbar[buf]);
+            tma_box_3d(w + G::CB_OFF, &tm.plane[1], cxa, cya, z, &ws.mbar[buf]);
+            tma_box_3d(w + G::CR_OFF, &tm.plane[2], cxa, cya, z, &ws.mbar[buf]);
+        }
+    };
+
+    int16_t* const tile0 = &ws.tile[0][0];
     for (int first = mb_begin; first < mb_end;) {
-        // ---- 1. macroblock records of the batch: as many as fit the tile's coded-block slots
-        // (lane i holds macroblock first+i; the records were requested during the previous batch)
+        // ---- 1. macroblock records of the batch: as many as fit the tile's coded-block slots, at most 16, inside one
+        // macroblock row (a coefficient record names its macroblock by its column modulo 16), with their coefficient
+        // records contiguous in the arena (they are inside a slice; anything else only shortens the batch)
         const int idx = first + lane;
         const bool have = idx < mb_end;
-        uint4 rec = rec_next;
+        const uint4 rec = rec_next;
         const int cnt = have ? __popc(MP2V_MB_CBP(rec.y)) : 0;
         const int ncoef_all = have ? (int)MP2V_MB_NCOEF(rec.y) : 0;
-        // one warp scan for both prefixes: coded blocks (<= 12 each) in the low half, records (<= 768 each) in the high half
-        int scan2 = cnt | (ncoef_all << 16);
+        int scan2 = cnt | (ncoef_all << 16);       // both prefixes in one scan: coded blocks (low half), records (high half)
 #pragma unroll
         for (int d = 1; d < 32; d <<= 1) {
             const int t = __shfl_up_sync(0xffffffffu, scan2, d);
             if (lane >= d) scan2 += t;
         }
         const int incl = scan2 & 0xffff;
-        const int nb = max(__popc(__ballot_sync(0xffffffffu, have && incl <= kSlots)), 1);
+        const int start = (scan2 >> 16) - ncoef_all;                     // this macroblock's first record in the batch's flat list
+        int nb = max(__popc(__ballot_sync(0xffffffffu, have && incl <= kSlots && lane < 16 && lane < mbw - mbx0)), 1);
+        uint32_t base_off = 0;                                           // arena index of flat record 0
+        bool any_records;
+        {
+            const uint32_t ne_mask = __ballot_sync(0xffffffffu, lane < nb && ncoef_all > 0);
+            any_records = ne_mask != 0;
+            const int f_ne = ne_mask ? __ffs(ne_mask) - 1 : 0;
+            base_off = __shfl_sync(0xffffffffu, rec.x - (uint32_t)start, f_ne);
+            const uint32_t gap = __ballot_sync(0xffffffffu, lane < nb && ncoef_all > 0 && rec.x - (uint32_t)start != base_off);
+            if (gap) nb = __ffs(gap) - 1;                                // (>= 1: the first macroblock with records defines base_off)
+        }
         const int base = incl - cnt;
         const int nslots = __shfl_sync(0xffffffffu, incl, nb - 1);
-        // request the next batch's records now; they arrive while this batch is processed
+        const int total = __shfl_sync(0xffffffffu, scan2, nb - 1) >> 16;
         rec_next = (idx + nb < mb_end) ? __ldg(reinterpret_cast<const uint4*>(pd.mb) + idx + nb) : make_uint4(0, 0, 0, 0);
 
-        // ---- 2. first macroblock's windows start loading now; they land while we dequantise and transform
-        {
-            const uint4 m0 = make_uint4(__shfl_sync(0xffffffffu, rec.x, 0), __shfl_sync(0xffffffffu, rec.y, 0),
-                                        __shfl_sync(0xffffffffu, rec.z, 0), __shfl_sync(0xffffffffu, rec.w, 0));
-            stage_windows<CF>(pd, batch, m0, mbx0, mby0, &ws.win[0][0][0], lane, lane_off_y, lane_off_c);
-            cp_async_commit();
+        // ---- 2. the first trip's records on their way (usually already requested during the previous batch), and the
+        // per-macroblock context of the dequantisation loop: {cbp | W row offset, first slot | qscale << 8 | shift << 16}
+        uint32_t c_nx = 0;
+        if (lane < total) c_nx = (base_off + (uint32_t)lane == pref_idx) ? pref_c : __ldg(pd.coef + base_off + lane);
+        if (lane < 16) {
+            const uint32_t ni = (rec.y & MP2V_MB_INTRA) ? 0u : 1u;
+            ws.mb_ctx[lane] = lane < nb ? make_uint2(MP2V_MB_CBP(rec.y) | (ni << 22), (uint32_t)base | (MP2V_MB_QSCALE(rec.y) << 8) | ((4u + ni) << 16))
+                                        : make_uint2(0u, 0u);            // (a record with a wrong column tag lands in slot 0 of the batch: garbage in, no fault)
         }
 
-        // ---- 3. zero the used slots (QFS[64] = {0}, mb_decoder.cpp:159), then dequantise + saturate + mismatch.
-        // All records of the batch are walked as ONE flat index space (lane = record), so sparse P/B
-        // macroblocks do not cost a loop trip each.
-        for (int i = lane; i < nslots * 8; i += 32)
-            reinterpret_cast<uint4*>(&ws.tile[i >> 3][0])[i & 7] = make_uint4(0, 0, 0, 0);
-        if (lane < kSlots) ws.bound[lane] = 0;
-        const int ncoef = lane < nb ? ncoef_all : 0;
-        const int total = __shfl_sync(0xffffffffu, scan2, nb - 1) >> 16;     // records of the nb macroblocks taken
-        const int start = (scan2 >> 16) - ncoef_all;                         // this lane's macroblock: first record index in the batch
-        const bool ne = ncoef > 0;
-        {   // compact list of the macroblocks that have records
-            const uint32_t ne_mask = __ballot_sync(0xffffffffu, ne);
-            if (ne) ws.mb_ctx[__popc(ne_mask & ((1u << lane) - 1u))] = make_uint4((uint32_t)start, rec.x, rec.y, (uint32_t)base);
+        // ---- 3. the first macroblocks' boxes start loading now; they land while we dequantise and transform
+        {
+            int ix = mbx0, iy = mby0;
+#pragma unroll
+            for (int b = 0; b < kWinBuf; b++) {
+                if (b < nb) issue_windows(__shfl_sync(0xffffffffu, rec.y, b), __shfl_sync(0xffffffffu, rec.z, b), __shfl_sync(0xffffffffu, rec.w, b), ix, iy, b);
+                if (++ix == mbw) { ix = 0; iy++; }
+            }
         }
+
+        // ---- 4. clear the used slots (QFS[64] = {0}, mb_decoder.cpp:159) and bounds; dequantise.  All records of the
+        // batch are ONE flat list (lane = record), so sparse P/B macroblocks do not cost a loop trip each.
+        for (int i = lane; i < nslots * 8; i += 32) reinterpret_cast<uint4*>(tile0)[(i >> 3) * (kTilePitch / 8) + (i & 7)] = make_uint4(0, 0, 0, 0);
+        if (lane < 7) reinterpret_cast<uint4*>(ws.bound)[lane] = make_uint4(0, 0, 0, 0);
         __syncwarp();
         uint32_t parity = 0;                 // bit s = parity of the coefficient sum of tile slot s
-        // Record f of the flat space belongs to the last macroblock whose first record index is <= f.  Per
-        // trip of 32 records the owners are found with two warp votes instead of a search per lane: the
-        // lanes that HOLD macroblocks mark where theirs starts inside the trip (REDUX.OR) and count the
-        // ones that started before it (ballot); a record lane then counts the marks up to itself.
-        // Software pipelined: the record of the NEXT trip is requested before the current one is
-        // processed, so its global-memory latency is off the critical path.
-        auto fetch = [&](int f0, uint32_t& c, uint4& ctx) {
-            const int rel = start - f0;
-            const uint32_t starts = __reduce_or_sync(0xffffffffu, (ne && (unsigned)rel < 32u) ? 1u << rel : 0u);
-            const int before = __popc(__ballot_sync(0xffffffffu, ne && rel < 0));
-            c = 0; ctx = make_uint4(0, 0, 0, 0);
-            if (f0 + lane < total) {
-                ctx = ws.mb_ctx[before + __popc(starts & (0xffffffffu >> (31 - lane))) - 1];
-                c = __ldg(pd.coef + ctx.y + (uint32_t)(f0 + lane - (int)ctx.x));
-            }
-        };
-        uint32_t c_nx;
-        uint4 ctx_nx;
-        fetch(0, c_nx, ctx_nx);
+        uint32_t col7 = 0;                   // bit s = column 7 of slot s holds a coefficient
+        const uint32_t mb0 = (uint32_t)mbx0 & 15u;
         for (int f0 = 0; f0 < total; f0 += 32) {
-            const int f = f0 + lane;
-            const uint32_t c = c_nx, m_bits = ctx_nx.z, slot0 = ctx_nx.w;
-            fetch(f0 + 32, c_nx, ctx_nx);
-            uint32_t pbit = 0;
-            if (f < total) {
-                const uint32_t cbp = MP2V_MB_CBP(m_bits);
+            const uint32_t c = c_nx;
+            const bool live = f0 + lane < total;
+            c_nx = (f0 + 32 + lane < total) ? __ldg(pd.coef + base_off + (uint32_t)(f0 + 32 + lane)) : 0u;      // next trip's record
+            uint32_t pbit = 0, c7bit = 0;
+            if (live) {
+                const uint2 ctx = ws.mb_ctx[((c >> 28) - mb0) & 15u];
+                const uint32_t cz = ctx.x, pk = ctx.y;
                 const int blk = (c >> 22) & 15;
-                if (cbp >> blk & 1) {        // a record naming an uncoded block is ignored (memory safety)
-                    const bool intra = (m_bits & MP2V_MB_INTRA) != 0;
-                    const int qs = MP2V_MB_QSCALE(m_bits);
-                    const int level = (int)(short)(c & 0xffffu);
-                    const int pos = (c >> 16) & 63;
-                    const int slot = (int)slot0 + __popc(cbp & ((1u << blk) - 1u));
-                    const bool raw = (c & MP2V_COEF_RAW) != 0, first = (c & MP2V_COEF_FIRST) != 0;
-                    const int w = s.W[(blk < 6 ? 0 : 2) + (intra ? 0 : 1)][pos];            // luma matrices for blocks 4,5 (:184-185)
-                    const int mag = abs(level);
-                    // intra (level*W*qs)>>4, non-intra ((2*level+1)*W*qs)>>5 (:142-143); "1s" is the latter with level 1 (:84)
-                    int val = ((intra ? mag : 2 * mag + 1) * w * qs) >> (intra ? 4 : 5);
-                    val = level < 0 ? -val : val;                                           // :144
-                    const int clamped = max(min((int)(short)val, 2047), -2048);             // int16 wrap, then clamp (:146)
-                    val = raw ? level : first ? val : clamped;                              // DC as is (:160); "1s" unclamped (:84)
-                    const int idx2 = s.scan[pos];                                           // pos 0 -> 0 for DC / "1s"
-                    const int av = abs(val);
-                    const int wsum = raw ? (av <= kMaxFirstCoef ? av * (int)s.bw[0] : kBoundWild)
-                                         : (av + 1) * (int)s.bw[idx2];   // +1: the mismatch toggle may change |F[63]| by one
-                    pbit = raw ? 0u : (uint32_t)(val & 1) << slot;                          // DC is not part of the sum (:160)
-                    ws.tile[slot][idx2] = (int16_t)val;
-                    atomicAdd(&ws.bound[slot], wsum);
-                }
+                const int slot = (int)(pk & 0xffu) + __popc(cz & 0xfffu & ((1u << blk) - 1u));      // <= kSlots even for a record naming an uncoded block
+                const int qs = (pk >> 8) & 0xff, sh = pk >> 16;
+                const int level = (int)(short)(c & 0xffffu);
+                const int pos = (c >> 16) & 63;
+                const bool raw = (c & MP2V_COEF_RAW) != 0, first_coef = (c & MP2V_COEF_FIRST) != 0;
+                const int w = (&s.W[0][0])[((CF > 1 && blk >= 6) ? 128 : 0) + ((cz >> 16) & 0x40) + pos];     // luma matrices for blocks 4,5 (:184-185)
+                const int mag = abs(level);
+                // intra (level*W*qs)>>4, non-intra ((2*level+1)*W*qs)>>5 (:142-143); "1s" is the latter with level 1 (:84)
+                int val = (((sh == 5 ? 2 * mag + 1 : mag) * w) * qs) >> sh;
+                val = level < 0 ? -val : val;                                              // :144
+                const int clamped = max(min((int)(short)val, 2047), -2048);                // int16 wrap, then clamp (:146)
+                val = raw ? level : first_coef ? val : clamped;                            // DC as is (:160); "1s" unclamped (:84)
+                const int idx2 = s.scan[pos];
+                const int av = abs(val), bwv = s.bwp[pos];
+                // weighted L1 norm for the saturation bound; +1: the mismatch toggle may change |F[63]| by one
+                const int wsum = raw ? (av <= kMaxFirstCoef ? av * bwv : kBoundWild) : (av + 1) * bwv;
+                pbit = raw ? 0u : (uint32_t)(val & 1) << slot;                             // DC is not part of the sum (:160)
+                c7bit = (idx2 & 7) == 7 ? 1u << slot : 0u;
+                tile0[slot * kTilePitch + idx2] = (int16_t)val;
+                atomicAdd(&ws.bound[slot], wsum);
             }
             parity ^= __reduce_xor_sync(0xffffffffu, pbit);
+            col7 |= __reduce_or_sync(0xffffffffu, c7bit);
+        }
+        // the next batch's first records (its list continues where this one ends, inside a slice): requested now, used
+        // after this batch's transform and output.  (Arenas are padded: 32 records past the last one stay inside the allocation.)
+        pref_idx = any_records ? base_off + (uint32_t)total + (uint32_t)lane : 0xffffffffu;
+        if (any_records) pref_c = __ldg(pd.coef + pref_idx);
+        __syncwarp();
+        // qfs[63] ^= (sum & 1) ^ 1 (:150-152) -- only where column 7 already holds something (see the header)
+        if (lane < nslots && (col7 >> lane & 1u)) tile0[lane * kTilePitch + 63] ^= (int16_t)(((parity >> lane) & 1u) ^ 1u);
+
+        // ---- 5. inverse transform; arithmetic variant for the whole batch from the per-block bounds (a toggled-in F[63] = 1 counts too)
+        const int bnd = lane < nslots ? ws.bound[lane] + (int)s.bwp[63] : 0;      // scan position 63 is tile index 63 in both scans
+        const bool p1_exact = __any_sync(0xffffffffu, bnd >= kBoundWild);
+        const bool p2_exact = __any_sync(0xffffffffu, bnd > kBoundLimit);
+        __syncwarp();
+        // pass 1: one lane per column, in place; the transform runs across the vector index k (idct_sse2.hpp:98)
+        // (no predication: the lanes of a last, partly filled trip transform whatever the tile rows behind the used
+        // slots hold -- every trip stays inside the tile's kTileRows -- and nobody reads those rows)
+        for (int i0 = 0; i0 < nslots * 8; i0 += 32) {
+            const int i = i0 + lane;
+            int16_t* p = tile0 + (i >> 3) * kTilePitch + (i & 7);
+            int x[8];
+#pragma unroll
+            for (int k = 0; k < 8; k++) x[k] = (int)p[k * 8];
+            if (p1_exact) idct_lane<0>(x[0], x[1], x[2], x[3], x[4], x[5], x[6], x[7]);
+            else if (p2_exact) idct_lane<1>(x[0], x[1], x[2], x[3], x[4], x[5], x[6], x[7]);
+            else idct_lane<2>(x[0], x[1], x[2], x[3], x[4], x[5], x[6], x[7]);     // the bound that clears pass 2 also bounds every pass-1 output
+#pragma unroll
+            for (int k = 0; k < 8; k++) p[k * 8] = (int16_t)x[k];
         }
         __syncwarp();
-        // qfs[63] ^= (sum & 1) ^ 1 for every coded block (:150-152)
-        if (lane < nslots) ws.tile[lane][63] ^= (int16_t)(((parity >> lane) & 1u) ^ 1u);
-        __syncwarp();
-
-        // ---- 4. IDCT, four lanes per coded block, 8 blocks per round; arithmetic variant chosen per round
-        for (int r0 = 0; r0 < nslots; r0 += 8) {
-            const int slot = r0 + (lane >> 2);
-            const bool active = slot < nslots;
-            const int bnd = active ? ws.bound[slot] + (int)s.bw[63] : 0;    // a toggled-in F[63] = 1 counts too
-            const bool p1_exact = __any_sync(0xffffffffu, bnd >= kBoundWild);
-            const bool p2_exact = __any_sync(0xffffffffu, bnd > kBoundLimit);
-            idct_round(&ws.tile[active ? slot : 0][0], lane & 3, active, p1_exact, p2_exact);
+        // pass 2: one lane per row of the transposed block (transpose_8x8_sse2 is the addressing); output r of
+        // row k is res[r][k], shifted down by 6 (idct_sse2.hpp:100-107)
+        for (int i0 = 0; i0 < nslots * 8; i0 += 32) {
+            const int i = i0 + lane;
+            int16_t* t = tile0 + (i >> 3) * kTilePitch;
+            const int k = i & 7;
+            const uint4 q = *reinterpret_cast<const uint4*>(t + k * 8);      // a quarter warp reads the 128 contiguous bytes of one block
+            int x[8] = {(int)(short)(q.x & 0xffffu), (int)q.x >> 16, (int)(short)(q.y & 0xffffu), (int)q.y >> 16,
+                        (int)(short)(q.z & 0xffffu), (int)q.z >> 16, (int)(short)(q.w & 0xffffu), (int)q.w >> 16};
+            __syncwarp();      // the eight rows of a block sit in one trip: all are in registers before any is overwritten
+            if (p2_exact) idct_lane<0>(x[0], x[1], x[2], x[3], x[4], x[5], x[6], x[7]);
+            else idct_lane<2>(x[0], x[1], x[2], x[3], x[4], x[5], x[6], x[7]);
+#pragma unroll
+            for (int r = 0; r < 8; r++) t[r * 8 + k] = (int16_t)(x[r] >> 6);      // _mm_srai_epi16(., 6)
         }
         __syncwarp();
 
-        // ---- 5. prediction + residual + clip + store; with two window buffers the next macroblock's
-        // windows load while this one is computed
+        // ---- 6. prediction + residual + clip + store, macroblock by macroblock
         int mbx = mbx0, mby = mby0;
         for (int mi = 0; mi < nb; mi++) {
-            const uint4 m = make_uint4(__shfl_sync(0xffffffffu, rec.x, mi), __shfl_sync(0xffffffffu, rec.y, mi),
-                                       __shfl_sync(0xffffffffu, rec.z, mi), __shfl_sync(0xffffffffu, rec.w, mi));
+            const uint32_t m_y = __shfl_sync(0xffffffffu, rec.y, mi), m_z = __shfl_sync(0xffffffffu, rec.z, mi), m_w = __shfl_sync(0xffffffffu, rec.w, mi);
             const int mbase = __shfl_sync(0xffffffffu, base, mi);
-            if (kWinBuf == 2) {
-                if (mi + 1 < nb) {
-                    const uint4 mn = make_uint4(__shfl_sync(0xffffffffu, rec.x, mi + 1), __shfl_sync(0xffffffffu, rec.y, mi + 1),
-                                                __shfl_sync(0xffffffffu, rec.z, mi + 1), __shfl_sync(0xffffffffu, rec.w, mi + 1));
-                    const int nbx = mbx + 1 == mbw ? 0 : mbx + 1, nby = mbx + 1 == mbw ? mby + 1 : mby;
-                    stage_windows<CF>(pd, batch, mn, nbx, nby, &ws.win[(mi + 1) & (kWinBuf - 1)][0][0], lane, lane_off_y, lane_off_c);
-                }
-                cp_async_commit();
-                cp_async_wait<1>();      // everything but the group just committed has landed: this macroblock's windows
-            } else {
-                if (mi > 0) { stage_windows<CF>(pd, batch, m, mbx, mby, &ws.win[0][0][0], lane, lane_off_y, lane_off_c); cp_async_commit(); }
-                cp_async_wait<0>();
+            const uint32_t cbp = MP2V_MB_CBP(m_y);
+            const bool intra = (m_y & MP2V_MB_INTRA) != 0;
+            const int buf = mi & (kWinBuf - 1);
+            uint32_t pred[NT][NW];
+#pragma unroll
+            for (int t = 0; t < NT; t++) {
+#pragma unroll
+                for (int j = 0; j < NW; j++) pred[t][j] = 0;
             }
+            if (!intra) {
+                mbar_wait(&ws.mbar[buf], (wphase >> buf) & 1u);
+                wphase ^= 1u << buf;
+                const int odd8 = (mbx & 1) << 3;      // (mbx * 8) & 15 for the 8-pixel-wide chroma of 4:2:0 / 4:2:2
+                bool have_pred = false;
+#pragma unroll
+                for (int d = 0; d < 2; d++) {
+                    if (!(m_y & (d ? MP2V_MB_BWD : MP2V_MB_FWD))) continue;      // warp-uniform
+                    const uint32_t mvw = d ? m_w : m_z;
+                    const int mvx = (int)(short)(mvw & 0xffffu), mvy = (int)mvw >> 16;
+#pragma unroll
+                    for (int t = 0; t < NT; t++) {
+                        // this unit's vector: luma as coded, chroma floor-halved where the format subsamples (mb_decoder.cpp:198-206)
+                        const int cx = (u_chroma[t] && CF < 3) ? mvx >> 1 : mvx, cy = (u_chroma[t] && CF < 2) ? mvy >> 1 : mvy;
+                        const int o = ((((u_chroma[t] && CF < 3) ? odd8 : 0) + (cx >> 1)) & 15) + u_xoff[t];
+                        uint32_t q[NW];
+                        pred_unit<NW>(&ws.win[buf][d][0] + u_woff[t], o, cx & 1, cy & 1, q);
+                        if (have_pred) {
+#pragma unroll
+                            for (int j = 0; j < NW; j++) pred[t][j] = avg4(q[j], pred[t][j]);      // avg(backward, forward) (mb_decoder.cpp:240-249)
+                        } else {
+#pragma unroll
+                            for (int j = 0; j < NW; j++) pred[t][j] = q[j];
+                        }
+                    }
+                    have_pred = true;
+                }
+            }
+            __syncwarp();      // every lane has read this buffer: the boxes of a later macroblock may overwrite it
+            if (mi + kWinBuf < nb) {
+                int ix = mbx, iy = mby;
+#pragma unroll
+                for (int a = 0; a < kWinBuf; a++) { if (++ix == mbw) { ix = 0; iy++; } }
+                const int nx = mi + kWinBuf;
+                issue_windows(__shfl_sync(0xffffffffu, rec.y, nx), __shfl_sync(0xffffffffu, rec.z, nx), __shfl_sync(0xffffffffu, rec.w, nx), ix, iy, buf);
+            }
+            const bool row_end = mbx + 1 == mbw;
+#pragma unroll
+            for (int t = 0; t < NT; t++) {
+                add_residual(ws.tile, mbase, cbp, u_below[t], u_blk[t], u_rr8[t], intra, pred[t][0], pred[t][1]);
+                if (CF == 1) {
+                    // whole rows: the right-hand block too for luma rows (the chroma lanes drop their upper two words)
+                    if (lane < 16) {
+                        add_residual(ws.tile, mbase, cbp, u_below[t] * 2u + 1u, u_blk[t] + 1, u_rr8[t], intra, pred[t][2], pred[t][3]);
+                        *reinterpret_cast<uint4*>(u_dst[t]) = make_uint4(pred[t][0], pred[t][1], pred[t][2], pred[t][3]);
+                    } else {
+                        *reinterpret_cast<uint2*>(u_dst[t]) = make_uint2(pred[t][0], pred[t][1]);
+                    }
+                } else {
+                    *reinterpret_cast<uint2*>(u_dst[t]) = make_uint2(pred[t][0], pred[t][1]);
+                }
+                u_dst[t] += row_end ? u_wrap[t] : u_adv[t];      // next macroblock: one to the right, or the first of the next macroblock row
+            }
+            if (row_end) { mbx = 0; mby++; } else mbx++;
             __syncwarp();
-            reconstruct_mb<CF>(pd, batch, m, mbx, mby, mbase, &ws.win[mi & (kWinBuf - 1)][0][0], ws.tile, lane);
-            __syncwarp();
-            if (++mbx == mbw) { mbx = 0; mby++; }
         }
-        cp_async_wait<0>();
         first += nb;
         mbx0 = mbx; mby0 = mby;
     }
 }
 
-}  // namespace mp2v
-
-namespace mp2v {
-#include "recon_kernel3.cuh"
-}
-
-namespace mp2v {
-
-// Which cut of the kernel launches: recon_kernel3 unless MP2V_RECON_KERNEL=2 (development A/B switch).
-static int kernel_generation() {
-    static const int gen = [] { const char* v = getenv("MP2V_RECON_KERNEL"); return (v && atoi(v) == 2) ? 2 : 3; }();
-    return gen;
-}
-
 template <int CF>
 static cudaError_t prepare_kernel3() {
-    return cudaFuncSetAttribute(v3::recon_kernel3<CF>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(sizeof(v3::cta_smem_t<CF>) + 128));
+    return cudaFuncSetAttribute(recon_kernel3<CF>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(sizeof(cta_smem_t<CF>) + 128));
 }
 
 // __constant__ symbols and function attributes are per device: initialise each device once (any thread)
@@ -734,11 +635,11 @@ cudaError_t make_frame_tmaps(int chroma_format, uint8_t* frames, const mp2v_fram
     }();
     if (!encode) return cudaErrorNotSupported;
     if (chroma_format < 1 || chroma_format > 3 || !out || n_frames < 1) return cudaErrorInvalidValue;
-    const cuuint32_t cbox_h = (chroma_format == 1 ? 8 : 16) + 1;      // v3::geo_t: every box is kBoxW = 32 bytes wide
+    const cuuint32_t cbox_h = (chroma_format == 1 ? 8 : 16) + 1;      // geo_t: every box is kBoxW = 32 bytes wide
     for (int p = 0; p < 3; p++) {
         const cuuint64_t gdim[3] = {(cuuint64_t)lay.width[p], (cuuint64_t)lay.height[p], (cuuint64_t)n_frames};
         const cuuint64_t gstride[2] = {(cuuint64_t)lay.stride[p], (cuuint64_t)frame_alloc};      // bytes, dimensions 1 and 2
-        const cuuint32_t box[3] = {(cuuint32_t)v3::kBoxW, p == 0 ? 17u : cbox_h, 1u};
+        const cuuint32_t box[3] = {(cuuint32_t)kBoxW, p == 0 ? 17u : cbox_h, 1u};
         const cuuint32_t estr[3] = {1, 1, 1};
         const CUresult r = encode(&out->plane[p], CU_TENSOR_MAP_DATA_TYPE_UINT8, 3, frames + lay.plane_offset[p], gdim, gstride, box, estr,
                                   CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_NONE, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
@@ -752,37 +653,20 @@ cudaError_t launch_recon(int chroma_format, const batch_desc_t& batch, const rec
     if (e != cudaSuccess) return e;
     if (batch.n_pics < 1 || batch.n_pics > kMaxBatch) return cudaErrorInvalidValue;
     const dim3 grid((unsigned)(batch.n_pics * batch.ctas_per_pic)), block(kCtaThreads);
-    if (kernel_generation() == 2) {
-        switch (chroma_format) {
-            case 1: recon_kernel<1><<<grid, block, 0, stream>>>(batch); break;
-            case 2: recon_kernel<2><<<grid, block, 0, stream>>>(batch); break;
-            case 3: recon_kernel<3><<<grid, block, 0, stream>>>(batch); break;
-            default: return cudaErrorInvalidValue;
-        }
-    } else {
-        switch (chroma_format) {
-            case 1: v3::recon_kernel3<1><<<grid, block, sizeof(v3::cta_smem_t<1>) + 128, stream>>>(batch, tm); break;
-            case 2: v3::recon_kernel3<2><<<grid, block, sizeof(v3::cta_smem_t<2>) + 128, stream>>>(batch, tm); break;
-            case 3: v3::recon_kernel3<3><<<grid, block, sizeof(v3::cta_smem_t<3>) + 128, stream>>>(batch, tm); break;
-            default: return cudaErrorInvalidValue;
-        }
+    switch (chroma_format) {
+        case 1: recon_kernel3<1><<<grid, block, sizeof(cta_smem_t<1>) + 128, stream>>>(batch, tm); break;
+        case 2: recon_kernel3<2><<<grid, block, sizeof(cta_smem_t<2>) + 128, stream>>>(batch, tm); break;
+        case 3: recon_kernel3<3><<<grid, block, sizeof(cta_smem_t<3>) + 128, stream>>>(batch, tm); break;
+        default: return cudaErrorInvalidValue;
     }
     return cudaGetLastError();
 }
 
 cudaError_t recon_kernel_attributes(int chroma_format, cudaFuncAttributes* out) {
-    if (kernel_generation() == 2) {
-        switch (chroma_format) {
-            case 1: return cudaFuncGetAttributes(out, recon_kernel<1>);
-            case 2: return cudaFuncGetAttributes(out, recon_kernel<2>);
-            case 3: return cudaFuncGetAttributes(out, recon_kernel<3>);
-            default: return cudaErrorInvalidValue;
-        }
-    }
     switch (chroma_format) {
-        case 1: return cudaFuncGetAttributes(out, v3::recon_kernel3<1>);
-        case 2: return cudaFuncGetAttributes(out, v3::recon_kernel3<2>);
-        case 3: return cudaFuncGetAttributes(out, v3::recon_kernel3<3>);
+        case 1: return cudaFuncGetAttributes(out, recon_kernel3<1>);
+        case 2: return cudaFuncGetAttributes(out, recon_kernel3<2>);
+        case 3: return cudaFuncGetAttributes(out, recon_kernel3<3>);
         default: return cudaErrorInvalidValue;
     }
 }

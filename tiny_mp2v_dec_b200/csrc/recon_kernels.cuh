@@ -49,7 +49,7 @@ struct batch_desc_t {
 };
 
 // TMA descriptors of the frame pool, one per plane: a [frame][row][pixel] tensor of bytes whose boxes are the
-// (w + 1) x (h + 1) reference windows of one macroblock (recon_kernel3.cuh)
+// (w + 1) x (h + 1) reference windows of one macroblock (recon_kernels.cu)
 struct alignas(64) recon_tmaps_t { CUtensorMap plane[3]; };
 // frames: address of frame 0 plane 0; frames lie frame_alloc bytes apart.  Fails (cudaErrorNotSupported /
 // cudaErrorInvalidValue) when the driver cannot encode the maps.

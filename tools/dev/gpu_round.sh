@@ -8,7 +8,6 @@ timeout 300 python __graft_entry__.py smoke > gpurun_out/${tag}_smoke.log 2>&1; 
 timeout 600 python -m pytest tests -m gpu -q --tb=line -p no:cacheprovider > gpurun_out/${tag}_tests.log 2>&1; echo "tests rc=$?" | tee -a gpurun_out/${tag}_tests.log
 tail -5 gpurun_out/${tag}_tests.log
 timeout 300 python tools/dev/quick_bench.py --all > gpurun_out/${tag}_qb.log 2>&1; echo "qb rc=$?"; cat gpurun_out/${tag}_qb.log
-MP2V_RECON_KERNEL=2 timeout 300 python tools/dev/quick_bench.py > gpurun_out/${tag}_qb_k2.log 2>&1; cat gpurun_out/${tag}_qb_k2.log
 for v in "$@"; do
   n=$(basename $v .so)
   MP2V_B200_LIB=$PWD/tiny_mp2v_dec_b200/_lib/variants/$n.so timeout 300 python tools/dev/quick_bench.py > gpurun_out/${tag}_qb_$n.log 2>&1; echo "== variant $n"; cat gpurun_out/${tag}_qb_$n.log

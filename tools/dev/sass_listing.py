@@ -13,9 +13,9 @@ for l in open(path).read().split("\n"):
         continue
     m = re.search(r'//## File ".*?([\w\.]+)", line (\d+)(.*)', l)
     if m:
-        f = m.group(1).replace("recon_kernel3.cuh", "k3").replace("recon_kernels.cu", "k2")
+        f = m.group(1).replace("recon_kernels.cu", "k")
         inl = re.findall(r'inlined at ".*?([\w\.]+)", line (\d+)', m.group(3))
-        cur = "%s:%s" % (f, m.group(2)) + "".join(" <%s:%s" % (a.replace("recon_kernel3.cuh", "k3").replace("recon_kernels.cu", "k2"), b) for a, b in inl)
+        cur = "%s:%s" % (f, m.group(2)) + "".join(" <%s:%s" % (a.replace("recon_kernels.cu", "k"), b) for a, b in inl)
         continue
     m = re.match(r"\s+/\*([0-9a-f]{4,5})\*/\s+(.*?);", l)
     if m:
