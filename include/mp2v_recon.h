@@ -59,7 +59,11 @@ enum {
 /* ---- per-macroblock record (16 bytes) --------------------------------------------------------
  * One per macroblock in raster order (skipped macroblocks included, resolved by the host to a
  * prediction-only record, mb_decoder.cpp:541-550).
- *   coef_off : index of this macroblock's first mp2v_coef_t in the picture's coefficient arena
+ *   coef_off : [30:0] index of this macroblock's first mp2v_coef_t in the picture's coefficient arena
+ *              [31]   field_dct  dct_type = 1 (frame pictures with frame_pred_frame_dct = 0): the luma blocks
+ *                                hold the two fields -- blocks 0,1 the even rows of the macroblock, 2,3 the
+ *                                odd rows -- and so do the chroma blocks of 4:2:2 / 4:4:4
+ *                                (mb_decoder.cpp:172-195; 4:2:0 chroma is always frame organised)
  *   bits     : [ 9: 0] n_coef   number of coefficient records (<= 12*64)
  *              [16:10] qscale   quantiser_scale 1..112 after q_scale_type mapping
  *                               (decoder.cpp:140-145, mb_decoder.cpp:555-563)
@@ -79,6 +83,8 @@ typedef struct mp2v_mb_info {
     int16_t  mv[2][2];
 } mp2v_mb_info_t;
 
+#define MP2V_MB_FIELD_DCT   (1u << 31)                       /* in coef_off */
+#define MP2V_MB_COEF_OFF(o) ((o) & 0x7fffffffu)
 #define MP2V_MB_NCOEF(b)   ((b) & 0x3ffu)
 #define MP2V_MB_QSCALE(b)  (((b) >> 10) & 0x7fu)
 #define MP2V_MB_CBP(b)     (((b) >> 17) & 0xfffu)
@@ -213,7 +219,8 @@ typedef struct mp2v_pic_syntax {
     int32_t intra_dc_precision;    /* 0..3                                                        */
     int32_t q_scale_type;
     int32_t intra_vlc_format;
-    int32_t reserved;
+    int32_t field_dct_syntax;      /* 1: frame_pred_frame_dct = 0 -- macroblock_modes carry frame_motion_type (only
+                                      frame-based prediction is accepted) and dct_type (mb_decoder.cpp:349-360)   */
 } mp2v_pic_syntax_t;
 typedef struct mp2v_slice_ref {
     const uint8_t* payload;        /* first byte after the 4-byte slice start code               */

@@ -13,6 +13,12 @@ CASES = {
     "texture420": (640, 368, 1, dict(seed=113, mode=2, n_gops=2, gop_n=9, gop_m=3, pct_intra_in_pb=3)),
     "texture444": (352, 288, 3, dict(seed=114, mode=2, n_gops=1, gop_n=7, gop_m=3, q_scale_type=1, alternate_scan=1)),
     "cif420_userdata": (352, 288, 1, dict(seed=115, n_gops=2, gop_n=6, gop_m=3, user_data_bytes=37)),
+    # field DCT: frame pictures with frame_pred_frame_dct = 0, frame-based prediction, dct_type = 1 in about half of the
+    # coded macroblocks.  The reference decodes these for 4:2:0 and 4:2:2 (mb_decoder.cpp:172-189); its 4:4:4 path writes
+    # outside the macroblock (:194-195, heap corruption at the bottom row), so there is no 4:4:4 entry here
+    "fielddct420_ipb": (352, 288, 1, dict(seed=116, n_gops=2, gop_n=9, gop_m=3, pct_field_dct=50)),
+    "fielddct422_altscan": (352, 288, 2, dict(seed=117, n_gops=2, gop_n=9, gop_m=3, pct_field_dct=60, alternate_scan=1, q_scale_type=1)),
+    "fielddct420_texture": (640, 368, 1, dict(seed=118, mode=2, n_gops=2, gop_n=9, gop_m=3, pct_intra_in_pb=3, pct_field_dct=40)),
     "tall420_vpos_ext": (32, 2816, 1, dict(seed=112, gop_n=4, gop_m=3)),
     "hd420_ipb": (1920, 1088, 1, dict(seed=110, gop_n=7, gop_m=3)),
     "hd422_ipb": (1920, 1088, 2, dict(seed=111, gop_n=4, gop_m=3)),

@@ -3,7 +3,7 @@ macroblock record and every coefficient record must come out exactly as it was e
 import numpy as np
 import pytest
 
-from tiny_mp2v_dec_b200.abi import mb_ncoef
+from tiny_mp2v_dec_b200.abi import MB_FIELD_DCT, mb_coef_off, mb_ncoef
 from tiny_mp2v_dec_b200.decoder import parse_stream
 from tiny_mp2v_dec_b200.streamgen import Stream
 
@@ -38,8 +38,9 @@ def check_stream(s, threads):
         assert np.array_equal(got.mb["mv"], want.mb["mv"]), "motion vectors differ in picture %d" % i
         # coefficient offsets differ (chunked arena vs dense), the records must not
         n_coef = mb_ncoef(got.mb["bits"]).astype(np.int64)
-        idx_g = np.repeat(got.mb["coef_off"].astype(np.int64), n_coef) + (np.arange(n_coef.sum()) - np.repeat(np.cumsum(n_coef) - n_coef, n_coef))
-        idx_w = np.repeat(want.mb["coef_off"].astype(np.int64), n_coef) + (np.arange(n_coef.sum()) - np.repeat(np.cumsum(n_coef) - n_coef, n_coef))
+        assert np.array_equal(got.mb["coef_off"] & MB_FIELD_DCT, want.mb["coef_off"] & MB_FIELD_DCT), "dct_type differs in picture %d" % i
+        idx_g = np.repeat(mb_coef_off(got.mb["coef_off"]).astype(np.int64), n_coef) + (np.arange(n_coef.sum()) - np.repeat(np.cumsum(n_coef) - n_coef, n_coef))
+        idx_w = np.repeat(mb_coef_off(want.mb["coef_off"]).astype(np.int64), n_coef) + (np.arange(n_coef.sum()) - np.repeat(np.cumsum(n_coef) - n_coef, n_coef))
         assert np.array_equal(got.coef[idx_g], want.coef[idx_w]), "coefficient records differ in picture %d" % i
 
 

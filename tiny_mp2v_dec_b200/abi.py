@@ -12,6 +12,12 @@ mb_dtype = np.dtype([("coef_off", "<u4"), ("bits", "<u4"), ("mv", "<i2", (2, 2))
 assert mb_dtype.itemsize == 16 and C.sizeof(MbInfo) == 16
 
 MB_INTRA, MB_FWD, MB_BWD = 1 << 29, 1 << 30, 1 << 31
+MB_FIELD_DCT = 1 << 31      # in coef_off
+
+
+def mb_coef_off(coef_off):
+    return coef_off & 0x7fffffff
+
 COEF_RAW, COEF_FIRST = 1 << 26, 1 << 27
 
 
@@ -57,7 +63,7 @@ class ReconStats(C.Structure):
 
 class PicSyntax(C.Structure):
     _fields_ = [("f_code", (C.c_int32 * 2) * 2), ("intra_dc_precision", C.c_int32), ("q_scale_type", C.c_int32),
-                ("intra_vlc_format", C.c_int32), ("reserved", C.c_int32)]
+                ("intra_vlc_format", C.c_int32), ("field_dct_syntax", C.c_int32)]
 
 
 class SliceRef(C.Structure):

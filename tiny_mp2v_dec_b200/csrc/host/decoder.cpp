@@ -188,12 +188,13 @@ void pipeline_t::feeder() {
         pp.dst_frame = t.dst; pp.l0_frame = t.l0; pp.l1_frame = t.l1;
         if (sh->stream_mode) {
             // stream-resident device parsing: the coded bytes are already on the device; the picture is its slices' offsets
-            if (!picture_in_envelope(info)) { sh->fail("only progressive frame pictures with frame prediction are supported (the reference's envelope)"); break; }
+            if (!picture_in_envelope(info)) { sh->fail("only frame pictures without concealment vectors are supported (the reference's envelope)"); break; }
             mp2v_pic_syntax_t sy{};
             for (int a = 0; a < 2; a++) for (int b = 0; b < 2; b++) sy.f_code[a][b] = info.f_code[a][b];
             sy.intra_dc_precision = info.intra_dc_precision;
             sy.q_scale_type = info.q_scale_type;
             sy.intra_vlc_format = info.intra_vlc_format;
+            sy.field_dct_syntax = info.frame_pred_frame_dct ? 0 : 1;
             slice_offsets.clear();
             for (const slice_ref_t& sr : t.src->slices) slice_offsets.push_back((uint32_t)(sr.payload - 4 - sh->stream_base));
             if (mp2v_recon_submit_stream_picture(recon, t.rp, &sy, slice_offsets.data(), (int)slice_offsets.size()) != MP2V_OK) {
@@ -213,7 +214,7 @@ void pipeline_t::feeder() {
         }
         if (sh->opt.gpu_vlc) {
             // device-side parsing: a worker stages the coded slices (one job per picture), submission stays in coded order
-            if (!picture_in_envelope(info)) { sh->fail("only progressive frame pictures with frame prediction are supported (the reference's envelope)"); break; }
+            if (!picture_in_envelope(info)) { sh->fail("only frame pictures without concealment vectors are supported (the reference's envelope)"); break; }
             t.n_jobs = 1;
             t.ts_queued = sh->now_ms();
             t.remaining.store(1);
@@ -380,6 +381,7 @@ void worker_main(shared_t* sh) {
                     sy.intra_dc_precision = info.intra_dc_precision;
                     sy.q_scale_type = info.q_scale_type;
                     sy.intra_vlc_format = info.intra_vlc_format;
+                    sy.field_dct_syntax = info.frame_pred_frame_dct ? 0 : 1;
                     std::vector<mp2v_slice_ref_t>& refs = slice_refs;
                     refs.clear();
                     for (const slice_ref_t& sr : t->src->slices) refs.push_back({sr.payload, sr.bytes, sr.code});

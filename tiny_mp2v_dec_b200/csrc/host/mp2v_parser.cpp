@@ -149,11 +149,12 @@ slice_syntax_t make_slice_syntax(const sequence_info_t& seq, const picture_info_
     sx.chroma_format = seq.chroma_format;
     sx.vertical_size = seq.vertical_size;
     sx.mbw = mbw; sx.mbh = mbh;
+    sx.field_dct_syntax = pic.frame_pred_frame_dct ? 0 : 1;
     return sx;
 }
 
 bool picture_in_envelope(const picture_info_t& pic) {
-    return pic.picture_structure == 3 && pic.frame_pred_frame_dct && !pic.concealment_motion_vectors;
+    return pic.picture_structure == 3 && !pic.concealment_motion_vectors;      // (frame_pred_frame_dct = 0: field DCT is decoded, field prediction is a slice error)
 }
 
 // Host side of parse_slice_core: the slice is parsed into the calling thread's scratch row, then

@@ -28,11 +28,12 @@ struct slice_syntax_t {
     int32_t chroma_format;            // 1, 2, 3
     int32_t vertical_size;            // > 2800: slices carry slice_vertical_position_extension
     int32_t mbw, mbh;
+    int32_t field_dct_syntax;         // frame_pred_frame_dct = 0: macroblock_modes carry frame_motion_type and dct_type
 };
 
 enum slice_error_t {
     SLICE_OK = 0, SLICE_ERR_ROW, SLICE_ERR_MBA, SLICE_ERR_ADDRESS, SLICE_ERR_SKIP_IN_I, SLICE_ERR_MBTYPE, SLICE_ERR_FCODE,
-    SLICE_ERR_MOTION, SLICE_ERR_CBP, SLICE_ERR_COEF, SLICE_ERR_CAPACITY, SLICE_ERR_MV_RANGE
+    SLICE_ERR_MOTION, SLICE_ERR_CBP, SLICE_ERR_COEF, SLICE_ERR_CAPACITY, SLICE_ERR_MV_RANGE, SLICE_ERR_MOTION_TYPE
 };
 
 inline const char* slice_error_string(int e) {
@@ -49,6 +50,7 @@ inline const char* slice_error_string(int e) {
         case SLICE_ERR_COEF: return "bad DCT coefficient syntax";
         case SLICE_ERR_CAPACITY: return "coefficient arena exhausted";
         case SLICE_ERR_MV_RANGE: return "motion vector points outside the reference frame";
+        case SLICE_ERR_MOTION_TYPE: return "field prediction / dual prime in a frame picture (only frame-based prediction is supported)";
         default: return "slice parse error";
     }
 }
@@ -359,12 +361,22 @@ MP2V_HDI int parse_slice_core(const uint8_t* payload, int slice_start_code, cons
             dc_pred.reset(dc_reset);
         }
         mp2v_mb_info_t& r = row[++mbx];
-        // ---- macroblock_type (no refill: the last increment code took at most 11 of the 33 bits, type and quantiser 11 more)
+        // ---- macroblock_type (no refill: the last increment code took at most 11 of the 33 bits, type, modes and quantiser 14 more)
         const vlc_entry_t te = T.mbtype[pct].look(br.peek(6));
         if (!te.len) { err = SLICE_ERR_MBTYPE; break; }
         br.skip(te.len);
         const int type = te.val;
         const bool intra = type & 0x02, fwd = type & 0x10, bwd = type & 0x08, pattern = type & 0x04;
+        // frame pictures with frame_pred_frame_dct = 0 (parse_modes, mb_decoder.cpp:347-360): frame_motion_type, dct_type
+        uint32_t field_dct = 0;
+        if (sx.field_dct_syntax) {
+            if (fwd || bwd) {
+                const uint32_t fmt = br.peek(2);
+                br.skip(2);
+                if (fmt != 2u) { err = SLICE_ERR_MOTION_TYPE; break; }       // 1 field-based, 3 dual prime (the reference: TODO)
+            }
+            if (intra || pattern) { field_dct = br.peek(1) ? MP2V_MB_FIELD_DCT : 0u; br.skip(1); }
+        }
         if (type & 0x20) { qscale = quantiser_scale_of((int)br.peek(5), sx.q_scale_type); br.skip(5); }
         // ---- motion vectors (frame prediction: one vector per direction)
         int mv[2][2] = {{0, 0}, {0, 0}};
@@ -412,7 +424,7 @@ MP2V_HDI int parse_slice_core(const uint8_t* payload, int slice_start_code, cons
                     if ((flags & (s ? MP2V_MB_BWD : MP2V_MB_FWD)) && !mv_inside(mbx, mb_row, mv[s][0], mv[s][1], mbw * 16, sx.mbh * 16)) err = SLICE_ERR_MV_RANGE;
             if (err) break;
         }
-        r.coef_off = coef_off_base + off;
+        r.coef_off = (coef_off_base + off) | field_dct;
         r.bits = MP2V_MB_BITS((uint32_t)(out - out_base) - off, qscale, cbp, flags);
         for (int s = 0; s < 2; s++) for (int t = 0; t < 2; t++) r.mv[s][t] = (int16_t)(intra ? 0 : mv[s][t]);
         prev_dirs = flags & (MP2V_MB_FWD | MP2V_MB_BWD);

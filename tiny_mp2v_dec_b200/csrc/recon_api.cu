@@ -616,7 +616,7 @@ static int account_and_validate(mp2v_recon* ctx, slot_t& s, bool validate, std::
         coded += (uint64_t)__builtin_popcount(MP2V_MB_CBP(bits) & cbp_mask);
         if (!validate) continue;
         if (MP2V_MB_CBP(bits) & ~cbp_mask) return bad(MP2V_ERR_RANGE, "coded_block_pattern names a block this chroma format does not have");
-        if ((uint64_t)r.coef_off + MP2V_MB_NCOEF(bits) > pp.n_coef) return bad(MP2V_ERR_RANGE, "macroblock coefficient range outside the arena");
+        if ((uint64_t)MP2V_MB_COEF_OFF(r.coef_off) + MP2V_MB_NCOEF(bits) > pp.n_coef) return bad(MP2V_ERR_RANGE, "macroblock coefficient range outside the arena");
         if (!(bits & MP2V_MB_INTRA)) {
             if (ndir == 0) return bad(MP2V_ERR_RANGE, "non-intra macroblock without a prediction direction");
             const int mbx = m % ctx->mbw, mby = m / ctx->mbw;
@@ -806,6 +806,7 @@ extern "C" MP2V_API int mp2v_recon_stage_slices(mp2v_recon_t* ctx, mp2v_picture_
     hdr.sx.chroma_format = ctx->cfg.chroma_format;
     hdr.sx.vertical_size = ctx->cfg.height;            // only compared with 2800 (slice_vertical_position_extension)
     hdr.sx.mbw = ctx->mbw; hdr.sx.mbh = ctx->mbh;
+    hdr.sx.field_dct_syntax = syntax->field_dct_syntax != 0;
     hdr.n_slices = (uint32_t)n_slices;
     hdr.slice_region = ctx->slice_region;
     hdr.data_off = (uint32_t)((kVlcParamsBytes + sizeof(vlc_pic_header_t) + (size_t)ctx->mbh * sizeof(vlc_slice_t) + 15) & ~(size_t)15);
@@ -1014,6 +1015,7 @@ extern "C" MP2V_API int mp2v_recon_submit_stream_picture(mp2v_recon_t* ctx, mp2v
     d.sx.chroma_format = ctx->cfg.chroma_format;
     d.sx.vertical_size = ctx->cfg.height;                 // only compared with 2800 (slice_vertical_position_extension)
     d.sx.mbw = ctx->mbw; d.sx.mbh = ctx->mbh;
+    d.sx.field_dct_syntax = syntax->field_dct_syntax != 0;
     d.n_slices = (uint32_t)n_slices;
     d.slice_region = ctx->slice_region;
     d.params_out = reinterpret_cast<mp2v_pic_params_t*>(s->d_staged);

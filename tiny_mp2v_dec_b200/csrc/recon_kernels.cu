@@ -331,7 +331,7 @@ recon_kernel3(const __grid_constant__ batch_desc_t batch, const __grid_constant_
     // trip of four-word units, the chroma lanes drop two words).  4:2:2 / 4:4:4: trips of 8-pixel half rows.
     constexpr int NT = CF == 1 ? 1 : CF == 2 ? 2 : 3;      // trips per macroblock
     constexpr int NW = CF == 1 ? 4 : 2;                    // words per unit
-    int u_woff[NT], u_xoff[NT], u_blk[NT], u_rr8[NT], u_adv[NT], u_wrap[NT];
+    int u_woff[NT], u_xoff[NT], u_blk[NT], u_rr8[NT], u_adv[NT], u_wrap[NT], u_field[NT];
     uint32_t u_below[NT];
     uint8_t* u_dst[NT];
     bool u_chroma[NT];
@@ -354,6 +354,13 @@ recon_kernel3(const __grid_constant__ batch_desc_t batch, const __grid_constant_
         u_blk[t] = blk;
         u_below[t] = (1u << blk) - 1u;
         u_rr8[t] = (r & 7) * 8;
+        // dct_type = 1 (mb_decoder.cpp:172-195): the two blocks above one another hold the two fields of their 16 rows:
+        // frame row r is row r >> 1 of the upper (even r) or lower (odd r) block.  4:2:0 chroma is frame organised.
+        int fblk = blk;
+        if (p == 0) fblk = (r & 1) * 2 + half;
+        else if (CF == 2) fblk = 3 + p + ((r & 1) << 1);
+        else if (CF == 3) fblk = 3 + p + ((r & 1) << 1) + 4 * half;
+        u_field[t] = (p == 0 || CF != 1) ? (fblk | ((r >> 1) * 8) << 8) : (blk | u_rr8[t] << 8);
         const int pw = p ? G::CW : 16, ph = p ? G::CH : 16;
         u_dst[t] = pd.dst[p] + (size_t)(mby0 * ph + r) * batch.stride[p] + mbx0 * pw + 8 * half;
         u_adv[t] = pw;                                                     // destination step to the next macroblock of the row ...
@@ -392,7 +399,9 @@ recon_kernel3(const __grid_constant__ batch_desc_t batch, const __grid_constant_
         // records contiguous in the arena (they are inside a slice; anything else only shortens the batch)
         const int idx = first + lane;
         const bool have = idx < mb_end;
-        const uint4 rec = rec_next;
+        uint4 rec = rec_next;
+        const uint32_t field_mbs = __ballot_sync(0xffffffffu, (rec.x & MP2V_MB_FIELD_DCT) != 0);      // bit i: macroblock i of the batch is field-DCT coded
+        rec.x = MP2V_MB_COEF_OFF(rec.x);
         const int cnt = have ? __popc(MP2V_MB_CBP(rec.y)) : 0;
         const int ncoef_all = have ? (int)MP2V_MB_NCOEF(rec.y) : 0;
         int scan2 = cnt | (ncoef_all << 16);       // both prefixes in one scan: coded blocks (low half), records (high half)
@@ -579,11 +588,17 @@ recon_kernel3(const __grid_constant__ batch_desc_t batch, const __grid_constant_
             const bool row_end = mbx + 1 == mbw;
 #pragma unroll
             for (int t = 0; t < NT; t++) {
-                add_residual(ws.tile, mbase, cbp, u_below[t], u_blk[t], u_rr8[t], intra, pred[t][0], pred[t][1]);
+                int blk = u_blk[t], rr8 = u_rr8[t];
+                uint32_t below = u_below[t];
+                if (field_mbs >> mi & 1u) {                                // warp-uniform
+                    blk = u_field[t] & 0xff; rr8 = u_field[t] >> 8;
+                    below = (1u << blk) - 1u;
+                }
+                add_residual(ws.tile, mbase, cbp, below, blk, rr8, intra, pred[t][0], pred[t][1]);
                 if (CF == 1) {
                     // whole rows: the right-hand block too for luma rows (the chroma lanes drop their upper two words)
                     if (lane < 16) {
-                        add_residual(ws.tile, mbase, cbp, u_below[t] * 2u + 1u, u_blk[t] + 1, u_rr8[t], intra, pred[t][2], pred[t][3]);
+                        add_residual(ws.tile, mbase, cbp, below * 2u + 1u, blk + 1, rr8, intra, pred[t][2], pred[t][3]);
                         *reinterpret_cast<uint4*>(u_dst[t]) = make_uint4(pred[t][0], pred[t][1], pred[t][2], pred[t][3]);
                     } else {
                         *reinterpret_cast<uint2*>(u_dst[t]) = make_uint2(pred[t][0], pred[t][1]);

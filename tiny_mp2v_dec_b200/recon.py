@@ -138,14 +138,14 @@ class Recon:
         self._ck(self.L.mp2v_recon_submit(self.h, pic))
 
     def submit_slices(self, pic, params, data, slices, f_code, intra_dc_precision=0, q_scale_type=0, intra_vlc_format=1,
-                      dst=0, l0=-1, l1=-1):
+                      dst=0, l0=-1, l1=-1, field_dct_syntax=0):
         """device-side parsing (contexts created with flags | RECON_DEVICE_VLC): data = uint8 array holding the
         coded picture, slices = [(payload offset in data, payload bytes, slice_start_code value), ...]"""
         p = pic.contents
         C.memmove(p.params, C.byref(params), C.sizeof(PicParams))
         p.params.contents.dst_frame, p.params.contents.l0_frame, p.params.contents.l1_frame = dst, l0, l1
         sy = PicSyntax(((C.c_int32 * 2) * 2)((C.c_int32 * 2)(*f_code[0]), (C.c_int32 * 2)(*f_code[1])),
-                       intra_dc_precision, q_scale_type, intra_vlc_format, 0)
+                       intra_dc_precision, q_scale_type, intra_vlc_format, field_dct_syntax)
         buf = np.ascontiguousarray(data, np.uint8)
         refs = (SliceRef * max(len(slices), 1))(*[SliceRef(buf.ctypes.data + off, n, code) for off, n, code in slices])
         self._ck(self.L.mp2v_recon_submit_slices(self.h, pic, C.byref(sy), refs, len(slices)))
@@ -163,13 +163,13 @@ class Recon:
         return np.ctypeslib.as_array(codes, shape=(n.value,)).copy() if n.value else np.zeros(0, np.uint32)
 
     def submit_stream_picture(self, pic, params, slice_offsets, f_code, intra_dc_precision=0, q_scale_type=0, intra_vlc_format=1,
-                              dst=0, l0=-1, l1=-1):
+                              dst=0, l0=-1, l1=-1, field_dct_syntax=0):
         """slice_offsets: byte offsets of the slices' START CODES in the resident stream"""
         p = pic.contents
         C.memmove(p.params, C.byref(params), C.sizeof(PicParams))
         p.params.contents.dst_frame, p.params.contents.l0_frame, p.params.contents.l1_frame = dst, l0, l1
         sy = PicSyntax(((C.c_int32 * 2) * 2)((C.c_int32 * 2)(*f_code[0]), (C.c_int32 * 2)(*f_code[1])),
-                       intra_dc_precision, q_scale_type, intra_vlc_format, 0)
+                       intra_dc_precision, q_scale_type, intra_vlc_format, field_dct_syntax)
         offs = (C.c_uint32 * max(len(slice_offsets), 1))(*[int(o) for o in slice_offsets])
         self._ck(self.L.mp2v_recon_submit_stream_picture(self.h, pic, C.byref(sy), offs, len(slice_offsets)))
 

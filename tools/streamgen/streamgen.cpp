@@ -154,9 +154,10 @@ struct mp2v_gen {
         bw.put(8, 4);
         for (int s = 0; s < 2; s++) for (int t = 0; t < 2; t++) bw.put(h.f_code[s][t], 4);
         bw.put(h.dc_prec, 2); bw.put(3, 2);         // frame picture
-        bw.put(0, 1); bw.put(1, 1); bw.put(0, 1);   // top_field_first, frame_pred_frame_dct, concealment_mv
+        const int fpfd = p.pct_field_dct > 0 ? 0 : 1;      // frame_pred_frame_dct = 0 only in interlaced frames (progressive_frame = 0)
+        bw.put(fpfd ? 0 : 1, 1); bw.put(fpfd, 1); bw.put(0, 1);   // top_field_first, frame_pred_frame_dct, concealment_mv
         bw.put(h.q_scale_type, 1); bw.put(1, 1); bw.put(h.alt_scan, 1);   // intra_vlc_format = 1
-        bw.put(0, 1); bw.put(p.chroma_format == 1 ? 1 : 0, 1); bw.put(1, 1); bw.put(0, 1);
+        bw.put(0, 1); bw.put(p.chroma_format == 1 && fpfd ? 1 : 0, 1); bw.put(fpfd, 1); bw.put(0, 1);   // repeat_first_field, chroma_420_type, progressive_frame, composite
         if (p.matrices_once && gop_tx_valid) {      // no extension: the matrices of the GOP's first picture stay in force
             for (int k = 0; k < 4; k++) {
                 memcpy(pic.tx[k], gop_tx[k], 64);
@@ -358,29 +359,33 @@ struct mp2v_gen {
     }
     // residual (or intra samples) of block b of macroblock (mbx, mby) -> quantised levels in SCAN order; returns true when any is non-zero.
     // dc_out: intra only, the quantised DC (dct_dc as transmitted at this precision)
-    bool quantise_block(const picture_t& pic, int b, int mbx, int mby, bool intra, const int* pred_y, const int* pred_c[2], int alt, int dc_prec, int qs,
-                        int levels[64], int* dc_out) {
+    // field_dct: the block holds one field of its half of the macroblock (rows two apart; the lower block starts on row 1)
+    bool quantise_block(const picture_t& pic, int b, int mbx, int mby, bool intra, bool field_dct, const int* pred_y, const int* pred_c[2], int alt, int dc_prec,
+                        int qs, int levels[64], int* dc_out) {
         const int cf = p.chroma_format;
-        int pl, bx, by;                                                    // plane and pixel origin of the block (mb_decoder.cpp:177-195)
-        const int cw = cf == 3 ? 16 : 8;
-        if (b < 4) { pl = 0; bx = mbx * 16 + 8 * (b & 1); by = mby * 16 + 8 * (b >> 1); }
+        int pl, bx, top, lower;                                            // plane, pixel column, macroblock's first row, upper / lower block (mb_decoder.cpp:177-195)
+        const int cw = cf == 3 ? 16 : 8, chh = cf == 1 ? 8 : 16;
+        if (b < 4) { pl = 0; bx = mbx * 16 + 8 * (b & 1); top = mby * 16; lower = b >> 1; }
         else {
             pl = 1 + (b & 1);
             const int k = (b - 4) >> 1;                                    // 0; 4:2:2 1 = lower; 4:4:4 2,3 = right column
             bx = mbx * cw + (cf == 3 ? 8 * (k >> 1) : 0);
-            by = mby * (cf == 1 ? 8 : 16) + 8 * (k & 1);
+            top = mby * chh; lower = k & 1;
         }
+        const bool fields = field_dct && (pl == 0 || cf != 1);             // 4:2:0 chroma is always frame organised (:172)
         const int W = cur_src.w[pl];
         int blk[64], F[64];
-        for (int y = 0; y < 8; y++)
+        for (int y = 0; y < 8; y++) {
+            const int row = fields ? lower + 2 * y : 8 * lower + y;        // inside the macroblock
             for (int x = 0; x < 8; x++) {
-                int v = cur_src.px[pl][(size_t)(by + y) * W + bx + x];
+                int v = cur_src.px[pl][(size_t)(top + row) * W + bx + x];
                 if (!intra) {
-                    if (pl == 0) v -= pred_y[(by - mby * 16 + y) * 16 + (bx - mbx * 16 + x)];
-                    else v -= pred_c[pl - 1][(by - mby * (cf == 1 ? 8 : 16) + y) * cw + (bx - mbx * cw + x)];
+                    if (pl == 0) v -= pred_y[row * 16 + (bx - mbx * 16 + x)];
+                    else v -= pred_c[pl - 1][row * cw + (bx - mbx * cw + x)];
                 }
                 blk[y * 8 + x] = v;
             }
+        }
         fdct8x8(blk, F);
         const scan_tables_t& st = scan_tables();
         const uint8_t* Wq = pic.params.W[(b < 6 ? 0 : 2) + (intra ? 0 : 1)];   // the reference's matrix choice (blocks 4, 5 use the luminance pair)
@@ -449,7 +454,7 @@ struct mp2v_gen {
         for (auto& x : th) x.join();
     }
 
-    struct mb_plan_t { bool intra, fwd, bwd; int mv[2][2]; uint32_t cbp; int dcq[12]; int16_t lv[12][64]; };
+    struct mb_plan_t { bool intra, fwd, bwd, field_dct; int mv[2][2]; uint32_t cbp; int dcq[12]; int16_t lv[12][64]; };
     std::vector<mb_plan_t> plan;
 
     void code_picture_texture(const pic_hdr_t& h, picture_t& pic, int t) {
@@ -488,6 +493,8 @@ struct mp2v_gen {
                                    (int)(hash32(((uint64_t)p.seed << 33) ^ ((uint64_t)pic_no << 21) ^ (uint64_t)(mby * mbw + mbx) ^ 0x5bd1e995u) % 100u) < p.pct_intra_in_pb;
                 if (intra) fwd = bwd = false;
                 m.intra = intra; m.fwd = fwd; m.bwd = bwd;
+                m.field_dct = p.pct_field_dct > 0 &&
+                              (int)(hash32(((uint64_t)p.seed << 31) ^ ((uint64_t)pic_no << 22) ^ (uint64_t)(mby * mbw + mbx) ^ 0x9e3779b9u) % 100u) < p.pct_field_dct;
                 memset(m.mv, 0, sizeof(m.mv));
                 const int* pc[2] = {pcb.data(), pcr.data()};
                 if (!intra) {
@@ -509,7 +516,7 @@ struct mp2v_gen {
                 m.cbp = 0;
                 int lv[64];
                 for (int b = 0; b < nblk; b++) {
-                    if (quantise_block(pic, b, mbx, mby, intra, py.data(), pc, h.alt_scan, h.dc_prec, qs, lv, &m.dcq[b])) m.cbp |= 1u << b;
+                    if (quantise_block(pic, b, mbx, mby, intra, m.field_dct, py.data(), pc, h.alt_scan, h.dc_prec, qs, lv, &m.dcq[b])) m.cbp |= 1u << b;
                     for (int i = 0; i < 64; i++) m.lv[b][i] = (int16_t)lv[i];
                 }
             }
@@ -565,6 +572,10 @@ struct mp2v_gen {
                 if (h.type == 2 && !intra && !pattern) fwd = true;         // "MC, not coded"
                 uint32_t type = intra ? 0x02 : (fwd ? 0x10 : 0) | (bwd ? 0x08 : 0) | (pattern ? 0x04 : 0);
                 bw.put(enc().mbtype[h.type][type]);
+                if (p.pct_field_dct > 0) {                                 // macroblock_modes with frame_pred_frame_dct = 0
+                    if (fwd || bwd) bw.put(2, 2);                          // frame_motion_type: frame-based
+                    if (intra || pattern) { bw.put(m.field_dct ? 1 : 0, 1); if (m.field_dct) rec.coef_off |= MP2V_MB_FIELD_DCT; }
+                }
                 for (int s2 = 0; s2 < 2; s2++) {
                     if (!(s2 ? bwd : fwd)) continue;
                     put_mv_component(mv[s2][0], pmv[s2][0], h.f_code[s2][0]);
@@ -586,7 +597,7 @@ struct mp2v_gen {
                 }
                 uint32_t fl = intra ? MP2V_MB_INTRA : (fwd ? MP2V_MB_FWD : 0u) | (bwd ? MP2V_MB_BWD : 0u);
                 if (!intra) for (int s2 = 0; s2 < 2; s2++) for (int k = 0; k < 2; k++) rec.mv[s2][k] = (int16_t)mv[s2][k];
-                rec.bits = MP2V_MB_BITS(pic.coef.size() - rec.coef_off, qscale, cbp, fl);
+                rec.bits = MP2V_MB_BITS(pic.coef.size() - MP2V_MB_COEF_OFF(rec.coef_off), qscale, cbp, fl);
                 pic.mb.push_back(rec);
                 prev_flags = fl;
             }
@@ -691,6 +702,10 @@ struct mp2v_gen {
                 const bool quant = (intra || pattern) && rng.pct(p.pct_mb_quant);
                 if (quant) type |= 0x20;
                 bw.put(enc().mbtype[h.type][type]);
+                if (p.pct_field_dct > 0) {                              // macroblock_modes with frame_pred_frame_dct = 0
+                    if (fwd || bwd) bw.put(2, 2);                       // frame_motion_type: frame-based
+                    if (intra || pattern) { const bool fd = rng.pct(p.pct_field_dct); bw.put(fd ? 1 : 0, 1); if (fd) rec.coef_off |= MP2V_MB_FIELD_DCT; }
+                }
                 if (quant) {
                     qcode = rng.range(1, p.qscale_code_max);
                     qscale = quantiser_scale_of(qcode, h.q_scale_type);
@@ -731,7 +746,7 @@ struct mp2v_gen {
                     if (!fwd && !bwd) fl |= MP2V_MB_FWD;      // P "no MC": forward, zero vector (mb_decoder.cpp:329-338)
                     for (int s = 0; s < 2; s++) for (int t = 0; t < 2; t++) rec.mv[s][t] = (int16_t)mv[s][t];
                 }
-                rec.bits = MP2V_MB_BITS(pic.coef.size() - rec.coef_off, qscale, cbp, fl);
+                rec.bits = MP2V_MB_BITS(pic.coef.size() - MP2V_MB_COEF_OFF(rec.coef_off), qscale, cbp, fl);
                 pic.mb.push_back(rec);
                 prev_flags = fl;
             }

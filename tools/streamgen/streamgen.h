@@ -46,6 +46,9 @@ typedef struct mp2v_gen_params {
     int32_t  texture_noise;        /* mode 2: per-frame noise amplitude (+-n grey levels, 0 = 3): sets the bit rate */
     int32_t  matrices_once;        /* 1: quant_matrix_extension only in the first picture of every GOP; later pictures keep those matrices
                                       (ISO/IEC 13818-2 6.3.11).  OUTSIDE the reference's envelope: it needs the extension in every picture */
+    int32_t  pct_field_dct;        /* > 0: pictures are coded with frame_pred_frame_dct = 0 (interlaced frame pictures, frame-based
+                                      prediction only: frame_motion_type = 2) and this % of the intra / pattern macroblocks use
+                                      dct_type = 1 (field DCT, mb_decoder.cpp:172-195, 357-360)                                */
 } mp2v_gen_params_t;
 
 typedef struct mp2v_gen mp2v_gen_t;
