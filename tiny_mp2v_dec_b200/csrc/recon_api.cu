@@ -500,14 +500,12 @@ static int launch_parse_batch(mp2v_recon* ctx) {
     }
     // Slices per warp: a parser thread's registers are held by its whole warp, and a lot of single-lane warps fills every
     // SM's register file (8 CTAs of 128 threads x 64 registers) for a millisecond -- the reconstruction launches of the
-    // lots before it then wait for room.  Two CTAs per SM and lot is the budget; larger lots put 2 or 4 slices in a warp
-    // (lanes of a warp that sit on different slices serialise where their paths differ, measured: no loss up to 4).
+    // lots before it then wait for room.  Lots of more than 16 pictures of 1080p put two slices in a warp (lanes of a warp
+    // that sit on different slices serialise where their paths differ; measured on the 120-picture call: 2 lanes 3.08 ms,
+    // 1 lane 3.5, 4 lanes 3.2, 8 lanes 3.6).  Launching the parse of a lot in parts ahead of the lot measured slower
+    // (parts queue up behind one another on the parse streams).
     int lanes = ctx->parse_lanes;
-    if (lanes == 0) {
-        const int warps_budget = 2 * ctx->sm_count * 4;
-        const int slices = n * ctx->mbh;
-        lanes = slices <= warps_budget ? 1 : slices <= 2 * warps_budget ? 2 : 4;
-    }
+    if (lanes == 0) lanes = n * ctx->mbh <= 2 * ctx->sm_count * 4 ? 1 : 2;
     CK(launch_vlc_stream(ctx->d_stream, b.d, ctx->desc_stride, n, ctx->mbh, lanes, ctx->d_tables, st), "slice parser kernel launch");
     CK(cudaEventRecord(b.done, st), "event record");
     if (ctx->trace && !ctx->parse_log.empty() && ctx->parse_log.back().end) CK(cudaEventRecord(ctx->parse_log.back().end, st), "event record");
