@@ -5,9 +5,11 @@
 //   NV12  (4:2:0)  the Y plane, then rows of interleaved Cb/Cr pairs                            1.5 bytes / pixel
 //   P010  (4:2:0)  the same layout with 16-bit samples, the 8 decoded bits in the high byte      3 bytes / pixel
 //   UYVY  (4:2:2)  packed Cb Y0 Cr Y1 per pixel pair                                              2 bytes / pixel
-// Pure byte movers, HBM-bound: up to 32 frames per launch (blockIdx.y); a CTA walks groups of output rows, a thread
+// Pure byte movers, HBM-bound: up to 96 frames per launch (blockIdx.y); a CTA walks groups of output rows, a thread
 // owns 16-pixel column units of those rows and issues all its loads before the first (streaming) store; no divisions.
 // Algorithmic bytes = frame bytes read + output bytes written.
+#include <algorithm>
+
 #include "recon_kernels.cuh"
 
 namespace mp2v {
@@ -22,12 +24,13 @@ __device__ __forceinline__ uint2 widen4(uint32_t v) { return make_uint2(__byte_p
 template <int FMT, int ROWS>
 __global__ void __launch_bounds__(kCvtThreads) convert_kernel(const __grid_constant__ convert_batch_t b) {
     const convert_frame_t& f = b.frame[blockIdx.y];
-    const int units_per_row = b.width >> 4;                   // width is a multiple of 16
+    constexpr int PX = 16;                                    // pixels per thread and row (8 with one 16-byte P010 store measured 53 % instead of 71 %)
+    const int units_per_row = b.width / PX;                    // width is a multiple of 16
     const int rows = FMT == MP2V_OUT_UYVY ? b.height : b.height + (b.height >> 1);
     constexpr int W = FMT == MP2V_OUT_NV12 ? 1 : 2;           // 16-byte stores per unit and row
     for (int r0 = blockIdx.x * ROWS; r0 < rows; r0 += gridDim.x * ROWS) {
         for (int xu = threadIdx.x; xu < units_per_row; xu += kCvtThreads) {
-            const int x = xu << 4;
+            const int x = xu * PX;
             uint4 v[ROWS][W];
 #pragma unroll
             for (int k = 0; k < ROWS; k++) {
@@ -61,7 +64,7 @@ __global__ void __launch_bounds__(kCvtThreads) convert_kernel(const __grid_const
 #pragma unroll
             for (int k = 0; k < ROWS; k++) {
                 if (r0 + k >= rows) continue;
-                uint4* dst = reinterpret_cast<uint4*>(f.dst + (size_t)(r0 + k) * b.dst_pitch + (size_t)x * W);
+                uint4* dst = reinterpret_cast<uint4*>(f.dst + (size_t)(r0 + k) * b.dst_pitch + (size_t)xu * (16 * W));
 #pragma unroll
                 for (int j = 0; j < W; j++) __stcs(dst + j, v[k][j]);
             }
@@ -75,9 +78,12 @@ cudaError_t launch_convert(int format, const convert_batch_t& batch, cudaStream_
     if (batch.n_frames < 1 || batch.n_frames > kMaxConvertBatch) return cudaErrorInvalidValue;
     const int rows = format == MP2V_OUT_UYVY ? batch.height : batch.height + (batch.height >> 1);
     const int rows_per_group = format == MP2V_OUT_NV12 ? 8 : 4;
-    int ctas = (rows + rows_per_group - 1) / rows_per_group;
-    const int cap = (148 * 16 + batch.n_frames - 1) / batch.n_frames;     // 16 resident CTAs of 128 threads per SM over the whole launch
-    if (ctas > cap) ctas = cap < 1 ? 1 : cap;                              // (one CTA per row group measured 9 % slower)
+    // one wave: 16 resident CTAs of 128 threads per SM over the whole launch, and every CTA of a frame the same number of
+    // row groups (1080p NV12: 204 groups of 8 rows = 68 CTAs x 3; an uneven split measured 5 % slower, one CTA per group 9 %)
+    const int groups = (rows + rows_per_group - 1) / rows_per_group;
+    const int cap = std::max(1, (148 * 16 + batch.n_frames - 1) / batch.n_frames);
+    const int rounds = (groups + cap - 1) / cap;
+    const int ctas = (groups + rounds - 1) / rounds;
     const dim3 grid((unsigned)ctas, (unsigned)batch.n_frames);
     switch (format) {
         case MP2V_OUT_NV12: convert_kernel<MP2V_OUT_NV12, 8><<<grid, kCvtThreads, 0, stream>>>(batch); break;

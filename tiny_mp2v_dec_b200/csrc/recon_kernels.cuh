@@ -8,7 +8,7 @@
 namespace mp2v {
 
 constexpr int kMaxBatch = 128;       // pictures fused into one launch (descriptors travel as kernel arguments: 104 B each, 13 KB of the 32 KB limit)
-constexpr int kMaxConvertBatch = 32; // frames per output-conversion launch
+constexpr int kMaxConvertBatch = 96; // frames per output-conversion launch (32-byte descriptors as kernel arguments: 3 KB)
 constexpr int kCtaThreads = 128;
 
 // A warp owns `mbs_per_warp` consecutive macroblocks and walks them in batches of <= MP2V_SLOTS coded
