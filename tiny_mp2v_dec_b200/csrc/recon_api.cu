@@ -28,14 +28,16 @@ enum slot_state_t { SLOT_FREE = 0, SLOT_FILLING, SLOT_QUEUED, SLOT_INFLIGHT, SLO
 
 struct slot_t {
     mp2v_picture_t pub{};
-    uint8_t* h_arena = nullptr;
+    uint8_t* h_arena = nullptr;        // (slices of the context's pools: one pinned, one device allocation for all slots)
     uint8_t* d_arena = nullptr;
+    const uint8_t* d_params = nullptr; // where the picture's parameter block lies on the device: the arena's head, or the staged block's
     slot_state_t state = SLOT_FREE;
     cudaEvent_t done = nullptr;        // the event of the launch that consumed the slot (an entry of the context's launch-event ring)
     uint64_t alg_bytes = 0;
     bool prechecked = false;           // account_and_validate already ran for the records now in the slot
     uint64_t seq = 0;                  // submission order, to recycle the oldest in-flight slot first
-    // device-side slice parsing (MP2V_RECON_DEVICE_VLC): staged bitstream, own stream, parse result
+    // device-side slice parsing (MP2V_RECON_DEVICE_VLC): staged bitstream + own stream (allocated by the first
+    // stage_slices of the slot: the stream-resident front end needs neither), parse result
     uint8_t* h_staged = nullptr;
     uint8_t* d_staged = nullptr;
     vlc_slice_status_t* h_status = nullptr;   // pinned + mapped: one entry per slice, written by the kernel
@@ -63,6 +65,7 @@ struct mp2v_recon {
     mp2v_frame_layout_t lay{};
     int nblk = 0, mbw = 0, mbh = 0, mb_count = 0, max_batch = 0;
     size_t frame_alloc = 0, arena_bytes = 0, coef_off = 0;
+    uint8_t* h_arena_pool = nullptr; uint8_t* d_arena_pool = nullptr; uint8_t* h_status_pool = nullptr;
     uint8_t* d_frames = nullptr;
     recon_tmaps_t tmaps{};                     // TMA descriptors of the frame pool (reference windows)
     std::vector<uint8_t*> h_frames;            // pinned mirrors, allocated on first map
@@ -187,14 +190,14 @@ static void destroy_ctx(mp2v_recon* ctx) {
     if (ctx->ev_stream_timed) cudaEventDestroy(ctx->ev_stream_timed);
     for (auto e : ctx->launch_ev) if (e) cudaEventDestroy(e);
     for (auto& s : ctx->slots) {
-        if (s.h_arena) cudaFreeHost(s.h_arena);
-        if (s.d_arena) cudaFree(s.d_arena);
         if (s.s_vlc) { cudaStreamSynchronize(s.s_vlc); cudaStreamDestroy(s.s_vlc); }
         if (s.vlc_done) cudaEventDestroy(s.vlc_done);
         if (s.h_staged) cudaFreeHost(s.h_staged);
         if (s.d_staged) cudaFree(s.d_staged);
-        if (s.h_status) cudaFreeHost(s.h_status);
     }
+    if (ctx->h_arena_pool) cudaFreeHost(ctx->h_arena_pool);
+    if (ctx->d_arena_pool) cudaFree(ctx->d_arena_pool);
+    if (ctx->h_status_pool) cudaFreeHost(ctx->h_status_pool);
     if (ctx->d_tables) cudaFree(ctx->d_tables);
     if (ctx->d_blank_mb) cudaFree(ctx->d_blank_mb);
     if (ctx->h_pool) cudaFreeHost(ctx->h_pool);
@@ -303,11 +306,24 @@ static int create_impl(mp2v_recon* ctx) {
         CK(cudaMalloc(&ctx->d_blank_mb, blank.size() * sizeof(mp2v_mb_info_t)), "cudaMalloc blank records");
         CK(cudaMemcpy(ctx->d_blank_mb, blank.data(), blank.size() * sizeof(mp2v_mb_info_t), cudaMemcpyHostToDevice), "H2D blank records");
     }
+    // One pinned and one device allocation hold the arenas of all slots (a context of 128 slots used to make 640 driver
+    // calls and pin 256 MB of staging nobody might use: 0.1 s per decoder object, measured with 64 decoders in a process).
     ctx->slots.resize(c.n_pictures);
+    ctx->arena_bytes = (ctx->arena_bytes + 255) & ~(size_t)255;
+    const size_t host_arena_stride = (host_arena_bytes + 255) & ~(size_t)255;
+    const size_t status_stride = ((size_t)ctx->mbh * sizeof(vlc_slice_status_t) + 63) & ~(size_t)63;
+    CK(cudaHostAlloc(&ctx->h_arena_pool, host_arena_stride * c.n_pictures, cudaHostAllocDefault), "cudaHostAlloc picture arenas");
+    CK(cudaMalloc(&ctx->d_arena_pool, ctx->arena_bytes * c.n_pictures), "cudaMalloc picture arenas");
+    uint8_t* d_status_pool = nullptr;
+    if (ctx->vlc) {
+        CK(cudaHostAlloc(&ctx->h_status_pool, status_stride * c.n_pictures, cudaHostAllocMapped), "cudaHostAlloc parse status");
+        CK(cudaHostGetDevicePointer(&d_status_pool, ctx->h_status_pool, 0), "cudaHostGetDevicePointer");
+    }
     for (int i = 0; i < c.n_pictures; i++) {
         slot_t& s = ctx->slots[i];
-        CK(cudaHostAlloc(&s.h_arena, host_arena_bytes, cudaHostAllocDefault), "cudaHostAlloc picture arena");
-        CK(cudaMalloc(&s.d_arena, ctx->arena_bytes), "cudaMalloc picture arena");
+        s.h_arena = ctx->h_arena_pool + host_arena_stride * i;
+        s.d_arena = ctx->d_arena_pool + ctx->arena_bytes * i;
+        s.d_params = s.d_arena;
         s.pub.params = reinterpret_cast<mp2v_pic_params_t*>(s.h_arena);
         s.pub.mb = reinterpret_cast<mp2v_mb_info_t*>(s.h_arena + kParamsBytes);
         s.pub.coef = host_cap ? reinterpret_cast<mp2v_coef_t*>(s.h_arena + ctx->coef_off) : nullptr;
@@ -315,14 +331,8 @@ static int create_impl(mp2v_recon* ctx) {
         s.pub.coef_capacity = host_cap;
         s.pub.slot = i;
         if (ctx->vlc) {
-            // the parameters travel with the staged bitstream: one H2D per picture
-            CK(cudaHostAlloc(&s.h_staged, ctx->staged_bytes, cudaHostAllocDefault), "cudaHostAlloc bitstream staging");
-            CK(cudaMalloc(&s.d_staged, ctx->staged_bytes), "cudaMalloc bitstream staging");
-            s.pub.params = reinterpret_cast<mp2v_pic_params_t*>(s.h_staged);
-            CK(cudaHostAlloc(&s.h_status, (size_t)ctx->mbh * sizeof(vlc_slice_status_t), cudaHostAllocMapped), "cudaHostAlloc parse status");
-            CK(cudaHostGetDevicePointer(&s.d_status, s.h_status, 0), "cudaHostGetDevicePointer");
-            CK(cudaStreamCreateWithFlags(&s.s_vlc, cudaStreamNonBlocking), "stream");
-            CK(cudaEventCreateWithFlags(&s.vlc_done, cudaEventDisableTiming), "event");
+            s.h_status = reinterpret_cast<vlc_slice_status_t*>(ctx->h_status_pool + status_stride * i);
+            s.d_status = reinterpret_cast<vlc_slice_status_t*>(d_status_pool + status_stride * i);
         }
     }
     if (ctx->vlc) {
@@ -381,7 +391,7 @@ extern "C" MP2V_API const char* mp2v_recon_last_error(mp2v_recon_t* ctx) {
 
 static void fill_desc(mp2v_recon* ctx, const slot_t& s, pic_desc_t& d) {
     const mp2v_pic_params_t& pp = *s.pub.params;
-    d.params = reinterpret_cast<const mp2v_pic_params_t*>(ctx->vlc ? s.d_staged : s.d_arena);
+    d.params = reinterpret_cast<const mp2v_pic_params_t*>(s.d_params);
     d.mb = reinterpret_cast<const mp2v_mb_info_t*>(s.d_arena + kParamsBytes);
     d.coef = reinterpret_cast<const mp2v_coef_t*>(s.d_arena + ctx->coef_off);
     for (int p = 0; p < 3; p++) {
@@ -794,6 +804,15 @@ extern "C" MP2V_API int mp2v_recon_stage_slices(mp2v_recon_t* ctx, mp2v_picture_
     if (syntax->intra_dc_precision < 0 || syntax->intra_dc_precision > 3) return fail(MP2V_ERR_ARG, "intra_dc_precision out of range");
     if (n_slices > ctx->mbh) return fail(MP2V_ERR_RANGE, "the device parser takes at most one slice per macroblock row");
     // ---- stage header + slice table + bitstream (the slot is the caller's: no lock)
+    if (!s->h_staged) {
+        // first use of this slot by the staged front end: its pinned + device staging block, stream and event
+        cudaError_t e = cudaSetDevice(ctx->cfg.device);
+        if (e == cudaSuccess) e = cudaHostAlloc(&s->h_staged, ctx->staged_bytes, cudaHostAllocDefault);
+        if (e == cudaSuccess) e = cudaMalloc(&s->d_staged, ctx->staged_bytes);
+        if (e == cudaSuccess) e = cudaStreamCreateWithFlags(&s->s_vlc, cudaStreamNonBlocking);
+        if (e == cudaSuccess) e = cudaEventCreateWithFlags(&s->vlc_done, cudaEventDisableTiming);
+        if (e != cudaSuccess) { std::lock_guard<std::mutex> lk(ctx->mu); return ctx->cuda_fail(e, "bitstream staging buffers"); }
+    }
     vlc_pic_header_t& hdr = *reinterpret_cast<vlc_pic_header_t*>(s->h_staged + kVlcParamsBytes);
     memset(&hdr, 0, sizeof(hdr));
     hdr.sx.picture_coding_type = pp.picture_coding_type;
@@ -835,6 +854,8 @@ extern "C" MP2V_API int mp2v_recon_stage_slices(mp2v_recon_t* ctx, mp2v_picture_
         staged_end = hdr.data_off + span + 16;
     }
     s->pub.params->n_coef = 0;
+    memcpy(s->h_staged, s->pub.params, sizeof(mp2v_pic_params_t));      // the parameters travel with the staged bitstream: one H2D per picture
+    s->d_params = s->d_staged;
     s->n_slices = n_slices;
     s->staged_end = staged_end;
     s->rows_covered = rows_covered;
@@ -1016,7 +1037,8 @@ extern "C" MP2V_API int mp2v_recon_submit_stream_picture(mp2v_recon_t* ctx, mp2v
     d.sx.field_dct_syntax = syntax->field_dct_syntax != 0;
     d.n_slices = (uint32_t)n_slices;
     d.slice_region = ctx->slice_region;
-    d.params_out = reinterpret_cast<mp2v_pic_params_t*>(s->d_staged);
+    d.params_out = reinterpret_cast<mp2v_pic_params_t*>(s->d_arena);
+    s->d_params = s->d_arena;
     d.mb = reinterpret_cast<mp2v_mb_info_t*>(s->d_arena + kParamsBytes);
     d.coef = reinterpret_cast<mp2v_coef_t*>(s->d_arena + ctx->coef_off);
     d.status = s->d_status;
