@@ -47,6 +47,13 @@ def test_threads_and_batching_do_not_change_the_output(threads, batch, lag, gpu_
     assert got == want
 
 
+@pytest.mark.parametrize("cf", [1, 2, 3])
+def test_matrices_loaded_once_per_gop_persist(cf, gpu_vlc):
+    """quant_matrix_extension (chroma matrices included) only in the first picture of each GOP"""
+    s = Stream(176, 144, cf, seed=70 + cf, n_gops=2, gop_n=7, gop_m=3, matrices_once=1)
+    assert Decoder(176, 144, cf, num_threads=2, gpu_vlc=gpu_vlc).decode(s.padded, s.size) == O.oracle_decode_stream(s)
+
+
 def test_no_reordering_gives_coded_order(gpu_vlc):
     s = Stream(176, 144, 1, seed=61, gop_n=7, gop_m=3)
     got = Decoder(176, 144, 1, num_threads=2, reordering=False, gpu_vlc=gpu_vlc).decode(s.padded, s.size)

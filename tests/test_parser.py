@@ -20,6 +20,12 @@ CASES = [
     (16, 16, 1, dict(seed=21, gop_n=4, gop_m=2)),
     (720, 576, 1, dict(seed=23, gop_n=6, gop_m=3, mode=1)),
     (1920, 1088, 1, dict(seed=18, gop_n=4, gop_m=3)),
+    # quant_matrix_extension (with distinct chroma matrices) only in the first picture of a GOP: the matrices persist
+    # until the next sequence header (ISO/IEC 13818-2 6.3.11) -- outside the reference's envelope, which needs the
+    # extension in every picture (decoder.cpp:187)
+    (176, 144, 2, dict(seed=24, n_gops=2, gop_n=7, gop_m=3, matrices_once=1)),
+    (176, 144, 3, dict(seed=25, n_gops=2, gop_n=7, gop_m=3, matrices_once=1, alternate_scan=1)),
+    (176, 144, 1, dict(seed=26, n_gops=2, gop_n=7, gop_m=3, matrices_once=1)),
 ]
 
 
