@@ -22,11 +22,11 @@ for k in range(n):
     cf = int(rng.integers(1, 4))
     big = w * h > 300000
     kw = dict(seed=int(rng.integers(1, 1 << 30)), n_gops=int(rng.integers(1, 3)), gop_n=int(rng.integers(1, 5 if big else 13)),
-              gop_m=int(rng.integers(1, 4)), mode=int(rng.integers(0, 2)), qscale_code_max=int(rng.choice([4, 12, 31])),
+              gop_m=int(rng.integers(1, 4)), mode=int(rng.integers(0, 3)), qscale_code_max=int(rng.choice([4, 12, 31])),
               alternate_scan=int(rng.integers(-1, 2)), q_scale_type=int(rng.integers(-1, 2)), intra_dc_precision=int(rng.integers(-1, 4)),
               pct_skipped=int(rng.choice([0, 15, 60])), pct_intra_in_pb=int(rng.choice([0, 10, 50])), pct_coded=int(rng.choice([0, 30, 70, 100])),
               pct_mb_quant=int(rng.choice([0, 10, 50])), pct_big_levels=int(rng.choice([0, 3, 30])), all_blocks_coded=int(rng.integers(0, 2)),
-              mv_range=int(rng.choice([0, 3, 24, 100])))
+              mv_range=int(rng.choice([0, 3, 24, 100])), pct_field_dct=int(rng.choice([0, 0, 30, 100])), matrices_once=int(rng.integers(0, 2)))
     if rng.integers(0, 4) == 0:
         kw["intra_only"] = 1
     try:
