@@ -1,4 +1,4 @@
-// Device-side slice parser (SURVEY.md 8(f) "what comes next": the entropy decode in front of the
+// Device-side slice parser and start-code scan (the entropy decode in front of the
 // reconstruction kernel).
 //
 // A slice is serial by construction -- every code's position depends on every code before it -- and
@@ -8,15 +8,22 @@
 // breadth, not speed per symbol: every slice of every picture in flight is parsed at once (pictures
 // have no parse-time dependencies, only reconstruction does), while the host only finds start codes.
 //
-// Mapping: `lanes` threads of each warp are active (1 by default).  Threads of a warp that sit on
-// different slices diverge at every block and macroblock boundary, so a warp's time is the SUM of
-// its lanes' paths; with one slice per warp the walk is a pure latency chain (table look-up -> shift
-// -> look-up) and the warps of all slices hide one another's latency.  The parser's issue-slot cost
-// is a few percent of the machine; the reconstruction kernel keeps the rest.
+// Mapping: `lanes` threads of each warp are active, each on its own slice.  Threads of a warp that sit on
+// different slices serialise wherever their paths differ (they wait for one another at block ends), so a
+// warp's time grows with its lanes; but a lane's registers are held by its whole warp, and a lot of
+// single-lane warps fills the register files and keeps the reconstruction launches of the previous lot out.
+// The launcher (recon_api.cu: launch_parse_batch) therefore puts one slice in a warp for small lots and two
+// for large ones -- measured best on the whole decode.  A slice's walk is a latency chain
+// (look-up -> shift -> look-up); the warps of all slices hide one another's latency, and the cost of the
+// kernel is its instruction count: two thirds of the issue slots of a resident decode, the
+// reconstruction kernel has the rest.
 //
-// Memory: tables (~155 KB, pointer-free, copied once) are read through the read-only path and stay
-// L1/L2 resident; the bitstream is read 12 aligned bytes at a time (bitreader_t::refill); records are
-// written sequentially by the owning thread and merge into full sectors in L2.
+// Memory: the run/level fast and long-code tables (24 KB) are copied to shared memory by every CTA; the other
+// tables (pointer-free, copied to the device once) are read through the read-only path and stay L1/L2
+// resident; the bitstream is read as aligned 32-bit words with a one-word look-ahead (bitreader.h); records
+// are written sequentially by the owning thread and merge into full sectors in L2.
+//
+// The same file holds the start-code scan of the stream-resident front end (scan_*_kernel below).
 #include "vlc_kernel.cuh"
 
 namespace mp2v {
