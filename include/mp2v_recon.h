@@ -319,6 +319,15 @@ MP2V_API int  mp2v_recon_timer_start(mp2v_recon_t* ctx);
 MP2V_API int  mp2v_recon_timer_stop(mp2v_recon_t* ctx, double* elapsed_ms);
 MP2V_API int  mp2v_recon_get_stats(mp2v_recon_t* ctx, mp2v_recon_stats_t* out, int reset);
 
+/* NUMA placement (multi-socket hosts): the context's pinned memory is allocated on the NUMA node of the device's PCIe
+ * root; threads that feed the context or read its mapped frames should run there too (the bundled decoder binds its
+ * feeder and output threads).  Returns that node, or -1 on a single-node host / when the kernel does not say /
+ * with MP2V_NUMA=0 -- then nothing is bound.
+ * mp2v_numa_parse_cpu_list: "0-3,8,10-11" -> 0 1 2 3 8 10 11 (the sysfs cpulist format); returns the number of CPUs
+ * (at most cap are stored), 0 for malformed input. */
+MP2V_API int  mp2v_recon_numa_node(mp2v_recon_t* ctx);
+MP2V_API int  mp2v_numa_parse_cpu_list(const char* list, int32_t* cpus, int cap);
+
 #ifdef __cplusplus
 }
 #endif

@@ -71,3 +71,21 @@ def test_no_gpu_no_fallback():
     s = Stream(64, 48, 1, seed=1, gop_n=2, gop_m=1)
     with pytest.raises(ReconError):
         Decoder(64, 48, 1, num_threads=1).decode(s.padded, s.size)
+
+
+def test_numa_cpu_list_parser():
+    """sysfs cpulist format (host/numa.cpp): ranges and singles, malformed input gives nothing"""
+    L = C.CDLL(build.PRODUCT_LIB)
+    L.mp2v_numa_parse_cpu_list.argtypes = [C.c_char_p, C.POINTER(C.c_int32), C.c_int]
+    out = (C.c_int32 * 64)()
+
+    def parse(text):
+        n = L.mp2v_numa_parse_cpu_list(text.encode(), out, 64)
+        return list(out[:min(n, 64)]) if n else []
+    assert parse("0-3,8,10-11\n") == [0, 1, 2, 3, 8, 10, 11]
+    assert parse("5") == [5]
+    assert parse("0-23") == list(range(24))
+    assert parse(" 1 , 3-4 ") == [1, 3, 4]
+    assert parse("") == [] and parse("3-1") == [] and parse("a-b") == [] and parse("1,,2") == [] and parse("1-") == []
+    assert L.mp2v_numa_parse_cpu_list(b"0-127", out, 64) == 128      # counts past the caller's capacity, stores 64
+    assert L.mp2v_recon_numa_node(None) == -1

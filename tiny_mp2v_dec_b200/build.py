@@ -24,7 +24,7 @@ ORACLE_LIB = os.path.join(ROOT, "oracle", "libmp2v_oracle.so")
 REF_LIB = os.path.join(ROOT, "oracle", "_ref", "libmp2v_ref.so")
 
 CUDA_SOURCES = ["recon_kernels.cu", "vlc_kernel.cu", "convert_kernel.cu", "recon_api.cu"]
-HOST_SOURCES = ["host/mp2v_parser.cpp", "host/stream_index.cpp", "host/decoder.cpp", "host/decoder_capi.cpp"]
+HOST_SOURCES = ["host/mp2v_parser.cpp", "host/stream_index.cpp", "host/decoder.cpp", "host/decoder_capi.cpp", "host/numa.cpp"]
 
 
 def _run(cmd, cwd=None):

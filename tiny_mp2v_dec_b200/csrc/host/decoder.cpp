@@ -23,6 +23,7 @@
 #include <thread>
 
 #include "mp2v_parser.h"
+#include "numa.h"
 #include "mp2v_recon.h"
 #include "stream_index.h"
 
@@ -144,6 +145,7 @@ void shared_t::fail(const std::string& why) {
 }
 
 void pipeline_t::feeder() {
+    bind_this_thread_to_numa_node(mp2v_recon_numa_node(recon));      // next to the device's pinned memory (no-op on single-node hosts)
     int refs[2] = {-1, -1};   // local task indices of the two live references
     std::vector<uint32_t> slice_offsets;
     auto unref = [&](int k) { if (k >= 0) release_frame_use(tasks[k].dst); };
@@ -286,6 +288,7 @@ void pipeline_t::on_parsed(pic_task_t* t) {
 }
 
 void pipeline_t::output() {
+    bind_this_thread_to_numa_node(mp2v_recon_numa_node(recon));
     const int n = (int)tasks.size();
     const int lag = sh->opt.output_lag < 0 ? 0 : sh->opt.output_lag;
     auto emit = [&](int k) -> bool {

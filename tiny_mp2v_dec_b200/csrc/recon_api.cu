@@ -14,6 +14,7 @@
 #include <string>
 #include <vector>
 
+#include "host/numa.h"
 #include "mp2v_recon.h"
 #include "recon_kernels.cuh"
 #include "vlc_kernel.cuh"
@@ -127,6 +128,7 @@ struct mp2v_recon {
     uint32_t* h_total = nullptr; uint32_t* d_total = nullptr;   // pinned + mapped
     cudaStream_t s_parse[kParseStreams] = {};
     int sm_count = 148;
+    int numa_node = -1;                        // of the device's PCIe root; -1 on single-node hosts
     int parse_rr = 0, n_parse_streams = 2, lot_cap = 0, parse_lanes = 0;      // dev knobs MP2V_PARSE_STREAMS / MP2V_LOT
     cudaEvent_t ev_stream = nullptr;           // the upload (and scan) of the resident stream
     cudaEvent_t ev_stream_timed = nullptr;     // MP2V_TRACE: the same moment with a timestamp
@@ -235,6 +237,12 @@ static int create_impl(mp2v_recon* ctx) {
     if (e != cudaSuccess || ndev == 0) return ctx->fail(MP2V_ERR_CUDA, std::string("no CUDA device: ") + cudaGetErrorString(e));
     if (c.device < 0 || c.device >= ndev) return ctx->fail(MP2V_ERR_ARG, "device ordinal out of range");
     CK(cudaSetDevice(c.device), "cudaSetDevice");
+    // the pinned memory of this context (record arenas, frame mirrors, parse status) is allocated while the calling thread
+    // sits on the device's NUMA node; a no-op on single-node hosts (host/numa.h)
+    char bus_id[32] = {0};
+    if (cudaDeviceGetPCIBusId(bus_id, (int)sizeof(bus_id), c.device) == cudaSuccess) ctx->numa_node = numa_node_of_pci_device(bus_id);
+    cudaGetLastError();
+    numa_scope_t numa_scope(ctx->numa_node);
     cudaFuncAttributes fa;
     e = recon_kernel_attributes(c.chroma_format, &fa);   // fails loudly when the sm_100a image cannot load on this device
     if (e != cudaSuccess) return ctx->cuda_fail(e, "reconstruction kernel image not usable on this device (built for sm_100a only)");
@@ -1066,6 +1074,15 @@ extern "C" MP2V_API int mp2v_recon_precheck(mp2v_recon_t* ctx, mp2v_picture_t* p
     if (rc != MP2V_OK) { std::lock_guard<std::mutex> lk(ctx->mu); return ctx->fail(rc, why); }
     s->prechecked = true;
     return MP2V_OK;
+}
+
+extern "C" MP2V_API int mp2v_recon_numa_node(mp2v_recon_t* ctx) { return ctx ? ctx->numa_node : -1; }
+
+extern "C" MP2V_API int mp2v_numa_parse_cpu_list(const char* list, int32_t* cpus, int cap) {
+    if (!list) return 0;
+    const std::vector<int> v = parse_cpu_list(list);
+    for (size_t i = 0; i < v.size() && (int)i < cap && cpus; i++) cpus[i] = v[i];
+    return (int)v.size();
 }
 
 extern "C" MP2V_API int mp2v_recon_flush(mp2v_recon_t* ctx) {

@@ -19,6 +19,7 @@ EXPORTS = [
     "mp2v_recon_sync", "mp2v_recon_reset", "mp2v_recon_upload", "mp2v_recon_run_resident", "mp2v_recon_download_frame",
     "mp2v_recon_map_frame", "mp2v_recon_upload_frame", "mp2v_recon_frame_device_ptrs", "mp2v_recon_convert_frames", "mp2v_recon_convert_frame_nv12", "mp2v_recon_convert_frames_nv12", "mp2v_recon_wait_frame",
     "mp2v_recon_set_timing", "mp2v_recon_get_stats", "mp2v_recon_timer_start", "mp2v_recon_timer_stop",
+    "mp2v_recon_numa_node", "mp2v_numa_parse_cpu_list",
 ]
 
 
@@ -62,6 +63,7 @@ def lib():
         L.mp2v_recon_convert_frames_nv12.argtypes = [C.c_void_p, P(C.c_int32), P(C.c_void_p), C.c_int, C.c_int32]
         L.mp2v_recon_convert_frames.argtypes = [C.c_void_p, C.c_int, P(C.c_int32), P(C.c_void_p), C.c_int, C.c_int32]
         L.mp2v_recon_wait_frame.argtypes = [C.c_void_p, C.c_int]
+        L.mp2v_recon_numa_node.argtypes = [C.c_void_p]
         L.mp2v_recon_set_timing.argtypes = [C.c_void_p, C.c_int]
         L.mp2v_recon_get_stats.argtypes = [C.c_void_p, P(ReconStats), C.c_int]
         L.mp2v_recon_timer_start.argtypes = [C.c_void_p]
@@ -233,6 +235,10 @@ class Recon:
         self._ck(self.L.mp2v_recon_wait_frame(self.h, frame_id))
 
     # ---- statistics
+    def numa_node(self):
+        """NUMA node the context's pinned memory was placed on, -1 on single-node hosts"""
+        return int(self.L.mp2v_recon_numa_node(self.h))
+
     def set_timing(self, on=True):
         self._ck(self.L.mp2v_recon_set_timing(self.h, 1 if on else 0))
 
