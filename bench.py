@@ -48,7 +48,7 @@ WORKLOADS = {
     # configs[0]: 1080p 4:2:2 IPB (the reference sample's hard-wired geometry)
     "1080p422_ipb": dict(width=1920, height=1088, chroma_format=2, config_id=1, gen=dict(n_gops=4, gop_n=15, gop_m=3, **TEX)),
     # configs[3]: 4K 4:4:4 IPB, 16 closed GOPs (sharded over the GPUs in one process when N > 1)
-    "2160p444_ipb": dict(width=3840, height=2160, chroma_format=3, config_id=4, gen=dict(n_gops=16, gop_n=6, gop_m=3, **TEX)),
+    "2160p444_ipb": dict(width=3840, height=2160, chroma_format=3, config_id=4, gen=dict(n_gops=16, gop_n=15, gop_m=3, **TEX)),
     # configs[4]: one of the 64 concurrent 720p 4:2:0 streams
     "720p420_ipb": dict(width=1280, height=720, chroma_format=1, config_id=5, gen=dict(n_gops=2, gop_n=15, gop_m=3, **TEX)),
     # the two 1080p shapes in random-syntax fuzz mode (stress: escapes, saturating levels, random matrices)

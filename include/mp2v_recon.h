@@ -243,15 +243,26 @@ MP2V_API int  mp2v_recon_submit_staged(mp2v_recon_t* ctx, mp2v_picture_t* pic);
  * -- and pictures are then handed over as byte offsets of their slices' start codes in that resident copy.  No byte of
  * the stream is touched by the host besides the headers it parses, there is no per-picture staging copy, and one kernel
  * launch parses the slices of every picture handed over since the previous launch.
- *   stream_begin   copies data[0, bytes) (or only the given ranges of it: the other devices of a GOP-sharded decode) and,
- *                  when `scan` is set, returns the ascending byte offsets of every 00 00 01 prefix (host memory owned by
- *                  the context, valid until the next stream_begin).  `data` must stay valid until the pictures of this
- *                  stream have been submitted (slice start codes are validated from it).  Pass page-locked memory for the
- *                  full copy rate.  Waits for the device parses of the previous stream.
- *   submit_stream_picture   like mp2v_recon_submit_slices with the slices named by offset; asynchronous, coded order. */
+ *   stream_begin   copies data[0, bytes) (or only the given ranges of it) and scans for start codes: scan = 1 returns the
+ *                  ascending byte offsets of every 00 00 01 prefix (host memory owned by the context, valid until the next
+ *                  stream_begin); scan = 2 only launches the scan -- fetch the list with mp2v_recon_stream_codes (several
+ *                  devices then copy and scan their parts of one stream at the same time); scan = 0 copies only.  With
+ *                  ranges, the scan covers ranges[0] alone (it must start on a 16-byte boundary): the codes that BEGIN in
+ *                  it, offsets relative to data.  `data` must stay valid until the pictures of this stream have been
+ *                  submitted (slice start codes are validated from it).  Pass page-locked memory for the full copy rate.
+ *                  Waits for the device parses of the previous stream.
+ *   stream_codes   waits for a scan launched with scan = 2 and returns its list.
+ *   stream_add     copies further ranges of the same stream (a device's own pictures, once the stream is indexed); the
+ *                  parse launches that follow wait for them.
+ *   submit_stream_picture   like mp2v_recon_submit_slices with the slices named by offset; asynchronous, coded order.
+ * GOP sharding over N devices (what the bundled decoder does): split the stream into N parts; stream_begin(part d, scan = 2)
+ * on every device, stream_codes on every device, concatenate the lists (they are ascending), index, then stream_add to every
+ * device the byte ranges of the pictures it will decode. */
 typedef struct mp2v_byte_range { size_t offset, bytes; } mp2v_byte_range_t;
 MP2V_API int  mp2v_recon_stream_begin(mp2v_recon_t* ctx, const uint8_t* data, size_t bytes, const mp2v_byte_range_t* ranges, int n_ranges,
                                       int scan, const uint32_t** codes, uint32_t* n_codes);
+MP2V_API int  mp2v_recon_stream_codes(mp2v_recon_t* ctx, const uint32_t** codes, uint32_t* n_codes);
+MP2V_API int  mp2v_recon_stream_add(mp2v_recon_t* ctx, const mp2v_byte_range_t* ranges, int n_ranges);
 MP2V_API int  mp2v_recon_submit_stream_picture(mp2v_recon_t* ctx, mp2v_picture_t* pic, const mp2v_pic_syntax_t* syntax,
                                                const uint32_t* slice_offsets, int n_slices);
 

@@ -136,10 +136,27 @@ def test_gop_sharding_over_two_devices(gpu_vlc):
         pytest.skip("needs two GPUs")
     s = Stream(352, 288, 1, seed=70, n_gops=5, gop_n=9, gop_m=3)
     want = O.oracle_decode_stream(s)
-    got = Decoder(352, 288, 1, num_threads=4, devices=(0, 1)).decode(s.padded, s.size)
+    got = Decoder(352, 288, 1, num_threads=4, devices=(0, 1), gpu_vlc=gpu_vlc).decode(s.padded, s.size)
     assert got == want
-    one = Decoder(352, 288, 1, num_threads=4, devices=(1,)).decode(s.padded, s.size)
+    one = Decoder(352, 288, 1, num_threads=4, devices=(1,), gpu_vlc=gpu_vlc).decode(s.padded, s.size)
     assert one == want
+
+
+@pytest.mark.parametrize("n_pipes,w,h,cf,kw", [
+    (2, 352, 288, 1, dict(seed=71, n_gops=5, gop_n=9, gop_m=3)),
+    (3, 176, 144, 2, dict(seed=72, n_gops=7, gop_n=4, gop_m=2, user_data_bytes=29)),
+    (4, 64, 48, 1, dict(seed=73, n_gops=2, gop_n=3, gop_m=1)),              # a stream shorter than the parts' 4 KiB granularity: empty parts
+    (8, 640, 368, 1, dict(seed=74, mode=2, n_gops=9, gop_n=6, gop_m=3)),
+])
+def test_gop_sharding_pipelines_share_the_scan(n_pipes, w, h, cf, kw):
+    """several pipelines (here: contexts on ONE GPU, so that a 1-GPU box runs it) each copy and scan one part of the
+    stream -- start codes straddle the part boundaries -- and then receive the byte ranges of their own GOPs"""
+    s = Stream(w, h, cf, **kw)
+    want = O.oracle_decode_stream(s)
+    d = Decoder(w, h, cf, num_threads=2, devices=(0,) * n_pipes)
+    assert d.decode(s.padded, s.size) == want
+    assert d.stats.vlc_launches > 0
+    assert d.decode(s.padded, s.size, download=False, want_output=False) is None and d.stats.frames == len(s.pictures)
 
 
 def test_empty_stream_decodes_to_nothing(gpu_vlc):

@@ -186,6 +186,47 @@ def test_stream_resident_api(cf):
     assert got == want
 
 
+def test_stream_scan_in_parts_equals_the_whole_scan():
+    """mp2v_recon_stream_begin(part, deferred) + stream_codes + stream_add: two contexts each copy and scan one part of a
+    stream (the cut placed INSIDE a start code prefix), the concatenated lists equal the scan of the whole stream, and a
+    context that only ever received its part plus the ranges of the pictures it decodes reconstructs them bit-exactly"""
+    s = Stream(352, 288, 1, seed=350, n_gops=2, gop_n=6, gop_m=3)
+    want = O.oracle_decode_stream(s)
+    fb = len(want) // len(s.pictures)
+    sc, pics = _coded_pictures(s)
+    whole = [int(x) for x in sc]
+    n = len(s.pictures)
+    # a 16-byte aligned cut right behind the first byte(s) of some start code prefix: the code begins in part 0, ends in part 1
+    cut = next(((o + 2) & ~15) for o in whole[len(whole) // 2:] if ((o + 2) & ~15) > o)
+    assert any(o < cut <= o + 2 for o in whole)
+    parts = [(0, cut), (cut, s.size - cut)]
+    with Recon(352, 288, 1, n_frames=n, n_pictures=n, flags=RECON_VALIDATE | RECON_DEVICE_VLC) as a, \
+         Recon(352, 288, 1, n_frames=n, n_pictures=n, flags=RECON_VALIDATE | RECON_DEVICE_VLC) as b:
+        for r, part in ((a, parts[0]), (b, parts[1])):
+            assert r.stream_begin(s.padded, s.size, part=part, deferred=True) is None
+        got_codes = a.stream_codes().tolist() + b.stream_codes().tolist()
+        assert got_codes == whole
+        with pytest.raises(ReconError, match="no start-code scan is pending"):
+            a.stream_codes()
+        # context b decodes the second GOP: it holds part 1 only, so the GOP's bytes that lie in part 0 are added
+        gop2 = [i for i, p in enumerate(s.pictures) if i >= n // 2]
+        lo = min(pics[i]["slices"][0] for i in gop2)
+        b.stream_add([(lo, s.size - lo)])
+        with pytest.raises(ReconError, match="outside the stream"):
+            b.stream_add([(s.size - 4, 64)])
+        for k, i in enumerate(gop2):
+            gp, cp = s.pictures[i], pics[i]
+            ref = lambda f: -1 if f < 0 else f - n // 2
+            pic = b.acquire()
+            b.submit_stream_picture(pic, gp.params, cp["slices"], cp["f_code"], gp.intra_dc_precision, gp.q_scale_type, 1,
+                                    dst=k, l0=ref(gp.params.l0_frame), l1=ref(gp.params.l1_frame))
+        b.sync()
+        disp = [f for f in s.display_order() if f >= n // 2]
+        for f in disp:
+            k = s.display_order().index(f)
+            assert b.download(f - n // 2) == want[k * fb:(k + 1) * fb]
+
+
 def test_stream_resident_api_checks_its_arguments():
     s = Stream(176, 144, 1, seed=340, gop_n=3, gop_m=1)
     sc, pics = _coded_pictures(s)

@@ -593,19 +593,42 @@ bool mp2v_decoder_c::impl_t::open_stream(mp2v_decoder_c& owner, uint8_t* buffer,
     stream_state_t& S = *last;
     S.buffer = buffer; S.len = len;
     stream_index_t& index = S.index;
-    // Device front end: the stream goes to the first device in one copy and a kernel lists its start codes
-    // (start_codes_search.hpp:7-26); the host only parses the headers those offsets point at.
+    // Device front end: the stream goes to the device in one copy and kernels list its start codes
+    // (start_codes_search.hpp:7-26); the host only parses the headers those offsets point at.  With several devices
+    // (GOP sharding) every device copies and scans ONE PART of the stream, all at the same time over their own PCIe
+    // links, and later receives the byte ranges of the pictures it decodes: no device ever holds the whole stream.
+    std::vector<uint32_t> merged_codes;
     if (opt.gpu_vlc && len > 0) {
         if (!prepare(true)) { last.reset(); return false; }
+        const std::vector<device_ctx_t>& vdevs = dev_sets[1];
         const uint32_t* codes = nullptr;
         uint32_t n_codes = 0;
-        mp2v_recon_t* r0 = dev_sets[1][0].recon;
-        const int rc = mp2v_recon_stream_begin(r0, buffer, (size_t)len, nullptr, 0, 1, &codes, &n_codes);
+        int rc = MP2V_OK;
+        mp2v_recon_t* failed_on = vdevs[0].recon;
+        if (vdevs.size() == 1) {
+            rc = mp2v_recon_stream_begin(vdevs[0].recon, buffer, (size_t)len, nullptr, 0, 1, &codes, &n_codes);
+        } else {
+            const size_t nd = vdevs.size();
+            const size_t part = ((((size_t)len + nd - 1) / nd) + 4095) & ~(size_t)4095;
+            for (size_t d = 0; d < nd && rc == MP2V_OK; d++) {
+                const size_t lo = std::min((size_t)len, d * part), hi = std::min((size_t)len, lo + part);
+                const mp2v_byte_range_t r{lo, hi - lo};
+                rc = mp2v_recon_stream_begin(vdevs[d].recon, buffer, (size_t)len, &r, 1, 2, nullptr, nullptr);
+                if (rc != MP2V_OK) failed_on = vdevs[d].recon;
+            }
+            for (size_t d = 0; d < nd && rc == MP2V_OK; d++) {
+                rc = mp2v_recon_stream_codes(vdevs[d].recon, &codes, &n_codes);
+                if (rc != MP2V_OK) { failed_on = vdevs[d].recon; break; }
+                merged_codes.insert(merged_codes.end(), codes, codes + n_codes);      // parts are in stream order: the list stays ascending
+            }
+            codes = merged_codes.data();
+            n_codes = (uint32_t)merged_codes.size();
+        }
         if (rc == MP2V_OK) {
             if (!index_stream_from_codes(buffer, (size_t)len, codes, n_codes, index)) { error = index.error; last.reset(); return false; }
             S.resident = true;
         } else if (rc != MP2V_ERR_RANGE) {        // (RANGE: a pathological number of start codes -- the host scan takes it)
-            error = std::string("stream upload: ") + mp2v_recon_last_error(r0);
+            error = std::string("stream upload: ") + mp2v_recon_last_error(failed_on);
             last.reset();
             return false;
         }
@@ -628,8 +651,8 @@ bool mp2v_decoder_c::impl_t::open_stream(mp2v_decoder_c& owner, uint8_t* buffer,
     if (!prepare(S.gpu_vlc)) { last.reset(); return false; }
     const std::vector<device_ctx_t>& devs = dev_sets[S.gpu_vlc ? 1 : 0];
     if (S.stream_mode && devs.size() > 1) {
-        // GOP sharding (chain g -> device g mod N): every other device receives only the byte ranges of its own pictures, at the same offsets
-        for (size_t d = 1; d < devs.size(); d++) {
+        // GOP sharding (chain g -> device g mod N): every device receives the byte ranges of its own pictures, at the same offsets
+        for (size_t d = 0; d < devs.size(); d++) {
             std::vector<mp2v_byte_range_t> ranges;
             for (const coded_picture_t& pic : index.pictures) {
                 if ((size_t)pic.gop % devs.size() != d || pic.slices.empty()) continue;
@@ -639,7 +662,7 @@ bool mp2v_decoder_c::impl_t::open_stream(mp2v_decoder_c& owner, uint8_t* buffer,
                 else ranges.push_back({lo, hi - lo});
             }
             if (ranges.empty()) continue;
-            if (mp2v_recon_stream_begin(devs[d].recon, buffer, (size_t)len, ranges.data(), (int)ranges.size(), 0, nullptr, nullptr) != MP2V_OK) {
+            if (mp2v_recon_stream_add(devs[d].recon, ranges.data(), (int)ranges.size()) != MP2V_OK) {
                 error = std::string("stream upload (CUDA device ") + std::to_string(devs[d].device) + "): " + mp2v_recon_last_error(devs[d].recon);
                 last.reset();
                 return false;

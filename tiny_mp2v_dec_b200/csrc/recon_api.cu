@@ -131,6 +131,7 @@ struct mp2v_recon {
     int numa_node = -1;                        // of the device's PCIe root; -1 on single-node hosts
     int parse_rr = 0, n_parse_streams = 2, lot_cap = 0, parse_lanes = 0;      // dev knobs MP2V_PARSE_STREAMS / MP2V_LOT
     cudaEvent_t ev_stream = nullptr;           // the upload (and scan) of the resident stream
+    bool scan_pending = false;                 // a start-code scan has been launched and its list not fetched yet
     cudaEvent_t ev_stream_timed = nullptr;     // MP2V_TRACE: the same moment with a timestamp
     struct parse_buf_t { uint8_t* h = nullptr; uint8_t* d = nullptr; cudaEvent_t done = nullptr; bool used = false; } parse_buf[kParseBufs];
     int parse_buf_rr = 0;
@@ -923,17 +924,36 @@ extern "C" MP2V_API int mp2v_recon_submit_slices(mp2v_recon_t* ctx, mp2v_picture
 // ---------------------------------------------------------------------------------------------
 // stream-resident front end
 
+// waits for the scan launched by stream_begin and hands out its list (ctx->mu held)
+static int fetch_codes_locked(mp2v_recon* ctx, const uint32_t** codes, uint32_t* n_codes) {
+    if (!ctx->scan_pending) return ctx->fail(MP2V_ERR_STATE, "stream_codes: no start-code scan is pending (mp2v_recon_stream_begin with scan)");
+    ctx->scan_pending = false;
+    CK(cudaSetDevice(ctx->cfg.device), "cudaSetDevice");
+    CK(cudaStreamSynchronize(ctx->s_parse[0]), "stream sync");
+    const uint32_t total = *ctx->h_total;
+    if (total > ctx->codes_cap) return ctx->fail(MP2V_ERR_RANGE, "stream_begin: more start codes than the scan list holds");
+    if (total) CK(cudaMemcpy(ctx->h_codes, ctx->d_codes, (size_t)total * sizeof(uint32_t), cudaMemcpyDeviceToHost), "D2H start codes");
+    ctx->stats.d2h_bytes += (uint64_t)total * sizeof(uint32_t);
+    *codes = ctx->h_codes;
+    *n_codes = total;
+    return MP2V_OK;
+}
+
 extern "C" MP2V_API int mp2v_recon_stream_begin(mp2v_recon_t* ctx, const uint8_t* data, size_t bytes, const mp2v_byte_range_t* ranges, int n_ranges,
                                                 int scan, const uint32_t** codes, uint32_t* n_codes) {
-    if (!ctx || (!data && bytes) || n_ranges < 0 || (n_ranges && !ranges) || (scan && (!codes || !n_codes))) return MP2V_ERR_ARG;
+    if (!ctx || (!data && bytes) || n_ranges < 0 || (n_ranges && !ranges) || scan < 0 || scan > 2 || (scan == 1 && (!codes || !n_codes))) return MP2V_ERR_ARG;
     std::lock_guard<std::mutex> lk(ctx->mu);
     if (!ctx->vlc) return ctx->fail(MP2V_ERR_STATE, "stream_begin: context was created without MP2V_RECON_DEVICE_VLC");
     if (bytes > 0x7ffffff0ull) return ctx->fail(MP2V_ERR_ARG, "stream_begin: stream too large");
+    for (int i = 0; i < n_ranges; i++)
+        if (ranges[i].offset > bytes || ranges[i].bytes > bytes - ranges[i].offset) return ctx->fail(MP2V_ERR_ARG, "stream_begin: range outside the stream");
+    if (scan && n_ranges && ranges[0].bytes && (ranges[0].offset & 15)) return ctx->fail(MP2V_ERR_ARG, "stream_begin: the scanned range must start on a 16-byte boundary");
     int rc = flush_locked(ctx);
     if (rc != MP2V_OK) return rc;
     CK(cudaSetDevice(ctx->cfg.device), "cudaSetDevice");
     // parses of the previous stream may still be reading it
     for (auto st : ctx->s_parse) if (st) CK(cudaStreamSynchronize(st), "stream sync");
+    ctx->scan_pending = false;
     const size_t need = ((bytes + 4095) & ~(size_t)4095) + 4096;         // the scan reads whole 4 KiB chunks + look-ahead; parsers read a few bytes past a slice
     if (need > ctx->stream_cap) {
         if (ctx->d_stream) CK(cudaFree(ctx->d_stream), "cudaFree");
@@ -944,21 +964,24 @@ extern "C" MP2V_API int mp2v_recon_stream_begin(mp2v_recon_t* ctx, const uint8_t
     }
     cudaStream_t st = ctx->s_parse[0];
     if (ctx->trace && !ctx->trace_base) { CK(cudaEventCreate(&ctx->trace_base), "event"); CK(cudaEventRecord(ctx->trace_base, st), "event record"); }
+    // what is scanned: the whole stream, or the first range (a device's part of a stream whose scan is shared among devices)
+    const size_t scan_len = n_ranges ? ranges[0].bytes : bytes, scan_lo = (n_ranges && scan_len) ? ranges[0].offset : 0;
     if (n_ranges == 0) {
         if (bytes) CK(cudaMemcpyAsync(ctx->d_stream, data, bytes, cudaMemcpyHostToDevice, st), "H2D stream");
         ctx->stats.h2d_bytes += bytes;
     } else {
         for (int i = 0; i < n_ranges; i++) {
-            if (ranges[i].offset > bytes || ranges[i].bytes > bytes - ranges[i].offset) return ctx->fail(MP2V_ERR_ARG, "stream_begin: range outside the stream");
-            if (ranges[i].bytes) CK(cudaMemcpyAsync(ctx->d_stream + ranges[i].offset, data + ranges[i].offset, ranges[i].bytes, cudaMemcpyHostToDevice, st), "H2D stream");
-            ctx->stats.h2d_bytes += ranges[i].bytes;
+            // a start code that begins in the last two bytes of the scanned range ends behind it: those bytes come along
+            const size_t n = (i == 0 && scan) ? std::min(bytes - ranges[i].offset, ranges[i].bytes + 32) : ranges[i].bytes;
+            if (n) CK(cudaMemcpyAsync(ctx->d_stream + ranges[i].offset, data + ranges[i].offset, n, cudaMemcpyHostToDevice, st), "H2D stream");
+            ctx->stats.h2d_bytes += n;
         }
     }
     CK(cudaMemsetAsync(ctx->d_stream + bytes, 0, need - bytes, st), "memset stream tail");
     ctx->stream_len = bytes;
     ctx->h_stream = data;
     if (scan) {
-        const size_t nblk = vlc_scan_blocks(bytes);
+        const size_t nblk = vlc_scan_blocks(scan_len);
         if (nblk + 1 > ctx->counts_cap) {
             if (ctx->d_counts) CK(cudaFree(ctx->d_counts), "cudaFree");
             ctx->d_counts = nullptr; ctx->counts_cap = 0;
@@ -966,7 +989,7 @@ extern "C" MP2V_API int mp2v_recon_stream_begin(mp2v_recon_t* ctx, const uint8_t
             ctx->counts_cap = nblk + 1 + 1024;
         }
         // a code every 64 bytes on average is far beyond any real stream (a 1080p slice is kilobytes); more than that takes the host path
-        const uint32_t cap = (uint32_t)std::max<size_t>(1u << 16, bytes / 64);
+        const uint32_t cap = (uint32_t)std::max<size_t>(1u << 16, scan_len / 64);
         if (cap > ctx->codes_cap) {
             if (ctx->d_codes) CK(cudaFree(ctx->d_codes), "cudaFree");
             if (ctx->h_codes) CK(cudaFreeHost(ctx->h_codes), "cudaFreeHost");
@@ -975,20 +998,37 @@ extern "C" MP2V_API int mp2v_recon_stream_begin(mp2v_recon_t* ctx, const uint8_t
             CK(cudaHostAlloc(&ctx->h_codes, (size_t)cap * sizeof(uint32_t), cudaHostAllocDefault), "cudaHostAlloc start codes");
             ctx->codes_cap = cap;
         }
-        CK(launch_start_code_scan(ctx->d_stream, bytes, ctx->d_counts, ctx->d_codes, ctx->codes_cap, ctx->d_total, st), "start code scan");
-        CK(cudaStreamSynchronize(st), "stream sync");
-        const uint32_t total = *ctx->h_total;
-        if (total > ctx->codes_cap) return ctx->fail(MP2V_ERR_RANGE, "stream_begin: more start codes than the scan list holds");
-        if (total) CK(cudaMemcpy(ctx->h_codes, ctx->d_codes, (size_t)total * sizeof(uint32_t), cudaMemcpyDeviceToHost), "D2H start codes");
-        ctx->stats.d2h_bytes += (uint64_t)total * sizeof(uint32_t);
-        *codes = ctx->h_codes;
-        *n_codes = total;
+        CK(launch_start_code_scan(ctx->d_stream + scan_lo, scan_len, (uint32_t)scan_lo, ctx->d_counts, ctx->d_codes, ctx->codes_cap, ctx->d_total, st), "start code scan");
+        ctx->scan_pending = true;
     }
     CK(cudaEventRecord(ctx->ev_stream, st), "event record");
     if (ctx->trace) {
         if (!ctx->ev_stream_timed) CK(cudaEventCreate(&ctx->ev_stream_timed), "event");
         CK(cudaEventRecord(ctx->ev_stream_timed, st), "event record");
     }
+    if (scan == 1) return fetch_codes_locked(ctx, codes, n_codes);
+    return MP2V_OK;
+}
+
+extern "C" MP2V_API int mp2v_recon_stream_codes(mp2v_recon_t* ctx, const uint32_t** codes, uint32_t* n_codes) {
+    if (!ctx || !codes || !n_codes) return MP2V_ERR_ARG;
+    std::lock_guard<std::mutex> lk(ctx->mu);
+    return fetch_codes_locked(ctx, codes, n_codes);
+}
+
+extern "C" MP2V_API int mp2v_recon_stream_add(mp2v_recon_t* ctx, const mp2v_byte_range_t* ranges, int n_ranges) {
+    if (!ctx || n_ranges < 0 || (n_ranges && !ranges)) return MP2V_ERR_ARG;
+    std::lock_guard<std::mutex> lk(ctx->mu);
+    if (!ctx->vlc || !ctx->d_stream || !ctx->h_stream) return ctx->fail(MP2V_ERR_STATE, "stream_add: no resident stream (mp2v_recon_stream_begin)");
+    for (int i = 0; i < n_ranges; i++)
+        if (ranges[i].offset > ctx->stream_len || ranges[i].bytes > ctx->stream_len - ranges[i].offset) return ctx->fail(MP2V_ERR_ARG, "stream_add: range outside the stream");
+    CK(cudaSetDevice(ctx->cfg.device), "cudaSetDevice");
+    cudaStream_t st = ctx->s_parse[0];
+    for (int i = 0; i < n_ranges; i++) {
+        if (ranges[i].bytes) CK(cudaMemcpyAsync(ctx->d_stream + ranges[i].offset, ctx->h_stream + ranges[i].offset, ranges[i].bytes, cudaMemcpyHostToDevice, st), "H2D stream");
+        ctx->stats.h2d_bytes += ranges[i].bytes;
+    }
+    CK(cudaEventRecord(ctx->ev_stream, st), "event record");      // parse launches from now on wait for these bytes too
     return MP2V_OK;
 }
 

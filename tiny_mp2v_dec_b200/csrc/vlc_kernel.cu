@@ -181,7 +181,7 @@ __global__ void __launch_bounds__(1024) scan_prefix_kernel(uint32_t* __restrict_
 }
 
 __global__ void __launch_bounds__(kScanThreads) scan_write_kernel(const uint8_t* __restrict__ s, size_t len, const uint32_t* __restrict__ counts,
-                                                                 uint32_t* __restrict__ codes, uint32_t cap) {
+                                                                 uint32_t* __restrict__ codes, uint32_t cap, uint32_t base) {
     const size_t pos = (size_t)blockIdx.x * kScanChunk + (size_t)threadIdx.x * 16;
     uint32_t m = start_code_mask(s, pos, len);
     const uint32_t c = __popc(m);
@@ -196,7 +196,7 @@ __global__ void __launch_bounds__(kScanThreads) scan_write_kernel(const uint8_t*
     while (m) {
         const int b = __ffs(m) - 1;
         m &= m - 1;
-        if (before < cap) codes[before] = (uint32_t)(pos + b);
+        if (before < cap) codes[before] = base + (uint32_t)(pos + b);
         before++;
     }
 }
@@ -205,13 +205,14 @@ __global__ void __launch_bounds__(kScanThreads) scan_write_kernel(const uint8_t*
 
 size_t vlc_scan_blocks(size_t len) { return (len + kScanChunk - 1) / kScanChunk; }
 
-cudaError_t launch_start_code_scan(const uint8_t* d_stream, size_t len, uint32_t* d_counts, uint32_t* d_codes, uint32_t cap, uint32_t* d_total, cudaStream_t stream) {
+cudaError_t launch_start_code_scan(const uint8_t* d_stream, size_t len, uint32_t base, uint32_t* d_counts, uint32_t* d_codes, uint32_t cap, uint32_t* d_total,
+                                   cudaStream_t stream) {
     const size_t nb = vlc_scan_blocks(len);
     if (nb == 0) return cudaMemsetAsync(d_total, 0, sizeof(uint32_t), stream);
-    if (len > 0xfffffff0ull) return cudaErrorInvalidValue;            // offsets are 32-bit (the decode API's length is an int anyway)
+    if (len > 0xfffffff0ull || (uint64_t)base + len > 0xfffffff0ull || ((uintptr_t)d_stream & 15)) return cudaErrorInvalidValue;      // 32-bit offsets, 16-byte loads
     scan_count_kernel<<<(unsigned)nb, kScanThreads, 0, stream>>>(d_stream, len, d_counts);
     scan_prefix_kernel<<<1, 1024, 0, stream>>>(d_counts, (uint32_t)nb, d_total);
-    scan_write_kernel<<<(unsigned)nb, kScanThreads, 0, stream>>>(d_stream, len, d_counts, d_codes, cap);
+    scan_write_kernel<<<(unsigned)nb, kScanThreads, 0, stream>>>(d_stream, len, d_counts, d_codes, cap, base);
     return cudaGetLastError();
 }
 

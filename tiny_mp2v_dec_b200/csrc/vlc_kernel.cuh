@@ -53,11 +53,14 @@ inline size_t vlc_stream_desc_bytes(int max_slices) { return (sizeof(vlc_stream_
 // parse every slice of n_pics pictures described at desc (device copy, desc_stride bytes apart) out of the resident stream
 cudaError_t launch_vlc_stream(const uint8_t* d_stream, const uint8_t* d_desc, size_t desc_stride, int n_pics, int max_slices, int lanes, const void* d_tables, cudaStream_t stream);
 
-// start-code scan of a device-resident stream (the reference's scan_start_codes, start_codes_search.hpp:7-26): byte offsets of
-// every 00 00 01 prefix in [0, len), ascending, into d_codes (capacity cap entries); *d_total = number found (may exceed cap: then
-// only the first cap were stored).  d_counts: scratch of vlc_scan_blocks(len) + 1 entries.  d_stream must be readable up to len + 32.
+// start-code scan of a device-resident stream (the reference's scan_start_codes, start_codes_search.hpp:7-26): the offsets of
+// every 00 00 01 prefix that STARTS in d_stream[0, len), ascending, each plus `base` (d_stream may be a 16-byte aligned part of
+// a longer stream), into d_codes (capacity cap entries); *d_total = number found (may exceed cap: then only the first cap were
+// stored).  d_counts: scratch of vlc_scan_blocks(len) + 1 entries.  d_stream must be readable, and hold the stream's bytes, up
+// to len + 32.
 size_t vlc_scan_blocks(size_t len);
-cudaError_t launch_start_code_scan(const uint8_t* d_stream, size_t len, uint32_t* d_counts, uint32_t* d_codes, uint32_t cap, uint32_t* d_total, cudaStream_t stream);
+cudaError_t launch_start_code_scan(const uint8_t* d_stream, size_t len, uint32_t base, uint32_t* d_counts, uint32_t* d_codes, uint32_t cap, uint32_t* d_total,
+                                   cudaStream_t stream);
 
 // the tables are copied to the device once per context
 cudaError_t vlc_upload_tables(void** d_tables);

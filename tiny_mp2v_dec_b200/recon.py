@@ -15,12 +15,16 @@ _lib = None
 
 EXPORTS = [
     "mp2v_frame_layout", "mp2v_recon_create", "mp2v_recon_destroy", "mp2v_recon_last_error",
-    "mp2v_recon_acquire_picture", "mp2v_recon_release_picture", "mp2v_recon_submit", "mp2v_recon_submit_slices", "mp2v_recon_stage_slices", "mp2v_recon_submit_staged", "mp2v_recon_stream_begin", "mp2v_recon_submit_stream_picture", "mp2v_recon_precheck", "mp2v_recon_flush",
+    "mp2v_recon_acquire_picture", "mp2v_recon_release_picture", "mp2v_recon_submit", "mp2v_recon_submit_slices", "mp2v_recon_stage_slices", "mp2v_recon_submit_staged", "mp2v_recon_stream_begin", "mp2v_recon_stream_codes", "mp2v_recon_stream_add", "mp2v_recon_submit_stream_picture", "mp2v_recon_precheck", "mp2v_recon_flush",
     "mp2v_recon_sync", "mp2v_recon_reset", "mp2v_recon_upload", "mp2v_recon_run_resident", "mp2v_recon_download_frame",
     "mp2v_recon_map_frame", "mp2v_recon_upload_frame", "mp2v_recon_frame_device_ptrs", "mp2v_recon_convert_frames", "mp2v_recon_convert_frame_nv12", "mp2v_recon_convert_frames_nv12", "mp2v_recon_wait_frame",
     "mp2v_recon_set_timing", "mp2v_recon_get_stats", "mp2v_recon_timer_start", "mp2v_recon_timer_stop",
     "mp2v_recon_numa_node", "mp2v_numa_parse_cpu_list",
 ]
+
+
+class ByteRange(C.Structure):
+    _fields_ = [("offset", C.c_size_t), ("bytes", C.c_size_t)]
 
 
 class ReconError(RuntimeError):
@@ -152,17 +156,34 @@ class Recon:
         refs = (SliceRef * max(len(slices), 1))(*[SliceRef(buf.ctypes.data + off, n, code) for off, n, code in slices])
         self._ck(self.L.mp2v_recon_submit_slices(self.h, pic, C.byref(sy), refs, len(slices)))
 
-    def stream_begin(self, data, size, scan=True):
+    def stream_begin(self, data, size, scan=True, part=None, deferred=False):
         """stream-resident front end: copy data[:size] (uint8 array, kept alive by the caller until the pictures are
-        submitted) to the device; with scan -> ascending offsets of every 00 00 01 prefix (numpy copy)"""
+        submitted) to the device; with scan -> ascending offsets of every 00 00 01 prefix (numpy copy).
+        part = (offset, bytes): copy and scan only that part (offset a multiple of 16); deferred: launch only, the
+        list comes from stream_codes()"""
         self._stream = np.ascontiguousarray(data, np.uint8)
         codes = C.POINTER(C.c_uint32)()
         n = C.c_uint32()
-        self._ck(self.L.mp2v_recon_stream_begin(self.h, self._stream.ctypes.data, size, None, 0, 1 if scan else 0,
-                                                C.byref(codes) if scan else None, C.byref(n) if scan else None))
-        if not scan:
+        rng = ByteRange(part[0], part[1]) if part is not None else None
+        mode = 0 if not scan else 2 if deferred else 1
+        self._ck(self.L.mp2v_recon_stream_begin(self.h, self._stream.ctypes.data, size, C.byref(rng) if rng is not None else None,
+                                                1 if rng is not None else 0, mode, C.byref(codes) if mode == 1 else None,
+                                                C.byref(n) if mode == 1 else None))
+        if mode != 1:
             return None
         return np.ctypeslib.as_array(codes, shape=(n.value,)).copy() if n.value else np.zeros(0, np.uint32)
+
+    def stream_codes(self):
+        """the list of a scan launched with stream_begin(..., deferred=True)"""
+        codes = C.POINTER(C.c_uint32)()
+        n = C.c_uint32()
+        self._ck(self.L.mp2v_recon_stream_codes(self.h, C.byref(codes), C.byref(n)))
+        return np.ctypeslib.as_array(codes, shape=(n.value,)).copy() if n.value else np.zeros(0, np.uint32)
+
+    def stream_add(self, ranges):
+        """copy further (offset, bytes) ranges of the resident stream"""
+        arr = (ByteRange * max(len(ranges), 1))(*[ByteRange(o, b) for o, b in ranges])
+        self._ck(self.L.mp2v_recon_stream_add(self.h, arr, len(ranges)))
 
     def submit_stream_picture(self, pic, params, slice_offsets, f_code, intra_dc_precision=0, q_scale_type=0, intra_vlc_format=1,
                               dst=0, l0=-1, l1=-1, field_dct_syntax=0):
