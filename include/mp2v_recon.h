@@ -15,15 +15,20 @@
  *   picture dependencies + display hand-off       threads.cpp, decoder.cpp:346-379   submit order + map_frame
  *   decode_slice -> parse_macroblock / parse_block decoder.cpp:107-152,              mp2v_recon_submit_slices:
  *     (VLC, DC / PMV prediction, skipped MBs)      mb_decoder.cpp:74-155, 521-641     slice-parallel parser kernel
- *   sample's planar YUV write from host memory    tiny_mp2v_dec.cpp:11-17            frame_device_ptrs / convert_frames_nv12
+ *   scan_start_codes over decode()'s buffer       start_codes_search.hpp:7-26,       mp2v_recon_stream_begin / _codes / _add:
+ *                                                 decoder.cpp:283-288                scan kernels over the device-resident stream
+ *   decode()'s slice start-code switch            decoder.cpp:318-326                mp2v_recon_submit_stream_picture (slice offsets)
+ *   sample's planar YUV write from host memory    tiny_mp2v_dec.cpp:11-17            frame_device_ptrs / convert_frames (NV12, P010, UYVY)
  *
- * Two ways in.  (1) A host slice parser (VLC, DC prediction, motion-vector prediction, skipped-
+ * Three ways in.  (1) A host slice parser (VLC, DC prediction, motion-vector prediction, skipped-
  * macroblock resolution) fills one mp2v_picture_t per coded picture in pinned memory and
- * mp2v_recon_submit() copies it to the device.  (2) With MP2V_RECON_DEVICE_VLC the caller hands over
- * the picture's coded slices (mp2v_recon_submit_slices) and a kernel produces the same records on
- * the device.  Either way the whole picture is reconstructed (batched with any other submitted
- * pictures that do not depend on each other) by hand-written sm_100a kernels.  There is no CPU
- * fallback: every entry point fails with MP2V_ERR_CUDA when no device / kernel image is usable.
+ * mp2v_recon_submit() copies it to the device.  With MP2V_RECON_DEVICE_VLC a kernel produces the same
+ * records on the device: (2) the caller hands over one picture's coded slices (mp2v_recon_submit_slices,
+ * staged and copied per picture), or (3) the whole elementary stream once (mp2v_recon_stream_begin) and
+ * then pictures as slice offsets into that resident copy (mp2v_recon_submit_stream_picture).  Either way
+ * the whole picture is reconstructed (batched with any other submitted pictures that do not depend
+ * on each other) by hand-written sm_100a kernels.  There is no CPU fallback: every entry point fails
+ * with MP2V_ERR_CUDA when no device / kernel image is usable.
  *
  * Plain C: pointers and sizes only, no C++ or torch types.  Thread-safety: one context may be used
  * from several threads for acquire / fill (disjoint pictures); submit, map and sync are serialised

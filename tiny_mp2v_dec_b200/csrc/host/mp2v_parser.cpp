@@ -164,7 +164,7 @@ slice_result_t parse_slice(const uint8_t* payload, int slice_start_code, const s
     slice_result_t res;
     auto fail = [&](const char* why) { res.ok = false; res.error = why; return res; };
     if (!picture_in_envelope(pic))
-        return fail("only progressive frame pictures with frame prediction are supported (the reference's envelope)");
+        return fail("only frame pictures without concealment vectors are supported (the reference's envelope)");
     const slice_syntax_t sx = make_slice_syntax(seq, pic, mbw, mbh);
     const int nblk = sx.chroma_format == 1 ? 6 : sx.chroma_format == 2 ? 8 : 12;
     mp2v_coef_t* const scratch = thread_scratch((size_t)mbw * nblk * 64u);
