@@ -179,18 +179,27 @@ MP2V_HDI bool parse_block(bitreader_t& br, mp2v_coef_t*& out, const vlc_decode_t
         *out++ = MP2V_COEF(neg ? -1 : 1, 0, b, MP2V_COEF_FIRST) | mb_bits;
         i = 1;
     }
-#ifdef __CUDA_ARCH__
-    // Device loop.  A slice thread's time is its instruction count (one lane of a warp, no ILP to speak of), so a
-    // fast symbol is: look up one pre-assembled word (shared memory), add it to the running {position, block}
-    // word q -- that IS the record -- store, keep its upper half as the next q.  q = ((i - 1) << 16 | block << 22
-    // | macroblock tag) modulo 2^32: a position past 63 carries into the block field and stays there, so the
-    // range check is ONE compare of q at the end of the block; what bounds the writes meanwhile is the record
-    // count (a block has at most 64 coefficients and every symbol is one).  Fast symbols are at most kFastBits
-    // = 11 bits long, so three of them fit the 33 bits a refill guarantees: one refill check per three symbols.
+    // Symbol loop, one source for both sides.  A fast symbol is: look up one pre-assembled word (the device keeps the
+    // tables in shared memory), add it to the running {position, block} word q -- that IS the record -- store, keep
+    // its upper half as the next q.  q = ((i - 1) << 16 | block << 22 | macroblock tag) modulo 2^32: a position past
+    // 63 carries into the block field and stays there, so the range check is ONE compare of q at the end of the block;
+    // what bounds the writes meanwhile is the record count (a block has at most 64 coefficients and every symbol is
+    // one).  Fast symbols are at most kFastBits = 11 bits long, so three of them fit the 33 bits a refill guarantees
+    // on the device (the host's 56 bits hold them too): one refill check per three symbols.
     {
         const bool b15 = table == &T.b15;
+#ifdef __CUDA_ARCH__
         const uint32_t fast = dev_fast + (b15 ? (4u << kFastBits) : 0u);
         const uint32_t long_codes = dev_fast + (8u << kFastBits) + (b15 ? (4u << coef_vlc_t::kLongBits) : 0u);
+#define MP2V_FAST_ENTRY(idx) lds_word(fast, (idx))
+#define MP2V_LONG_ENTRY(idx) lds_word(long_codes, (idx))
+#else
+        (void)dev_fast;
+        const uint32_t* const fast = b15 ? T.b15.gpu_fast : T.b14.gpu_fast;
+        const uint32_t* const long_codes = b15 ? T.b15.gpu_long : T.b14.gpu_long;
+#define MP2V_FAST_ENTRY(idx) fast[(idx)]
+#define MP2V_LONG_ENTRY(idx) long_codes[(idx)]
+#endif
         uint32_t q = (((uint32_t)i << 16) | blk_bits) - 0x10000u;
         mp2v_coef_t* const o0 = out;
         uint32_t n = 0;                                        // records stored by this loop; 32-bit index, not a 64-bit pointer bump
@@ -202,7 +211,7 @@ MP2V_HDI bool parse_block(bitreader_t& br, mp2v_coef_t*& out, const vlc_decode_t
             for (;;) {
                 br.refill();
 #define MP2V_FAST_SYMBOL                                                                   \
-                e = lds_word(fast, br.peek(kFastBits));                                   \
+                e = MP2V_FAST_ENTRY(br.peek(kFastBits));                                   \
                 if ((int32_t)e < 0 || n == n_max) break;   /* not fast, or a 65th coefficient */ \
                 br.skip((int)(e >> 24));                                                   \
                 { const uint32_t rec = q + (e & 0x007fffffu); o0[n++] = rec; q = rec & 0xffff0000u; }
@@ -225,7 +234,7 @@ MP2V_HDI bool parse_block(bitreader_t& br, mp2v_coef_t*& out, const vlc_decode_t
                 inc = ((((w >> 12) & 63u) + 1u) << 16) | ((((w & 0xfffu) ^ 0x800u) - 0x800u) & 0xffffu);
                 len = 24u;
             } else if ((w >> (24 - coef_vlc_t::kLongZeros)) == 0u) {
-                const uint32_t l = lds_word(long_codes, (w >> (24 - coef_vlc_t::kLongZeros - coef_vlc_t::kLongBits)) & ((1u << coef_vlc_t::kLongBits) - 1u));
+                const uint32_t l = MP2V_LONG_ENTRY((w >> (24 - coef_vlc_t::kLongZeros - coef_vlc_t::kLongBits)) & ((1u << coef_vlc_t::kLongBits) - 1u));
                 if ((int32_t)l < 0) break;                     // no such code
                 inc = l & 0x007fffffu;
                 len = l >> 24;
@@ -238,50 +247,11 @@ MP2V_HDI bool parse_block(bitreader_t& br, mp2v_coef_t*& out, const vlc_decode_t
             o0[n++] = rec;
             q = rec & 0xffff0000u;
         }
+#undef MP2V_FAST_ENTRY
+#undef MP2V_LONG_ENTRY
         out = o0 + n;
         return ok && ((q ^ blk_bits) >> 22) == 0;              // i + run never passed 63
     }
-#else
-    // Host loop.  Symbols decoded per refill: an escape is 24 bits, so two of any kind fit the 56 bits a
-    // refill guarantees (the first round reuses the refill above: at most 22 bits were consumed since).
-    for (;;) {
-        MP2V_UNROLL2
-        for (int rep = 0; rep < 2; rep++) {
-            const coef_fast_t f = table->look_fast(br.peek(kFastBits));
-            int run, level;
-            if (f.run < kFastEob) {
-                br.skip(f.len);
-                run = f.run; level = f.level;
-            } else if (f.run == kFastEob) {
-                br.skip(f.len);
-                return true;
-            } else {
-                const coef_entry_t e = table->look(br.peek(17));
-                if (e.level > 0) {
-                    br.skip(e.len);
-                    const int neg = (int)br.peek(1);
-                    br.skip(1);
-                    run = e.run;
-                    level = (e.level ^ -neg) + neg;
-                } else if (e.level == kCoefEob && e.len) {
-                    br.skip(e.len);
-                    return true;
-                } else if (e.level == kCoefEsc && e.len) {     // 6-bit run, 12-bit two's complement level
-                    br.skip(6);
-                    run = (int)br.peek(6); br.skip(6);
-                    level = ((int)br.peek(12) ^ 0x800) - 0x800; br.skip(12);
-                } else {
-                    return false;
-                }
-            }
-            i += run;
-            if (i > 63) return false;
-            *out++ = (uint32_t)(uint16_t)level | ((uint32_t)i << 16) | blk_bits;
-            i++;
-        }
-        br.refill();
-    }
-#endif
 }
 
 // the reference does not clamp vectors: one that leaves the frame is an error here

@@ -64,24 +64,16 @@ struct flat_vlc_t {
     MP2V_HD inline vlc_entry_t look(uint32_t peek_bits) const { return fetch_entry(&e[peek_bits]); }
 };
 
-// Fast path of the run/level decoder: one lookup on the next 11 bits resolves code AND sign for
-// every symbol whose code + sign bit fit (all the frequent ones); anything else falls back to the
-// two-level table.  4 bytes per entry, 8 KB per table.
-struct alignas(4) coef_fast_t {
-    int16_t level;     // signed level (fast symbols); unused otherwise
-    uint8_t run;       // 0..63 fast symbol; kFastEob / kFastSlow markers
-    uint8_t len;       // bits consumed including the sign bit (fast symbols and end of block)
-};
-constexpr uint8_t kFastEob = 64, kFastSlow = 65;
+// Fast path of the run/level decoder: one lookup on the next 11 bits resolves code AND sign for every symbol whose
+// code + sign bit fit (all the frequent ones) into a word that is added to the running record (slice_core.h);
+// anything else is an escape or one of the long codes below.
 constexpr int kFastBits = 11;
 
 struct coef_vlc_t {
     static constexpr int ROOT = 8, LEAF = 9;                      // longest code is 16 bits (+ sign)
-    coef_fast_t fast[1 << kFastBits];
-    // The same table pre-assembled for the device parser, whose cost is instructions per symbol: a fast
-    // symbol's coefficient record is `q + (entry & 0x7fffff)` where q carries block and position:
+    // A fast symbol's coefficient record is `q + (entry & 0x7fffff)` where q carries block and position:
     //   [15:0] level (two's complement)  [22:16] run + 1  [27:24] bits consumed (incl. sign)
-    //   [31] not a fast symbol -> [30] end of block (then [27:24] = its length), else take the two-level table
+    //   [31] not a fast symbol -> [30] end of block (then [27:24] = its length), else an escape or a long code
     uint32_t gpu_fast[1 << kFastBits];
     // ... and the codes the fast table does not hold: besides the escape (prefix 000001) they all start with seven
     // zeros and are 12..16 bits long, so the ten bits behind the zeros resolve code and sign:
@@ -99,16 +91,13 @@ struct coef_vlc_t {
         }
         for (uint32_t i = 0; i < (1u << kFastBits); i++) {
             const coef_entry_t e = look(i << (17 - kFastBits));
-            coef_fast_t f{0, kFastSlow, 0};
+            gpu_fast[i] = 0x80000000u;
             if (e.len && e.level > 0 && e.len + 1 <= kFastBits) {
                 const int neg = (int)(i >> (kFastBits - 1 - e.len)) & 1;
-                f.level = (int16_t)(neg ? -e.level : e.level); f.run = e.run; f.len = (uint8_t)(e.len + 1);
+                gpu_fast[i] = (uint32_t)(uint16_t)(neg ? -e.level : e.level) | ((uint32_t)(e.run + 1) << 16) | ((uint32_t)(e.len + 1) << 24);
             } else if (e.len && e.level == kCoefEob && e.len <= kFastBits) {
-                f.run = kFastEob; f.len = e.len;
+                gpu_fast[i] = 0xc0000000u | ((uint32_t)e.len << 24);
             }
-            fast[i] = f;
-            gpu_fast[i] = f.run < kFastEob ? ((uint32_t)(uint16_t)f.level | ((uint32_t)(f.run + 1) << 16) | ((uint32_t)f.len << 24))
-                        : f.run == kFastEob ? (0xc0000000u | ((uint32_t)f.len << 24)) : 0x80000000u;
         }
     }
     static constexpr int MAX_LEAVES = 8;                          // distinct 8-bit prefixes with longer codes (B.14/B.15 need 6)
@@ -143,7 +132,6 @@ struct coef_vlc_t {
         if (!r.sub) return r;
         return fetch_entry(&leaves[((size_t)(r.sub - 1) << LEAF) + (peek17 & ((1u << LEAF) - 1u))]);
     }
-    MP2V_HD inline coef_fast_t look_fast(uint32_t peek11) const { return fetch_entry(&fast[peek11]); }
 };
 
 // dct_dc_size + dct_dc_differential in one lookup on the next 12 bits (covers sizes whose code and
