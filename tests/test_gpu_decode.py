@@ -54,6 +54,14 @@ def test_matrices_loaded_once_per_gop_persist(cf, gpu_vlc):
     assert Decoder(176, 144, cf, num_threads=2, gpu_vlc=gpu_vlc).decode(s.padded, s.size) == O.oracle_decode_stream(s)
 
 
+@pytest.mark.parametrize("cf,kw", [(1, dict(pct_big_levels=10)), (2, dict(mode=2, pct_intra_in_pb=20)), (3, dict(intra_only=1, pct_field_dct=50))])
+def test_intra_vlc_format_0(cf, kw, gpu_vlc):
+    """intra blocks coded with table B.14 (intra_vlc_format = 0): outside the reference's envelope (it crashes, SURVEY.md 8c);
+    the oracle reconstructs the generator's ground-truth records"""
+    s = Stream(320, 192, cf, seed=80 + cf, n_gops=2, gop_n=5, gop_m=2, intra_vlc_table0=1, **kw)
+    assert Decoder(320, 192, cf, num_threads=2, gpu_vlc=gpu_vlc).decode(s.padded, s.size) == O.oracle_decode_stream(s)
+
+
 def test_no_reordering_gives_coded_order(gpu_vlc):
     s = Stream(176, 144, 1, seed=61, gop_n=7, gop_m=3)
     got = Decoder(176, 144, 1, num_threads=2, reordering=False, gpu_vlc=gpu_vlc).decode(s.padded, s.size)

@@ -26,6 +26,11 @@ CASES = [
     (176, 144, 2, dict(seed=24, n_gops=2, gop_n=7, gop_m=3, matrices_once=1)),
     (176, 144, 3, dict(seed=25, n_gops=2, gop_n=7, gop_m=3, matrices_once=1, alternate_scan=1)),
     (176, 144, 1, dict(seed=26, n_gops=2, gop_n=7, gop_m=3, matrices_once=1)),
+    # intra_vlc_format = 0: intra blocks code their AC coefficients with table B.14 -- the reference takes the non-intra
+    # first-coefficient path for them and crashes (mb_decoder.cpp:79-88); the generator's ground truth is the oracle
+    (176, 144, 1, dict(seed=27, n_gops=2, gop_n=7, gop_m=3, intra_vlc_table0=1, pct_big_levels=10)),
+    (176, 144, 3, dict(seed=28, n_gops=1, gop_n=5, gop_m=2, intra_vlc_table0=1, mode=2, pct_intra_in_pb=20)),
+    (320, 192, 2, dict(seed=29, intra_only=1, gop_n=3, intra_vlc_table0=1, pct_field_dct=50)),
 ]
 
 

@@ -17,7 +17,7 @@ class GenParams(C.Structure):
                 ("pct_mb_quant", C.c_int32), ("pct_big_levels", C.c_int32), ("all_blocks_coded", C.c_int32),
                 ("natural_mean_coefs", C.c_int32), ("unclamped_mv", C.c_int32),
                 ("user_data_bytes", C.c_int32), ("texture_noise", C.c_int32), ("matrices_once", C.c_int32),
-                ("pct_field_dct", C.c_int32)]
+                ("pct_field_dct", C.c_int32), ("intra_vlc_table0", C.c_int32)]
 
 
 class GenPicture(C.Structure):

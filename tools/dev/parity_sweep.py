@@ -26,7 +26,7 @@ for k in range(n):
               alternate_scan=int(rng.integers(-1, 2)), q_scale_type=int(rng.integers(-1, 2)), intra_dc_precision=int(rng.integers(-1, 4)),
               pct_skipped=int(rng.choice([0, 15, 60])), pct_intra_in_pb=int(rng.choice([0, 10, 50])), pct_coded=int(rng.choice([0, 30, 70, 100])),
               pct_mb_quant=int(rng.choice([0, 10, 50])), pct_big_levels=int(rng.choice([0, 3, 30])), all_blocks_coded=int(rng.integers(0, 2)),
-              mv_range=int(rng.choice([0, 3, 24, 100])), pct_field_dct=int(rng.choice([0, 0, 30, 100])), matrices_once=int(rng.integers(0, 2)))
+              mv_range=int(rng.choice([0, 3, 24, 100])), pct_field_dct=int(rng.choice([0, 0, 30, 100])), matrices_once=int(rng.integers(0, 2)), intra_vlc_table0=int(rng.integers(0, 2)))
     if rng.integers(0, 4) == 0:
         kw["intra_only"] = 1
     try:

@@ -156,7 +156,7 @@ struct mp2v_gen {
         bw.put(h.dc_prec, 2); bw.put(3, 2);         // frame picture
         const int fpfd = p.pct_field_dct > 0 ? 0 : 1;      // frame_pred_frame_dct = 0 only in interlaced frames (progressive_frame = 0)
         bw.put(fpfd ? 0 : 1, 1); bw.put(fpfd, 1); bw.put(0, 1);   // top_field_first, frame_pred_frame_dct, concealment_mv
-        bw.put(h.q_scale_type, 1); bw.put(1, 1); bw.put(h.alt_scan, 1);   // intra_vlc_format = 1
+        bw.put(h.q_scale_type, 1); bw.put(p.intra_vlc_table0 ? 0 : 1, 1); bw.put(h.alt_scan, 1);   // q_scale_type, intra_vlc_format, alternate_scan
         bw.put(0, 1); bw.put(p.chroma_format == 1 && fpfd ? 1 : 0, 1); bw.put(fpfd, 1); bw.put(0, 1);   // repeat_first_field, chroma_420_type, progressive_frame, composite
         if (p.matrices_once && gop_tx_valid) {      // no extension: the matrices of the GOP's first picture stay in force
             for (int k = 0; k < 4; k++) {
@@ -254,7 +254,7 @@ struct mp2v_gen {
                 bw.put("1"); bw.put(level < 0, 1);
                 pic.coef.push_back(MP2V_COEF(level, 0, b, MP2V_COEF_FIRST) | MP2V_COEF_MB(cur_mbx));
             } else {
-                put_run_level(intra, run, level);
+                put_run_level(intra && !p.intra_vlc_table0, run, level);
                 pic.coef.push_back(MP2V_COEF(level, i, b, 0) | MP2V_COEF_MB(cur_mbx));
             }
             i++;
@@ -263,7 +263,7 @@ struct mp2v_gen {
             bw.put("1"); bw.put(0, 1);
             pic.coef.push_back(MP2V_COEF(1, 0, b, MP2V_COEF_FIRST) | MP2V_COEF_MB(cur_mbx));
         }
-        bw.put(intra ? kEobB15 : kEobB14);
+        bw.put((intra && !p.intra_vlc_table0) ? kEobB15 : kEobB14);
     }
 
     // ------------------------------------------------------------------ mode 2: texture content
@@ -434,13 +434,13 @@ struct mp2v_gen {
                 bw.put("1"); bw.put(level < 0, 1);
                 pic.coef.push_back(MP2V_COEF(level, 0, b, MP2V_COEF_FIRST) | MP2V_COEF_MB(cur_mbx));
             } else {
-                put_run_level(intra, run, level);
+                put_run_level(intra && !p.intra_vlc_table0, run, level);
                 pic.coef.push_back(MP2V_COEF(level, i, b, 0) | MP2V_COEF_MB(cur_mbx));
             }
             first = false;
             run = 0;
         }
-        bw.put(intra ? kEobB15 : kEobB14);
+        bw.put((intra && !p.intra_vlc_table0) ? kEobB15 : kEobB14);
     }
 
     // rows of a picture are analysed on several threads (results do not depend on the thread count)

@@ -49,6 +49,8 @@ typedef struct mp2v_gen_params {
     int32_t  pct_field_dct;        /* > 0: pictures are coded with frame_pred_frame_dct = 0 (interlaced frame pictures, frame-based
                                       prediction only: frame_motion_type = 2) and this % of the intra / pattern macroblocks use
                                       dct_type = 1 (field DCT, mb_decoder.cpp:172-195, 357-360)                                */
+    int32_t  intra_vlc_table0;     /* 1: intra_vlc_format = 0 -- intra blocks code their AC coefficients with table B.14 like non-intra
+                                      blocks (default: intra_vlc_format = 1, table B.15)                                        */
 } mp2v_gen_params_t;
 
 typedef struct mp2v_gen mp2v_gen_t;
