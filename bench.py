@@ -344,6 +344,9 @@ def kernel_roofline(wl, stream, steps, warmup, device, peak, world=1):
             "algorithmic_bytes_per_launch": round(st.algorithmic_bytes / launches), "launch_ms": round(st.kernel_ms / launches, 4),
             "frames_per_s_kernel_only": round(n * steps / (dev_ms * 1e-3), 1),
             "timed": "kernel alone over device-resident records, %d steps, CUDA event pair around every launch" % steps,
+            # share of the kernel's batches (<= 24 coded blocks) whose range bound forced the saturating IDCT arithmetic
+            "idct_exact_path": {"batches": int(st.idct_batches), "pass2_fraction": round(st.idct_exact_pass2 / max(int(st.idct_batches), 1), 5),
+                                "pass1_fraction": round(st.idct_exact_pass1 / max(int(st.idct_batches), 1), 5)},
             "host_parse": {"wall_s": round(parse_wall, 4), "cpu_s": round(parse_cpu, 4), "fps_per_core": round(n / parse_cpu, 1) if parse_cpu > 0 else None}}, \
         n * steps / launches
 

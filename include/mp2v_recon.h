@@ -326,6 +326,9 @@ typedef struct mp2v_recon_stats {
                                       one per batch of pictures handed over with submit_stream_picture) */
     uint64_t vlc_slices;           /* slices handed to the device parser                          */
     uint64_t vlc_coefs;            /* coefficient records it wrote (parses completed so far)      */
+    uint64_t idct_batches;         /* batches of <= 24 coded blocks transformed (when timing is enabled) ...            */
+    uint64_t idct_exact_pass2;     /* ... of them those whose range bound forced the saturating arithmetic in pass 2 ...  */
+    uint64_t idct_exact_pass1;     /* ... and in pass 1 too (an intra DC outside the analysed range)                      */
 } mp2v_recon_stats_t;
 MP2V_API int  mp2v_recon_set_timing(mp2v_recon_t* ctx, int enable);
 /* CUDA-event stopwatch on the context's compute stream (the stream every kernel is launched on):

@@ -58,7 +58,8 @@ class FrameLayout(C.Structure):
 class ReconStats(C.Structure):
     _fields_ = [("pictures", C.c_uint64), ("launches", C.c_uint64), ("h2d_bytes", C.c_uint64), ("d2h_bytes", C.c_uint64),
                 ("algorithmic_bytes", C.c_uint64), ("kernel_ms", C.c_double),
-                ("vlc_launches", C.c_uint64), ("vlc_slices", C.c_uint64), ("vlc_coefs", C.c_uint64)]
+                ("vlc_launches", C.c_uint64), ("vlc_slices", C.c_uint64), ("vlc_coefs", C.c_uint64),
+                ("idct_batches", C.c_uint64), ("idct_exact_pass2", C.c_uint64), ("idct_exact_pass1", C.c_uint64)]
 
 
 class PicSyntax(C.Structure):

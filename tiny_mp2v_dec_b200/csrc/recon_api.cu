@@ -128,6 +128,7 @@ struct mp2v_recon {
     uint32_t* h_total = nullptr; uint32_t* d_total = nullptr;   // pinned + mapped
     cudaStream_t s_parse[kParseStreams] = {};
     int sm_count = 148;
+    unsigned long long* d_counters = nullptr;  // batch_desc_t::counters
     int numa_node = -1;                        // of the device's PCIe root; -1 on single-node hosts
     int parse_rr = 0, n_parse_streams = 2, lot_cap = 0, parse_lanes = 0;      // dev knobs MP2V_PARSE_STREAMS / MP2V_LOT
     cudaEvent_t ev_stream = nullptr;           // the upload (and scan) of the resident stream
@@ -201,6 +202,7 @@ static void destroy_ctx(mp2v_recon* ctx) {
     if (ctx->h_arena_pool) cudaFreeHost(ctx->h_arena_pool);
     if (ctx->d_arena_pool) cudaFree(ctx->d_arena_pool);
     if (ctx->h_status_pool) cudaFreeHost(ctx->h_status_pool);
+    if (ctx->d_counters) cudaFree(ctx->d_counters);
     if (ctx->d_tables) cudaFree(ctx->d_tables);
     if (ctx->d_blank_mb) cudaFree(ctx->d_blank_mb);
     if (ctx->h_pool) cudaFreeHost(ctx->h_pool);
@@ -275,6 +277,8 @@ static int create_impl(mp2v_recon* ctx) {
     for (auto& ev : ctx->launch_ev) CK(cudaEventCreateWithFlags(&ev, cudaEventDisableTiming), "event");
     if (const char* v = getenv("MP2V_TRACE")) ctx->trace = atoi(v) != 0;
     CK(cudaDeviceGetAttribute(&ctx->sm_count, cudaDevAttrMultiProcessorCount, c.device), "device attribute");
+    CK(cudaMalloc(&ctx->d_counters, 3 * sizeof(unsigned long long)), "cudaMalloc counters");
+    CK(cudaMemset(ctx->d_counters, 0, 3 * sizeof(unsigned long long)), "cudaMemset counters");
     ctx->auto_dl = (c.flags & MP2V_RECON_AUTO_DOWNLOAD) != 0;
     ctx->mirror_valid.assign(c.n_frames, 0);
     ctx->read_ev.assign(c.n_frames, nullptr);
@@ -418,6 +422,7 @@ static int launch_slots(mp2v_recon* ctx, const int* ids, int n, bool download = 
     b.mbw = ctx->mbw; b.mbh = ctx->mbh; b.mb_count = ctx->mb_count;
     for (int p = 0; p < 3; p++) b.stride[p] = ctx->lay.stride[p];
     b.mbs_per_warp = choose_mbs_per_warp(ctx->cfg.chroma_format, (long long)n * ctx->mb_count);
+    b.counters = ctx->timing ? ctx->d_counters : nullptr;
     const int g = b.mbs_per_warp * (kCtaThreads / 32);
     b.ctas_per_pic = (ctx->mb_count + g - 1) / g;
     for (int i = 0; i < n; i++) fill_desc(ctx, ctx->slots[ids[i]], b.pic[i]);
@@ -1458,6 +1463,13 @@ extern "C" MP2V_API int mp2v_recon_get_stats(mp2v_recon_t* ctx, mp2v_recon_stats
             ctx->timing_pool.push_back(pr.first); ctx->timing_pool.push_back(pr.second);
         }
         ctx->timed.clear();
+    }
+    if (ctx->timing && ctx->d_counters) {
+        unsigned long long c[3] = {0, 0, 0};
+        CK(cudaStreamSynchronize(ctx->s_compute), "stream sync");
+        CK(cudaMemcpy(c, ctx->d_counters, sizeof(c), cudaMemcpyDeviceToHost), "D2H counters");
+        ctx->stats.idct_batches = c[0]; ctx->stats.idct_exact_pass2 = c[1]; ctx->stats.idct_exact_pass1 = c[2];
+        if (reset) CK(cudaMemset(ctx->d_counters, 0, sizeof(c)), "cudaMemset counters");
     }
     *out = ctx->stats;
     if (reset) ctx->stats = mp2v_recon_stats_t{};

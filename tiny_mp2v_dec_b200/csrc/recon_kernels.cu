@@ -368,6 +368,7 @@ recon_kernel3(const __grid_constant__ batch_desc_t batch, const __grid_constant_
     }
 
     uint32_t wphase = 0;                                   // bit b: parity the next wait on buffer b expects
+    uint32_t path_counts = 0;                              // batches | exact pass 2 << 8 | exact pass 1 << 16
     uint4 rec_next = (mb_begin + lane < mb_end) ? __ldg(reinterpret_cast<const uint4*>(pd.mb) + mb_begin + lane) : make_uint4(0, 0, 0, 0);
     // the 32 coefficient records behind the previous batch's last one: the next batch's first trip when its list continues there
     uint32_t pref_idx = 0xffffffffu, pref_c = 0;
@@ -501,6 +502,7 @@ recon_kernel3(const __grid_constant__ batch_desc_t batch, const __grid_constant_
         const int bnd = lane < nslots ? ws.bound[lane] + (int)s.bwp[63] : 0;      // scan position 63 is tile index 63 in both scans
         const bool p1_exact = __any_sync(0xffffffffu, bnd >= kBoundWild);
         const bool p2_exact = __any_sync(0xffffffffu, bnd > kBoundLimit);
+        path_counts += 1u + (p2_exact ? 1u << 8 : 0u) + (p1_exact ? 1u << 16 : 0u);      // (a warp's run is at most 60 batches)
         __syncwarp();
         // pass 1: one lane per column, in place; the transform runs across the vector index k (idct_sse2.hpp:98)
         // (no predication: the lanes of a last, partly filled trip transform whatever the tile rows behind the used
@@ -613,6 +615,13 @@ recon_kernel3(const __grid_constant__ batch_desc_t batch, const __grid_constant_
         }
         first += nb;
         mbx0 = mbx; mby0 = mby;
+    }
+    if (lane == 0 && batch.counters) {
+        atomicAdd(&batch.counters[0], (unsigned long long)(path_counts & 0xffu));
+        if (path_counts >> 8) {
+            atomicAdd(&batch.counters[1], (unsigned long long)((path_counts >> 8) & 0xffu));
+            atomicAdd(&batch.counters[2], (unsigned long long)(path_counts >> 16));
+        }
     }
 }
 

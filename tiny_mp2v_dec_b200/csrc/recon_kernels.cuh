@@ -46,6 +46,9 @@ struct batch_desc_t {
     int32_t stride[3];
     int32_t ctas_per_pic;
     int32_t mbs_per_warp;
+    // (optional) device counters: [0] batches transformed, [1] of them with the exact (saturating) arithmetic in pass 2,
+    // [2] in pass 1 as well -- how often the range analysis fails to prove a batch safe
+    unsigned long long* counters;
 };
 
 // TMA descriptors of the frame pool, one per plane: a [frame][row][pixel] tensor of bytes whose boxes are the
